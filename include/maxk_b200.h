@@ -1,0 +1,148 @@
+/*
+ * maxk_b200.h -- C ABI of libmaxk_b200.so: the B200 (sm_100a) implementation of the
+ * MaxK-GNN sparse-aggregation hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers, sizes
+ * and a CUDA stream (a cudaStream_t passed as void*; NULL = legacy default stream);
+ * no torch types, no allocation, no hidden synchronisation unless stated.  All
+ * pointers are BORROWED: the caller owns the buffers and must keep them alive until
+ * the stream has drained (same convention as the reference shims,
+ * cuda_kernel_wrappers.cu:36-93).
+ *
+ * Return value: MAXK_OK (0) or a MAXK_ERR_* code; maxk_last_error() gives the
+ * message for the calling thread.  Unlike the reference shims (which printf on
+ * cudaGetLastError and return void, cuda_kernel_wrappers.cu:52-55) errors are reported.
+ *
+ * Citations "ref: file:line" are into julius-sk/spgemm-new and name the reference
+ * interface each function replaces.  Layouts:
+ *   CSR            indptr int32[N+1], indices int32[E], values float32[E]; row = destination
+ *   work list      int32[4*W] = (row, loc, len, 0) per task, len <= warp_max_nz (64)
+ *   CBSR           sp_data float32[N,k] + sp_index uint8[N,k], row-major, k <= D <= 256
+ */
+#ifndef MAXK_B200_H_
+#define MAXK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAXK_OK 0
+#define MAXK_ERR_INVALID_ARGUMENT 1
+#define MAXK_ERR_CUDA 2
+#define MAXK_ERR_UNSUPPORTED 3
+
+#define MAXK_ABI_VERSION 1
+#define MAXK_WARP_MAX_NZ 64 /* ref: kernels/generate_meta.py:9 */
+#define MAXK_MAX_DIM 256    /* selectors are uint8 (ref: spmm_maxk.cu:17) */
+
+/* Layout-compatible stand-in for CUDA's dim3 so that C callers can bind the
+ * reference-named shims below (ref: cuda_kernel_bindings.cpp:11-35). */
+typedef struct maxk_dim3 {
+    unsigned int x, y, z;
+} maxk_dim3;
+
+int maxk_abi_version(void);
+const char *maxk_last_error(void);
+/* Number of kernels this library has launched in the calling process (for bench.py's
+ * gpu_launches claim). */
+int64_t maxk_launch_count(void);
+/* Bench/test hook (not part of the reference surface): run length, in tasks per warp, of
+ * the forward / backward kernels; a value <= 0 leaves that knob unchanged. */
+int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp);
+
+/* ---- a4: work list (replaces kernels/generate_meta.py:8-48 and the disk round trip of
+ * load_warp4_metadata, cuda_kernel_bindings.cpp:287-317) ------------------------------
+ * Two calls because the caller allocates the output:
+ *   1. maxk_worklist_count  -> W (synchronises `stream` once to return the count) and
+ *      fills `workspace` (maxk_worklist_workspace_bytes(num_rows) bytes, device);
+ *   2. maxk_worklist_fill   -> writes int32[4*W] records, bit-identical to
+ *      generate_meta.py's .warp4 file for the same indptr.                            */
+int64_t maxk_worklist_workspace_bytes(int64_t num_rows);
+int maxk_worklist_count(const int32_t *indptr, int64_t num_rows, int32_t warp_max_nz,
+                        void *workspace, int64_t *num_tasks_host, void *stream);
+int maxk_worklist_fill(const int32_t *indptr, int64_t num_rows, int32_t warp_max_nz,
+                       const void *workspace, int32_t *warp4, int64_t num_tasks, void *stream);
+
+/* ---- a1: MaxK / TopK -> CBSR (replaces topk, kernels/maxk_kernel.cu:23-96, and the
+ * torch::topk stand-ins kernels/spmm_bindings.cpp:163-204, utils/models.py:39,48) -----
+ * Exact top-k per row, ties -> lowest column, emitted in ascending column order;
+ * values are bit copies.  NaN ranks largest, -0 == +0.  d % 4 == 0, 1 <= k <= d <= 256.
+ * dense_out (optional, may be NULL): x * mask, float32[n,d] (MaxK.forward,
+ * utils/models.py:48-52).  sp_data / sp_index may be NULL when only dense_out is wanted. */
+int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t k, float *sp_data,
+                       uint8_t *sp_index, float *dense_out, void *stream);
+/* uint8 flavour of the reference kernel's own data type (cuda_topk_maxk,
+ * cuda_kernel_bindings.cpp:164-201). d % 8 == 0. */
+int maxk_topk_cbsr_u8(const uint8_t *x, int64_t n, int32_t d, int32_t k, uint8_t *value,
+                      uint8_t *index, void *stream);
+
+/* ---- a2: forward row-wise-product SpGEMM  Y = A * X_cbsr (replaces
+ * spmm_kernel_opt2_sparse_v3, kernels/spmm_maxk.cu:17-106; spmm_maxk_forward,
+ * cuda_kernel_bindings.cpp:42-104) -----------------------------------------------------
+ * out float32[num_rows_out, d] is fully DEFINED by the call (no pre-zero needed, not
+ * accumulated -- SURVEY Q2).  Task rows must be non-decreasing (what generate_meta.py
+ * produces).  Selectors of one CBSR row must be distinct.  d % 4 == 0.      */
+int maxk_spgemm_forward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
+                        const float *values, const float *sp_data, const uint8_t *sp_index,
+                        int32_t k, float *out, int64_t num_rows_out, int32_t d, void *stream);
+
+/* ---- a3: backward outer-product sampled SSpMM  dXc = sample(A^T dY, sp_index)
+ * (replaces spmm_kernel_opt2_sparse_backward_v3, kernels/spmm_maxk_backward.cu:15-115;
+ * spmm_maxk_backward, cuda_kernel_bindings.cpp:106-161) ----------------------------------
+ * dxc float32[num_cbsr_rows, k].  accumulate == 0: dxc is zero-filled first (defined
+ * output); accumulate != 0: contributions are added to the existing content (used by
+ * the multi-GPU local/remote split).                                                   */
+int maxk_sspmm_backward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
+                        const float *values, const float *dy, const uint8_t *sp_index,
+                        int32_t k, int32_t d, float *dxc, int64_t num_cbsr_rows,
+                        int32_t accumulate, void *stream);
+
+/* ---- a5: CBSR <-> dense (replaces the .item() double loop utils/models.py:136-141 and
+ * the mask multiply of MaxK.backward, utils/models.py:55-59) -----------------------------
+ * scatter: dense[i, sp_index[i,j]] = sp_data[i,j], zeros elsewhere (dense fully defined)
+ * gather : sp_data[i,j] = dense[i, sp_index[i,j]]
+ * mask   : out[i,c] = in[i,c] if c in sp_index[i,:] else 0                              */
+int maxk_cbsr_scatter(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k,
+                      int32_t d, float *dense, void *stream);
+int maxk_cbsr_gather(const float *dense, const uint8_t *sp_index, int64_t n, int32_t k,
+                     int32_t d, float *sp_data, void *stream);
+int maxk_cbsr_mask(const float *in, const uint8_t *sp_index, int64_t n, int32_t k, int32_t d,
+                   float *out, void *stream);
+
+/* ---- multi-GPU wire format ("new"): one record per node,
+ * k*float32 followed by k*uint8, padded to a 16-byte multiple, so that one all-gather
+ * moves both arrays.  record_bytes = maxk_cbsr_record_bytes(k).                         */
+int32_t maxk_cbsr_record_bytes(int32_t k);
+int maxk_cbsr_pack(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k,
+                   void *records, void *stream);
+int maxk_cbsr_unpack(const void *records, int64_t n, int32_t k, float *sp_data,
+                     uint8_t *sp_index, void *stream);
+
+/* ---- reference-named launch shims (ref: cuda_kernel_wrappers.cu:38-91, declared in
+ * cuda_kernel_bindings.cpp:11-35).  Same argument lists, so the reference's binding
+ * file links against this library unchanged.  grid/block/shared_size are accepted and
+ * IGNORED (the library picks its own launch shape); the kernels run on the legacy
+ * default stream like the reference's; vout is overwritten, not accumulated.  Errors are
+ * printed (reference behaviour) and also retrievable through maxk_last_error().        */
+void spmm_kernel_opt2_sparse_v3_wrapper(const int *warp4, const int *idx, const float *val,
+                                        const float *vin_data, const uint8_t *vin_selector,
+                                        float *vout, const int num_v, const int num_e,
+                                        const int feat_in, const int dim_sparse,
+                                        const int num_warps, maxk_dim3 grid, maxk_dim3 block,
+                                        int shared_size);
+void spmm_kernel_opt2_sparse_backward_v3_wrapper(const int *warp4, const int *idx,
+                                                 const float *val, const float *vin_data,
+                                                 const uint8_t *vin_selector, float *vout,
+                                                 const int num_v, const int num_e,
+                                                 const int feat_in, const int dim_sparse,
+                                                 const int num_warps, maxk_dim3 grid,
+                                                 maxk_dim3 block, int shared_size);
+void topk_kernel_wrapper(uint8_t *data, uint8_t *value, uint8_t *index, unsigned int k, int N,
+                         int dim_origin, maxk_dim3 grid, maxk_dim3 block, int shared_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAXK_B200_H_ */

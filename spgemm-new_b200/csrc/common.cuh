@@ -1,0 +1,81 @@
+// common.cuh -- shared device/host helpers for libmaxk_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "maxk_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmaxk_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace maxk {
+
+constexpr int kWarp = 32;
+constexpr int kNumSMs = 148;  // B200
+
+// ---- host-side error plumbing (thread local) -------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+void count_launch(int n = 1);
+
+#define MAXK_REQUIRE(cond, ...)                    \
+    do {                                           \
+        if (!(cond)) {                             \
+            ::maxk::set_error(__VA_ARGS__);        \
+            return MAXK_ERR_INVALID_ARGUMENT;      \
+        }                                          \
+    } while (0)
+
+#define MAXK_CUDA(expr)                                         \
+    do {                                                        \
+        cudaError_t _e = (expr);                                \
+        if (_e != cudaSuccess) return ::maxk::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define MAXK_LAUNCH_CHECK(name)                                   \
+    do {                                                          \
+        ::maxk::count_launch();                                   \
+        cudaError_t _e = cudaGetLastError();                      \
+        if (_e != cudaSuccess) return ::maxk::cuda_fail(_e, name); \
+    } while (0)
+
+// ---- cache-hinted memory access ----------------------------------------------------------
+// Streams that are read exactly once (CSR indices/values, work list, dY): evict-first so
+// they do not push the L2-resident CBSR (5k bytes/node) out of the 126 MB L2.
+__device__ __forceinline__ int ld_stream_s32(const int *p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream_f32(const float *p) { return __ldcs(p); }
+__device__ __forceinline__ int4 ld_stream_int4(const int4 *p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p) { return __ldcs(p); }
+
+// Gathers that are re-read by many CTAs (CBSR rows): read-only path, normal allocation.
+__device__ __forceinline__ float ld_gather_f32(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float4 ld_gather_f4(const float4 *p) { return __ldg(p); }
+__device__ __forceinline__ unsigned ld_gather_u32(const unsigned *p) { return __ldg(p); }
+__device__ __forceinline__ unsigned char ld_gather_u8(const unsigned char *p) { return __ldg(p); }
+
+__device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) { __stcs(p, v); }
+
+// 128-bit vector reduction (sm_90+): one REDG.E.ADD.F32x4 instead of four scalar REDGs.
+__device__ __forceinline__ void red_add_f4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a),
+                 "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f1(float *addr, float a)
+{
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b)
+{
+    return (a + b - 1) / b;
+}
+
+}  // namespace maxk

@@ -1,0 +1,229 @@
+// sspmm_backward.cu -- backward outer-product sampled SSpMM for sm_100a:
+//     dXc[j, l] += val[e] * dY[r, sp_index[j, l]]      for every edge e = (r -> j)
+// i.e. (A^T dY) evaluated only at the positions MaxK kept (CBSR layout).
+//
+// Replaces spmm_kernel_opt2_sparse_backward_v3 (ref: kernels/spmm_maxk_backward.cu:15-115).
+// Same outer-product (scatter) form -- the gather form would read a full 1 KB dY row per
+// edge instead of k selector bytes -- mapped differently (DESIGN.md "backward kernel"):
+//   * a warp owns a contiguous run of tasks and stages dY[row,:] in shared memory once per
+//     row, not once per task;
+//   * work inside a task is flattened to (edge, 4-slot group) items so that all 32 lanes
+//     are busy for every k (the reference idles lanes for k < 32 and warps for k < 32);
+//   * each item reads 4 selector bytes with one 32-bit load and emits ONE 128-bit vector
+//     reduction (red.global.add.v4.f32) instead of four scalar atomics: E*k/4 REDGs
+//     instead of E*k (ref: spmm_maxk_backward.cu:80,101);
+//   * (idx,val) pairs are fetched coalesced one task ahead; UNROLL items per lane are in
+//     flight so the selector gathers overlap;
+//   * 64-bit offsets throughout.
+// dXc (4k B/node) and the selectors (k B/node) stay L2-resident; HBM traffic is the CSR
+// stream plus one read of dY.
+#include "common.cuh"
+
+namespace maxk {
+
+constexpr int BWD_WPB = 8;
+constexpr int BWD_UNROLL = 4;
+constexpr int BWD_STAGE = 64;
+
+struct BwdEdgeRegs {
+    int i0, i1;
+    float v0, v1;
+};
+__device__ __forceinline__ void bwd_fetch_edges(BwdEdgeRegs &r, const int *__restrict__ idx,
+                                                const float *__restrict__ val, int64_t loc, int len,
+                                                int lane)
+{
+    r.i0 = r.i1 = 0;
+    r.v0 = r.v1 = 0.f;
+    if (lane < len) {
+        r.i0 = ld_stream_s32(idx + loc + lane);
+        r.v0 = ld_stream_f32(val + loc + lane);
+    }
+    if (lane + 32 < len) {
+        r.i1 = ld_stream_s32(idx + loc + lane + 32);
+        r.v1 = ld_stream_f32(val + loc + lane + 32);
+    }
+}
+__device__ __forceinline__ void bwd_stage_edges(const BwdEdgeRegs &r, int2 *stage, int lane)
+{
+    __syncwarp();
+    stage[lane] = make_int2(r.i0, __float_as_int(r.v0));
+    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));
+    __syncwarp();
+}
+
+// GLOG2 >= 0: k == 4 << GLOG2 (vector path, shifts);  GLOG2 == -1: k % 4 == 0, runtime
+// divide;  GLOG2 == -2: any k, scalar reductions.
+template <int GLOG2>
+__device__ __forceinline__ void bwd_process_batch(const int2 *stage, int len, const float *dys,
+                                                  const unsigned char *__restrict__ sp_index,
+                                                  float *__restrict__ dxc, int k, int lane)
+{
+    if constexpr (GLOG2 == -2) {
+        const int items = len * k;
+        for (int i = lane; i < items; i += 32) {
+            const int e = i / k, l = i - e * k;
+            const int2 ev = stage[e];
+            const int64_t base = (int64_t)ev.x * k + l;
+            const float g = dys[ld_gather_u8(sp_index + base)];
+            red_add_f1(dxc + base, __int_as_float(ev.y) * g);
+        }
+    } else {
+        const int groups = (GLOG2 >= 0) ? (1 << GLOG2) : (k >> 2);
+        const int items = len * groups;
+        for (int i0 = lane; i0 < items; i0 += 32 * BWD_UNROLL) {
+            int2 ev[BWD_UNROLL];
+            int q[BWD_UNROLL];
+            unsigned s4[BWD_UNROLL];
+#pragma unroll
+            for (int u = 0; u < BWD_UNROLL; ++u) {
+                const int i = i0 + 32 * u;
+                if (i < items) {
+                    int e;
+                    if constexpr (GLOG2 >= 0) {
+                        e = i >> GLOG2;
+                        q[u] = i & (groups - 1);
+                    } else {
+                        e = i / groups;
+                        q[u] = i - e * groups;
+                    }
+                    ev[u] = stage[e];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BWD_UNROLL; ++u) {
+                if (i0 + 32 * u < items)
+                    s4[u] = ld_gather_u32(
+                        reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + q[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < BWD_UNROLL; ++u) {
+                if (i0 + 32 * u < items) {
+                    const float w = __int_as_float(ev[u].y);
+                    const float g0 = dys[s4[u] & 0xff];
+                    const float g1 = dys[(s4[u] >> 8) & 0xff];
+                    const float g2 = dys[(s4[u] >> 16) & 0xff];
+                    const float g3 = dys[s4[u] >> 24];
+                    red_add_f4(dxc + (int64_t)ev[u].x * k + 4 * q[u], w * g0, w * g1, w * g2, w * g3);
+                }
+            }
+        }
+    }
+}
+
+template <int GLOG2>
+__global__ void __launch_bounds__(BWD_WPB * 32)
+sspmm_bwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *__restrict__ idx,
+                 const float *__restrict__ val, const float *__restrict__ dy,
+                 const unsigned char *__restrict__ sp_index, int k, int d, float *__restrict__ dxc,
+                 int tasks_per_warp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *dys = reinterpret_cast<float *>(smem_raw) + warp * d;
+    int2 *stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + BWD_WPB * d) +
+                  warp * BWD_STAGE;
+
+    const int64_t t0 = ((int64_t)blockIdx.x * BWD_WPB + warp) * tasks_per_warp;
+    if (t0 >= num_tasks) return;
+    const int64_t t1 = min(t0 + (int64_t)tasks_per_warp, num_tasks);
+
+    int4 info = ld_stream_int4(warp4 + t0);
+    BwdEdgeRegs pre;
+    bwd_fetch_edges(pre, idx, val, info.y, min(info.z, BWD_STAGE), lane);
+
+    int cur_row = -1;
+    for (int64_t t = t0; t < t1; ++t) {
+        const bool has_next = (t + 1 < t1);
+        int4 ninfo = info;
+        if (has_next) ninfo = ld_stream_int4(warp4 + t + 1);
+
+        if (info.x != cur_row) {  // stage dY[row,:] once per row
+            cur_row = info.x;
+            __syncwarp();
+            const float *src = dy + (int64_t)cur_row * d;
+            for (int c = lane * 4; c < d; c += 128)
+                *reinterpret_cast<float4 *>(dys + c) =
+                    ld_stream_f4(reinterpret_cast<const float4 *>(src + c));
+            // visibility is ordered by the __syncwarp pair in bwd_stage_edges below
+        }
+        const int64_t loc = info.y;
+        const int len = info.z;
+        bwd_stage_edges(pre, stage, lane);
+        if (has_next) bwd_fetch_edges(pre, idx, val, ninfo.y, min(ninfo.z, BWD_STAGE), lane);
+        bwd_process_batch<GLOG2>(stage, min(len, BWD_STAGE), dys, sp_index, dxc, k, lane);
+        for (int off = BWD_STAGE; off < len; off += BWD_STAGE) {
+            BwdEdgeRegs more;
+            const int ln = min(len - off, BWD_STAGE);
+            bwd_fetch_edges(more, idx, val, loc + off, ln, lane);
+            bwd_stage_edges(more, stage, lane);
+            bwd_process_batch<GLOG2>(stage, ln, dys, sp_index, dxc, k, lane);
+        }
+        info = ninfo;
+    }
+}
+
+template <int GLOG2>
+static int launch_bwd(const int32_t *warp4, int64_t W, const int32_t *idx, const float *val,
+                      const float *dy, const uint8_t *sp_index, int k, int d, float *dxc,
+                      int tasks_per_warp, cudaStream_t st)
+{
+    const size_t smem = (size_t)BWD_WPB * d * sizeof(float) + (size_t)BWD_WPB * BWD_STAGE * sizeof(int2);
+    const int64_t chunks = ceil_div<int64_t>(W, tasks_per_warp);
+    const int64_t grid = ceil_div<int64_t>(chunks, BWD_WPB);
+    if (grid > 0x7fffffffLL) {
+        set_error("maxk_sspmm_backward: grid too large");
+        return MAXK_ERR_UNSUPPORTED;
+    }
+    sspmm_bwd_kernel<GLOG2><<<(unsigned)grid, BWD_WPB * 32, smem, st>>>(
+        reinterpret_cast<const int4 *>(warp4), W, idx, val, dy, sp_index, k, d, dxc, tasks_per_warp);
+    MAXK_LAUNCH_CHECK("sspmm_bwd_kernel");
+    return MAXK_OK;
+}
+
+int g_bwd_tasks_per_warp = 16;
+
+}  // namespace maxk
+
+using namespace maxk;
+
+extern "C" int maxk_sspmm_backward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
+                                   const float *values, const float *dy, const uint8_t *sp_index,
+                                   int32_t k, int32_t d, float *dxc, int64_t num_cbsr_rows,
+                                   int32_t accumulate, void *stream)
+{
+    MAXK_REQUIRE(num_tasks >= 0 && num_cbsr_rows >= 0, "maxk_sspmm_backward: negative size");
+    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
+                 "maxk_sspmm_backward: d=%d must be a multiple of 4 in [4,256]", d);
+    MAXK_REQUIRE(k >= 1 && k <= d, "maxk_sspmm_backward: k=%d must be in [1,d=%d]", k, d);
+    MAXK_REQUIRE(dxc != nullptr || num_cbsr_rows == 0, "maxk_sspmm_backward: dxc is NULL");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (num_cbsr_rows == 0) return MAXK_OK;
+    if (!accumulate) {
+        MAXK_CUDA(cudaMemsetAsync(dxc, 0, (size_t)num_cbsr_rows * k * sizeof(float), st));
+        count_launch();
+    }
+    if (num_tasks == 0) return MAXK_OK;
+    MAXK_REQUIRE(warp4 && indices && values && dy && sp_index,
+                 "maxk_sspmm_backward: NULL input pointer");
+    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
+                 "maxk_sspmm_backward: dy and warp4 must be 16-byte aligned");
+    const int tpw = g_bwd_tasks_per_warp;
+    const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(dxc) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(sp_index) & 3) == 0);
+#define MAXK_BWD_GO(G) \
+    return launch_bwd<G>(warp4, num_tasks, indices, values, dy, sp_index, k, d, dxc, tpw, st)
+    if (!vec) MAXK_BWD_GO(-2);
+    switch (k) {
+        case 4: MAXK_BWD_GO(0);
+        case 8: MAXK_BWD_GO(1);
+        case 16: MAXK_BWD_GO(2);
+        case 32: MAXK_BWD_GO(3);
+        case 64: MAXK_BWD_GO(4);
+        case 128: MAXK_BWD_GO(5);
+        case 256: MAXK_BWD_GO(6);
+        default: MAXK_BWD_GO(-1);
+    }
+#undef MAXK_BWD_GO
+}

@@ -1,0 +1,119 @@
+"""Autograd Functions of the reference's model layer, on the B200 kernels.
+
+    MaxK.apply(input, k)                                   utils/models.py:28-59
+    SpGEMMFunction.apply(features, (indptr, indices, values), maxk)   utils/models.py:61-149
+
+Same signatures and return shapes.  Differences, all deliberate:
+  * no try/except fallbacks: a failing kernel raises (Q13);
+  * SpGEMMFunction.backward returns the true gradient mask * (A^T dY), built on device by
+    the SSpMM kernel + a scatter kernel instead of N*k .item() calls (models.py:136-141);
+  * the work list is generated on device and cached per graph instead of being re-read
+    from a file inside every call (Q10).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+_WL_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_WL_CACHE_MAX = 16
+
+
+def worklist_for(indptr: torch.Tensor) -> torch.Tensor:
+    """Work list of a CSR graph, cached per indptr tensor (the cache holds a reference to the
+    tensor, so its storage -- and therefore the key -- cannot be recycled while cached)."""
+    if indptr.dtype != torch.int32:
+        indptr = indptr.int()
+    indptr = indptr.contiguous()
+    key = (indptr.data_ptr(), indptr.numel(), str(indptr.device), indptr._version)
+    hit = _WL_CACHE.get(key)
+    if hit is not None:
+        _WL_CACHE.move_to_end(key)
+        return hit[1]
+    warp4 = ops.build_worklist(indptr)
+    _WL_CACHE[key] = (indptr, warp4)
+    while len(_WL_CACHE) > _WL_CACHE_MAX:
+        _WL_CACHE.popitem(last=False)
+    return warp4
+
+
+class MaxK(Function):
+    """MaxK nonlinearity: keep the k largest entries of every row, zero the rest."""
+
+    @staticmethod
+    def forward(ctx, input, k=1):
+        x = input.contiguous()
+        _, sp_index, dense = ops.topk_cbsr(x, k, want_dense=True)
+        ctx.save_for_backward(sp_index)
+        return dense
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (sp_index,) = ctx.saved_tensors
+        return ops.cbsr_mask(grad_output.contiguous(), sp_index), None
+
+
+class SpGEMMFunction(Function):
+    """Y = A @ MaxK_k(features) through TopK->CBSR + forward SpGEMM; backward through the
+    sampled SSpMM.  `values` are taken as given (1 = sum, 1/deg = mean, 1/sqrt(d_i d_j) = GCN;
+    SURVEY Q11)."""
+
+    @staticmethod
+    def forward(ctx, features, graph_data, maxk):
+        indptr, indices, values = graph_data
+        x = features.contiguous()
+        warp4 = worklist_for(indptr)
+        indices = indices.int().contiguous() if indices.dtype != torch.int32 else indices.contiguous()
+        values = values.float().contiguous() if values.dtype != torch.float32 else values.contiguous()
+        sp_data, sp_index = ops.topk_cbsr(x, maxk)
+        n_rows = indptr.numel() - 1
+        out = ops.spgemm_forward(warp4, indices, values, sp_data, sp_index,
+                                 feat_dim=x.shape[1], num_rows=n_rows)
+        ctx.save_for_backward(warp4, indices, values, sp_index)
+        ctx.feat_dim = x.shape[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        warp4, indices, values, sp_index = ctx.saved_tensors
+        dxc = ops.sspmm_backward(warp4, indices, values, grad_output.contiguous(), sp_index)
+        return ops.cbsr_scatter(dxc, sp_index, ctx.feat_dim), None, None
+
+
+class CBSRAggregate(Function):
+    """CBSR-native aggregation for layers that keep activations sparse end to end:
+    Y = A @ scatter(sp_data, sp_index); gradient flows to sp_data only (CBSR layout)."""
+
+    @staticmethod
+    def forward(ctx, sp_data, sp_index, warp4, indices, values, feat_dim, num_rows):
+        out = ops.spgemm_forward(warp4, indices, values, sp_data.contiguous(), sp_index,
+                                 feat_dim=feat_dim, num_rows=num_rows)
+        ctx.save_for_backward(warp4, indices, values, sp_index)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        warp4, indices, values, sp_index = ctx.saved_tensors
+        dxc = ops.sspmm_backward(warp4, indices, values, grad_output.contiguous(), sp_index)
+        return dxc, None, None, None, None, None, None
+
+
+class TopKCBSR(Function):
+    """x -> (sp_data, sp_index) with gradient dX = scatter(d sp_data, sp_index)."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        sp_data, sp_index = ops.topk_cbsr(x.contiguous(), k)
+        ctx.save_for_backward(sp_index)
+        ctx.feat_dim = x.shape[1]
+        ctx.mark_non_differentiable(sp_index)
+        return sp_data, sp_index
+
+    @staticmethod
+    def backward(ctx, g_data, _g_index):
+        (sp_index,) = ctx.saved_tensors
+        return ops.cbsr_scatter(g_data.contiguous(), sp_index, ctx.feat_dim), None

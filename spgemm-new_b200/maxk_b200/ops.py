@@ -1,0 +1,244 @@
+"""Tensor-level operators over the C ABI (libmaxk_b200.so).
+
+Each function validates its arguments the way the reference bindings do with
+TORCH_CHECK (cuda_kernel_bindings.cpp:52-62 -> RuntimeError), allocates the outputs with
+torch on the inputs' device, and launches on torch's current CUDA stream.  torch is used
+for device memory and streams only; every kernel is in csrc/.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+FULL_DIM = 256  # cuda_kernel_bindings.cpp:70
+
+
+def _req(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _cuda(t: torch.Tensor, name: str, dtype=None, contiguous: bool = True) -> None:
+    _req(isinstance(t, torch.Tensor), f"{name} must be a tensor")
+    _req(t.is_cuda, f"{name} must be CUDA tensor")
+    if dtype is not None:
+        _req(t.dtype == dtype, f"{name} must be {str(dtype).replace('torch.', '')}")
+    if contiguous:
+        _req(t.is_contiguous(), f"{name} must be contiguous")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------ a4
+def build_worklist(indptr: torch.Tensor, warp_max_nz: int = _cabi.WARP_MAX_NZ) -> torch.Tensor:
+    """On-device work list, flat int32[4W] (row, loc, len, 0) -- bit-identical to the
+    .warp4 file kernels/generate_meta.py:30-48 writes for the same indptr."""
+    lib = _cabi.load()
+    _cuda(indptr, "indptr", torch.int32)
+    _req(indptr.dim() == 1 and indptr.numel() >= 1, "indptr must be 1-D with N+1 entries")
+    n = indptr.numel() - 1
+    with torch.cuda.device(indptr.device):
+        ws = torch.empty(int(lib.maxk_worklist_workspace_bytes(n)), dtype=torch.uint8,
+                         device=indptr.device)
+        w = ctypes.c_int64(0)
+        _cabi.check(lib.maxk_worklist_count(indptr.data_ptr(), n, warp_max_nz, ws.data_ptr(),
+                                            ctypes.byref(w), _stream(indptr)))
+        out = torch.empty(4 * w.value, dtype=torch.int32, device=indptr.device)
+        _cabi.check(lib.maxk_worklist_fill(indptr.data_ptr(), n, warp_max_nz, ws.data_ptr(),
+                                           out.data_ptr(), w.value, _stream(indptr)))
+    return out
+
+
+# ------------------------------------------------------------------------------ a1
+def topk_cbsr(x: torch.Tensor, k: int, want_dense: bool = False, want_cbsr: bool = True):
+    """fp32 MaxK: (sp_data f32[N,k], sp_index u8[N,k][, dense f32[N,D]])."""
+    lib = _cabi.load()
+    _cuda(x, "Input", None)
+    _req(x.dim() == 2, "Input must be 2D tensor")
+    _req(x.dtype == torch.float32, "Input must be float32")
+    n, d = x.shape
+    _req(0 < k <= d, "Invalid k value")
+    sp_data = sp_index = dense = None
+    with torch.cuda.device(x.device):
+        if want_cbsr:
+            sp_data = torch.empty((n, k), dtype=torch.float32, device=x.device)
+            sp_index = torch.empty((n, k), dtype=torch.uint8, device=x.device)
+        if want_dense:
+            dense = torch.empty_like(x)
+        _cabi.check(lib.maxk_topk_cbsr_f32(x.data_ptr(), n, d, k, _ptr(sp_data), _ptr(sp_index),
+                                           _ptr(dense), _stream(x)))
+    if want_cbsr and want_dense:
+        return sp_data, sp_index, dense
+    if want_dense:
+        return dense
+    return sp_data, sp_index
+
+
+def topk_cbsr_u8(x: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _cabi.load()
+    _cuda(x, "Input", None)
+    _req(x.dim() == 2, "Input must be 2D tensor")
+    _req(x.dtype == torch.uint8, "Input must be uint8 tensor")
+    n, d = x.shape
+    _req(0 < k <= d, "Invalid k value")
+    with torch.cuda.device(x.device):
+        val = torch.empty((n, k), dtype=torch.uint8, device=x.device)
+        ind = torch.empty((n, k), dtype=torch.uint8, device=x.device)
+        _cabi.check(lib.maxk_topk_cbsr_u8(x.data_ptr(), n, d, k, val.data_ptr(), ind.data_ptr(),
+                                          _stream(x)))
+    return val, ind
+
+
+# ------------------------------------------------------------------------------ a2
+def spgemm_forward(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
+                   sp_data: torch.Tensor, sp_index: torch.Tensor, num_warps: Optional[int] = None,
+                   dim_sparse: Optional[int] = None, feat_dim: int = FULL_DIM,
+                   num_rows: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _cabi.load()
+    _cuda(warp4, "warp4_metadata", torch.int32)
+    _cuda(indices, "indices", torch.int32)
+    _cuda(values, "values", torch.float32)
+    _cuda(sp_data, "input_data", torch.float32)
+    _cuda(sp_index, "sparse_selector", torch.uint8)
+    _req(sp_data.dim() == 2 and sp_index.shape == sp_data.shape,
+         "input_data and sparse_selector must both be [N, k]")
+    k = sp_data.shape[1]
+    _req(dim_sparse is None or dim_sparse == k, f"dim_sparse={dim_sparse} != input_data.size(1)={k}")
+    w = warp4.numel() // 4
+    _req(num_warps is None or 0 <= num_warps <= w, "num_warps exceeds the work list")
+    w = w if num_warps is None else num_warps
+    _req(indices.numel() == values.numel(), "indices and values differ in length")
+    n_out = sp_data.shape[0] if num_rows is None else int(num_rows)  # bindings.cpp:65
+    with torch.cuda.device(sp_data.device):
+        if out is None:
+            out = torch.empty((n_out, feat_dim), dtype=torch.float32, device=sp_data.device)
+        else:
+            _cuda(out, "out", torch.float32)
+            _req(tuple(out.shape) == (n_out, feat_dim), "out has the wrong shape")
+        _cabi.check(lib.maxk_spgemm_forward(warp4.data_ptr(), w, indices.data_ptr(),
+                                            values.data_ptr(), sp_data.data_ptr(),
+                                            sp_index.data_ptr(), k, out.data_ptr(), n_out,
+                                            feat_dim, _stream(sp_data)))
+    return out
+
+
+# ------------------------------------------------------------------------------ a3
+def sspmm_backward(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
+                   grad_output: torch.Tensor, sp_index: torch.Tensor,
+                   num_warps: Optional[int] = None, dim_sparse: Optional[int] = None,
+                   out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    lib = _cabi.load()
+    _cuda(warp4, "warp4_metadata", torch.int32)
+    _cuda(indices, "indices", torch.int32)
+    _cuda(values, "values", torch.float32)
+    _cuda(grad_output, "grad_output", torch.float32)
+    _cuda(sp_index, "sparse_selector", torch.uint8)
+    _req(grad_output.dim() == 2 and sp_index.dim() == 2, "grad_output and sparse_selector must be 2-D")
+    k = sp_index.shape[1]
+    _req(dim_sparse is None or dim_sparse == k, f"dim_sparse={dim_sparse} != sparse_selector.size(1)={k}")
+    d = grad_output.shape[1]
+    w = warp4.numel() // 4
+    _req(num_warps is None or 0 <= num_warps <= w, "num_warps exceeds the work list")
+    w = w if num_warps is None else num_warps
+    n_cbsr = sp_index.shape[0]
+    with torch.cuda.device(grad_output.device):
+        if out is None:
+            _req(not accumulate, "accumulate=True needs an `out` tensor")
+            out = torch.empty((n_cbsr, k), dtype=torch.float32, device=grad_output.device)
+        else:
+            _cuda(out, "out", torch.float32)
+            _req(tuple(out.shape) == (n_cbsr, k), "out has the wrong shape")
+        _cabi.check(lib.maxk_sspmm_backward(warp4.data_ptr(), w, indices.data_ptr(),
+                                            values.data_ptr(), grad_output.data_ptr(),
+                                            sp_index.data_ptr(), k, d, out.data_ptr(), n_cbsr,
+                                            1 if accumulate else 0, _stream(grad_output)))
+    return out
+
+
+# ------------------------------------------------------------------------------ a5
+def cbsr_scatter(sp_data: torch.Tensor, sp_index: torch.Tensor, feat_dim: int = FULL_DIM) -> torch.Tensor:
+    lib = _cabi.load()
+    _cuda(sp_data, "sp_data", torch.float32)
+    _cuda(sp_index, "sp_index", torch.uint8)
+    _req(sp_data.shape == sp_index.shape and sp_data.dim() == 2, "sp_data/sp_index must be [N,k]")
+    n, k = sp_data.shape
+    with torch.cuda.device(sp_data.device):
+        dense = torch.empty((n, feat_dim), dtype=torch.float32, device=sp_data.device)
+        _cabi.check(lib.maxk_cbsr_scatter(sp_data.data_ptr(), sp_index.data_ptr(), n, k, feat_dim,
+                                          dense.data_ptr(), _stream(sp_data)))
+    return dense
+
+
+def cbsr_gather(dense: torch.Tensor, sp_index: torch.Tensor) -> torch.Tensor:
+    lib = _cabi.load()
+    _cuda(dense, "dense", torch.float32)
+    _cuda(sp_index, "sp_index", torch.uint8)
+    n, d = dense.shape
+    k = sp_index.shape[1]
+    _req(sp_index.shape[0] == n, "row count mismatch")
+    with torch.cuda.device(dense.device):
+        out = torch.empty((n, k), dtype=torch.float32, device=dense.device)
+        _cabi.check(lib.maxk_cbsr_gather(dense.data_ptr(), sp_index.data_ptr(), n, k, d,
+                                         out.data_ptr(), _stream(dense)))
+    return out
+
+
+def cbsr_mask(dense: torch.Tensor, sp_index: torch.Tensor) -> torch.Tensor:
+    """dense * mask(sp_index)  (MaxK.backward, utils/models.py:55-59)."""
+    lib = _cabi.load()
+    _cuda(dense, "dense", torch.float32)
+    _cuda(sp_index, "sp_index", torch.uint8)
+    n, d = dense.shape
+    k = sp_index.shape[1]
+    _req(sp_index.shape[0] == n, "row count mismatch")
+    with torch.cuda.device(dense.device):
+        out = torch.empty_like(dense)
+        _cabi.check(lib.maxk_cbsr_mask(dense.data_ptr(), sp_index.data_ptr(), n, k, d,
+                                       out.data_ptr(), _stream(dense)))
+    return out
+
+
+# -------------------------------------------------------------- multi-GPU wire format
+def cbsr_record_bytes(k: int) -> int:
+    return int(_cabi.load().maxk_cbsr_record_bytes(k))
+
+
+def cbsr_pack(sp_data: torch.Tensor, sp_index: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _cabi.load()
+    _cuda(sp_data, "sp_data", torch.float32)
+    _cuda(sp_index, "sp_index", torch.uint8)
+    n, k = sp_data.shape
+    rb = cbsr_record_bytes(k)
+    with torch.cuda.device(sp_data.device):
+        if out is None:
+            out = torch.empty((n, rb), dtype=torch.uint8, device=sp_data.device)
+        _req(out.is_contiguous() and out.numel() >= n * rb, "records buffer too small")
+        _cabi.check(lib.maxk_cbsr_pack(sp_data.data_ptr(), sp_index.data_ptr(), n, k,
+                                       out.data_ptr(), _stream(sp_data)))
+    return out
+
+
+def cbsr_unpack(records: torch.Tensor, n: int, k: int):
+    lib = _cabi.load()
+    _cuda(records, "records", torch.uint8)
+    _req(records.numel() >= n * cbsr_record_bytes(k), "records buffer too small")
+    with torch.cuda.device(records.device):
+        sp_data = torch.empty((n, k), dtype=torch.float32, device=records.device)
+        sp_index = torch.empty((n, k), dtype=torch.uint8, device=records.device)
+        _cabi.check(lib.maxk_cbsr_unpack(records.data_ptr(), n, k, sp_data.data_ptr(),
+                                         sp_index.data_ptr(), _stream(records)))
+    return sp_data, sp_index
+
+
+def set_tuning(fwd_tasks_per_warp: int = 0, bwd_tasks_per_warp: int = 0) -> None:
+    _cabi.check(_cabi.load().maxk_set_tuning(fwd_tasks_per_warp, bwd_tasks_per_warp))
