@@ -1,0 +1,439 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the MaxK-GNN sparse-aggregation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl own|reference] [--k 32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): SpGEMM + SSpMM algorithmic GB/s on the synthetic Reddit-shaped
+graph (N = 232 965, E = 114 615 892, hidden 256, k = 32): one STEP = one forward row-wise
+SpGEMM  Y = A * X_cbsr  plus one backward sampled SSpMM  dXc = sample(A^T dY).
+   value    = (B_fwd + B_bwd) / device time, inputs resident in HBM   
+   e2e      = same bytes / time of HostAggregator.step() on pinned HOST buffers
+              (H2D X and dY, TopK, both kernels, D2H Y and dXc inside the timed region)
+   roofline = dominant kernel's algorithmic GB/s against MEASURED_PEAKS.json's HBM figure
+   cpu_baseline = the reference's CPU path (torch.topk + CSR SpMM, oracle/cpu_path.py) on a
+              bounded row-sample of the same graph, on this box's host cores
+N > 1: the adjacency is 1-D row-partitioned (balanced by nnz) over the ranks; every step
+all-gathers the CBSR features and reduce-scatters the CBSR-shaped partial gradients with
+NCCL (strong scaling: the graph is fixed).
+`--impl reference` times the reference's CPU implementation of the same step on a bounded
+sample (rank 0 only).  One JSON line on stdout; everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "spgemm-new_b200"))
+
+import torch  # noqa: E402
+
+METRIC = "spgemm_sspmm_algorithmic_GBps"
+UNIT = "GB/s"
+FEAT_DIM = 256
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback ("of fallback")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:  # pragma: no cover
+            pass
+    return HBM_FALLBACK_GBS, "fallback"
+
+
+def dram_traffic(kernel: str, k: int):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(p)).get(f"{kernel}_k{k}")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_ev = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            log("clock sampling unavailable:", e)
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+             0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+             0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_ev.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # pragma: no cover
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_ev.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------
+def make_reddit(device, seed=0):
+    from maxk_b200 import graphs
+    scale = float(os.environ.get("MAXK_BENCH_SCALE", "1.0"))  # < 1 only for smoke runs
+    t0 = time.time()
+    g = graphs.make_graph("reddit", seed=seed, device=device, values="uniform", scale=scale)
+    log(f"[graph] reddit-shaped N={g['v_num']} E={g['e_num']} on {device} in {time.time() - t0:.1f}s")
+    return g, scale
+
+
+def cpu_sample(g, frac_rows: float):
+    """First rows of the graph (a contiguous row block keeps the degree mix) as a CPU problem."""
+    n = g["v_num"]
+    rows = max(64, int(n * frac_rows))
+    indptr = g["indptr"][: rows + 1].cpu()
+    e = int(indptr[-1])
+    return {"indptr": indptr, "indices": g["indices"][:e].cpu(), "values": g["values"][:e].cpu(),
+            "rows": rows, "e": e, "n_cols": n}
+
+
+def run_cpu_reference(g, k, steps, warmup, target_step_s=2.0):
+    """The reference's CPU path on a bounded sample; returns (GB/s, info dict)."""
+    from maxk_b200 import graphs
+    from oracle import cpu_path
+    cores = cpu_path.set_threads()
+    n = g["v_num"]
+    gen = torch.Generator().manual_seed(123)
+    x = torch.rand(n, FEAT_DIM, generator=gen)
+    # pilot on 1/128 of the rows to size the sample for ~target_step_s per step
+    frac = 1.0 / 128
+    s = cpu_sample(g, frac)
+    agg = cpu_path.CpuAggregation(s["indptr"], s["indices"], s["values"], n_cols=n)
+    dy = torch.rand(s["rows"], FEAT_DIM, generator=gen)
+    agg.step(x, dy, k)
+    _, t = agg.timed_step(x, dy, k)
+    frac = min(1.0, max(frac, frac * target_step_s / max(t, 1e-3)))
+    s = cpu_sample(g, frac)
+    agg = cpu_path.CpuAggregation(s["indptr"], s["indices"], s["values"], n_cols=n)
+    dy = torch.rand(s["rows"], FEAT_DIM, generator=gen)
+    deg = (s["indptr"][1:] - s["indptr"][:-1]).long()
+    w = int(((deg + 63) // 64).sum())
+    b = graphs.algorithmic_bytes(s["rows"], s["e"], w, k, FEAT_DIM, n_cbsr=n)
+    step_bytes = b["fwd"] + b["bwd"]
+    for _ in range(warmup):
+        agg.step(x, dy, k)
+    times = []
+    for _ in range(steps):
+        _, t = agg.timed_step(x, dy, k)
+        times.append(t)
+    ms = 1e3 * sum(times) / len(times)
+    value = step_bytes / (ms * 1e-3) / 1e9
+    info = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {s['rows']} of {n} rows ({s['e']} of {g['e_num']} edges) of the same "
+                      f"Reddit-shaped graph, k={k}, torch.topk + torch.sparse.mm CSR (fwd) / A^T CSR (bwd), "
+                      f"fp32, {cores} threads",
+            "ms_per_step": ms, "edges_per_s": s["e"] * 2 / (ms * 1e-3)}
+    return value, ms, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--k", type=int, default=32)
+    ap.add_argument("--sweep", action="store_true", help="also time k=8/16/64, TopK and the work list")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-kernels", action="store_true",
+                    help="also time the reference CUDA kernels (oracle/_ref) on the same inputs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        g, scale = make_reddit(dev)
+        value, ms, info = run_cpu_reference(g, args.k, max(1, args.steps), max(0, args.warmup))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "reddit-shaped SpGEMM+SSpMM k=%d hidden 256 (bounded row sample on CPU)" % args.k,
+                           "k": args.k, "feat_dim": FEAT_DIM, "graph_scale": scale},
+                "cpu_baseline": info,
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ----------------------------------------------------------------------------- own arm
+    if not torch.cuda.is_available():
+        log("bench.py --impl own needs a CUDA device (no CPU fallback).")
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from maxk_b200 import _cabi, graphs, ops
+    from maxk_b200.host import HostAggregator
+
+    g, scale = make_reddit(dev)          # same seed on every rank -> identical graph
+    n, e, k = g["v_num"], g["e_num"], args.k
+    peak, peak_src = measured_peak()
+
+    if world > 1:
+        from maxk_b200.dist import DistAggregator, partition_rows_by_nnz
+        bounds = partition_rows_by_nnz(g["indptr"], world)
+        agg = DistAggregator.from_global_csr(g["indptr"], g["indices"], g["values"], bounds, rank, k,
+                                             FEAT_DIM)
+        del g["indices"], g["values"]
+        torch.cuda.empty_cache()
+        n_loc = agg.n_local
+        gen = torch.Generator(dev).manual_seed(123 + rank)
+        x_loc = torch.rand(n_loc, FEAT_DIM, device=dev, generator=gen)
+        dy_loc = torch.rand(n_loc, FEAT_DIM, device=dev, generator=gen)
+        w_total = torch.tensor([agg.num_tasks], device=dev, dtype=torch.int64)
+        dist.all_reduce(w_total)
+        w = int(w_total)
+
+        def step():
+            sp_data, sp_index = agg.topk_and_exchange(x_loc)
+            agg.forward(sp_data, sp_index)
+            agg.backward(dy_loc, sp_index)
+        fwd_ms = bwd_ms = None
+    else:
+        warp4 = ops.build_worklist(g["indptr"])
+        w = warp4.numel() // 4
+        gen = torch.Generator(dev).manual_seed(123)
+        x = torch.rand(n, FEAT_DIM, device=dev, generator=gen)
+        dy = torch.rand(n, FEAT_DIM, device=dev, generator=gen)
+        sp_data, sp_index = ops.topk_cbsr(x, k)
+        y = torch.empty(n, FEAT_DIM, device=dev)
+        dxc = torch.empty(n, k, device=dev)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        step_no = [-1]
+
+        def step():
+            i = step_no[0]
+            if i >= 0:
+                ev[i][0].record()
+            ops.spgemm_forward(warp4, g["indices"], g["values"], sp_data, sp_index, out=y, num_rows=n)
+            if i >= 0:
+                ev[i][1].record()
+            ops.sspmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dxc)
+            if i >= 0:
+                ev[i][2].record()
+
+    bytes_ = graphs.algorithmic_bytes(n, e, w, k, FEAT_DIM)
+    step_bytes = bytes_["fwd"] + bytes_["bwd"]
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    launches0 = _cabi.launch_count()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_start.record()
+    for i in range(args.steps):
+        if world == 1:
+            step_no[0] = i
+        step()
+    t_stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = t_start.elapsed_time(t_stop)
+    launches = _cabi.launch_count() - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t)
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt)
+    ms_per_step = total_ms / args.steps
+    value = step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    extra = {}
+    roofline = None
+    if world == 1:
+        step_no[0] = -1
+        fwd_ms = sum(a[0].elapsed_time(a[1]) for a in ev) / args.steps
+        bwd_ms = sum(a[1].elapsed_time(a[2]) for a in ev) / args.steps
+        dom, dom_ms, dom_bytes = (("spgemm_fwd", fwd_ms, bytes_["fwd"]) if fwd_ms >= bwd_ms
+                                  else ("sspmm_bwd", bwd_ms, bytes_["bwd"]))
+        ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "peak_source": f"of {peak_src}",
+                    "traffic": dram_traffic(dom, k), "algorithmic_bytes": dom_bytes, "ms": dom_ms}
+        extra["kernels"] = {
+            "spgemm_fwd": {"ms": fwd_ms, "GBps": bytes_["fwd"] / fwd_ms / 1e6,
+                           "frac_of_hbm_peak": bytes_["fwd"] / fwd_ms / 1e6 / peak,
+                           "edges_per_s": e / (fwd_ms * 1e-3)},
+            "sspmm_bwd": {"ms": bwd_ms, "GBps": bytes_["bwd"] / bwd_ms / 1e6,
+                          "frac_of_hbm_peak": bytes_["bwd"] / bwd_ms / 1e6 / peak,
+                          "edges_per_s": e / (bwd_ms * 1e-3)}}
+        log(f"[own] fwd {fwd_ms:.3f} ms  bwd {bwd_ms:.3f} ms  step {ms_per_step:.3f} ms  "
+            f"{value:.0f} GB/s  roofline {dom} {roofline['frac']:.3f} of {peak_src} peak")
+    extra["edges_per_s"] = 2 * e / (ms_per_step * 1e-3)
+    extra["num_tasks"] = w
+
+    # ------------------------------------------------------------------ optional sweeps
+    def timeit(fn, iters=10, warm=3):
+        for _ in range(warm):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    if world == 1 and args.sweep:
+        sweep = {}
+        for kk in (8, 16, 32, 64):
+            sd, si = ops.topk_cbsr(x, kk)
+            dx2 = torch.empty(n, kk, device=dev)
+            bb = graphs.algorithmic_bytes(n, e, w, kk, FEAT_DIM)
+            tf = timeit(lambda: ops.spgemm_forward(warp4, g["indices"], g["values"], sd, si, out=y, num_rows=n))
+            tb = timeit(lambda: ops.sspmm_backward(warp4, g["indices"], g["values"], dy, si, out=dx2))
+            tt = timeit(lambda: ops.topk_cbsr(x, kk))
+            sweep[f"k{kk}"] = {"fwd_ms": tf, "bwd_ms": tb, "topk_ms": tt,
+                               "fwd_frac": bb["fwd"] / tf / 1e6 / peak, "bwd_frac": bb["bwd"] / tb / 1e6 / peak,
+                               "topk_frac": bb["topk"] / tt / 1e6 / peak}
+            log(f"[sweep] k={kk}: fwd {tf:.3f} ms ({sweep[f'k{kk}']['fwd_frac']:.2f}) "
+                f"bwd {tb:.3f} ms ({sweep[f'k{kk}']['bwd_frac']:.2f}) topk {tt:.3f} ms ({sweep[f'k{kk}']['topk_frac']:.2f})")
+        tm = timeit(lambda: ops.build_worklist(g["indptr"]))
+        sweep["worklist_ms"] = tm
+        sweep["worklist_frac"] = bytes_["meta"] / tm / 1e6 / peak
+        extra["sweep"] = sweep
+    if world == 1 and args.ref_kernels:
+        from oracle import ref_kernels as R
+        if R.available():
+            yr = torch.zeros(n, FEAT_DIM, device=dev)
+            dr = torch.zeros(n, k, device=dev)
+            tf = timeit(lambda: R.spmm_forward(warp4, g["indices"], g["values"], sp_data, sp_index, FEAT_DIM, out=yr), 4, 4)
+            tb = timeit(lambda: R.spmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dr), 4, 4)
+            extra["reference_kernels_on_this_gpu"] = {
+                "fwd_ms": tf, "bwd_ms": tb, "note": "kernels/*.cu compiled unmodified for sm_100a, reference "
+                "launch shape, outputs not re-zeroed (reference protocol, spmm_base.h:56-74)"}
+            log(f"[ref kernels] fwd {tf:.3f} ms  bwd {tb:.3f} ms")
+
+    # ------------------------------------------------------------------------------ e2e
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        host = HostAggregator(g["indptr"], g["indices"], g["values"], k, FEAT_DIM, dev)
+        xh = x.cpu().pin_memory()
+        dyh = dy.cpu().pin_memory()
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            host.step(xh, dyh)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            host.step(xh, dyh)
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+        e2e = {"value": step_bytes / (e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_ms,
+               "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
+               "steps": e_steps, "includes": "H2D X+dY (pinned), TopK->CBSR, SpGEMM, SSpMM, D2H Y+dXc"}
+        log(f"[e2e] {e_ms:.2f} ms/step  {e2e['value']:.0f} GB/s")
+        del host, xh, dyh
+    elif world > 1:
+        e2e = None
+
+    # ------------------------------------------------------------------ CPU baseline leg
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            _, _, cpu_baseline = run_cpu_reference(g, k, steps=3, warmup=1, target_step_s=3.0)
+            log(f"[cpu] {cpu_baseline['value']:.2f} GB/s on {cpu_baseline['cores']} threads")
+        except Exception as ex:  # pragma: no cover
+            log("cpu baseline failed:", ex)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"reddit-shaped graph N={n} E={e}: forward SpGEMM + backward SSpMM, "
+                                       f"k={k}, hidden {FEAT_DIM}",
+                           "k": k, "feat_dim": FEAT_DIM, "num_tasks": w, "graph_scale": scale,
+                           "parallelism": ("single GPU" if world == 1 else
+                                           f"1-D row partition x{world}, CBSR all-gather + reduce-scatter (NCCL)"),
+                           "l2": "inputs larger than L2 (CSR stream 917 MB per kernel); CBSR operand "
+                                 "(37 MB) is L2-resident by design",
+                           "step_algorithmic_bytes": step_bytes},
+                "clocks": clocks, "gpu_launches": launches}
+        if roofline:
+            line["roofline"] = roofline
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if e2e:
+            line["e2e"] = e2e
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -28,6 +28,13 @@
 extern "C" {
 #endif
 
+/* the library is built with -fvisibility=hidden; only the ABI below is exported */
+#if defined(__GNUC__)
+#define MAXK_API __attribute__((visibility("default")))
+#else
+#define MAXK_API
+#endif
+
 #define MAXK_OK 0
 #define MAXK_ERR_INVALID_ARGUMENT 1
 #define MAXK_ERR_CUDA 2
@@ -43,14 +50,14 @@ typedef struct maxk_dim3 {
     unsigned int x, y, z;
 } maxk_dim3;
 
-int maxk_abi_version(void);
-const char *maxk_last_error(void);
+MAXK_API int maxk_abi_version(void);
+MAXK_API const char *maxk_last_error(void);
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * gpu_launches claim). */
-int64_t maxk_launch_count(void);
+MAXK_API int64_t maxk_launch_count(void);
 /* Bench/test hook (not part of the reference surface): run length, in tasks per warp, of
  * the forward / backward kernels; a value <= 0 leaves that knob unchanged. */
-int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp);
+MAXK_API int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp);
 
 /* ---- a4: work list (replaces kernels/generate_meta.py:8-48 and the disk round trip of
  * load_warp4_metadata, cuda_kernel_bindings.cpp:287-317) ------------------------------
@@ -59,10 +66,10 @@ int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp);
  *      fills `workspace` (maxk_worklist_workspace_bytes(num_rows) bytes, device);
  *   2. maxk_worklist_fill   -> writes int32[4*W] records, bit-identical to
  *      generate_meta.py's .warp4 file for the same indptr.                            */
-int64_t maxk_worklist_workspace_bytes(int64_t num_rows);
-int maxk_worklist_count(const int32_t *indptr, int64_t num_rows, int32_t warp_max_nz,
+MAXK_API int64_t maxk_worklist_workspace_bytes(int64_t num_rows);
+MAXK_API int maxk_worklist_count(const int32_t *indptr, int64_t num_rows, int32_t warp_max_nz,
                         void *workspace, int64_t *num_tasks_host, void *stream);
-int maxk_worklist_fill(const int32_t *indptr, int64_t num_rows, int32_t warp_max_nz,
+MAXK_API int maxk_worklist_fill(const int32_t *indptr, int64_t num_rows, int32_t warp_max_nz,
                        const void *workspace, int32_t *warp4, int64_t num_tasks, void *stream);
 
 /* ---- a1: MaxK / TopK -> CBSR (replaces topk, kernels/maxk_kernel.cu:23-96, and the
@@ -71,11 +78,11 @@ int maxk_worklist_fill(const int32_t *indptr, int64_t num_rows, int32_t warp_max
  * values are bit copies.  NaN ranks largest, -0 == +0.  d % 4 == 0, 1 <= k <= d <= 256.
  * dense_out (optional, may be NULL): x * mask, float32[n,d] (MaxK.forward,
  * utils/models.py:48-52).  sp_data / sp_index may be NULL when only dense_out is wanted. */
-int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t k, float *sp_data,
+MAXK_API int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t k, float *sp_data,
                        uint8_t *sp_index, float *dense_out, void *stream);
 /* uint8 flavour of the reference kernel's own data type (cuda_topk_maxk,
  * cuda_kernel_bindings.cpp:164-201). d % 8 == 0. */
-int maxk_topk_cbsr_u8(const uint8_t *x, int64_t n, int32_t d, int32_t k, uint8_t *value,
+MAXK_API int maxk_topk_cbsr_u8(const uint8_t *x, int64_t n, int32_t d, int32_t k, uint8_t *value,
                       uint8_t *index, void *stream);
 
 /* ---- a2: forward row-wise-product SpGEMM  Y = A * X_cbsr (replaces
@@ -84,7 +91,7 @@ int maxk_topk_cbsr_u8(const uint8_t *x, int64_t n, int32_t d, int32_t k, uint8_t
  * out float32[num_rows_out, d] is fully DEFINED by the call (no pre-zero needed, not
  * accumulated -- SURVEY Q2).  Task rows must be non-decreasing (what generate_meta.py
  * produces).  Selectors of one CBSR row must be distinct.  d % 4 == 0.      */
-int maxk_spgemm_forward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
+MAXK_API int maxk_spgemm_forward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                         const float *values, const float *sp_data, const uint8_t *sp_index,
                         int32_t k, float *out, int64_t num_rows_out, int32_t d, void *stream);
 
@@ -94,7 +101,7 @@ int maxk_spgemm_forward(const int32_t *warp4, int64_t num_tasks, const int32_t *
  * dxc float32[num_cbsr_rows, k].  accumulate == 0: dxc is zero-filled first (defined
  * output); accumulate != 0: contributions are added to the existing content (used by
  * the multi-GPU local/remote split).                                                   */
-int maxk_sspmm_backward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
+MAXK_API int maxk_sspmm_backward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                         const float *values, const float *dy, const uint8_t *sp_index,
                         int32_t k, int32_t d, float *dxc, int64_t num_cbsr_rows,
                         int32_t accumulate, void *stream);
@@ -104,20 +111,20 @@ int maxk_sspmm_backward(const int32_t *warp4, int64_t num_tasks, const int32_t *
  * scatter: dense[i, sp_index[i,j]] = sp_data[i,j], zeros elsewhere (dense fully defined)
  * gather : sp_data[i,j] = dense[i, sp_index[i,j]]
  * mask   : out[i,c] = in[i,c] if c in sp_index[i,:] else 0                              */
-int maxk_cbsr_scatter(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k,
+MAXK_API int maxk_cbsr_scatter(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k,
                       int32_t d, float *dense, void *stream);
-int maxk_cbsr_gather(const float *dense, const uint8_t *sp_index, int64_t n, int32_t k,
+MAXK_API int maxk_cbsr_gather(const float *dense, const uint8_t *sp_index, int64_t n, int32_t k,
                      int32_t d, float *sp_data, void *stream);
-int maxk_cbsr_mask(const float *in, const uint8_t *sp_index, int64_t n, int32_t k, int32_t d,
+MAXK_API int maxk_cbsr_mask(const float *in, const uint8_t *sp_index, int64_t n, int32_t k, int32_t d,
                    float *out, void *stream);
 
 /* ---- multi-GPU wire format ("new"): one record per node,
  * k*float32 followed by k*uint8, padded to a 16-byte multiple, so that one all-gather
  * moves both arrays.  record_bytes = maxk_cbsr_record_bytes(k).                         */
-int32_t maxk_cbsr_record_bytes(int32_t k);
-int maxk_cbsr_pack(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k,
+MAXK_API int32_t maxk_cbsr_record_bytes(int32_t k);
+MAXK_API int maxk_cbsr_pack(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k,
                    void *records, void *stream);
-int maxk_cbsr_unpack(const void *records, int64_t n, int32_t k, float *sp_data,
+MAXK_API int maxk_cbsr_unpack(const void *records, int64_t n, int32_t k, float *sp_data,
                      uint8_t *sp_index, void *stream);
 
 /* ---- reference-named launch shims (ref: cuda_kernel_wrappers.cu:38-91, declared in
@@ -126,20 +133,20 @@ int maxk_cbsr_unpack(const void *records, int64_t n, int32_t k, float *sp_data,
  * IGNORED (the library picks its own launch shape); the kernels run on the legacy
  * default stream like the reference's; vout is overwritten, not accumulated.  Errors are
  * printed (reference behaviour) and also retrievable through maxk_last_error().        */
-void spmm_kernel_opt2_sparse_v3_wrapper(const int *warp4, const int *idx, const float *val,
+MAXK_API void spmm_kernel_opt2_sparse_v3_wrapper(const int *warp4, const int *idx, const float *val,
                                         const float *vin_data, const uint8_t *vin_selector,
                                         float *vout, const int num_v, const int num_e,
                                         const int feat_in, const int dim_sparse,
                                         const int num_warps, maxk_dim3 grid, maxk_dim3 block,
                                         int shared_size);
-void spmm_kernel_opt2_sparse_backward_v3_wrapper(const int *warp4, const int *idx,
+MAXK_API void spmm_kernel_opt2_sparse_backward_v3_wrapper(const int *warp4, const int *idx,
                                                  const float *val, const float *vin_data,
                                                  const uint8_t *vin_selector, float *vout,
                                                  const int num_v, const int num_e,
                                                  const int feat_in, const int dim_sparse,
                                                  const int num_warps, maxk_dim3 grid,
                                                  maxk_dim3 block, int shared_size);
-void topk_kernel_wrapper(uint8_t *data, uint8_t *value, uint8_t *index, unsigned int k, int N,
+MAXK_API void topk_kernel_wrapper(uint8_t *data, uint8_t *value, uint8_t *index, unsigned int k, int N,
                          int dim_origin, maxk_dim3 grid, maxk_dim3 block, int shared_size);
 
 #ifdef __cplusplus

@@ -8,4 +8,7 @@ first operator call does, and fails loudly if it is missing.
 from . import _cabi, ops  # noqa: F401
 from .autograd import CBSRAggregate, MaxK, SpGEMMFunction, TopKCBSR, worklist_for  # noqa: F401
 
-__all__ = ["ops", "MaxK", "SpGEMMFunction", "CBSRAggregate", "TopKCBSR", "worklist_for"]
+from .host import HostAggregator  # noqa: F401,E402
+
+__all__ = ["ops", "MaxK", "SpGEMMFunction", "CBSRAggregate", "TopKCBSR", "worklist_for",
+           "HostAggregator"]

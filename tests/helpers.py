@@ -1,0 +1,49 @@
+"""Shared helpers for the GPU parity tests: seeded problems on host (numpy, for the oracle)
+and on the device (torch, for the C-ABI path)."""
+import numpy as np
+import torch
+
+from oracle import oracle as O
+
+RTOL, ATOL = 1e-5, 1e-6  # BASELINE.json north_star: fp32 rtol 1e-5 / atol 1e-6
+
+
+class Problem:
+    def __init__(self, n=600, avg=30.0, k=32, d=256, seed=1, kind="powerlaw", empty_frac=0.05,
+                 max_deg=None, n_cols=None, selector="topk", warp_max_nz=64, values="uniform"):
+        rng = np.random.default_rng(seed)
+        self.n, self.k, self.d = n, k, d
+        self.n_cols = n if n_cols is None else n_cols
+        self.indptr, self.idx = O.synth_graph(n, avg, seed=seed, kind=kind, empty_frac=empty_frac,
+                                              max_deg=max_deg, n_cols=self.n_cols)
+        e = self.idx.shape[0]
+        self.val = (rng.random(e, dtype=np.float32) if values == "uniform"
+                    else np.ones(e, np.float32))
+        self.x = rng.random((self.n_cols, d), dtype=np.float32)
+        if selector == "topk":          # ascending columns (our TopK / the reference kernel)
+            self.sp_data, self.sp_index = O.topk_cbsr(self.x, k)
+        elif selector == "torch":       # descending values (torch.topk order, models.py:48)
+            v, i = torch.topk(torch.from_numpy(self.x), k, dim=1)
+            self.sp_data, self.sp_index = v.numpy().copy(), i.numpy().astype(np.uint8)
+        else:                           # random distinct columns (main.cu:120-133)
+            self.sp_index = np.argsort(rng.random((self.n_cols, d)), axis=1)[:, :k].astype(np.uint8)
+            self.sp_data = rng.random((self.n_cols, k), dtype=np.float32)
+        self.w4 = O.worklist(self.indptr, warp_max_nz)
+        self.dy = rng.random((n, d), dtype=np.float32)
+
+    def cuda(self):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+        return dict(indptr=t(self.indptr), indices=t(self.idx), values=t(self.val), x=t(self.x),
+                    sp_data=t(self.sp_data), sp_index=t(self.sp_index), warp4=t(self.w4), dy=t(self.dy))
+
+    def fwd_oracle(self):
+        return O.spgemm_forward(self.w4, self.idx, self.val, self.sp_data, self.sp_index, self.d,
+                                n_out=self.n)
+
+    def bwd_oracle(self):
+        return O.sspmm_backward(self.w4, self.idx, self.val, self.dy, self.sp_index)
+
+
+def assert_close(got: torch.Tensor, want: np.ndarray, what=""):
+    g = got.detach().cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(g, want, rtol=RTOL, atol=ATOL, err_msg=what)

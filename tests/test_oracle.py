@@ -188,3 +188,21 @@ def test_q1_mask_known_answer():
     m16 = O.q1_forward_dropped(w, 16)
     hit = np.nonzero(m16.any(axis=1))[0]
     assert hit.min() >= w - 24
+
+
+def test_cpu_path_port_matches_oracle():
+    """oracle/cpu_path.py (torch.topk + CSR SpMM, the reference's CPU path restated) against
+    the C oracle on tie-free data."""
+    import torch
+    from oracle.cpu_path import CpuAggregation
+    indptr, idx, val, x, sp_data, sp_index, w4 = _problem(n=400, avg=25.0, k=32, seed=12)
+    rng = np.random.default_rng(3)
+    dy = rng.random((400, 256), dtype=np.float32)
+    agg = CpuAggregation(torch.from_numpy(indptr), torch.from_numpy(idx), torch.from_numpy(val))
+    y, dx = agg.step(torch.from_numpy(x), torch.from_numpy(dy), 32)
+    np.testing.assert_allclose(y.numpy(), O.spgemm_forward(w4, idx, val, sp_data, sp_index, 256),
+                               rtol=1e-5, atol=1e-6)
+    dxc = O.sspmm_backward(w4, idx, val, dy, sp_index)
+    want = np.zeros((400, 256))
+    np.put_along_axis(want, sp_index.astype(np.int64), dxc, axis=1)
+    np.testing.assert_allclose(dx.numpy(), want, rtol=1e-5, atol=1e-6)
