@@ -95,6 +95,14 @@ MAXK_API int maxk_spgemm_forward(const int32_t *warp4, int64_t num_tasks, const 
                         const float *values, const float *sp_data, const uint8_t *sp_index,
                         int32_t k, float *out, int64_t num_rows_out, int32_t d, void *stream);
 
+/* Same, but with accumulate != 0 every contribution is ADDED to the existing content of
+ * `out` (no zero-fill, vector reductions for every row): used by the multi-GPU
+ * local-column / remote-column split. */
+MAXK_API int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
+                            const float *values, const float *sp_data, const uint8_t *sp_index,
+                            int32_t k, float *out, int64_t num_rows_out, int32_t d,
+                            int32_t accumulate, void *stream);
+
 /* ---- a3: backward outer-product sampled SSpMM  dXc = sample(A^T dY, sp_index)
  * (replaces spmm_kernel_opt2_sparse_backward_v3, kernels/spmm_maxk_backward.cu:15-115;
  * spmm_maxk_backward, cuda_kernel_bindings.cpp:106-161) ----------------------------------

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(FWD_WPB * 32, fwd_min_blocks(EPL))
 spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *__restrict__ idx,
                   const float *__restrict__ val, const float *__restrict__ sp_data,
                   const unsigned char *__restrict__ sp_index, int k, float *__restrict__ out, int d,
-                  int tasks_per_warp)
+                  int tasks_per_warp, int accumulate)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -201,9 +201,11 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
 
     int4 info = ld_stream_int4(warp4 + t0);
     const int first_row = info.x;
-    const bool first_shared = (t0 > 0) && (__ldg(&warp4[t0 - 1].x) == first_row);
-    bool last_shared = false;
-    if (t1 < num_tasks) last_shared = (__ldg(&warp4[t1].x) == __ldg(&warp4[t1 - 1].x));
+    // accumulate mode (multi-GPU local/remote split): every row is added to what is there
+    const bool first_shared = accumulate || ((t0 > 0) && (__ldg(&warp4[t0 - 1].x) == first_row));
+    bool last_shared = accumulate;
+    if (!accumulate && t1 < num_tasks)
+        last_shared = (__ldg(&warp4[t1].x) == __ldg(&warp4[t1 - 1].x));
 
     EdgeRegs pre;
     fwd_fetch_edges(pre, idx, val, info.y, min(info.z, FWD_STAGE), lane);
@@ -215,7 +217,8 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
         if (has_next) ninfo = ld_stream_int4(warp4 + t + 1);
 
         if (info.x != cur_row) {
-            fwd_flush_row(acc, out, cur_row, d, lane, first_shared && cur_row == first_row);
+            fwd_flush_row(acc, out, cur_row, d, lane,
+                          accumulate || (first_shared && cur_row == first_row));
             cur_row = info.x;
         }
         const int64_t loc = info.y;
@@ -241,7 +244,7 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
 template <int EPL, bool EXACT>
 static int launch_fwd(const int32_t *warp4, int64_t W, const int32_t *idx, const float *val,
                       const float *sp_data, const uint8_t *sp_index, int k, float *out, int d,
-                      int tasks_per_warp, cudaStream_t st)
+                      int tasks_per_warp, int accumulate, cudaStream_t st)
 {
     const size_t smem = (size_t)FWD_WPB * d * sizeof(float) + (size_t)FWD_WPB * FWD_STAGE * sizeof(int2);
     const int64_t chunks = ceil_div<int64_t>(W, tasks_per_warp);
@@ -252,7 +255,7 @@ static int launch_fwd(const int32_t *warp4, int64_t W, const int32_t *idx, const
     }
     spgemm_fwd_kernel<EPL, EXACT><<<(unsigned)grid, FWD_WPB * 32, smem, st>>>(
         reinterpret_cast<const int4 *>(warp4), W, idx, val, sp_data, sp_index, k, out, d,
-        tasks_per_warp);
+        tasks_per_warp, accumulate);
     MAXK_LAUNCH_CHECK("spgemm_fwd_kernel");
     return MAXK_OK;
 }
@@ -268,6 +271,16 @@ extern "C" int maxk_spgemm_forward(const int32_t *warp4, int64_t num_tasks, cons
                                    const uint8_t *sp_index, int32_t k, float *out,
                                    int64_t num_rows_out, int32_t d, void *stream)
 {
+    return maxk_spgemm_forward_acc(warp4, num_tasks, indices, values, sp_data, sp_index, k, out,
+                                   num_rows_out, d, /*accumulate=*/0, stream);
+}
+
+extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
+                                       const int32_t *indices, const float *values,
+                                       const float *sp_data, const uint8_t *sp_index, int32_t k,
+                                       float *out, int64_t num_rows_out, int32_t d,
+                                       int32_t accumulate, void *stream)
+{
     MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0, "maxk_spgemm_forward: negative size");
     MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
                  "maxk_spgemm_forward: d=%d must be a multiple of 4 in [4,256]", d);
@@ -280,8 +293,10 @@ extern "C" int maxk_spgemm_forward(const int32_t *warp4, int64_t num_tasks, cons
     if (num_rows_out == 0) return MAXK_OK;
     // Output is DEFINED by this call: empty rows and rows shared between
     // two warps' runs start from zero.
-    MAXK_CUDA(cudaMemsetAsync(out, 0, (size_t)num_rows_out * d * sizeof(float), st));
-    count_launch();
+    if (!accumulate) {
+        MAXK_CUDA(cudaMemsetAsync(out, 0, (size_t)num_rows_out * d * sizeof(float), st));
+        count_launch();
+    }
     if (num_tasks == 0) return MAXK_OK;
     MAXK_REQUIRE(warp4 && indices && values && sp_data && sp_index,
                  "maxk_spgemm_forward: NULL input pointer");
@@ -294,9 +309,9 @@ extern "C" int maxk_spgemm_forward(const int32_t *warp4, int64_t num_tasks, cons
     case E:                                                                                       \
         return (exact && vec_ok)                                                                  \
                    ? launch_fwd<E, true>(warp4, num_tasks, indices, values, sp_data, sp_index, k, \
-                                         out, d, tpw, st)                                         \
+                                         out, d, tpw, accumulate, st)                             \
                    : launch_fwd<E, false>(warp4, num_tasks, indices, values, sp_data, sp_index,   \
-                                          k, out, d, tpw, st);
+                                          k, out, d, tpw, accumulate, st);
     switch (epl) {
         MAXK_FWD_CASE(1)
         MAXK_FWD_CASE(2)

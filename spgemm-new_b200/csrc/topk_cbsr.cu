@@ -196,10 +196,10 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
     MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
                  "maxk_topk_cbsr_f32: d=%d must be a multiple of 4 in [4,256]", d);
     MAXK_REQUIRE(k >= 1 && k <= d, "maxk_topk_cbsr_f32: Invalid k value (k=%d, d=%d)", k, d);
+    if (n == 0) return MAXK_OK;
     MAXK_REQUIRE((sp_data == nullptr) == (sp_index == nullptr),
                  "maxk_topk_cbsr_f32: sp_data and sp_index must both be given or both NULL");
     MAXK_REQUIRE(sp_index != nullptr || dense_out != nullptr, "maxk_topk_cbsr_f32: no output");
-    if (n == 0) return MAXK_OK;
     MAXK_REQUIRE(x != nullptr, "maxk_topk_cbsr_f32: x is NULL");
     MAXK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(dense_out) & 15) == 0,
@@ -219,8 +219,8 @@ extern "C" int maxk_topk_cbsr_u8(const uint8_t *x, int64_t n, int32_t d, int32_t
     MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
                  "maxk_topk_cbsr_u8: d=%d must be a multiple of 4 in [4,256]", d);
     MAXK_REQUIRE(k >= 1 && k <= d, "maxk_topk_cbsr_u8: Invalid k value (k=%d, d=%d)", k, d);
-    MAXK_REQUIRE(value != nullptr && index != nullptr, "maxk_topk_cbsr_u8: NULL output");
     if (n == 0) return MAXK_OK;
+    MAXK_REQUIRE(value != nullptr && index != nullptr, "maxk_topk_cbsr_u8: NULL output");
     MAXK_REQUIRE(x != nullptr && (reinterpret_cast<uintptr_t>(x) & 3) == 0,
                  "maxk_topk_cbsr_u8: x must be non-NULL and 4-byte aligned");
     const int64_t grid = ceil_div<int64_t>(n, TOPK_WPB);

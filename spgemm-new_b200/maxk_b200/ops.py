@@ -103,7 +103,8 @@ def topk_cbsr_u8(x: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
 def spgemm_forward(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
                    sp_data: torch.Tensor, sp_index: torch.Tensor, num_warps: Optional[int] = None,
                    dim_sparse: Optional[int] = None, feat_dim: int = FULL_DIM,
-                   num_rows: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   num_rows: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                   accumulate: bool = False) -> torch.Tensor:
     lib = _cabi.load()
     _cuda(warp4, "warp4_metadata", torch.int32)
     _cuda(indices, "indices", torch.int32)
@@ -121,14 +122,15 @@ def spgemm_forward(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Ten
     n_out = sp_data.shape[0] if num_rows is None else int(num_rows)  # bindings.cpp:65
     with torch.cuda.device(sp_data.device):
         if out is None:
+            _req(not accumulate, "accumulate=True needs an `out` tensor")
             out = torch.empty((n_out, feat_dim), dtype=torch.float32, device=sp_data.device)
         else:
             _cuda(out, "out", torch.float32)
             _req(tuple(out.shape) == (n_out, feat_dim), "out has the wrong shape")
-        _cabi.check(lib.maxk_spgemm_forward(warp4.data_ptr(), w, indices.data_ptr(),
-                                            values.data_ptr(), sp_data.data_ptr(),
-                                            sp_index.data_ptr(), k, out.data_ptr(), n_out,
-                                            feat_dim, _stream(sp_data)))
+        _cabi.check(lib.maxk_spgemm_forward_acc(warp4.data_ptr(), w, indices.data_ptr(),
+                                                values.data_ptr(), sp_data.data_ptr(),
+                                                sp_index.data_ptr(), k, out.data_ptr(), n_out,
+                                                feat_dim, 1 if accumulate else 0, _stream(sp_data)))
     return out
 
 
