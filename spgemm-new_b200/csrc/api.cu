@@ -13,6 +13,7 @@ static std::atomic<int64_t> g_launches{0};
 
 extern int g_fwd_tasks_per_warp;
 extern int g_bwd_tasks_per_warp;
+extern int g_fwd_copies;
 
 void set_error(const char *fmt, ...)
 {
@@ -44,6 +45,13 @@ extern "C" int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp)
 {
     if (fwd_tasks_per_warp > 0) g_fwd_tasks_per_warp = fwd_tasks_per_warp;
     if (bwd_tasks_per_warp > 0) g_bwd_tasks_per_warp = bwd_tasks_per_warp;
+    return MAXK_OK;
+}
+
+// Bench/test hook: number of accumulator copies of the forward kernel (0 = automatic).
+extern "C" int maxk_set_forward_copies(int copies)
+{
+    g_fwd_copies = copies < 0 ? 0 : copies;
     return MAXK_OK;
 }
 

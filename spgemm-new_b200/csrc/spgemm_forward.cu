@@ -3,90 +3,84 @@
 // Replaces spmm_kernel_opt2_sparse_v3 (ref: kernels/spmm_maxk.cu:17-106).  Same math,
 // different machine mapping (DESIGN.md "forward kernel"):
 //   * a warp owns a CONTIGUOUS run of tasks from the edge-balanced work list and keeps
-//     one output row (d floats) in shared memory across consecutive tasks of the same
-//     row, so a row is written once per run instead of once per 64-nnz task;
-//   * rows wholly inside a run are written with plain 128-bit streaming stores; only
-//     rows that straddle two runs use 128-bit vector reductions (red.global.add.v4.f32);
+//     one output row in shared memory across consecutive tasks of the same row, so a row
+//     is written once per run instead of once per 64-nnz task;
+//   * rows wholly inside a run are written with plain streaming stores; only rows that
+//     straddle two runs use vector reductions (red.global.add.v4.f32);
 //   * the task's (idx,val) pairs are fetched coalesced one task ahead and broadcast from
-//     shared memory; neighbour CBSR rows are gathered UNROLL edges at a time (one 128 B
-//     value line + one k-byte selector line per edge) before the shared-memory
-//     accumulate, so each warp keeps 2*UNROLL independent gathers in flight;
+//     shared memory; neighbour CBSR rows are gathered U instructions ahead (one 128 B value
+//     line + one k-byte selector line per edge) before the shared-memory accumulate;
+//   * k < 32 (k = 16, 8, ...): 32/k edges share one instruction (lane l -> edge l % E,
+//     entry l / E), each edge slot accumulating into its OWN copy of the row, so all 32
+//     lanes work for every k (the reference idles 32-k lanes per edge and, for k < 32, the
+//     warps >= 12k/32);
+//   * the kernel is bound by L1TEX data-pipe wavefronts (ncu: 93 % of peak): per edge one
+//     value-line gather, one selector-line gather, one staging broadcast and a read-modify-
+//     write whose 32 random columns cost ~3.3 wavefronts for the load and again for the
+//     store.  Interleaved accumulator copies (acc[c*R + lane % R]) were built to cut those
+//     conflicts and measured: they do not pay (the worst bank still serialises ~3 lanes
+//     unless R = 32), so R = E is the default and the other values stay as a tuning knob;
 //   * 64-bit row offsets (ref uses int: overflow beyond 8.39 M nodes).
-// HBM-bound by design: CSR stream + one write of Y; the CBSR operand (5k B/node) lives
-// in the 126 MB L2.  No tensor cores: 2 flops per >= 5 bytes gathered.
+// HBM traffic is the CSR stream + one write of Y; the CBSR operand (5k B/node) lives in
+// the 126 MB L2.  No tensor cores: 2 flops per >= 5 bytes gathered.
 #include "common.cuh"
 
 namespace maxk {
 
-constexpr int FWD_WPB = 8;     // warps per CTA
-// edges gathered per batch: gathers in flight per lane stay ~8, so fewer edges per batch
-// when a lane owns more entries of each CBSR row
-#ifndef MAXK_FWD_UNROLL1
-#define MAXK_FWD_UNROLL1 4  // k <= 32
-#endif
-#ifndef MAXK_FWD_MINB1
-#define MAXK_FWD_MINB1 4    // CTAs/SM the register budget is capped for (k <= 64)
-#endif
-__host__ __device__ constexpr int fwd_unroll(int epl)
-{
-    return epl == 1 ? MAXK_FWD_UNROLL1
-                    : (epl == 2 ? (MAXK_FWD_UNROLL1 + 1) / 2 : (epl <= 4 ? 2 : 1));
-}
-__host__ __device__ constexpr int fwd_min_blocks(int epl) { return epl <= 2 ? MAXK_FWD_MINB1 : 2; }
 constexpr int FWD_STAGE = 64;  // staged (idx,val) pairs per warp == MAXK_WARP_MAX_NZ
 
 #ifndef MAXK_FWD_SYNCWARP
 #define MAXK_FWD_SYNCWARP 1
 #endif
 
-__device__ __forceinline__ void fwd_flush_row(float *acc, float *__restrict__ out, int64_t row,
-                                              int d, int lane, bool shared_row)
-{
-    __syncwarp();
-    float *dst = out + row * (int64_t)d;
-    for (int c = lane * 4; c < d; c += 128) {
-        float4 v = *reinterpret_cast<float4 *>(acc + c);
-        *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (shared_row)
-            red_add_f4(dst + c, v.x, v.y, v.z, v.w);
-        else
-            st_stream_f4(reinterpret_cast<float4 *>(dst + c), v);
-    }
-    __syncwarp();
-}
-
-// Per-lane slice of one neighbour's CBSR row: EPL entries.
-template <int EPL, bool EXACT>
-struct Slice {
-    float v[EPL];
-    unsigned char s[EPL];
+// One kernel variant.  KL lanes per edge (32 for k >= 32 or odd k; k itself for k = 16,8,4,2,1),
+// EPL entries per lane (k > 32), EXACT: k == KL*EPL with aligned operands (vector gathers),
+// R accumulator copies, WPB warps per CTA, U gather instructions in flight, MINB CTAs/SM
+// the register budget is capped for.
+template <int KL_, int EPL_, bool EXACT_, int R_, int WPB_, int U_, int MINB_>
+struct FwdCfg {
+    static constexpr int KL = KL_, EPL = EPL_, R = R_, WPB = WPB_, U = U_, MINB = MINB_;
+    static constexpr bool EXACT = EXACT_;
+    static constexpr int E = 32 / KL_;  // edges per instruction
+    static_assert(KL_ * E == 32 && (R_ % E) == 0 && R_ >= E, "copies must separate edge slots");
+    static_assert(KL_ == 32 || EPL_ == 1, "sub-warp edges have one entry per lane");
 };
 
-template <int EPL, bool EXACT>
-__device__ __forceinline__ void fwd_gather(Slice<EPL, EXACT> &sl, const float *__restrict__ sp_data,
+template <class C>
+struct Slice {
+    float v[C::EPL];
+    unsigned char s[C::EPL];
+};
+
+template <class C>
+__device__ __forceinline__ void fwd_gather(Slice<C> &sl, const float *__restrict__ sp_data,
                                            const unsigned char *__restrict__ sp_index, int col,
                                            int k, int lane)
 {
     const int64_t base = (int64_t)col * k;
-    if constexpr (EXACT && EPL == 1) {
+    if constexpr (C::KL < 32) {
+        const int entry = lane / C::E;
+        sl.v[0] = ld_gather_f32(sp_data + base + entry);
+        sl.s[0] = ld_gather_u8(sp_index + base + entry);
+    } else if constexpr (C::EXACT && C::EPL == 1) {
         sl.v[0] = ld_gather_f32(sp_data + base + lane);
         sl.s[0] = ld_gather_u8(sp_index + base + lane);
-    } else if constexpr (EXACT && EPL == 2) {
+    } else if constexpr (C::EXACT && C::EPL == 2) {
         // lane owns entries 2*lane, 2*lane+1: one 64-bit + one 16-bit load
         float2 f = __ldg(reinterpret_cast<const float2 *>(sp_data + base) + lane);
         unsigned short u = __ldg(reinterpret_cast<const unsigned short *>(sp_index + base) + lane);
         sl.v[0] = f.x; sl.v[1] = f.y;
         sl.s[0] = (unsigned char)(u & 0xff); sl.s[1] = (unsigned char)(u >> 8);
-    } else if constexpr (EXACT && EPL == 4) {
+    } else if constexpr (C::EXACT && C::EPL == 4) {
         float4 f = ld_gather_f4(reinterpret_cast<const float4 *>(sp_data + base) + lane);
         unsigned u = ld_gather_u32(reinterpret_cast<const unsigned *>(sp_index + base) + lane);
         sl.v[0] = f.x; sl.v[1] = f.y; sl.v[2] = f.z; sl.v[3] = f.w;
         sl.s[0] = u & 0xff; sl.s[1] = (u >> 8) & 0xff; sl.s[2] = (u >> 16) & 0xff; sl.s[3] = u >> 24;
     } else {
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) {
+        for (int i = 0; i < C::EPL; ++i) {
             const int l = lane + 32 * i;
-            if (EXACT || l < k) {
+            if (C::EXACT || l < k) {
                 sl.v[i] = ld_gather_f32(sp_data + base + l);
                 sl.s[i] = ld_gather_u8(sp_index + base + l);
             } else {
@@ -97,18 +91,19 @@ __device__ __forceinline__ void fwd_gather(Slice<EPL, EXACT> &sl, const float *_
     }
 }
 
-template <int EPL, bool EXACT>
-__device__ __forceinline__ void fwd_accumulate(const Slice<EPL, EXACT> &sl, float *acc, float w,
-                                               int k, int lane)
+// acc_lane = acc + lane % R.  Lanes of one instruction that share a copy belong to ONE
+// CBSR row -> distinct columns (precondition Q4); lanes of different edges use different
+// copies.  So the plain read-modify-write cannot collide inside a warp.
+template <class C>
+__device__ __forceinline__ void fwd_accumulate(const Slice<C> &sl, float *acc_lane, float w, int k,
+                                               int lane, bool valid)
 {
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-        // entries handled by one instruction belong to ONE CBSR row -> distinct columns
-        // (precondition Q4), so the plain read-modify-write cannot collide inside a warp.
-        bool on = true;
-        if constexpr (!EXACT) on = (lane + 32 * i) < k;
+    for (int i = 0; i < C::EPL; ++i) {
+        bool on = valid;
+        if constexpr (C::KL == 32 && !C::EXACT) on = on && ((lane + 32 * i) < k);
         if (on) {
-            float *a = acc + sl.s[i];
+            float *a = acc_lane + (int)sl.s[i] * C::R;
             *a = fmaf(w, sl.v[i], *a);  // FFMA, like the reference
         }
 #if MAXK_FWD_SYNCWARP
@@ -117,38 +112,96 @@ __device__ __forceinline__ void fwd_accumulate(const Slice<EPL, EXACT> &sl, floa
     }
 }
 
-template <int EPL, bool EXACT>
-__device__ __forceinline__ void fwd_process_batch(const int2 *stage, int len, float *acc,
+template <class C>
+__device__ __forceinline__ void fwd_process_batch(const int2 *stage, int len, float *acc_lane,
                                                   const float *__restrict__ sp_data,
                                                   const unsigned char *__restrict__ sp_index,
                                                   int k, int lane)
 {
-    constexpr int FWD_UNROLL = fwd_unroll(EPL);
+    constexpr int U = C::U, E = C::E, STEP = U * E;
+    const int e = lane & (E - 1);
     int j = 0;
-    for (; j + FWD_UNROLL <= len; j += FWD_UNROLL) {
-        int2 ev[FWD_UNROLL];
-        Slice<EPL, EXACT> sl[FWD_UNROLL];
+    for (; j + STEP <= len; j += STEP) {  // every lane has an edge
+        int2 ev[U];
+        Slice<C> sl[U];
 #pragma unroll
-        for (int u = 0; u < FWD_UNROLL; ++u) ev[u] = stage[j + u];
+        for (int u = 0; u < U; ++u) ev[u] = stage[j + u * E + e];
 #pragma unroll
-        for (int u = 0; u < FWD_UNROLL; ++u) fwd_gather<EPL, EXACT>(sl[u], sp_data, sp_index, ev[u].x, k, lane);
+        for (int u = 0; u < U; ++u) fwd_gather<C>(sl[u], sp_data, sp_index, ev[u].x, k, lane);
 #pragma unroll
-        for (int u = 0; u < FWD_UNROLL; ++u)
-            fwd_accumulate<EPL, EXACT>(sl[u], acc, __int_as_float(ev[u].y), k, lane);
+        for (int u = 0; u < U; ++u)
+            fwd_accumulate<C>(sl[u], acc_lane, __int_as_float(ev[u].y), k, lane, true);
     }
-    if (j < len) {  // predicated tail group (len is warp-uniform)
-        int2 ev[FWD_UNROLL];
-        Slice<EPL, EXACT> sl[FWD_UNROLL];
+    if (j < len) {  // predicated tail group
+        int2 ev[U];
+        Slice<C> sl[U];
 #pragma unroll
-        for (int u = 0; u < FWD_UNROLL; ++u)
-            if (j + u < len) ev[u] = stage[j + u];
+        for (int u = 0; u < U; ++u) {
+            ev[u] = make_int2(0, 0);
+            if (j + u * E + e < len) ev[u] = stage[j + u * E + e];
+        }
 #pragma unroll
-        for (int u = 0; u < FWD_UNROLL; ++u)
-            if (j + u < len) fwd_gather<EPL, EXACT>(sl[u], sp_data, sp_index, ev[u].x, k, lane);
+        for (int u = 0; u < U; ++u)
+            if (j + u * E + e < len) fwd_gather<C>(sl[u], sp_data, sp_index, ev[u].x, k, lane);
 #pragma unroll
-        for (int u = 0; u < FWD_UNROLL; ++u)
-            if (j + u < len) fwd_accumulate<EPL, EXACT>(sl[u], acc, __int_as_float(ev[u].y), k, lane);
+        for (int u = 0; u < U; ++u) {
+            if (j + u * E < len)  // warp-uniform: skip instructions no lane needs
+                fwd_accumulate<C>(sl[u], acc_lane, __int_as_float(ev[u].y), k, lane,
+                                  j + u * E + e < len);
+        }
     }
+}
+
+// Sum the R copies of the row, write it out (plain store or vector reduction) and clear
+// the accumulator.  Copies of one column are contiguous (acc[c*R + r]).
+template <class C>
+__device__ __forceinline__ void fwd_flush_row(float *acc, float *__restrict__ out, int64_t row,
+                                              int d, int lane, bool shared_row)
+{
+    constexpr int R = C::R;
+    __syncwarp();
+    float *dst = out + row * (int64_t)d;
+    const int total = d * R;
+    for (int base = 0; base < total; base += 128) {  // warp-uniform trip count (shuffles below)
+        const int i = base + lane * 4;
+        const bool in = i < total;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) {
+            v = *reinterpret_cast<float4 *>(acc + i);
+            *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if constexpr (R == 1) {
+            if (in) {
+                if (shared_row)
+                    red_add_f4(dst + i, v.x, v.y, v.z, v.w);
+                else
+                    st_stream_f4(reinterpret_cast<float4 *>(dst + i), v);
+            }
+        } else if constexpr (R == 2) {
+            const float s0 = v.x + v.y, s1 = v.z + v.w;
+            float *p = dst + (i >> 1);
+            if (in) {
+                if (shared_row) {
+                    red_add_f1(p, s0);
+                    red_add_f1(p + 1, s1);
+                } else {
+                    __stcs(reinterpret_cast<float2 *>(p), make_float2(s0, s1));
+                }
+            }
+        } else {
+            float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+            for (int o = 1; o < R / 4; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (in && (lane & (R / 4 - 1)) == 0) {
+                float *p = dst + i / R;
+                if (shared_row)
+                    red_add_f1(p, s);
+                else
+                    __stcs(p, s);
+            }
+        }
+    }
+    __syncwarp();
 }
 
 // coalesced fetch of up to FWD_STAGE (idx,val) pairs of one task into registers
@@ -179,8 +232,8 @@ __device__ __forceinline__ void fwd_stage_edges(const EdgeRegs &r, int2 *stage, 
     __syncwarp();
 }
 
-template <int EPL, bool EXACT>
-__global__ void __launch_bounds__(FWD_WPB * 32, fwd_min_blocks(EPL))
+template <class C>
+__global__ void __launch_bounds__(C::WPB * 32, C::MINB)
 spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *__restrict__ idx,
                   const float *__restrict__ val, const float *__restrict__ sp_data,
                   const unsigned char *__restrict__ sp_index, int k, float *__restrict__ out, int d,
@@ -188,16 +241,17 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *acc = reinterpret_cast<float *>(smem_raw) + warp * d;
-    int2 *stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + FWD_WPB * d) +
+    float *acc = reinterpret_cast<float *>(smem_raw) + warp * d * C::R;
+    int2 *stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + C::WPB * d * C::R) +
                   warp * FWD_STAGE;
+    float *acc_lane = acc + (lane & (C::R - 1));
 
-    const int64_t t0 = ((int64_t)blockIdx.x * FWD_WPB + warp) * tasks_per_warp;
+    const int64_t t0 = ((int64_t)blockIdx.x * C::WPB + warp) * tasks_per_warp;
     if (t0 >= num_tasks) return;  // no CTA-wide barrier below
     const int64_t t1 = min(t0 + (int64_t)tasks_per_warp, num_tasks);
 
-    for (int c = lane * 4; c < d; c += 128)
-        *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane * 4; i < d * C::R; i += 128)
+        *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
 
     int4 info = ld_stream_int4(warp4 + t0);
     const int first_row = info.x;
@@ -217,50 +271,115 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
         if (has_next) ninfo = ld_stream_int4(warp4 + t + 1);
 
         if (info.x != cur_row) {
-            fwd_flush_row(acc, out, cur_row, d, lane,
-                          accumulate || (first_shared && cur_row == first_row));
+            fwd_flush_row<C>(acc, out, cur_row, d, lane,
+                             accumulate || (first_shared && cur_row == first_row));
             cur_row = info.x;
         }
         const int64_t loc = info.y;
         const int len = info.z;
-        const int len0 = min(len, FWD_STAGE);
         fwd_stage_edges(pre, stage, lane);
         if (has_next)  // next task's CSR slice streams in while this task's gathers run
             fwd_fetch_edges(pre, idx, val, ninfo.y, min(ninfo.z, FWD_STAGE), lane);
-        fwd_process_batch<EPL, EXACT>(stage, len0, acc, sp_data, sp_index, k, lane);
+        fwd_process_batch<C>(stage, min(len, FWD_STAGE), acc_lane, sp_data, sp_index, k, lane);
         for (int off = FWD_STAGE; off < len; off += FWD_STAGE) {  // len > 64: foreign work lists
             EdgeRegs more;
             const int ln = min(len - off, FWD_STAGE);
             fwd_fetch_edges(more, idx, val, loc + off, ln, lane);
             fwd_stage_edges(more, stage, lane);
-            fwd_process_batch<EPL, EXACT>(stage, ln, acc, sp_data, sp_index, k, lane);
+            fwd_process_batch<C>(stage, ln, acc_lane, sp_data, sp_index, k, lane);
         }
         info = ninfo;
     }
-    fwd_flush_row(acc, out, cur_row, d, lane,
-                  last_shared || (first_shared && cur_row == first_row));
+    fwd_flush_row<C>(acc, out, cur_row, d, lane,
+                     last_shared || (first_shared && cur_row == first_row));
 }
 
-template <int EPL, bool EXACT>
-static int launch_fwd(const int32_t *warp4, int64_t W, const int32_t *idx, const float *val,
-                      const float *sp_data, const uint8_t *sp_index, int k, float *out, int d,
-                      int tasks_per_warp, int accumulate, cudaStream_t st)
+struct FwdArgs {
+    const int32_t *warp4;
+    int64_t W;
+    const int32_t *idx;
+    const float *val;
+    const float *sp_data;
+    const uint8_t *sp_index;
+    int k;
+    float *out;
+    int d;
+    int tasks_per_warp;
+    int accumulate;
+    cudaStream_t st;
+};
+
+template <class C>
+static int launch_fwd(const FwdArgs &a)
 {
-    const size_t smem = (size_t)FWD_WPB * d * sizeof(float) + (size_t)FWD_WPB * FWD_STAGE * sizeof(int2);
-    const int64_t chunks = ceil_div<int64_t>(W, tasks_per_warp);
-    const int64_t grid = ceil_div<int64_t>(chunks, FWD_WPB);
+    const size_t smem = (size_t)C::WPB * a.d * C::R * sizeof(float) +
+                        (size_t)C::WPB * FWD_STAGE * sizeof(int2);
+    if (smem > 48 * 1024) {
+        static bool opted_in = false;  // per variant; benign if raced
+        if (!opted_in) {
+            MAXK_CUDA(cudaFuncSetAttribute(spgemm_fwd_kernel<C>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            opted_in = true;
+        }
+    }
+    const int64_t chunks = ceil_div<int64_t>(a.W, a.tasks_per_warp);
+    const int64_t grid = ceil_div<int64_t>(chunks, C::WPB);
     if (grid > 0x7fffffffLL) {
         set_error("maxk_spgemm_forward: grid too large");
         return MAXK_ERR_UNSUPPORTED;
     }
-    spgemm_fwd_kernel<EPL, EXACT><<<(unsigned)grid, FWD_WPB * 32, smem, st>>>(
-        reinterpret_cast<const int4 *>(warp4), W, idx, val, sp_data, sp_index, k, out, d,
-        tasks_per_warp, accumulate);
+    spgemm_fwd_kernel<C><<<(unsigned)grid, C::WPB * 32, smem, a.st>>>(
+        reinterpret_cast<const int4 *>(a.warp4), a.W, a.idx, a.val, a.sp_data, a.sp_index, a.k,
+        a.out, a.d, a.tasks_per_warp, a.accumulate);
     MAXK_LAUNCH_CHECK("spgemm_fwd_kernel");
     return MAXK_OK;
 }
 
 int g_fwd_tasks_per_warp = 16;  // tunable through maxk_set_tuning (bench sweeps)
+int g_fwd_copies = 0;           // 0 = automatic choice of R
+
+// launch shape per R:      R<=2: 8 warps, U=4, 64 regs   R=4: 8 warps, U=4
+//                          R=8 : 8 warps (68 KB/CTA, 3 CTAs/SM), U=8
+//                          R=16: 4 warps (66 KB/CTA, 3 CTAs/SM), U=8
+template <int KL, int EPL, bool EXACT, int R>
+static int launch_fwd_r(const FwdArgs &a)
+{
+    constexpr int U1 = (EPL == 1) ? 4 : (EPL == 2 ? 2 : (EPL <= 4 ? 2 : 1));
+    if constexpr (R <= 4)
+        return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, (EPL <= 2 ? 4 : 2)>>(a);
+    else if constexpr (R == 8)
+        return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, 2 * U1, 3>>(a);
+    else if constexpr (R == 16)
+        return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 4, 2 * U1, 3>>(a);
+    else
+        return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 2>>(a);
+}
+
+// pick R among the instantiated copies for this edge width (R >= E always)
+template <int KL, int EPL, bool EXACT>
+static int launch_fwd_pick(const FwdArgs &a, int want_r)
+{
+    constexpr int E = 32 / KL;
+    if constexpr (KL == 32 && (EPL > 2 || !EXACT)) {
+        return launch_fwd_r<KL, EPL, EXACT, 1>(a);
+    } else if constexpr (E == 32) {
+        return launch_fwd_r<KL, EPL, EXACT, 32>(a);
+    } else {
+        if constexpr (E < 16) {
+            if (want_r >= 16) return launch_fwd_r<KL, EPL, EXACT, 16>(a);
+        }
+        if constexpr (E < 8) {
+            if (want_r >= 8) return launch_fwd_r<KL, EPL, EXACT, 8>(a);
+        }
+        if constexpr (E < 4) {
+            if (want_r >= 4) return launch_fwd_r<KL, EPL, EXACT, 4>(a);
+        }
+        if constexpr (E < 2) {
+            if (want_r >= 2) return launch_fwd_r<KL, EPL, EXACT, 2>(a);
+        }
+        return launch_fwd_r<KL, EPL, EXACT, E>(a);
+    }
+}
 
 }  // namespace maxk
 
@@ -300,18 +419,28 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
     if (num_tasks == 0) return MAXK_OK;
     MAXK_REQUIRE(warp4 && indices && values && sp_data && sp_index,
                  "maxk_spgemm_forward: NULL input pointer");
-    const int epl = (k + 31) / 32;
-    const bool exact = (k % 32 == 0);
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(sp_data) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(sp_index) & 3) == 0);
-    const int tpw = g_fwd_tasks_per_warp;
-#define MAXK_FWD_CASE(E)                                                                          \
-    case E:                                                                                       \
-        return (exact && vec_ok)                                                                  \
-                   ? launch_fwd<E, true>(warp4, num_tasks, indices, values, sp_data, sp_index, k, \
-                                         out, d, tpw, accumulate, st)                             \
-                   : launch_fwd<E, false>(warp4, num_tasks, indices, values, sp_data, sp_index,   \
-                                          k, out, d, tpw, accumulate, st);
+    FwdArgs a{warp4, num_tasks, indices, values, sp_data, sp_index, k, out, d,
+              g_fwd_tasks_per_warp, accumulate, st};
+    // R: accumulator copies.  Measured on B200 (profiles/r01_sweep_copies.md): R = E (one copy
+    // per edge slot) is fastest on every BASELINE shape -- with 1 < R < 32 the worst bank
+    // still serialises ~3 lanes, and R >= 16 costs more occupancy than it saves.
+    const int want_r = g_fwd_copies > 0 ? g_fwd_copies : 1;
+    switch (k) {
+        case 16: return launch_fwd_pick<16, 1, true>(a, want_r);
+        case 8: return launch_fwd_pick<8, 1, true>(a, want_r);
+        case 4: return launch_fwd_pick<4, 1, true>(a, want_r);
+        case 2: return launch_fwd_pick<2, 1, true>(a, want_r);
+        case 1: return launch_fwd_pick<1, 1, true>(a, want_r);
+        default: break;
+    }
+    const int epl = (k + 31) / 32;
+    const bool exact = (k % 32 == 0) && vec_ok;
+#define MAXK_FWD_CASE(EP)                                                         \
+    case EP:                                                                      \
+        return exact ? launch_fwd_pick<32, EP, true>(a, want_r)                   \
+                     : launch_fwd_pick<32, EP, false>(a, want_r);
     switch (epl) {
         MAXK_FWD_CASE(1)
         MAXK_FWD_CASE(2)

@@ -244,3 +244,8 @@ def cbsr_unpack(records: torch.Tensor, n: int, k: int):
 
 def set_tuning(fwd_tasks_per_warp: int = 0, bwd_tasks_per_warp: int = 0) -> None:
     _cabi.check(_cabi.load().maxk_set_tuning(fwd_tasks_per_warp, bwd_tasks_per_warp))
+
+
+def set_forward_copies(copies: int = 0) -> None:
+    """Accumulator copies of the forward kernel (0 = automatic); bench/test hook."""
+    _cabi.check(_cabi.load().maxk_set_forward_copies(int(copies)))

@@ -153,6 +153,29 @@ def test_run_length_invariance(ops, tpw):
     assert_close(dxc, p.bwd_oracle())
 
 
+@pytest.mark.parametrize("copies", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("k", [32, 64, 16, 8, 4, 2, 1, 18])
+def test_forward_accumulator_copies(ops, k, copies):
+    """Every (edge width, accumulator copies) variant of the forward kernel gives the same
+    result; rows are flushed as plain stores, reductions (shared rows) and in accumulate mode."""
+    p = Problem(n=150, avg=120.0, k=k, seed=7 * k + copies, empty_frac=0.1)
+    g = p.cuda()
+    want = p.fwd_oracle()
+    try:
+        ops.set_forward_copies(copies)
+        for tpw in (16, 2):
+            ops.set_tuning(tpw, 0)
+            y = ops.spgemm_forward(g["warp4"], g["indices"], g["values"], g["sp_data"], g["sp_index"],
+                                   num_rows=p.n)
+            assert_close(y, want, f"k={k} copies={copies} tpw={tpw}")
+        ops.spgemm_forward(g["warp4"], g["indices"], g["values"], g["sp_data"], g["sp_index"],
+                           num_rows=p.n, out=y, accumulate=True)
+        assert_close(y, 2 * want, "accumulate")
+    finally:
+        ops.set_forward_copies(0)
+        ops.set_tuning(16, 16)
+
+
 def test_output_is_defined_not_accumulated(ops):
     """results do not depend on what the output buffers held before."""
     p = Problem(n=500, avg=20.0, k=32, seed=8, empty_frac=0.3)
