@@ -46,19 +46,22 @@ class CpuAggregation:
         mask.scatter_(1, idx, 1)
         return x * mask, mask
 
-    def forward(self, x, k):
-        h, mask = self.maxk(x, k)
-        return torch.sparse.mm(self.a, h), mask
+    def prepare(self, x, k):
+        """MaxK on the CPU (outside the timed step, like the GPU arm whose step is
+        SpGEMM + SSpMM on an already sparsified operand)."""
+        return self.maxk(x, k)
+
+    def forward(self, h):
+        return torch.sparse.mm(self.a, h)
 
     def backward(self, dy, mask):
         return torch.sparse.mm(self.at, dy) * mask
 
-    def step(self, x, dy, k):
-        y, mask = self.forward(x, k)
-        dx = self.backward(dy, mask)
-        return y, dx
+    def step(self, h, dy, mask):
+        """one forward aggregation + one backward (gradient w.r.t. the MaxK input)"""
+        return self.forward(h), self.backward(dy, mask)
 
-    def timed_step(self, x, dy, k):
+    def timed_step(self, h, dy, mask):
         t0 = time.perf_counter()
-        out = self.step(x, dy, k)
+        out = self.step(h, dy, mask)
         return out, time.perf_counter() - t0

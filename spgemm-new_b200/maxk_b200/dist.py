@@ -126,8 +126,12 @@ class DistAggregator:
         """TopK on the local rows, then start the all-gather of the CBSR block.  Returns the
         gathered (sp_data, sp_index) buffers; `forward` waits for the exchange."""
         sd, si = self.ops.topk_cbsr(x_loc, self.k)
-        self.loc_data[: self.n_local].copy_(sd)
-        self.loc_index[: self.n_local].copy_(si)
+        return self.exchange(sd, si)
+
+    def exchange(self, sp_data_loc: torch.Tensor, sp_index_loc: torch.Tensor):
+        """Start the all-gather of this rank's CBSR block (k fp32 + k uint8 per node)."""
+        self.loc_data[: self.n_local].copy_(sp_data_loc)
+        self.loc_index[: self.n_local].copy_(sp_index_loc)
         if self.world > 1:
             self._pending = [dist.all_gather_into_tensor(self.g_data, self.loc_data, group=self.group,
                                                          async_op=True),

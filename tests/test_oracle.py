@@ -199,7 +199,8 @@ def test_cpu_path_port_matches_oracle():
     rng = np.random.default_rng(3)
     dy = rng.random((400, 256), dtype=np.float32)
     agg = CpuAggregation(torch.from_numpy(indptr), torch.from_numpy(idx), torch.from_numpy(val))
-    y, dx = agg.step(torch.from_numpy(x), torch.from_numpy(dy), 32)
+    h, mask = agg.prepare(torch.from_numpy(x), 32)
+    y, dx = agg.step(h, torch.from_numpy(dy), mask)
     np.testing.assert_allclose(y.numpy(), O.spgemm_forward(w4, idx, val, sp_data, sp_index, 256),
                                rtol=1e-5, atol=1e-6)
     dxc = O.sspmm_backward(w4, idx, val, dy, sp_index)
