@@ -1,0 +1,29 @@
+#!/usr/bin/env python3
+"""TopK timing / instruction-count driver (several value distributions)."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "spgemm-new_b200"))
+import torch
+from maxk_b200 import ops
+n = 232965
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm): fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); s.record()
+    for _ in range(iters): fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+g = torch.Generator("cuda").manual_seed(1)
+dists = (("uniform", torch.rand(n, 256, device="cuda", generator=g)),
+         ("normal", torch.randn(n, 256, device="cuda", generator=g)),
+         ("relu_normal", torch.randn(n, 256, device="cuda", generator=g).relu()),
+         ("quantised", (torch.rand(n, 256, device="cuda", generator=g) * 8).floor()))
+for name, x in dists:
+    for k in (8, 32, 64):
+        if quick:
+            ops.topk_cbsr(x, k); continue
+        t = timeit(lambda: ops.topk_cbsr(x, k))
+        b = 4 * n * 256 + 5 * n * k
+        print(f"topk {name:12s} k={k:3d}: {t*1e3:7.1f} us  {b/t/1e6:7.0f} GB/s  frac {b/t/1e6/6543.7:.3f}", flush=True)
+torch.cuda.synchronize()

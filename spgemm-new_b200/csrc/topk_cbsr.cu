@@ -7,8 +7,10 @@
 // 32-bit keys of the fp32 values themselves (no uint8 quantisation), with a
 // warp-uniform threshold (Q5/Q6), for any k and N (Q7) and with an exact tie rule (Q8):
 //   * one warp per row, 8 elements per lane in registers (two 128-bit loads per lane);
-//   * MSB-first radix select over only the bit positions that actually vary in the row
-//     (warp AND/OR reduction), one REDUX per bit, early exit when the count hits k;
+//   * bracketing search for the k-th largest key: one REDUX-counted probe per step,
+//     alternating value-space interpolation and bisection, ending as soon as a probe
+//     separates exactly k elements (v1 walked the key bit by bit: ~20 probes per row and
+//     785 warp instructions, issue-bound at 0.23 of the HBM peak);
 //   * emission positions from one packed warp scan; optional dense x*mask output
 //     (MaxK.forward, utils/models.py:48-52) from the same registers.
 // Pure streaming kernel: 4*d bytes read + 5*k bytes written per row -> HBM-bound.
@@ -18,12 +20,19 @@ namespace maxk {
 
 constexpr int TOPK_WPB = 8;
 
-__device__ __forceinline__ unsigned f32_order_key(float f)
+// order-preserving key of an fp32 bit pattern, branch-free:
+// NaN ranks largest (torch rule), -0 == +0, otherwise unsigned order == float order
+__device__ __forceinline__ unsigned f32_order_key(unsigned b)
 {
-    unsigned b = __float_as_uint(f);
-    if ((b & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;  // NaN ranks largest (torch rule)
-    if (b == 0x80000000u) b = 0u;                              // -0 == +0
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    const unsigned a = b & 0x7fffffffu;
+    b = (a == 0u) ? 0u : b;
+    const unsigned key = b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+    return (a > 0x7f800000u) ? 0xffffffffu : key;
+}
+// inverse (canonical NaN / -0 aside)
+__device__ __forceinline__ float key_to_f32(unsigned key)
+{
+    return __uint_as_float((key & 0x80000000u) ? (key ^ 0x80000000u) : ~key);
 }
 
 __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane)
@@ -36,6 +45,14 @@ __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane)
     return v;
 }
 
+__device__ __forceinline__ int warp_count_ge(const unsigned (&key)[8], unsigned m)
+{
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c += (key[i] >= m) ? 1 : 0;
+    return __reduce_add_sync(0xffffffffu, c);
+}
+
 // Element i of a lane sits at column  (i < 4 ? 4*lane + i : 128 + 4*lane + (i-4)):
 // group 0 of every lane precedes group 1 of every lane in column order.
 template <bool U8>
@@ -43,9 +60,11 @@ __global__ void __launch_bounds__(TOPK_WPB * 32)
 topk_cbsr_kernel(const void *__restrict__ x_, int64_t n, int d, int k, void *__restrict__ out_val_,
                  unsigned char *__restrict__ out_idx, float *__restrict__ dense_out)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * TOPK_WPB + (threadIdx.x >> 5);
-    if (row >= n) return;
+    __shared__ unsigned s_val[TOPK_WPB][MAXK_MAX_DIM];
+    __shared__ unsigned char s_idx[TOPK_WPB][MAXK_MAX_DIM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * TOPK_WPB + warp;
+    if (row >= n) return;  // warp-uniform; no CTA barrier below
 
     const int c0 = 4 * lane, c1 = 128 + 4 * lane;
     const bool ok0 = c0 < d, ok1 = c1 < d;
@@ -54,8 +73,8 @@ topk_cbsr_kernel(const void *__restrict__ x_, int64_t n, int d, int k, void *__r
     unsigned raw[8];  // fp32 bit patterns or byte values (bit-copied to the output)
     if constexpr (U8) {
         const unsigned char *x = static_cast<const unsigned char *>(x_) + row * d;
-        unsigned wa = ok0 ? __ldcs(reinterpret_cast<const unsigned *>(x + c0)) : 0u;
-        unsigned wb = ok1 ? __ldcs(reinterpret_cast<const unsigned *>(x + c1)) : 0u;
+        const unsigned wa = ok0 ? __ldcs(reinterpret_cast<const unsigned *>(x + c0)) : 0u;
+        const unsigned wb = ok1 ? __ldcs(reinterpret_cast<const unsigned *>(x + c1)) : 0u;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             raw[i] = (wa >> (8 * i)) & 0xff;
@@ -72,53 +91,86 @@ topk_cbsr_kernel(const void *__restrict__ x_, int64_t n, int d, int k, void *__r
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             raw[i] = __float_as_uint(f[i]);
-            key[i] = ((i < 4) ? ok0 : ok1) ? f32_order_key(f[i]) : 0u;  // valid keys are >= 0x007fffff
+            // valid keys are >= 0x007fffff (-inf); 0 marks "no element"
+            key[i] = ((i < 4) ? ok0 : ok1) ? f32_order_key(raw[i]) : 0u;
         }
     }
 
-    // ---- bit positions that vary among the row's valid keys ----------------------------
-    unsigned land = 0xffffffffu, lor = 0u;
+    // ---- k-th largest key by bracketing search ------------------------------------------
+    // Invariant: count(key >= L) = cL >= k  and  count(key >= H) = cH < k,  L < H.
+    // A probe is one REDUX-counted compare of the 8 register keys.  Probes interpolate on
+    // the counts -- in VALUE space for fp32, where activations are far closer to
+    // piecewise-linear than in the exponent|mantissa key space -- and fall back to key-space
+    // bisection whenever the same end point moved twice in a row, so smooth data needs a
+    // handful of probes and adversarial data at most O(32) bisections.  The search ends on a
+    // probe that separates exactly k elements (no tie at the threshold) or with H == L + 1,
+    // i.e. L is the k-th largest key and ties at L are resolved by column order.
+    unsigned lmin = 0xffffffffu, lmax = 0u;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const bool ok = (i < 4) ? ok0 : ok1;
-        if (ok) {
-            land &= key[i];
-            lor |= key[i];
-        }
+        lmax = max(lmax, key[i]);
+        lmin = min(lmin, key[i] == 0u ? 0xffffffffu : key[i]);
     }
-    land = __reduce_and_sync(0xffffffffu, land);
-    lor = __reduce_or_sync(0xffffffffu, lor);
-    const unsigned common = land;        // bits set in every key
-    unsigned vary = land ^ lor;          // bits that differ somewhere
-
-    // ---- MSB-first radix select of the k-th largest key --------------------------------
-    unsigned decided = 0u;  // accepted varying bits
-    unsigned thr = 0u;      // selection threshold
-    bool exact = false;     // count(key >= thr) == k
-    while (vary) {
-        const int b = 31 - __clz(vary);
-        vary &= ~(1u << b);
-        const unsigned himask = ~((1u << b) - 1u);
-        const unsigned cand = (decided | common | (1u << b)) & himask;
-        int cnt = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cnt += (key[i] >= cand) ? 1 : 0;
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (cnt >= k) {
-            decided |= (1u << b);
-            if (cnt == k) {
-                thr = cand;
+    unsigned L = __reduce_min_sync(0xffffffffu, lmin);
+    unsigned H = __reduce_max_sync(0xffffffffu, lmax);
+    int cL = d;
+    int cH = warp_count_ge(key, H);
+    unsigned thr;        // selection threshold
+    bool exact = false;  // count(key >= thr) == k
+    if (cH >= k) {       // the maximum itself is (tied for) the k-th largest
+        thr = H;
+        exact = (cH == k);
+    } else if (cL == k) {  // k == d: everything is kept
+        thr = L;
+        exact = true;
+    } else {
+        int stuck = 0;  // +n: L moved n times in a row, -n: H did
+        while (true) {
+            if (H - L == 1u) {  // cL > k > cH  ->  ties at L
+                thr = L;
+                break;
+            }
+            unsigned M = L + ((H - L) >> 1);
+            if (stuck < 2 && stuck > -2) {
+                const float frac = ((float)(cL - k) - 0.5f) * __frcp_rn((float)(cL - cH));
+                if constexpr (U8) {  // byte keys are already linear
+                    const unsigned g = L + (unsigned)((float)(H - L) * frac);
+                    if (g > L && g < H) M = g;
+                } else {
+                    const float fl = key_to_f32(L), fh = key_to_f32(H);
+                    const float fm = fmaf(fh - fl, frac, fl);
+                    if (fm > fl && fm < fh) {  // false for inf/NaN end points
+                        const unsigned g = f32_order_key(__float_as_uint(fm));
+                        if (g > L && g < H) M = g;
+                    }
+                }
+            } else {
+                stuck = 0;
+            }
+            const int c = warp_count_ge(key, M);
+            if (c == k) {
+                thr = M;
                 exact = true;
                 break;
             }
+            if (c > k) {
+                L = M;
+                cL = c;
+                stuck = stuck > 0 ? stuck + 1 : 1;
+            } else {
+                H = M;
+                cH = c;
+                stuck = stuck < 0 ? stuck - 1 : -1;
+            }
         }
     }
+
     unsigned sel = 0u;  // bit i: element i selected
     if (exact) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) sel |= (key[i] >= thr) ? (1u << i) : 0u;
     } else {
-        thr = decided | common;  // exact k-th largest key; ties at thr are possible
+        // thr is the exact k-th largest key; ties at thr are taken in ascending column order
         unsigned gt = 0u, eq = 0u;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -126,7 +178,7 @@ topk_cbsr_kernel(const void *__restrict__ x_, int64_t n, int d, int k, void *__r
             eq |= (key[i] == thr) ? (1u << i) : 0u;
         }
         const int n_gt = __reduce_add_sync(0xffffffffu, __popc(gt));
-        const int need = k - n_gt;  // ties taken in ascending column order
+        const int need = k - n_gt;
         const unsigned e0 = __popc(eq & 0xfu), e1 = __popc(eq >> 4);
         const unsigned inc = warp_incl_scan(e0 | (e1 << 16), lane);
         const unsigned tot0 = __shfl_sync(0xffffffffu, inc, 31) & 0xffffu;
@@ -146,25 +198,40 @@ topk_cbsr_kernel(const void *__restrict__ x_, int64_t n, int d, int k, void *__r
         }
     }
 
-    // ---- emission: ascending column order ----------------------------------------------
+    // ---- emission: ascending column order, staged in shared memory so that the global
+    // stores are coalesced (one 4k-byte value line + one k-byte selector line per row) ------
     if (out_idx != nullptr) {
         const unsigned n0 = __popc(sel & 0xfu), n1 = __popc(sel >> 4);
         const unsigned inc = warp_incl_scan(n0 | (n1 << 16), lane);
         const unsigned tot0 = __shfl_sync(0xffffffffu, inc, 31) & 0xffffu;
         int p0 = (int)(inc & 0xffffu) - (int)n0;
         int p1 = (int)tot0 + (int)(inc >> 16) - (int)n1;
-        unsigned char *oi = out_idx + row * k;
+        unsigned *sv = s_val[warp];
+        unsigned char *si = s_idx[warp];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
             if (sel & (1u << i)) {
-                const int p = (i < 4) ? p0++ : p1++;
-                const int col = (i < 4) ? (c0 + i) : (c1 + i - 4);
-                if constexpr (U8)
-                    (static_cast<unsigned char *>(out_val_) + row * k)[p] = (unsigned char)raw[i];
-                else
-                    (static_cast<unsigned *>(out_val_) + row * k)[p] = raw[i];
-                oi[p] = (unsigned char)col;
+                sv[p0] = raw[i];
+                si[p0] = (unsigned char)(c0 + i);
+                ++p0;
             }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (sel & (16u << i)) {
+                sv[p1] = raw[4 + i];
+                si[p1] = (unsigned char)(c1 + i);
+                ++p1;
+            }
+        }
+        __syncwarp();
+        unsigned char *oi = out_idx + row * k;
+        for (int j = lane; j < k; j += 32) {
+            if constexpr (U8)
+                (static_cast<unsigned char *>(out_val_) + row * k)[j] = (unsigned char)sv[j];
+            else
+                (static_cast<unsigned *>(out_val_) + row * k)[j] = sv[j];
+            oi[j] = si[j];
         }
     }
     if constexpr (!U8) {
