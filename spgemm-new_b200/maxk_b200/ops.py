@@ -60,8 +60,9 @@ def build_worklist(indptr: torch.Tensor, warp_max_nz: int = _cabi.WARP_MAX_NZ) -
 
 
 # ------------------------------------------------------------------------------ a1
-def topk_cbsr(x: torch.Tensor, k: int, want_dense: bool = False, want_cbsr: bool = True):
-    """fp32 MaxK: (sp_data f32[N,k], sp_index u8[N,k][, dense f32[N,D]])."""
+def topk_cbsr(x: torch.Tensor, k: int, want_dense: bool = False, want_cbsr: bool = True, out=None):
+    """fp32 MaxK: (sp_data f32[N,k], sp_index u8[N,k][, dense f32[N,D]]).
+    out=(sp_data, sp_index): write the CBSR pair into caller-provided contiguous tensors."""
     lib = _cabi.load()
     _cuda(x, "Input", None)
     _req(x.dim() == 2, "Input must be 2D tensor")
@@ -70,7 +71,13 @@ def topk_cbsr(x: torch.Tensor, k: int, want_dense: bool = False, want_cbsr: bool
     _req(0 < k <= d, "Invalid k value")
     sp_data = sp_index = dense = None
     with torch.cuda.device(x.device):
-        if want_cbsr:
+        if want_cbsr and out is not None:
+            sp_data, sp_index = out
+            _cuda(sp_data, "out[0]", torch.float32)
+            _cuda(sp_index, "out[1]", torch.uint8)
+            _req(tuple(sp_data.shape) == (n, k) and tuple(sp_index.shape) == (n, k),
+                 "out tensors must be [N, k]")
+        elif want_cbsr:
             sp_data = torch.empty((n, k), dtype=torch.float32, device=x.device)
             sp_index = torch.empty((n, k), dtype=torch.uint8, device=x.device)
         if want_dense:

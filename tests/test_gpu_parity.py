@@ -292,6 +292,23 @@ def test_dropin_modules():
     np.testing.assert_array_equal(sk.topk_nonlinearity(g["x"], 32).cpu().numpy(), O.maxk_dense(p.x, 32))
 
 
+@pytest.mark.parametrize("chunks", [1, 3, 4])
+def test_host_aggregator_end_to_end(chunks):
+    """Host buffers in, host buffers out (what bench.py's e2e times), chunked and overlapped."""
+    from maxk_b200 import HostAggregator
+    p = Problem(n=900, avg=60.0, k=32, seed=77, empty_frac=0.1)
+    g = p.cuda()
+    host = HostAggregator(g["indptr"], g["indices"], g["values"], 32, 256, "cuda", chunks=chunks)
+    xh = torch.from_numpy(p.x).pin_memory()
+    dyh = torch.from_numpy(p.dy).pin_memory()
+    for _ in range(2):  # buffers are reused across steps
+        y, dxc = host.step(xh, dyh)
+        assert not y.is_cuda and not dxc.is_cuda
+        np.testing.assert_allclose(y.numpy().astype(np.float64), p.fwd_oracle(), rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(dxc.numpy().astype(np.float64), p.bwd_oracle(), rtol=RTOL, atol=ATOL)
+    assert host.h2d_bytes == 2 * 900 * 256 * 4 and host.d2h_bytes == 900 * 256 * 4 + 900 * 32 * 4
+
+
 def test_reference_named_shims():
     """The reference's own extern "C" launch shims (cuda_kernel_wrappers.cu:38-91), same argument
     lists (dim3 by value), resolved from libmaxk_b200.so."""
