@@ -177,8 +177,9 @@ class DistAggregator:
                 h = dist.reduce_scatter_tensor(self.rs_out, self.partial, group=self.group, async_op=True)
             else:
                 _reduce_scatter(self.rs_out, self.partial, self.rank, self.group)
+            own = g_index[self.rank * self.max_rows:(self.rank + 1) * self.max_rows]
             loc = self.ops.sspmm_backward(lp["warp4"], lp["indices"], lp["values"], dy_loc,
-                                          self.loc_index, out=None)
+                                          own, out=None)
             if h is not None:
                 h.wait()
             self.rs_out[: self.n_local].add_(loc[: self.n_local])

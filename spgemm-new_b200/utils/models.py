@@ -1,0 +1,145 @@
+"""CBSR-native MaxK-GNN layers: SAGE / GCN / GIN with the constructor and `forward(g, x)`
+signatures of the reference's utils/models.py:151-392 (and upstream utils/models_old.py),
+re-expressed on (sp_data, sp_index) so the dense masked activation is never fed to the
+aggregation:
+
+    Linear -> TopK->CBSR -> dropout on the k CBSR values -> SpGEMM (values = 1, 1/deg, sym-norm)
+           -> + (1+eps)*h for GIN / + fc_self(h) for SAGE -> LayerNorm
+
+`g` is a maxk_b200.graph.Graph (one GPU) or DistGraph (row partition); both expose
+`aggregate(sp_data, sp_index, kind, feat_dim)`.  Layer variants: SAGE applies
+MaxK before BOTH branches like upstream (models_old.py:55-60); `fork_variant=True` gives
+the fork's un-sparsified self branch with sum aggregation (models.py:227-253).
+Dropout acts on the CBSR values: same distribution as torch's dense dropout on the masked
+tensor, different RNG stream (parity tests run with p = 0 / eval()).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.nn.init as init
+from torch.nn import Linear
+
+from maxk_b200.autograd import MaxK, SpGEMMFunction, TopKCBSR  # noqa: F401  (re-exported like the reference)
+from maxk_b200 import ops
+from torch.autograd import Function
+
+
+class _Scatter(Function):
+    """(sp_data, sp_index) -> dense [N, D]; gradient = gather at the selector."""
+
+    @staticmethod
+    def forward(ctx, sp_data, sp_index, feat_dim):
+        ctx.save_for_backward(sp_index)
+        return ops.cbsr_scatter(sp_data.contiguous(), sp_index, feat_dim)
+
+    @staticmethod
+    def backward(ctx, g):
+        (sp_index,) = ctx.saved_tensors
+        return ops.cbsr_gather(g.contiguous(), sp_index), None, None
+
+
+def _sparsify(x, k, nonlinear, p, training):
+    """MaxK (or ReLU) + dropout, returned as CBSR.  For ReLU the row is kept dense (k = D)."""
+    if nonlinear == "maxk":
+        sp_data, sp_index = TopKCBSR.apply(x, k)
+    else:
+        if nonlinear == "relu":
+            x = F.relu(x)
+        sp_data, sp_index = TopKCBSR.apply(x, x.shape[1])  # all columns, ascending
+    if p > 0 and training:
+        sp_data = F.dropout(sp_data, p, True)
+    return sp_data, sp_index
+
+
+class _Base(nn.Module):
+    def __init__(self, in_size, hid_size, num_hid_layers, out_size, maxk, feat_drop, norm, nonlinear):
+        super().__init__()
+        assert hid_size <= 256 and hid_size % 4 == 0, "selectors are uint8: hidden <= 256 (SURVEY Q3)"
+        self.num_layers, self.hid, self.maxk = num_hid_layers, hid_size, maxk
+        self.p, self.norm, self.nonlinear = feat_drop, norm, nonlinear
+        self.lin_in = Linear(in_size, hid_size)
+        self.lin_out = Linear(hid_size, out_size)
+        init.xavier_uniform_(self.lin_in.weight)
+        init.xavier_uniform_(self.lin_out.weight)
+        self.normlayers = nn.ModuleList(
+            [nn.LayerNorm(hid_size, elementwise_affine=True) if norm else nn.Identity()
+             for _ in range(num_hid_layers)])
+
+
+class SAGE(_Base):
+    """models_old.py:26-67 (upstream) / models.py:151-297 (fork)."""
+
+    def __init__(self, in_size, hid_size, num_hid_layers, out_size, maxk=32, feat_drop=0.5, norm=False,
+                 nonlinear="maxk", fork_variant=False):
+        super().__init__(in_size, hid_size, num_hid_layers, out_size, maxk, feat_drop, norm, nonlinear)
+        self.fork_variant = fork_variant
+        self.fc_self_layers = nn.ModuleList([Linear(hid_size, hid_size, bias=not fork_variant)
+                                             for _ in range(num_hid_layers)])
+        self.fc_neigh_layers = nn.ModuleList([Linear(hid_size, hid_size, bias=False)
+                                              for _ in range(num_hid_layers)])
+        for i in range(num_hid_layers):
+            init.xavier_uniform_(self.fc_self_layers[i].weight)
+            init.xavier_uniform_(self.fc_neigh_layers[i].weight)
+
+    def forward(self, g, x):
+        x = self.lin_in(x)
+        for i in range(self.num_layers):
+            if self.fork_variant:   # models.py:230-253: sum aggregation, self branch on raw x, dropout after
+                sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, 0.0, False)
+                x = self.fc_self_layers[i](x) + self.fc_neigh_layers[i](
+                    g.aggregate(sp_data, sp_index, "sum", self.hid))
+                x = F.dropout(x, self.p, self.training)
+            else:                   # SAGEConv("mean", feat_drop): dropout(maxk(x)) feeds both branches
+                sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
+                h = _Scatter.apply(sp_data, sp_index, self.hid)
+                x = self.fc_self_layers[i](h) + self.fc_neigh_layers[i](
+                    g.aggregate(sp_data, sp_index, "mean", self.hid))
+            x = self.normlayers[i](x)
+        return self.lin_out(x)
+
+
+class GCN(_Base):
+    """models.py:300-345: lin_in->relu; per layer Linear -> MaxK -> dropout -> GraphConv(norm='both',
+    weight=None, bias) -> LayerNorm."""
+
+    def __init__(self, in_size, hid_size, num_hid_layers, out_size, maxk=32, feat_drop=0.5, norm=False,
+                 nonlinear="maxk"):
+        super().__init__(in_size, hid_size, num_hid_layers, out_size, maxk, feat_drop, norm, nonlinear)
+        self.linlayers = nn.ModuleList([Linear(hid_size, hid_size) for _ in range(num_hid_layers)])
+        for l in self.linlayers:
+            init.xavier_uniform_(l.weight)
+        self.conv_bias = nn.ParameterList([nn.Parameter(torch.zeros(hid_size)) for _ in range(num_hid_layers)])
+
+    def forward(self, g, x):
+        x = self.lin_in(x).relu()
+        for i in range(self.num_layers):
+            x = self.linlayers[i](x)
+            sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
+            x = g.aggregate(sp_data, sp_index, "gcn", self.hid) + self.conv_bias[i]
+            x = self.normlayers[i](x)
+        return self.lin_out(x)
+
+
+class GIN(_Base):
+    """models.py:347-392: per layer Linear -> MaxK -> dropout -> GINConv(learn_eps=True):
+    (1 + eps) * h + sum_j h_j -> LayerNorm."""
+
+    def __init__(self, in_size, hid_size, num_hid_layers, out_size, maxk=32, feat_drop=0.5, norm=False,
+                 nonlinear="maxk"):
+        super().__init__(in_size, hid_size, num_hid_layers, out_size, maxk, feat_drop, norm, nonlinear)
+        self.linlayers = nn.ModuleList([Linear(hid_size, hid_size) for _ in range(num_hid_layers)])
+        for l in self.linlayers:
+            init.xavier_uniform_(l.weight)
+        self.eps = nn.ParameterList([nn.Parameter(torch.zeros(1)) for _ in range(num_hid_layers)])
+
+    def forward(self, g, x):
+        x = self.lin_in(x).relu()
+        for i in range(self.num_layers):
+            x = self.linlayers[i](x)
+            sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
+            h = _Scatter.apply(sp_data, sp_index, self.hid)
+            x = (1.0 + self.eps[i]) * h + g.aggregate(sp_data, sp_index, "sum", self.hid)
+            x = self.normlayers[i](x)
+        return self.lin_out(x)
