@@ -56,11 +56,15 @@ MAXK_API const char *maxk_last_error(void);
  * gpu_launches claim). */
 MAXK_API int64_t maxk_launch_count(void);
 /* Bench/test hook (not part of the reference surface): run length, in tasks per warp, of
- * the forward / backward kernels; a value <= 0 leaves that knob unchanged. */
+ * the forward / backward kernels; 0 leaves that knob unchanged, a negative value returns it
+ * to its automatic choice. */
 MAXK_API int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp);
 /* Bench/test hook: accumulator copies R of the forward kernel (1, 2, 4, 8, 16; rounded down
  * to an instantiated value and up to the edges-per-instruction count); 0 = automatic. */
 MAXK_API int maxk_set_forward_copies(int copies);
+/* Bench/test hook: launch shape of the forward kernel (1 = 8-warp CTAs, 2 = 2-warp CTAs,
+ * 3 = 8-warp CTAs with twice the gathers in flight); 0 = automatic. */
+MAXK_API int maxk_set_forward_depth(int depth);
 
 /* ---- a4: work list (replaces kernels/generate_meta.py:8-48 and the disk round trip of
  * load_warp4_metadata, cuda_kernel_bindings.cpp:287-317) ------------------------------

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --maxfail=10 -k "topk or dropin or autograd or layout or host_agg or models or full_size" > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+tail -5 gpurun_out/pytest.log
+python scripts/topk_probe.py

@@ -16,6 +16,7 @@ ap.add_argument("--shape", default="reddit")
 ap.add_argument("--ks", default="32,16,8,64")
 ap.add_argument("--copies", default="0,1,2,4,8,16")
 ap.add_argument("--tpw", default="16")
+ap.add_argument("--depth", default="0")
 ap.add_argument("--bwd-tpw", default="")
 ap.add_argument("--iters", type=int, default=10)
 a = ap.parse_args()
@@ -48,14 +49,17 @@ for k in [int(v) for v in a.ks.split(",")]:
     b = graphs.algorithmic_bytes(n, e, w, k)
     for tpw in [int(v) for v in a.tpw.split(",")]:
         for c in [int(v) for v in a.copies.split(",")]:
-            ops.set_forward_copies(c)
-            ops.set_tuning(tpw, 0)
-            t = timeit(lambda: ops.spgemm_forward(w4, g["indices"], g["values"], sd, si, out=y, num_rows=n), a.iters)
-            r = {"kernel": "fwd", "shape": a.shape, "k": k, "copies": c, "tpw": tpw, "ms": round(t, 4),
-                 "frac": round(b["fwd"] / t / 1e6 / peak, 3)}
-            res.append(r)
-            print(json.dumps(r), flush=True)
+            for dep in [int(v) for v in a.depth.split(",")]:
+                ops.set_forward_copies(c)
+                ops.set_forward_depth(dep)
+                ops.set_tuning(tpw, 0)
+                t = timeit(lambda: ops.spgemm_forward(w4, g["indices"], g["values"], sd, si, out=y, num_rows=n), a.iters)
+                r = {"kernel": "fwd", "shape": a.shape, "k": k, "copies": c, "tpw": tpw, "depth": dep,
+                     "ms": round(t, 4), "frac": round(b["fwd"] / t / 1e6 / peak, 3)}
+                res.append(r)
+                print(json.dumps(r), flush=True)
     ops.set_forward_copies(0)
+    ops.set_forward_depth(0)
     if a.bwd_tpw:
         dxc = torch.empty(n, k, device="cuda")
         for tpw in [int(v) for v in a.bwd_tpw.split(",")]:

@@ -14,6 +14,7 @@ static std::atomic<int64_t> g_launches{0};
 extern int g_fwd_tasks_per_warp;
 extern int g_bwd_tasks_per_warp;
 extern int g_fwd_copies;
+extern int g_fwd_depth;
 
 void set_error(const char *fmt, ...)
 {
@@ -40,11 +41,19 @@ extern "C" const char *maxk_last_error(void) { return g_err; }
 extern "C" int64_t maxk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // Bench/test hook: run lengths (tasks per warp) of the forward / backward kernels.
-// value <= 0 leaves the knob unchanged.  Not part of the reference surface.
+// 0 leaves a knob unchanged, a negative value returns it to automatic.
+// Not part of the reference surface.
 extern "C" int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp)
 {
-    if (fwd_tasks_per_warp > 0) g_fwd_tasks_per_warp = fwd_tasks_per_warp;
-    if (bwd_tasks_per_warp > 0) g_bwd_tasks_per_warp = bwd_tasks_per_warp;
+    if (fwd_tasks_per_warp != 0) g_fwd_tasks_per_warp = fwd_tasks_per_warp < 0 ? 0 : fwd_tasks_per_warp;
+    if (bwd_tasks_per_warp != 0) g_bwd_tasks_per_warp = bwd_tasks_per_warp < 0 ? 0 : bwd_tasks_per_warp;
+    return MAXK_OK;
+}
+
+// Bench/test hook: launch shape of the forward kernel (see spgemm_forward.cu; 0 = automatic).
+extern "C" int maxk_set_forward_depth(int depth)
+{
+    g_fwd_depth = depth < 0 ? 0 : depth;
     return MAXK_OK;
 }
 

@@ -78,4 +78,13 @@ __host__ __device__ constexpr T ceil_div(T a, T b)
     return (a + b - 1) / b;
 }
 
+// Run length (tasks per warp) of the forward / backward kernels when the caller did not fix
+// it: 16 on big graphs, shorter on small ones so that the grid still fills 148 SMs x 32
+// warps several times over (measured on the Flickr shape: 0.078 ms at 2-4 vs 0.119 ms at 16).
+inline int auto_tasks_per_warp(int64_t num_tasks)
+{
+    const int64_t t = num_tasks / (int64_t)(kNumSMs * 32 * 8);
+    return (int)(t < 1 ? 1 : (t > 16 ? 16 : t));
+}
+
 }  // namespace maxk

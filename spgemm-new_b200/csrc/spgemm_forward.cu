@@ -112,6 +112,10 @@ __device__ __forceinline__ void fwd_accumulate(const Slice<C> &sl, float *acc_la
     }
 }
 
+// (A rolling pipeline -- re-issue a slot's gather right after its accumulate -- was built and
+// measured: 1.5-2x SLOWER on every shape.  The staging read, the gather and the accumulate of
+// one slot then form one dependent chain per edge, whereas the batch form below issues U
+// staging reads, U gathers and U accumulates back to back.  profiles/r01_forward_pipeline.md)
 template <class C>
 __device__ __forceinline__ void fwd_process_batch(const int2 *stage, int len, float *acc_lane,
                                                   const float *__restrict__ sp_data,
@@ -232,12 +236,39 @@ __device__ __forceinline__ void fwd_stage_edges(const EdgeRegs &r, int2 *stage, 
     __syncwarp();
 }
 
+// zero-fill rows [r0, r1) of the output (rows without tasks: isolated destination nodes)
+__device__ __forceinline__ void fwd_zero_rows(float *__restrict__ out, int64_t r0, int64_t r1, int d,
+                                              int lane)
+{
+    if (r0 >= r1) return;
+    float4 *p = reinterpret_cast<float4 *>(out + r0 * d);
+    const int64_t n4 = (r1 - r0) * (d >> 2);
+    for (int64_t i = lane; i < n4; i += 32) st_stream_f4(p + i, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+// Rows that straddle two warps' runs are combined with vector reductions and therefore have
+// to start from zero: one warp per run boundary clears the row that crosses it.  Together
+// with the gap fill inside the main kernel this replaces a memset of the whole output
+// (4*N*D bytes of extra HBM writes: 2.5 GB, 0.4 ms, on the ogbn-products shape).
+__global__ void __launch_bounds__(256)
+spgemm_fwd_clear_shared_rows(const int4 *__restrict__ warp4, int64_t num_tasks, int tasks_per_warp,
+                             float *__restrict__ out, int d)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5) + 1;  // boundary index
+    const int64_t t = b * tasks_per_warp;
+    if (t >= num_tasks) return;
+    const int row = __ldg(&warp4[t].x);
+    if (__ldg(&warp4[t - 1].x) != row) return;
+    fwd_zero_rows(out, row, row + 1, d, lane);
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::WPB * 32, C::MINB)
 spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *__restrict__ idx,
                   const float *__restrict__ val, const float *__restrict__ sp_data,
                   const unsigned char *__restrict__ sp_index, int k, float *__restrict__ out, int d,
-                  int tasks_per_warp, int accumulate)
+                  int tasks_per_warp, int accumulate, int64_t num_rows_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,25 +285,32 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
         *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
 
     int4 info = ld_stream_int4(warp4 + t0);
+    int4 ninfo = info;  // task t+1, loaded one task early so that its CSR slice can be
+    if (t0 + 1 < t1) ninfo = ld_stream_int4(warp4 + t0 + 1);  // prefetched without a stall
     const int first_row = info.x;
+    const int prev_row = (t0 > 0) ? __ldg(&warp4[t0 - 1].x) : -1;
     // accumulate mode (multi-GPU local/remote split): every row is added to what is there
-    const bool first_shared = accumulate || ((t0 > 0) && (__ldg(&warp4[t0 - 1].x) == first_row));
+    const bool first_shared = accumulate || (prev_row == first_row);
     bool last_shared = accumulate;
     if (!accumulate && t1 < num_tasks)
         last_shared = (__ldg(&warp4[t1].x) == __ldg(&warp4[t1 - 1].x));
 
     EdgeRegs pre;
     fwd_fetch_edges(pre, idx, val, info.y, min(info.z, FWD_STAGE), lane);
+    // Output rows without tasks are DEFINED as zero: each run fills the gap in
+    // front of its first row and the gaps between its rows; the last run fills the tail.
+    if (!accumulate) fwd_zero_rows(out, (int64_t)prev_row + 1, first_row, d, lane);
 
     int cur_row = first_row;
     for (int64_t t = t0; t < t1; ++t) {
         const bool has_next = (t + 1 < t1);
-        int4 ninfo = info;
-        if (has_next) ninfo = ld_stream_int4(warp4 + t + 1);
+        int4 nninfo = ninfo;
+        if (t + 2 < t1) nninfo = ld_stream_int4(warp4 + t + 2);
 
         if (info.x != cur_row) {
             fwd_flush_row<C>(acc, out, cur_row, d, lane,
                              accumulate || (first_shared && cur_row == first_row));
+            if (!accumulate) fwd_zero_rows(out, (int64_t)cur_row + 1, info.x, d, lane);
             cur_row = info.x;
         }
         const int64_t loc = info.y;
@@ -289,9 +327,11 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
             fwd_process_batch<C>(stage, ln, acc_lane, sp_data, sp_index, k, lane);
         }
         info = ninfo;
+        ninfo = nninfo;
     }
     fwd_flush_row<C>(acc, out, cur_row, d, lane,
                      last_shared || (first_shared && cur_row == first_row));
+    if (!accumulate && t1 == num_tasks) fwd_zero_rows(out, (int64_t)cur_row + 1, num_rows_out, d, lane);
 }
 
 struct FwdArgs {
@@ -307,6 +347,8 @@ struct FwdArgs {
     int tasks_per_warp;
     int accumulate;
     cudaStream_t st;
+    int depth;
+    int64_t num_rows_out;
 };
 
 template <class C>
@@ -330,13 +372,14 @@ static int launch_fwd(const FwdArgs &a)
     }
     spgemm_fwd_kernel<C><<<(unsigned)grid, C::WPB * 32, smem, a.st>>>(
         reinterpret_cast<const int4 *>(a.warp4), a.W, a.idx, a.val, a.sp_data, a.sp_index, a.k,
-        a.out, a.d, a.tasks_per_warp, a.accumulate);
+        a.out, a.d, a.tasks_per_warp, a.accumulate, a.num_rows_out);
     MAXK_LAUNCH_CHECK("spgemm_fwd_kernel");
     return MAXK_OK;
 }
 
-int g_fwd_tasks_per_warp = 16;  // tunable through maxk_set_tuning (bench sweeps)
+int g_fwd_tasks_per_warp = 0;   // run length; 0 = automatic; tunable through maxk_set_tuning
 int g_fwd_copies = 0;           // 0 = automatic choice of R
+int g_fwd_depth = 0;            // launch shape: 1 = 8-warp CTAs, 2 = 2-warp CTAs, 3 = 2x deeper gathers; 0 = automatic
 
 // launch shape per R:      R<=2: 8 warps, U=4, 64 regs   R=4: 8 warps, U=4
 //                          R=8 : 8 warps (68 KB/CTA, 3 CTAs/SM), U=8
@@ -345,6 +388,21 @@ template <int KL, int EPL, bool EXACT, int R>
 static int launch_fwd_r(const FwdArgs &a)
 {
     constexpr int U1 = (EPL == 1) ? 4 : (EPL == 2 ? 2 : (EPL <= 4 ? 2 : 1));
+    if constexpr (R <= 2 && EPL <= 2) {
+        // deeper gather pipelines for graphs whose CBSR operand does not fit the L2 (the
+        // gathers then pay DRAM latency): 2x / 4x the edges in flight per warp, paid for with
+        // registers (3 / 2 CTAs per SM)
+        // CTA shape (measured, profiles/r01_forward_pipeline.md): graphs of short rows are
+        // latency-bound on the CBSR gathers and run lengths vary a lot, so 2-warp CTAs (no
+        // warp idles until the slowest of 8 finishes) are 12 % faster on the products shape;
+        // deeper gather pipelines (2x / 4x U) and register-capped variants (48 / 40 registers
+        // for more warps) were measured too and lose to spills and lost occupancy.
+        switch (a.depth) {
+            case 2: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16>>(a);     // 2-warp CTAs
+            case 3: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, 2 * U1, 3>>(a);  // deeper
+            default: break;
+        }
+    }
     if constexpr (R <= 4)
         return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, (EPL <= 2 ? 4 : 2)>>(a);
     else if constexpr (R == 8)
@@ -412,17 +470,36 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
     if (num_rows_out == 0) return MAXK_OK;
     // Output is DEFINED by this call: empty rows and rows shared between
     // two warps' runs start from zero.
-    if (!accumulate) {
-        MAXK_CUDA(cudaMemsetAsync(out, 0, (size_t)num_rows_out * d * sizeof(float), st));
-        count_launch();
+    if (num_tasks == 0) {
+        if (!accumulate) {
+            MAXK_CUDA(cudaMemsetAsync(out, 0, (size_t)num_rows_out * d * sizeof(float), st));
+            count_launch();
+        }
+        return MAXK_OK;
     }
-    if (num_tasks == 0) return MAXK_OK;
     MAXK_REQUIRE(warp4 && indices && values && sp_data && sp_index,
                  "maxk_spgemm_forward: NULL input pointer");
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(sp_data) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(sp_index) & 3) == 0);
+    // Run length (tasks per warp): 16 amortises the row flush on big graphs; small graphs get
+    // shorter runs so that the grid still fills 148 SMs x 32 warps several times over.
+    int tpw = g_fwd_tasks_per_warp;
+    if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
+    // CTA shape: mostly single-task rows (W < 2N) -> 2-warp CTAs, see launch_fwd_r
+    int shape = g_fwd_depth;
+    if (shape <= 0) shape = (num_tasks < 2 * num_rows_out) ? 2 : 1;
     FwdArgs a{warp4, num_tasks, indices, values, sp_data, sp_index, k, out, d,
-              g_fwd_tasks_per_warp, accumulate, st};
+              tpw, accumulate, st, shape, num_rows_out};
+    // Output is DEFINED by this call without a memset of the whole of it: rows
+    // shared between two runs are cleared here, rows without tasks inside the main kernel.
+    if (!accumulate) {
+        const int64_t boundaries = (num_tasks - 1) / a.tasks_per_warp;
+        if (boundaries > 0) {
+            spgemm_fwd_clear_shared_rows<<<(unsigned)ceil_div<int64_t>(boundaries, 8), 256, 0, st>>>(
+                reinterpret_cast<const int4 *>(warp4), num_tasks, a.tasks_per_warp, out, d);
+            MAXK_LAUNCH_CHECK("spgemm_fwd_clear_shared_rows");
+        }
+    }
     // R: accumulator copies.  Measured on B200 (profiles/r01_sweep_copies.md): R = E (one copy
     // per edge slot) is fastest on every BASELINE shape -- with 1 < R < 32 the worst bank
     // still serialises ~3 lanes, and R >= 16 costs more occupancy than it saves.

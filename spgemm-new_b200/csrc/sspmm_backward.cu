@@ -181,7 +181,7 @@ static int launch_bwd(const int32_t *warp4, int64_t W, const int32_t *idx, const
     return MAXK_OK;
 }
 
-int g_bwd_tasks_per_warp = 16;
+int g_bwd_tasks_per_warp = 0;  // run length; 0 = automatic (as in the forward kernel)
 
 }  // namespace maxk
 
@@ -209,7 +209,8 @@ extern "C" int maxk_sspmm_backward(const int32_t *warp4, int64_t num_tasks, cons
     MAXK_REQUIRE((reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
                  "maxk_sspmm_backward: dy and warp4 must be 16-byte aligned");
-    const int tpw = g_bwd_tasks_per_warp;
+    int tpw = g_bwd_tasks_per_warp;
+    if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
     const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(dxc) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(sp_index) & 3) == 0);
 #define MAXK_BWD_GO(G) \

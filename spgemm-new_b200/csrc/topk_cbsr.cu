@@ -2,23 +2,32 @@
 // CBSR (k values + k uint8 column ids, ascending column order, ties -> lowest column).
 //
 // Replaces `topk` (ref: kernels/maxk_kernel.cu:23-96) and its float facade
-// (cuda_kernel_bindings.cpp:203-238).  The reference idea -- bisect for a threshold with
-// warp votes, then compact with ballot/popc -- is kept, but done on order-preserving
-// 32-bit keys of the fp32 values themselves (no uint8 quantisation), with a
-// warp-uniform threshold (Q5/Q6), for any k and N (Q7) and with an exact tie rule (Q8):
+// (cuda_kernel_bindings.cpp:203-238).  The reference idea -- search for a threshold with
+// warp-wide counts, then compact with a scan -- is kept, but done on the fp32 values
+// themselves (no uint8 quantisation), with a warp-uniform threshold (Q5/Q6), for
+// any k and N (Q7) and with an exact tie rule (Q8):
 //   * one warp per row, 8 elements per lane in registers (two 128-bit loads per lane);
-//   * bracketing search for the k-th largest key: one REDUX-counted probe per step,
-//     alternating value-space interpolation and bisection, ending as soon as a probe
-//     separates exactly k elements (v1 walked the key bit by bit: ~20 probes per row and
-//     785 warp instructions, issue-bound at 0.23 of the HBM peak);
-//   * emission positions from one packed warp scan; optional dense x*mask output
-//     (MaxK.forward, utils/models.py:48-52) from the same registers.
-// Pure streaming kernel: 4*d bytes read + 5*k bytes written per row -> HBM-bound.
+//   * fp32 fast path: the threshold is searched in VALUE space with plain float compares
+//     (`!(x < t)`, so NaN ranks largest and -0 == +0 for free) -- an Illinois-weighted
+//     regula falsi on count(x >= t) - k between the row minimum and maximum, one
+//     REDUX-counted probe (8 FSETP + 8 SEL + 4 IADD3 + POPC + REDUX) per step, ending on the first probe
+//     that separates exactly k elements.  No keys, no key<->float conversions in the loop
+//     (v3 spent 77 instructions per probe on them; v1 walked the key bit by bit);
+//   * rows the fast path cannot finish (ties at the k-th value, +-inf end points, a bracket
+//     that collapsed to adjacent floats) fall to the robust key-space search, which
+//     resolves ties by column order exactly;
+//   * emission positions from one packed warp scan, staged in shared memory so the global
+//     stores are coalesced; optional dense x*mask output (MaxK.forward,
+//     utils/models.py:48-52) from the same registers.
+// Pure streaming kernel: 4*d bytes read + 5*k bytes written per row -> HBM-bound by design;
+// the instruction count per row decides how close it gets (profiles/r01_topk_*.md).
 #include "common.cuh"
 
 namespace maxk {
 
 constexpr int TOPK_WPB = 8;
+constexpr int TOPK_FAST_MAX_PROBES = 14;  // then the key-space search takes over
+constexpr int TOPK_FAST_MAX_RUN = 5;      // same end point moved this often in a row -> ties likely
 
 // order-preserving key of an fp32 bit pattern, branch-free:
 // NaN ranks largest (torch rule), -0 == +0, otherwise unsigned order == float order
@@ -53,58 +62,37 @@ __device__ __forceinline__ int warp_count_ge(const unsigned (&key)[8], unsigned 
     return __reduce_add_sync(0xffffffffu, c);
 }
 
+// lane mask (bit i) of elements NOT below t: NaN elements always qualify (they rank largest).
+// Sums of distinct bits compile to FSETP + SEL per element and one IADD3 per two elements;
+// the count is the POPC of the mask and the final probe's mask IS the selection.
+__device__ __forceinline__ unsigned lane_mask_nlt(const float (&x)[8], float t)
+{
+    unsigned m = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m += !(x[i] < t) ? (1u << i) : 0u;
+    return m;
+}
+
+__device__ __forceinline__ float rcp_approx(float v)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 // Element i of a lane sits at column  (i < 4 ? 4*lane + i : 128 + 4*lane + (i-4)):
 // group 0 of every lane precedes group 1 of every lane in column order.
+
+// ---- robust selection on order-preserving keys (u8 rows; fp32 rows the fast path left) ----
+// key 0 marks "no element" (columns >= d).  Returns the lane's selection mask (bit i).
+// Invariant of the search: count(key >= L) = cL >= k  and  count(key >= H) = cH < k,  L < H.
+// Probes interpolate on the counts -- in VALUE space for fp32 -- and fall back to key-space
+// bisection whenever the same end point moved twice in a row; the search ends on a probe
+// that separates exactly k elements or with H == L + 1, i.e. L is the k-th largest key and
+// the ties at L are taken in ascending column order.
 template <bool U8>
-__global__ void __launch_bounds__(TOPK_WPB * 32)
-topk_cbsr_kernel(const void *__restrict__ x_, int64_t n, int d, int k, void *__restrict__ out_val_,
-                 unsigned char *__restrict__ out_idx, float *__restrict__ dense_out)
+__device__ __forceinline__ unsigned topk_select_by_keys(const unsigned (&key)[8], int d, int k, int lane)
 {
-    __shared__ unsigned s_val[TOPK_WPB][MAXK_MAX_DIM];
-    __shared__ unsigned char s_idx[TOPK_WPB][MAXK_MAX_DIM];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row = (int64_t)blockIdx.x * TOPK_WPB + warp;
-    if (row >= n) return;  // warp-uniform; no CTA barrier below
-
-    const int c0 = 4 * lane, c1 = 128 + 4 * lane;
-    const bool ok0 = c0 < d, ok1 = c1 < d;
-
-    unsigned key[8];
-    unsigned raw[8];  // fp32 bit patterns or byte values (bit-copied to the output)
-    if constexpr (U8) {
-        const unsigned char *x = static_cast<const unsigned char *>(x_) + row * d;
-        const unsigned wa = ok0 ? __ldcs(reinterpret_cast<const unsigned *>(x + c0)) : 0u;
-        const unsigned wb = ok1 ? __ldcs(reinterpret_cast<const unsigned *>(x + c1)) : 0u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            raw[i] = (wa >> (8 * i)) & 0xff;
-            raw[4 + i] = (wb >> (8 * i)) & 0xff;
-            key[i] = ok0 ? raw[i] + 1u : 0u;  // 0 is reserved for "no element"
-            key[4 + i] = ok1 ? raw[4 + i] + 1u : 0u;
-        }
-    } else {
-        const float *x = static_cast<const float *>(x_) + row * d;
-        float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
-        if (ok0) a = ld_stream_f4(reinterpret_cast<const float4 *>(x + c0));
-        if (ok1) b = ld_stream_f4(reinterpret_cast<const float4 *>(x + c1));
-        const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            raw[i] = __float_as_uint(f[i]);
-            // valid keys are >= 0x007fffff (-inf); 0 marks "no element"
-            key[i] = ((i < 4) ? ok0 : ok1) ? f32_order_key(raw[i]) : 0u;
-        }
-    }
-
-    // ---- k-th largest key by bracketing search ------------------------------------------
-    // Invariant: count(key >= L) = cL >= k  and  count(key >= H) = cH < k,  L < H.
-    // A probe is one REDUX-counted compare of the 8 register keys.  Probes interpolate on
-    // the counts -- in VALUE space for fp32, where activations are far closer to
-    // piecewise-linear than in the exponent|mantissa key space -- and fall back to key-space
-    // bisection whenever the same end point moved twice in a row, so smooth data needs a
-    // handful of probes and adversarial data at most O(32) bisections.  The search ends on a
-    // probe that separates exactly k elements (no tie at the threshold) or with H == L + 1,
-    // i.e. L is the k-th largest key and ties at L are resolved by column order.
     unsigned lmin = 0xffffffffu, lmax = 0u;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -123,44 +111,58 @@ topk_cbsr_kernel(const void *__restrict__ x_, int64_t n, int d, int k, void *__r
     } else if (cL == k) {  // k == d: everything is kept
         thr = L;
         exact = true;
+    } else if (H - L == 1u) {
+        thr = L;
     } else {
-        int stuck = 0;  // +n: L moved n times in a row, -n: H did
-        while (true) {
-            if (H - L == 1u) {  // cL > k > cH  ->  ties at L
-                thr = L;
-                break;
-            }
-            unsigned M = L + ((H - L) >> 1);
-            if (stuck < 2 && stuck > -2) {
-                const float frac = ((float)(cL - k) - 0.5f) * __frcp_rn((float)(cL - cH));
-                if constexpr (U8) {  // byte keys are already linear
-                    const unsigned g = L + (unsigned)((float)(H - L) * frac);
-                    if (g > L && g < H) M = g;
-                } else {
-                    const float fl = key_to_f32(L), fh = key_to_f32(H);
-                    const float fm = fmaf(fh - fl, frac, fl);
-                    if (fm > fl && fm < fh) {  // false for inf/NaN end points
-                        const unsigned g = f32_order_key(__float_as_uint(fm));
-                        if (g > L && g < H) M = g;
-                    }
+        // ties at the row minimum (e.g. post-ReLU zeros filling the tail of the top-k):
+        // one probe settles it instead of a walk down the whole key range
+        const int c1 = warp_count_ge(key, L + 1u);
+        if (c1 < k) {
+            thr = L;
+        } else if (c1 == k) {
+            thr = L + 1u;
+            exact = true;
+        } else {
+            L = L + 1u;
+            cL = c1;
+            int stuck = 0;  // +n: L moved n times in a row, -n: H did
+            while (true) {
+                if (H - L == 1u) {  // cL > k > cH  ->  ties at L
+                    thr = L;
+                    break;
                 }
-            } else {
-                stuck = 0;
-            }
-            const int c = warp_count_ge(key, M);
-            if (c == k) {
-                thr = M;
-                exact = true;
-                break;
-            }
-            if (c > k) {
-                L = M;
-                cL = c;
-                stuck = stuck > 0 ? stuck + 1 : 1;
-            } else {
-                H = M;
-                cH = c;
-                stuck = stuck < 0 ? stuck - 1 : -1;
+                unsigned M = L + ((H - L) >> 1);
+                if (stuck < 2 && stuck > -2) {
+                    const float frac = ((float)(cL - k) - 0.5f) * __frcp_rn((float)(cL - cH));
+                    if constexpr (U8) {  // byte keys are already linear
+                        const unsigned g = L + (unsigned)((float)(H - L) * frac);
+                        if (g > L && g < H) M = g;
+                    } else {
+                        const float fl = key_to_f32(L), fh = key_to_f32(H);
+                        const float fm = fmaf(fh - fl, frac, fl);
+                        if (fm > fl && fm < fh) {  // false for inf/NaN end points
+                            const unsigned g = f32_order_key(__float_as_uint(fm));
+                            if (g > L && g < H) M = g;
+                        }
+                    }
+                } else {
+                    stuck = 0;
+                }
+                const int c = warp_count_ge(key, M);
+                if (c == k) {
+                    thr = M;
+                    exact = true;
+                    break;
+                }
+                if (c > k) {
+                    L = M;
+                    cL = c;
+                    stuck = stuck > 0 ? stuck + 1 : 1;
+                } else {
+                    H = M;
+                    cH = c;
+                    stuck = stuck < 0 ? stuck - 1 : -1;
+                }
             }
         }
     }
@@ -197,58 +199,191 @@ topk_cbsr_kernel(const void *__restrict__ x_, int64_t n, int d, int k, void *__r
             }
         }
     }
+    return sel;
+}
 
-    // ---- emission: ascending column order, staged in shared memory so that the global
-    // stores are coalesced (one 4k-byte value line + one k-byte selector line per row) ------
-    if (out_idx != nullptr) {
-        const unsigned n0 = __popc(sel & 0xfu), n1 = __popc(sel >> 4);
-        const unsigned inc = warp_incl_scan(n0 | (n1 << 16), lane);
-        const unsigned tot0 = __shfl_sync(0xffffffffu, inc, 31) & 0xffffu;
-        int p0 = (int)(inc & 0xffffu) - (int)n0;
-        int p1 = (int)tot0 + (int)(inc >> 16) - (int)n1;
-        unsigned *sv = s_val[warp];
-        unsigned char *si = s_idx[warp];
+// Out-of-line copy for the fp32 kernel: the fast path must not pay registers for it.  The
+// bit patterns travel by value (registers), the keys are built here.
+__device__ __noinline__ unsigned topk_select_slow_f32(unsigned r0, unsigned r1, unsigned r2,
+                                                      unsigned r3, unsigned r4, unsigned r5,
+                                                      unsigned r6, unsigned r7, bool ok0, bool ok1,
+                                                      int d, int k, int lane)
+{
+    const unsigned raw[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
+    unsigned key[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (sel & (1u << i)) {
-                sv[p0] = raw[i];
-                si[p0] = (unsigned char)(c0 + i);
-                ++p0;
-            }
-        }
+    for (int i = 0; i < 8; ++i)  // valid keys are >= 0x007fffff (-inf); 0 = "no element"
+        key[i] = ((i < 4) ? ok0 : ok1) ? f32_order_key(raw[i]) : 0u;
+    return topk_select_by_keys<false>(key, d, k, lane);
+}
+
+// ---- emission: ascending column order, staged in shared memory so that the global stores
+// are coalesced (one 4k-byte value line + one k-byte selector line per row) -----------------
+// stage: 2 * MAXK_MAX_DIM words of this warp (values, then column ids as words so that one
+// address register serves both stores).
+template <bool U8>
+__device__ __forceinline__ void topk_emit(unsigned sel, const unsigned (&raw)[8], unsigned *stage,
+                                          int lane, int k, int64_t row, int c0, int c1,
+                                          void *__restrict__ out_val_,
+                                          unsigned char *__restrict__ out_idx)
+{
+    const unsigned n0 = __popc(sel & 0xfu), n1 = __popc(sel >> 4);
+    const unsigned inc = warp_incl_scan(n0 | (n1 << 16), lane);
+    const unsigned tot0 = __shfl_sync(0xffffffffu, inc, 31) & 0xffffu;
+    unsigned *w0 = stage + ((inc & 0xffffu) - n0);
+    unsigned *w1 = stage + (tot0 + (inc >> 16) - n1);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (sel & (16u << i)) {
-                sv[p1] = raw[4 + i];
-                si[p1] = (unsigned char)(c1 + i);
-                ++p1;
-            }
-        }
-        __syncwarp();
-        unsigned char *oi = out_idx + row * k;
-        for (int j = lane; j < k; j += 32) {
-            if constexpr (U8)
-                (static_cast<unsigned char *>(out_val_) + row * k)[j] = (unsigned char)sv[j];
-            else
-                (static_cast<unsigned *>(out_val_) + row * k)[j] = sv[j];
-            oi[j] = si[j];
+    for (int i = 0; i < 4; ++i) {
+        if (sel & (1u << i)) {
+            w0[0] = raw[i];
+            w0[MAXK_MAX_DIM] = (unsigned)(c0 + i);
+            ++w0;
         }
     }
-    if constexpr (!U8) {
-        if (dense_out != nullptr) {
-            float *o = dense_out + row * d;
-            float4 a, b;
-            a.x = (sel & 1u) ? __uint_as_float(raw[0]) : 0.f;
-            a.y = (sel & 2u) ? __uint_as_float(raw[1]) : 0.f;
-            a.z = (sel & 4u) ? __uint_as_float(raw[2]) : 0.f;
-            a.w = (sel & 8u) ? __uint_as_float(raw[3]) : 0.f;
-            b.x = (sel & 16u) ? __uint_as_float(raw[4]) : 0.f;
-            b.y = (sel & 32u) ? __uint_as_float(raw[5]) : 0.f;
-            b.z = (sel & 64u) ? __uint_as_float(raw[6]) : 0.f;
-            b.w = (sel & 128u) ? __uint_as_float(raw[7]) : 0.f;
-            if (ok0) st_stream_f4(reinterpret_cast<float4 *>(o + c0), a);
-            if (ok1) st_stream_f4(reinterpret_cast<float4 *>(o + c1), b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (sel & (16u << i)) {
+            w1[0] = raw[4 + i];
+            w1[MAXK_MAX_DIM] = (unsigned)(c1 + i);
+            ++w1;
         }
+    }
+    __syncwarp();
+    unsigned char *oi = out_idx + row * k + lane;
+    const unsigned *sv = stage + lane;
+    if constexpr (U8) {
+        unsigned char *ov = static_cast<unsigned char *>(out_val_) + row * k + lane;
+#pragma unroll 1
+        for (int j = lane; j < k; j += 32, sv += 32, ov += 32, oi += 32) {
+            *ov = (unsigned char)sv[0];
+            *oi = (unsigned char)sv[MAXK_MAX_DIM];
+        }
+    } else {
+        unsigned *ov = static_cast<unsigned *>(out_val_) + row * k + lane;
+#pragma unroll 1
+        for (int j = lane; j < k; j += 32, sv += 32, ov += 32, oi += 32) {
+            *ov = sv[0];
+            *oi = (unsigned char)sv[MAXK_MAX_DIM];
+        }
+    }
+}
+
+// ---- uint8 rows (the reference kernel's own data type): key-space search only ------------
+__global__ void __launch_bounds__(TOPK_WPB * 32)
+topk_cbsr_u8_kernel(const unsigned char *__restrict__ x_, int64_t n, int d, int k,
+                    unsigned char *__restrict__ out_val, unsigned char *__restrict__ out_idx)
+{
+    __shared__ unsigned s_stage[TOPK_WPB][2 * MAXK_MAX_DIM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * TOPK_WPB + warp;
+    if (row >= n) return;  // warp-uniform; no CTA barrier below
+    const int c0 = 4 * lane, c1 = 128 + 4 * lane;
+    const bool ok0 = c0 < d, ok1 = c1 < d;
+    const unsigned char *x = x_ + row * d;
+    const unsigned wa = ok0 ? __ldcs(reinterpret_cast<const unsigned *>(x + c0)) : 0u;
+    const unsigned wb = ok1 ? __ldcs(reinterpret_cast<const unsigned *>(x + c1)) : 0u;
+    unsigned key[8], raw[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        raw[i] = (wa >> (8 * i)) & 0xff;
+        raw[4 + i] = (wb >> (8 * i)) & 0xff;
+        key[i] = ok0 ? raw[i] + 1u : 0u;  // 0 is reserved for "no element"
+        key[4 + i] = ok1 ? raw[4 + i] + 1u : 0u;
+    }
+    const unsigned sel = topk_select_by_keys<true>(key, d, k, lane);
+    topk_emit<true>(sel, raw, s_stage[warp], lane, k, row, c0, c1, out_val, out_idx);
+}
+
+// ---- fp32 rows ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(TOPK_WPB * 32)
+topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k,
+                     float *__restrict__ out_val, unsigned char *__restrict__ out_idx,
+                     float *__restrict__ dense_out)
+{
+    __shared__ unsigned s_stage[TOPK_WPB][2 * MAXK_MAX_DIM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * TOPK_WPB + warp;
+    if (row >= n) return;  // warp-uniform; no CTA barrier below
+
+    const int c0 = 4 * lane, c1 = 128 + 4 * lane;
+    const bool ok0 = c0 < d, ok1 = c1 < d;
+    const float *xr = x_ + row * d;
+    const float ninf = __uint_as_float(0xff800000u), pinf = __uint_as_float(0x7f800000u);
+    float4 a = make_float4(ninf, ninf, ninf, ninf), b = a;  // columns >= d never qualify
+    if (ok0) a = ld_stream_f4(reinterpret_cast<const float4 *>(xr + c0));
+    if (ok1) b = ld_stream_f4(reinterpret_cast<const float4 *>(xr + c1));
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+
+    // row minimum / maximum (fminf/fmaxf skip NaN; an all-NaN lane yields NaN -> key 0xffffffff)
+    const float hi0 = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), hi1 = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));
+    const float lo0 = fminf(fminf(a.x, a.y), fminf(a.z, a.w)), lo1 = fminf(fminf(b.x, b.y), fminf(b.z, b.w));
+    const float lmax = fmaxf(hi0, hi1);
+    const float lmin = fminf(ok0 ? lo0 : pinf, ok1 ? lo1 : pinf);
+    float fh = key_to_f32(__reduce_max_sync(0xffffffffu, f32_order_key(__float_as_uint(lmax))));
+    float fl = key_to_f32(__reduce_min_sync(0xffffffffu, f32_order_key(__float_as_uint(lmin))));
+
+    // ---- fast path: regula falsi (Illinois weights) on g(t) = count(!(x < t)) - k --------
+    // g(fl) = d - k >= 0 is exact (every element, NaN included, is not below the minimum);
+    // g(fh) = 1 - k is an estimate (the maximum may be tied): it only steers the first
+    // probes.  A probe with g == 0 is a proof -- exactly k elements are not below fm -- so
+    // the result does not depend on the estimates; anything else leaves to the key search.
+    unsigned sel = 0u;
+    bool done = false;
+    if (k == d) {
+        sel = (ok0 ? 0x0fu : 0u) | (ok1 ? 0xf0u : 0u);
+        done = true;
+    } else {
+        float gl = (float)(d - k), gh = fminf((float)(1 - k), -0.5f);
+        int run = 0;  // +n: fl moved n times in a row, -n: fh did
+#pragma unroll 1
+        for (int it = 0; it < TOPK_FAST_MAX_PROBES; ++it) {
+            float fm = fmaf(fh - fl, gl * rcp_approx(gl - gh), fl);
+            if (!(fm > fl && fm < fh)) {
+                fm = 0.5f * fl + 0.5f * fh;
+                if (!(fm > fl && fm < fh)) break;  // adjacent floats, infinite or NaN end points
+            }
+            sel = lane_mask_nlt(x, fm);
+            const int g = __reduce_add_sync(0xffffffffu, __popc(sel)) - k;
+            if (g == 0) {
+                done = true;
+                break;
+            }
+            if (g > 0) {
+                fl = fm;
+                gl = (float)g;
+                if (run > 0) gh *= 0.5f;
+                run = run > 0 ? run + 1 : 1;
+            } else {
+                fh = fm;
+                gh = (float)g;
+                if (run < 0) gl *= 0.5f;
+                run = run < 0 ? run - 1 : -1;
+            }
+            if (run >= TOPK_FAST_MAX_RUN || run <= -TOPK_FAST_MAX_RUN) break;
+        }
+    }
+    unsigned raw[8];  // fp32 bit patterns (bit-copied to the output)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) raw[i] = __float_as_uint(x[i]);
+    if (!done)
+        sel = topk_select_slow_f32(raw[0], raw[1], raw[2], raw[3], raw[4], raw[5], raw[6], raw[7],
+                                   ok0, ok1, d, k, lane);
+
+    if (out_idx != nullptr)
+        topk_emit<false>(sel, raw, s_stage[warp], lane, k, row, c0, c1, out_val, out_idx);
+    if (dense_out != nullptr) {
+        float *o = dense_out + row * d;
+        float4 va, vb;
+        va.x = (sel & 1u) ? x[0] : 0.f;
+        va.y = (sel & 2u) ? x[1] : 0.f;
+        va.z = (sel & 4u) ? x[2] : 0.f;
+        va.w = (sel & 8u) ? x[3] : 0.f;
+        vb.x = (sel & 16u) ? x[4] : 0.f;
+        vb.y = (sel & 32u) ? x[5] : 0.f;
+        vb.z = (sel & 64u) ? x[6] : 0.f;
+        vb.w = (sel & 128u) ? x[7] : 0.f;
+        if (ok0) st_stream_f4(reinterpret_cast<float4 *>(o + c0), va);
+        if (ok1) st_stream_f4(reinterpret_cast<float4 *>(o + c1), vb);
     }
 }
 
@@ -273,9 +408,9 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
                  "maxk_topk_cbsr_f32: x and dense_out must be 16-byte aligned");
     const int64_t grid = ceil_div<int64_t>(n, TOPK_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_topk_cbsr_f32: n too large");
-    topk_cbsr_kernel<false><<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    topk_cbsr_f32_kernel<<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         x, n, d, k, sp_data, sp_index, dense_out);
-    MAXK_LAUNCH_CHECK("topk_cbsr_kernel<f32>");
+    MAXK_LAUNCH_CHECK("topk_cbsr_f32_kernel");
     return MAXK_OK;
 }
 
@@ -292,8 +427,8 @@ extern "C" int maxk_topk_cbsr_u8(const uint8_t *x, int64_t n, int32_t d, int32_t
                  "maxk_topk_cbsr_u8: x must be non-NULL and 4-byte aligned");
     const int64_t grid = ceil_div<int64_t>(n, TOPK_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_topk_cbsr_u8: n too large");
-    topk_cbsr_kernel<true><<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, n, d, k, value, index, nullptr);
-    MAXK_LAUNCH_CHECK("topk_cbsr_kernel<u8>");
+    topk_cbsr_u8_kernel<<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, n, d, k, value, index);
+    MAXK_LAUNCH_CHECK("topk_cbsr_u8_kernel");
     return MAXK_OK;
 }

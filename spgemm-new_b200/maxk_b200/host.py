@@ -16,7 +16,8 @@ TopK is per row, so it runs chunk by chunk as X arrives; the forward needs the w
 operand, but it is launched per block of output rows (the work list is in row order, so a
 row block is a contiguous task range) and every finished block of Y starts its download
 while the next block is computed; the dY upload hides behind the forward, the Y download
-behind the backward.  This is what bench.py's `e2e` times.
+behind the backward.  Across steps, `submit`/`result` overlap the next step's uploads with
+this step's kernels and downloads.  This is what bench.py's `e2e` times.
 """
 from __future__ import annotations
 
@@ -26,9 +27,28 @@ from . import ops
 from .autograd import worklist_for
 
 
+class _Slot:
+    """Device inputs/outputs and pinned host outputs of one in-flight step."""
+
+    def __init__(self, n_rows, n_cols, d, k, dev):
+        self.x_d = torch.empty((n_cols, d), dtype=torch.float32, device=dev)
+        self.dy_d = torch.empty((n_rows, d), dtype=torch.float32, device=dev)
+        self.y_d = torch.empty((n_rows, d), dtype=torch.float32, device=dev)
+        self.dxc_d = torch.empty((n_cols, k), dtype=torch.float32, device=dev)
+        self.y_h = torch.empty((n_rows, d), dtype=torch.float32, pin_memory=True)
+        self.dxc_h = torch.empty((n_cols, k), dtype=torch.float32, pin_memory=True)
+        self.inputs_free = None   # event: the kernels that read x_d / dy_d have finished
+        self.done = None          # event: y_h / dxc_h are complete
+
+
 class HostAggregator:
+    """`step(x, dy)` is the synchronous call.  `submit(x, dy)` / `result(ticket)` is the same
+    work as a two-deep pipeline: with two slots of buffers the upload of step i+1 runs while
+    step i computes and downloads, so a stream of steps is bound by the busier PCIe direction
+    (X + dY going up) instead of by the sum of the stages."""
+
     def __init__(self, indptr, indices, values, k: int, feat_dim: int = 256, device="cuda",
-                 n_cols=None, chunks: int = 4):
+                 n_cols=None, chunks: int = 4, slots: int = 2):
         self.device = torch.device(device)
         self.k, self.d = int(k), int(feat_dim)
         self.indptr = indptr.to(self.device, torch.int32).contiguous()
@@ -38,18 +58,15 @@ class HostAggregator:
         self.n_cols = int(n_cols if n_cols is not None else self.n_rows)
         self.warp4 = worklist_for(self.indptr)
         dev = self.device
-        self.x_d = torch.empty((self.n_cols, self.d), dtype=torch.float32, device=dev)
-        self.dy_d = torch.empty((self.n_rows, self.d), dtype=torch.float32, device=dev)
-        self.y_d = torch.empty((self.n_rows, self.d), dtype=torch.float32, device=dev)
-        self.dxc_d = torch.empty((self.n_cols, self.k), dtype=torch.float32, device=dev)
+        self.slots = [_Slot(self.n_rows, self.n_cols, self.d, self.k, dev) for _ in range(max(1, slots))]
+        self._submitted = 0
         self.sp_data = torch.empty((self.n_cols, self.k), dtype=torch.float32, device=dev)
         self.sp_index = torch.empty((self.n_cols, self.k), dtype=torch.uint8, device=dev)
-        self.y_h = torch.empty((self.n_rows, self.d), dtype=torch.float32, pin_memory=True)
-        self.dxc_h = torch.empty((self.n_cols, self.k), dtype=torch.float32, pin_memory=True)
         self.s_in = torch.cuda.Stream(dev)
+        self.s_main = torch.cuda.Stream(dev)
         self.s_out = torch.cuda.Stream(dev)
-        self.h2d_bytes = (self.x_d.numel() + self.dy_d.numel()) * 4
-        self.d2h_bytes = (self.y_h.numel() + self.dxc_h.numel()) * 4
+        self.h2d_bytes = (self.n_cols + self.n_rows) * self.d * 4
+        self.d2h_bytes = (self.n_rows * self.d + self.n_cols * self.k) * 4
         # row blocks with ~equal nnz; a block of rows is a contiguous range of tasks
         chunks = max(1, min(int(chunks), self.n_rows))
         ip = self.indptr.long()
@@ -63,50 +80,73 @@ class HostAggregator:
         self.task_bounds = tasks_before[torch.tensor(self.row_bounds, device=dev)].tolist()
         self.col_bounds = [(self.n_cols * c) // chunks for c in range(chunks)] + [self.n_cols]
 
-    def step(self, x_host: torch.Tensor, dy_host: torch.Tensor):
-        """x_host f32[n_cols, d], dy_host f32[n_rows, d] (pinned for full speed) ->
-        (y_host f32[n_rows, d], dxc_host f32[n_cols, k]); results are valid on return."""
-        main = torch.cuda.current_stream(self.device)
-        self.s_in.wait_stream(main)   # previous step's kernels are done with x_d / dy_d
-        self.s_out.wait_stream(main)
-        # --- X upload in column-node chunks, TopK chunk by chunk behind it
+    def submit(self, x_host: torch.Tensor, dy_host: torch.Tensor) -> int:
+        """Enqueue one step on host tensors x_host f32[n_cols, d], dy_host f32[n_rows, d]
+        (pinned for full speed) and return a ticket for `result`.  At most len(slots) steps
+        may be in flight: the ticket's host buffers are reused by the submit after next."""
+        slot = self.slots[self._submitted % len(self.slots)]
+        ticket = self._submitted
+        self._submitted += 1
+        main, s_in, s_out = self.s_main, self.s_in, self.s_out
+        main.wait_stream(torch.cuda.current_stream(self.device))
+        if slot.inputs_free is not None:
+            s_in.wait_event(slot.inputs_free)  # this slot's previous kernels are done with x_d / dy_d
+        if slot.done is not None:
+            main.wait_event(slot.done)         # ... and its previous downloads with y_d / dxc_d
+        col_chunks = list(zip(self.col_bounds[:-1], self.col_bounds[1:]))
+        # --- X upload in column-node chunks, TopK chunk by chunk behind it; then dY
         x_events = []
-        with torch.cuda.stream(self.s_in):
-            for c0, c1 in zip(self.col_bounds[:-1], self.col_bounds[1:]):
-                self.x_d[c0:c1].copy_(x_host[c0:c1], non_blocking=True)
+        with torch.cuda.stream(s_in):
+            for c0, c1 in col_chunks:
+                slot.x_d[c0:c1].copy_(x_host[c0:c1], non_blocking=True)
                 ev = torch.cuda.Event()
-                ev.record(self.s_in)
+                ev.record(s_in)
                 x_events.append(ev)
-            self.dy_d.copy_(dy_host, non_blocking=True)
+            slot.dy_d.copy_(dy_host, non_blocking=True)
             ev_dy = torch.cuda.Event()
-            ev_dy.record(self.s_in)
-        for (c0, c1), ev in zip(zip(self.col_bounds[:-1], self.col_bounds[1:]), x_events):
-            main.wait_event(ev)
-            if c1 > c0:
-                ops.topk_cbsr(self.x_d[c0:c1], self.k, out=(self.sp_data[c0:c1], self.sp_index[c0:c1]))
-        # --- forward per block of output rows, each block's Y downloaded as soon as it is done
-        self.y_d.zero_()
-        w4 = self.warp4.view(-1, 4)
-        for (r0, r1), (t0, t1) in zip(zip(self.row_bounds[:-1], self.row_bounds[1:]),
-                                       zip(self.task_bounds[:-1], self.task_bounds[1:])):
-            if t1 > t0:
-                ops.spgemm_forward(w4[t0:t1].reshape(-1), self.indices, self.values, self.sp_data,
-                                   self.sp_index, feat_dim=self.d, num_rows=self.n_rows,
-                                   out=self.y_d, accumulate=True)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(ev)
-                self.y_h[r0:r1].copy_(self.y_d[r0:r1], non_blocking=True)
-        # --- backward behind the dY upload; dXc download last
-        main.wait_event(ev_dy)
-        ops.sspmm_backward(self.warp4, self.indices, self.values, self.dy_d, self.sp_index,
-                           out=self.dxc_d)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(ev)
-            self.dxc_h.copy_(self.dxc_d, non_blocking=True)
-        main.wait_stream(self.s_out)
-        main.synchronize()
-        return self.y_h, self.dxc_h
+            ev_dy.record(s_in)
+        with torch.cuda.stream(main):
+            for (c0, c1), ev in zip(col_chunks, x_events):
+                main.wait_event(ev)
+                if c1 > c0:
+                    ops.topk_cbsr(slot.x_d[c0:c1], self.k, out=(self.sp_data[c0:c1], self.sp_index[c0:c1]))
+            # --- forward per block of output rows, each block's Y downloaded as soon as it is done
+            slot.y_d.zero_()
+            w4 = self.warp4.view(-1, 4)
+            for (r0, r1), (t0, t1) in zip(zip(self.row_bounds[:-1], self.row_bounds[1:]),
+                                           zip(self.task_bounds[:-1], self.task_bounds[1:])):
+                if t1 > t0:
+                    ops.spgemm_forward(w4[t0:t1].reshape(-1), self.indices, self.values, self.sp_data,
+                                       self.sp_index, feat_dim=self.d, num_rows=self.n_rows,
+                                       out=slot.y_d, accumulate=True)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev)
+                    slot.y_h[r0:r1].copy_(slot.y_d[r0:r1], non_blocking=True)
+            # --- backward behind the dY upload; dXc download last
+            main.wait_event(ev_dy)
+            ops.sspmm_backward(self.warp4, self.indices, self.values, slot.dy_d, self.sp_index,
+                               out=slot.dxc_d)
+            slot.inputs_free = torch.cuda.Event()
+            slot.inputs_free.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(slot.inputs_free)
+            slot.dxc_h.copy_(slot.dxc_d, non_blocking=True)
+            slot.done = torch.cuda.Event()
+            slot.done.record(s_out)
+        return ticket
+
+    def result(self, ticket: int):
+        """Block until the step behind `ticket` is complete; returns (y_host f32[n_rows, d],
+        dxc_host f32[n_cols, k]) -- pinned buffers owned by the aggregator, valid until the
+        submit after next reuses them."""
+        if not (self._submitted - len(self.slots) <= ticket < self._submitted):
+            raise RuntimeError(f"HostAggregator.result: ticket {ticket} is no longer in flight")
+        slot = self.slots[ticket % len(self.slots)]
+        slot.done.synchronize()
+        return slot.y_h, slot.dxc_h
+
+    def step(self, x_host: torch.Tensor, dy_host: torch.Tensor):
+        """Synchronous form: results are valid on return."""
+        return self.result(self.submit(x_host, dy_host))

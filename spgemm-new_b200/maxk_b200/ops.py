@@ -253,6 +253,11 @@ def set_tuning(fwd_tasks_per_warp: int = 0, bwd_tasks_per_warp: int = 0) -> None
     _cabi.check(_cabi.load().maxk_set_tuning(fwd_tasks_per_warp, bwd_tasks_per_warp))
 
 
+def set_forward_depth(depth: int = 0) -> None:
+    """Gather pipeline depth multiplier of the forward kernel (0 = automatic); bench/test hook."""
+    _cabi.check(_cabi.load().maxk_set_forward_depth(int(depth)))
+
+
 def set_forward_copies(copies: int = 0) -> None:
     """Accumulator copies of the forward kernel (0 = automatic); bench/test hook."""
     _cabi.check(_cabi.load().maxk_set_forward_copies(int(copies)))

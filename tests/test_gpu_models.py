@@ -99,4 +99,6 @@ def test_training_reduces_loss_and_dropout_is_on_cbsr_values():
     assert losses[-1] < 0.8 * losses[0]
     model.eval()
     a, b = model(G, feats), model(G, feats)
-    assert torch.equal(a, b)           # eval is deterministic up to reductions on unshared rows
+    # eval has no dropout; rows split over several warps' runs are combined with reductions
+    # whose order is free (as with the reference's atomics), so equality is up to fp32 rounding
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)

@@ -148,7 +148,7 @@ def test_run_length_invariance(ops, tpw):
                                num_rows=p.n)
         dxc = ops.sspmm_backward(g["warp4"], g["indices"], g["values"], g["dy"], g["sp_index"])
     finally:
-        ops.set_tuning(16, 16)
+        ops.set_tuning(-1, -1)
     assert_close(y, p.fwd_oracle())
     assert_close(dxc, p.bwd_oracle())
 
@@ -173,7 +173,52 @@ def test_forward_accumulator_copies(ops, k, copies):
         assert_close(y, 2 * want, "accumulate")
     finally:
         ops.set_forward_copies(0)
-        ops.set_tuning(16, 16)
+        ops.set_tuning(-1, -1)
+
+
+@pytest.mark.parametrize("shape", [1, 2, 3])
+@pytest.mark.parametrize("k", [32, 16, 64])
+def test_forward_launch_shapes(ops, k, shape):
+    """8-warp CTAs, 2-warp CTAs and the deeper gather pipeline give the same result, and rows
+    without tasks are zero although the output is not memset (poisoned buffer)."""
+    p = Problem(n=400, avg=20.0, k=k, seed=31 * k + shape, empty_frac=0.3)
+    g = p.cuda()
+    want = p.fwd_oracle()
+    try:
+        ops.set_forward_depth(shape)
+        for tpw in (-1, 1, 5):
+            ops.set_tuning(tpw, 0)
+            y = torch.full((p.n, 256), float("nan"), device="cuda")
+            ops.spgemm_forward(g["warp4"], g["indices"], g["values"], g["sp_data"], g["sp_index"],
+                               num_rows=p.n, out=y)
+            assert_close(y, want, f"k={k} shape={shape} tpw={tpw}")
+    finally:
+        ops.set_forward_depth(0)
+        ops.set_tuning(-1, -1)
+
+
+def test_forward_gap_rows_are_zeroed(ops):
+    """Leading, interior and trailing rows without edges (and an output taller than the last
+    task row) come back as zeros from a poisoned buffer."""
+    n = 97
+    deg = np.zeros(n, np.int64)
+    deg[[5, 6, 40, 41, 42, 80]] = [3, 200, 1, 70, 64, 129]
+    indptr = np.zeros(n + 1, np.int32)
+    indptr[1:] = np.cumsum(deg)
+    rng = np.random.default_rng(3)
+    e = int(indptr[-1])
+    indices = rng.integers(0, n, e).astype(np.int32)
+    values = rng.random(e, dtype=np.float32)
+    x = rng.standard_normal((n, 256)).astype(np.float32)
+    sp_data, sp_index = O.topk_cbsr(x, 32)
+    want = O.spgemm_forward(O.worklist(indptr), indices, values, sp_data, sp_index, d=256, n_out=n + 10)
+    w4 = ops.build_worklist(_cu(indptr))
+    for tpw in (-1, 1, 2, 16):
+        ops.set_tuning(tpw, 0)
+        y = torch.full((n + 10, 256), float("nan"), device="cuda")
+        ops.spgemm_forward(w4, _cu(indices), _cu(values), _cu(sp_data), _cu(sp_index), num_rows=n + 10, out=y)
+        assert_close(y, want, f"tpw={tpw}")
+    ops.set_tuning(-1, -1)
 
 
 def test_output_is_defined_not_accumulated(ops):
@@ -307,6 +352,34 @@ def test_host_aggregator_end_to_end(chunks):
         np.testing.assert_allclose(y.numpy().astype(np.float64), p.fwd_oracle(), rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(dxc.numpy().astype(np.float64), p.bwd_oracle(), rtol=RTOL, atol=ATOL)
     assert host.h2d_bytes == 2 * 900 * 256 * 4 and host.d2h_bytes == 900 * 256 * 4 + 900 * 32 * 4
+
+
+def test_host_aggregator_pipelined_submit_result():
+    """submit/result keeps two steps in flight (uploads of step i+1 behind the kernels of step
+    i); every step sees its own inputs and tickets expire when their buffers are reused."""
+    from maxk_b200 import HostAggregator
+    p = Problem(n=700, avg=40.0, k=32, seed=78, empty_frac=0.1)
+    g = p.cuda()
+    host = HostAggregator(g["indptr"], g["indices"], g["values"], 32, 256, "cuda", chunks=3)
+    scales = [1.0, -2.0, 0.5, 3.0, -1.0]
+    xs = [torch.from_numpy(p.x * s).pin_memory() for s in scales]
+    dys = [torch.from_numpy(p.dy * (s + 1.5)).pin_memory() for s in scales]
+    prev = None
+    for i, s in enumerate(scales):
+        t = host.submit(xs[i], dys[i])
+        if prev is not None:
+            j, tj = prev
+            y, dxc = host.result(tj)
+            pj = Problem(n=700, avg=40.0, k=32, seed=78, empty_frac=0.1)
+            pj.x = p.x * scales[j]
+            pj.dy = p.dy * (scales[j] + 1.5)
+            pj.sp_data, pj.sp_index = O.topk_cbsr(pj.x, 32)
+            np.testing.assert_allclose(y.numpy().astype(np.float64), pj.fwd_oracle(), rtol=RTOL, atol=ATOL)
+            np.testing.assert_allclose(dxc.numpy().astype(np.float64), pj.bwd_oracle(), rtol=RTOL, atol=ATOL)
+        prev = (i, t)
+    host.result(prev[1])
+    with pytest.raises(RuntimeError):
+        host.result(0)
 
 
 def test_reference_named_shims():
