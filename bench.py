@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="also time k=8/16/64, TopK and the work list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--comm", choices=("peer", "nccl"), default="peer",
+                    help="N>1: our fused kernels over NVLink peer memory (default) or NCCL collectives")
     ap.add_argument("--ref-kernels", action="store_true",
                     help="also time the reference CUDA kernels (oracle/_ref) on the same inputs")
     args = ap.parse_args()
@@ -236,8 +238,27 @@ def main():
     if world > 1:
         from maxk_b200.dist import DistAggregator, partition_rows_by_nnz
         bounds = partition_rows_by_nnz(g["indptr"], world)
-        agg = DistAggregator.from_global_csr(g["indptr"], g["indices"], g["values"], bounds, rank, k,
-                                             FEAT_DIM)
+        comm = args.comm
+        agg = None
+        if comm == "peer":
+            # fused push all-gather + SpGEMM kernel and pull reduce-scatter over NVLink peer
+            # memory (maxk_b200/peer.py).  If CUDA IPC cannot be set up on this box every rank
+            # agrees to use the NCCL collectives instead -- a transport choice, still our kernels.
+            from maxk_b200.peer import PeerAggregator
+            try:
+                agg = PeerAggregator.from_global_csr(g["indptr"], g["indices"], g["values"], bounds,
+                                                     rank, k, FEAT_DIM, copy_ctas=16)
+                ok = 1
+            except Exception as exc:  # noqa: BLE001
+                log(f"[rank {rank}] peer-memory path unavailable: {exc}")
+                ok = 0
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag) == 0:
+                agg, comm = None, "nccl"
+        if agg is None:
+            agg = DistAggregator.from_global_csr(g["indptr"], g["indices"], g["values"], bounds, rank, k,
+                                                 FEAT_DIM)
         del g["indices"], g["values"]
         torch.cuda.empty_cache()
         n_loc = agg.n_local
@@ -436,7 +457,10 @@ def main():
                                        f"k={k}, hidden {FEAT_DIM}",
                            "k": k, "feat_dim": FEAT_DIM, "num_tasks": w, "graph_scale": scale,
                            "parallelism": ("single GPU" if world == 1 else
-                                           f"1-D row partition x{world}, CBSR all-gather + reduce-scatter (NCCL)"),
+                                           (f"1-D row partition x{world}, fused push all-gather + SpGEMM kernel and pull "
+                                            "reduce-scatter over NVLink peer memory (own kernels, no NCCL on the data path)"
+                                            if comm == "peer" else
+                                            f"1-D row partition x{world}, CBSR all-gather + reduce-scatter (NCCL)")),
                            "l2": "inputs larger than L2 (CSR stream 917 MB per kernel); CBSR operand "
                                  "(37 MB) is L2-resident by design",
                            "step_algorithmic_bytes": step_bytes},

@@ -43,6 +43,7 @@ extern "C" {
 #define MAXK_ABI_VERSION 1
 #define MAXK_WARP_MAX_NZ 64 /* ref: kernels/generate_meta.py:9 */
 #define MAXK_MAX_DIM 256    /* selectors are uint8 (ref: spmm_maxk.cu:17) */
+#define MAXK_PEER_MAX 16    /* ranks of one NVLink domain addressed by the peer-memory path */
 
 /* Layout-compatible stand-in for CUDA's dim3 so that C callers can bind the
  * reference-named shims below (ref: cuda_kernel_bindings.cpp:11-35). */
@@ -141,6 +142,57 @@ MAXK_API int maxk_cbsr_pack(const float *sp_data, const uint8_t *sp_index, int64
                    void *records, void *stream);
 MAXK_API int maxk_cbsr_unpack(const void *records, int64_t n, int32_t k, float *sp_data,
                      uint8_t *sp_index, void *stream);
+
+/* ---- multi-GPU over NVLink peer memory (new: the reference is single-GPU) -----
+ * One process per GPU.  Buffers that peers read are allocated with maxk_peer_alloc, their
+ * 64-byte CUDA IPC handles are exchanged by the host (torch.distributed in the Python layer)
+ * and mapped with maxk_peer_open.  A maxk_peer_ctx lists, for every rank r of the job, this
+ * process's mapping of r's buffers (entry [rank] = the process's own allocations):
+ *   g_data / g_index  gathered CBSR operand, float32 / uint8 [world * block_rows, k]; rank r
+ *                     writes rows [r * block_rows, r * block_rows + rows_of[r]) of its own
+ *                     buffer itself (TopK in place) and the fused forward pushes them into
+ *                     the same rows of every peer's buffer;
+ *   partial           CBSR-shaped partial gradients, float32 [world * block_rows, k];
+ *   flags             uint32[64] per rank, zero-initialised: [1] = last epoch whose partial
+ *                     gradients are published, [16 + r] = last epoch whose CBSR block from
+ *                     rank r has arrived in this rank's buffer (written by rank r);
+ *   local_sync        uint32[4] in the process's own memory, zero-initialised.
+ * Epochs are step numbers that only grow; buffers alternate between two contexts by epoch
+ * parity so that nobody overwrites what a slower peer still reads.  block_rows % 16 == 0.
+ * Every device-side wait is bounded (about 5 s) and traps instead of hanging.             */
+typedef struct maxk_peer_ctx {
+    int32_t world, rank, k, block_rows;
+    int32_t rows_of[MAXK_PEER_MAX];
+    void *g_data[MAXK_PEER_MAX];
+    void *g_index[MAXK_PEER_MAX];
+    void *partial[MAXK_PEER_MAX];
+    void *flags[MAXK_PEER_MAX];
+    void *local_sync;
+} maxk_peer_ctx;
+
+/* cudaMalloc + cudaIpcGetMemHandle (handle_out: 64 bytes); memory is zero-filled. */
+MAXK_API int maxk_peer_alloc(int64_t bytes, void **dev_ptr, void *handle_out);
+MAXK_API int maxk_peer_free(void *dev_ptr);
+/* cudaIpcOpenMemHandle of a peer's allocation (enables peer access lazily) / close it. */
+MAXK_API int maxk_peer_open(const void *handle, void **dev_ptr);
+MAXK_API int maxk_peer_close(void *dev_ptr);
+/* Stream-ordered system-scope release store *flag_word = epoch (after the backward kernel on
+ * the same stream: flags[rank] + 1). */
+MAXK_API int maxk_peer_publish(void *flag_word, uint32_t epoch, void *stream);
+/* Fused all-gather + forward SpGEMM: ONE kernel whose first copy_ctas CTAs push this rank's
+ * CBSR block to the peers over NVLink while the others aggregate.  The work list / CSR is the
+ * concatenation [tasks whose columns this rank owns | tasks reading other ranks' columns],
+ * columns remapped to rows of the gathered buffer; tasks from wait_from_task on wait for the
+ * peers' blocks to arrive.  out float32[num_rows_out, d] is defined by the call.  k = ctx->k must be
+ * 8, 16 or a multiple of 32.                                                              */
+MAXK_API int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoch, const int32_t *warp4,
+                              int64_t num_tasks, int64_t wait_from_task, const int32_t *indices,
+                              const float *values, float *out, int64_t num_rows_out, int32_t d,
+                              int32_t copy_ctas, void *stream);
+/* Pull reduce-scatter: waits until every peer has published `epoch` in flags[.][1], then
+ * out[i, :] = sum over ranks r (in rank order: deterministic) of partial_r[rank's block][i, :],
+ * out float32[rows_of[rank], k].                                                          */
+MAXK_API int maxk_reduce_scatter_pull(const maxk_peer_ctx *ctx, uint32_t epoch, float *out, void *stream);
 
 /* ---- reference-named launch shims (ref: cuda_kernel_wrappers.cu:38-91, declared in
  * cuda_kernel_bindings.cpp:11-35).  Same argument lists, so the reference's binding

@@ -42,6 +42,7 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--tf32", action="store_true", help="TF32 tensor cores for the dense Linear layers")
 ap.add_argument("--no-split", action="store_true")
+ap.add_argument("--comm", choices=("nccl", "peer"), default="nccl")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0"))
@@ -59,7 +60,7 @@ g = graphs.make_graph(a.shape, seed=0, device=dev, values="ones", scale=a.scale)
 n = g["v_num"]
 if world > 1:
     bounds = partition_rows_by_nnz(g["indptr"], world)
-    G = DistGraph(g["indptr"], g["indices"], bounds, rank, split=not a.no_split)
+    G = DistGraph(g["indptr"], g["indices"], bounds, rank, split=not a.no_split, comm=a.comm)
     lo, hi = bounds[rank], bounds[rank + 1]
 else:
     G = Graph(g["indptr"], g["indices"])

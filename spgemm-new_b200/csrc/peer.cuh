@@ -1,0 +1,294 @@
+// peer.cuh -- device side of the multi-GPU path over NVLink peer memory (one process per GPU,
+// buffers shared with CUDA IPC; the reference has no multi-GPU code at all).
+//
+// Protocol (all flags are monotonically increasing step numbers, "epochs"):
+//   * every rank owns a gathered CBSR buffer [world * block_rows, k] (values + selectors) that
+//     its peers have mapped.  TopK writes the rank's own block in place (stream order makes
+//     it visible to the fused forward kernel that follows);
+//   * the fused forward kernel's first `copy_ctas` CTAs PUSH that block into every peer's
+//     buffer with 128-bit stores over NVLink -- posted writes stream at link speed from a few
+//     CTAs, whereas reads are capped by the outstanding requests one SM may have (measured:
+//     a pull delivered 1.7 GB/s per CTA whatever the unroll) -- and the last of them to finish
+//     raises flag word [16 + rank] = epoch in every peer's flag array (system-scope release
+//     after a system fence);
+//   * the other CTAs aggregate the tasks on this rank's own columns straight away and, before
+//     the first task that reads other ranks' columns, wait until the flag words of all peers
+//     in their OWN memory (local polling, nothing crosses NVLink) show the epoch;
+//   * the backward publishes flag word [1] = epoch after the SSpMM; the reduce-scatter kernel
+//     waits for it on every peer and pulls its block of each partial gradient;
+//   * buffers are double-buffered by epoch parity on the host side, so no "done reading"
+//     handshake is needed: a rank can only finish step e-1 after every peer has pushed its
+//     block of step e-1, i.e. after that peer has finished reading the buffers of step e-2.
+// Every spin is bounded: a peer that never arrives traps the kernel instead of hanging the GPU.
+#pragma once
+
+#include "common.cuh"
+
+namespace maxk {
+
+struct PeerArgs {
+    int copy_ctas, world, rank, k;
+    int use_tma;  // push through cp.async.bulk (needs PEER_TMA_SMEM + 128 bytes of dynamic smem)
+    unsigned epoch;
+    int block_rows;
+    long long wait_from_task;
+    int rows_of[MAXK_PEER_MAX];
+    float *g_data[MAXK_PEER_MAX];           // rank r's gathered value buffer ([rank] = own)
+    unsigned char *g_index[MAXK_PEER_MAX];  // rank r's gathered selector buffer
+    unsigned *flags[MAXK_PEER_MAX];         // rank r's flag words ([rank] = own)
+    unsigned *local_sync;                   // own memory: [1] arrival counter of the copy CTAs
+};
+struct NoPeer {};
+template <bool P>
+struct PeerParam {
+    using type = NoPeer;
+};
+template <>
+struct PeerParam<true> {
+    using type = PeerArgs;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Peer data is immutable between its publication and the epoch after next, and this kernel
+// has not touched these lines before (L1 starts clean at launch), so a weak streaming load is
+// safe -- and unlike a volatile (system-scope) load it moves full 128-byte requests over NVLink.
+__device__ __forceinline__ uint4 ld_peer_u4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+
+constexpr long long PEER_SPIN_LIMIT_CYCLES = 10000000000LL;  // ~5 s at 1.9 GHz
+
+template <bool SYS>
+__device__ __forceinline__ void peer_spin_until(const unsigned *flag, unsigned epoch, int who)
+{
+    const long long t0 = clock64();
+    while (true) {
+        const unsigned v = SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag);
+        if ((int)(v - epoch) >= 0) return;
+        __nanosleep(200);  // back off: thousands of waiting warps must not starve the copy CTAs
+        if (clock64() - t0 > PEER_SPIN_LIMIT_CYCLES) {
+            printf("libmaxk_b200: timed out waiting for %s %d (flag %u, want %u)\n",
+                   SYS ? "peer rank" : "the gather of block", who, v, epoch);
+            __trap();
+        }
+    }
+}
+
+// this CTA's share (cta of nctas) of a `bytes`-long copy; 16 x 128 bits in flight per thread
+__device__ __forceinline__ void peer_copy_slice(unsigned char *dst, const unsigned char *src,
+                                                long long bytes, int cta, int nctas)
+{
+    constexpr int U = 16;
+    const long long n16 = bytes >> 4;
+    const long long lo = n16 * cta / nctas, hi = n16 * (cta + 1) / nctas;
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    for (long long base = lo; base < hi; base += (long long)nthr * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + (long long)u * nthr + tid;
+            if (i < hi) v[u] = ld_peer_u4(s + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = base + (long long)u * nthr + tid;
+            if (i < hi) d[i] = v[u];
+        }
+    }
+    if (cta == 0) {  // tail bytes of a length that is not a multiple of 16
+        for (long long i = (n16 << 4) + tid; i < bytes; i += nthr)
+            dst[i] = *reinterpret_cast<const volatile unsigned char *>(src + i);
+    }
+}
+
+// ---- the same push through the TMA unit -----------------------------------------------------
+// The aggregating CTAs keep the SM's load/store pipe ~93 % busy, so copy warps that share an SM
+// with them crawl (measured: 10 GB/s per copy CTA with 128-bit LDG/STG).  Bulk asynchronous
+// copies do not go through that pipe: one thread stages 16 KB chunks of the block in shared
+// memory (cp.async.bulk global -> shared, mbarrier completion) and fans each chunk out to
+// every peer (cp.async.bulk shared -> global over NVLink, bulk-group completion); the block
+// is read once, not world-1 times.
+constexpr int PEER_TMA_CHUNK = 16384;
+constexpr int PEER_TMA_STAGES = 2;
+constexpr int PEER_TMA_SMEM = PEER_TMA_CHUNK * PEER_TMA_STAGES;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void tma_load_chunk(unsigned dst_smem, const void *src, unsigned bytes,
+                                               unsigned mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            dst_smem),
+        "l"(src), "r"(bytes), "r"(mbar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PEER_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PEER_MBAR_DONE;\n"
+        "bra PEER_MBAR_WAIT;\n"
+        "PEER_MBAR_DONE:\n"
+        "}" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_chunk(void *dst, unsigned src_smem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+
+// thread 0 of a copy CTA: this CTA's share of `bytes` (a multiple of 16) from own memory to the
+// same offset of every peer buffer.  `stage_smem`: PEER_TMA_SMEM bytes, 128-byte aligned;
+// `mbar`: PEER_TMA_STAGES initialised mbarriers; `phase`: their parity bits, carried between calls.
+__device__ __forceinline__ void peer_tma_fanout(const PeerArgs &a, unsigned char *const *dst_base,
+                                                const unsigned char *src, long long byte_off,
+                                                long long bytes, int cta, unsigned stage_smem,
+                                                unsigned mbar0, unsigned &phase, int &chunks_issued)
+{
+    const long long n16 = bytes >> 4;
+    const long long lo = (n16 * cta / a.copy_ctas) << 4, hi = (n16 * (cta + 1) / a.copy_ctas) << 4;
+    const long long nchunks = (hi - lo + PEER_TMA_CHUNK - 1) / PEER_TMA_CHUNK;
+    if (nchunks <= 0) return;
+    auto chunk_bytes = [&](long long c) -> unsigned {
+        const long long b = hi - (lo + c * PEER_TMA_CHUNK);
+        return (unsigned)(b < PEER_TMA_CHUNK ? b : PEER_TMA_CHUNK);
+    };
+    auto load = [&](long long c) {
+        const int st = chunks_issued % PEER_TMA_STAGES;
+        // the stores that last read this stage (two chunks ago) must be done with it
+        if (chunks_issued >= PEER_TMA_STAGES) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        tma_load_chunk(stage_smem + st * PEER_TMA_CHUNK, src + byte_off + lo + c * PEER_TMA_CHUNK,
+                       chunk_bytes(c), mbar0 + 8 * st);
+        ++chunks_issued;
+    };
+    int first = chunks_issued;
+    load(0);
+    for (long long c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) load(c + 1);
+        const int st = (first + (int)c) % PEER_TMA_STAGES;
+        mbar_wait(mbar0 + 8 * st, (phase >> st) & 1u);
+        phase ^= (1u << st);
+        const unsigned nb = chunk_bytes(c);
+        const long long off = byte_off + lo + c * PEER_TMA_CHUNK;
+        for (int s = 1; s < a.world; ++s) {
+            const int p = (a.rank + s) % a.world;
+            tma_store_chunk(dst_base[p] + off, stage_smem + st * PEER_TMA_CHUNK, nb);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+
+constexpr int PEER_FLAG_BWD = 1;       // flag word: partial gradients published
+constexpr int PEER_FLAG_ARRIVED = 16;  // flag words [16 + r]: CBSR block of rank r has arrived
+
+// copy CTAs of the fused forward kernel: push this rank's CBSR block to every other rank
+__device__ __forceinline__ void peer_push_block(const PeerArgs &a, int cta, unsigned char *smem)
+{
+    const long long row0 = (long long)a.rank * a.block_rows;
+    const long long nel = (long long)a.rows_of[a.rank] * a.k;
+    if (a.use_tma) {
+        __shared__ __align__(8) unsigned long long mbar[PEER_TMA_STAGES];
+        if (threadIdx.x == 0) {
+            const unsigned mbar0 = smem_u32(mbar);
+            for (int i = 0; i < PEER_TMA_STAGES; ++i)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8 * i) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+            unsigned phase = 0u;
+            int issued = 0;
+            unsigned char *dd[MAXK_PEER_MAX], *di[MAXK_PEER_MAX];
+            for (int r = 0; r < a.world; ++r) {
+                dd[r] = reinterpret_cast<unsigned char *>(a.g_data[r]);
+                di[r] = a.g_index[r];
+            }
+            const unsigned stage = (smem_u32(smem) + 127u) & ~127u;
+            peer_tma_fanout(a, dd, dd[a.rank], row0 * a.k * 4, (nel * 4) & ~15LL, cta, stage, mbar0, phase, issued);
+            peer_tma_fanout(a, di, di[a.rank], row0 * a.k, nel & ~15LL, cta, stage, mbar0, phase, issued);
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all remote writes performed
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        if (cta == 0 && (nel & 15)) {  // selector tail of a block whose byte count is not 16-aligned
+            const long long t0 = nel & ~15LL;
+            for (int s = 1; s < a.world; ++s) {
+                const int p = (a.rank + s) % a.world;
+                for (long long i = t0 + threadIdx.x; i < nel; i += blockDim.x)
+                    a.g_index[p][row0 * a.k + i] = a.g_index[a.rank][row0 * a.k + i];
+            }
+        }
+    } else {
+        const unsigned char *own_d = reinterpret_cast<const unsigned char *>(a.g_data[a.rank] + row0 * a.k);
+        const unsigned char *own_i = a.g_index[a.rank] + row0 * a.k;
+        for (int s = 1; s < a.world; ++s) {
+            const int p = (a.rank + s) % a.world;  // staggered: rank r writes to r+1 first
+            peer_copy_slice(reinterpret_cast<unsigned char *>(a.g_data[p] + row0 * a.k), own_d, nel * 4,
+                            cta, a.copy_ctas);
+            peer_copy_slice(a.g_index[p] + row0 * a.k, own_i, nel, cta, a.copy_ctas);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // this CTA's remote stores before the arrival count
+        unsigned arrived;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;"
+                     : "=r"(arrived)
+                     : "l"(a.local_sync + 1)
+                     : "memory");
+        if (arrived == (unsigned)a.copy_ctas - 1u) {  // last copy CTA: the whole block is out
+            a.local_sync[1] = 0u;
+            __threadfence_system();
+            for (int s = 1; s < a.world; ++s) {
+                const int p = (a.rank + s) % a.world;
+                st_release_sys(a.flags[p] + PEER_FLAG_ARRIVED + a.rank, a.epoch);
+            }
+        }
+    }
+}
+
+// aggregating warps: block until every peer's block has arrived (lane r watches rank r's word
+// in this rank's own flag array)
+__device__ __forceinline__ void peer_wait_gathered(const PeerArgs &a, int lane)
+{
+    if (lane < a.world && lane != a.rank)
+        peer_spin_until<true>(a.flags[a.rank] + PEER_FLAG_ARRIVED + lane, a.epoch, lane);
+    __syncwarp();
+}
+
+}  // namespace maxk

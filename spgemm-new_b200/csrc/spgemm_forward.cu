@@ -24,6 +24,7 @@
 // HBM traffic is the CSR stream + one write of Y; the CBSR operand (5k B/node) lives in
 // the 126 MB L2.  No tensor cores: 2 flops per >= 5 bytes gathered.
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace maxk {
 
@@ -37,10 +38,14 @@ constexpr int FWD_STAGE = 64;  // staged (idx,val) pairs per warp == MAXK_WARP_M
 // EPL entries per lane (k > 32), EXACT: k == KL*EPL with aligned operands (vector gathers),
 // R accumulator copies, WPB warps per CTA, U gather instructions in flight, MINB CTAs/SM
 // the register budget is capped for.
-template <int KL_, int EPL_, bool EXACT_, int R_, int WPB_, int U_, int MINB_>
+template <int KL_, int EPL_, bool EXACT_, int R_, int WPB_, int U_, int MINB_, bool PEER_ = false>
 struct FwdCfg {
     static constexpr int KL = KL_, EPL = EPL_, R = R_, WPB = WPB_, U = U_, MINB = MINB_;
     static constexpr bool EXACT = EXACT_;
+    // PEER: fused multi-GPU variant -- the first CTAs of the grid push this rank's CBSR block
+    // to the other ranks over NVLink while the rest aggregate; gathers then use coherent loads
+    // because the operand is being written by the peers during the kernel (peer.cuh)
+    static constexpr bool PEER = PEER_;
     static constexpr int E = 32 / KL_;  // edges per instruction
     static_assert(KL_ * E == 32 && (R_ % E) == 0 && R_ >= E, "copies must separate edge slots");
     static_assert(KL_ == 32 || EPL_ == 1, "sub-warp edges have one entry per lane");
@@ -52,28 +57,39 @@ struct Slice {
     unsigned char s[C::EPL];
 };
 
-template <class C>
-__device__ __forceinline__ void fwd_gather(Slice<C> &sl, const float *__restrict__ sp_data,
-                                           const unsigned char *__restrict__ sp_index, int col,
-                                           int k, int lane)
+// read-only path for an operand that is constant during the kernel; plain (coherent) loads
+// when other CTAs of the same kernel are still filling it (PEER)
+template <bool PEER, typename T>
+__device__ __forceinline__ T fwd_ld(const T *p)
 {
+    if constexpr (PEER)
+        return *p;
+    else
+        return __ldg(p);
+}
+
+template <class C>
+__device__ __forceinline__ void fwd_gather(Slice<C> &sl, const float *sp_data,
+                                           const unsigned char *sp_index, int col, int k, int lane)
+{
+    constexpr bool P = C::PEER;
     const int64_t base = (int64_t)col * k;
     if constexpr (C::KL < 32) {
         const int entry = lane / C::E;
-        sl.v[0] = ld_gather_f32(sp_data + base + entry);
-        sl.s[0] = ld_gather_u8(sp_index + base + entry);
+        sl.v[0] = fwd_ld<P>(sp_data + base + entry);
+        sl.s[0] = fwd_ld<P>(sp_index + base + entry);
     } else if constexpr (C::EXACT && C::EPL == 1) {
-        sl.v[0] = ld_gather_f32(sp_data + base + lane);
-        sl.s[0] = ld_gather_u8(sp_index + base + lane);
+        sl.v[0] = fwd_ld<P>(sp_data + base + lane);
+        sl.s[0] = fwd_ld<P>(sp_index + base + lane);
     } else if constexpr (C::EXACT && C::EPL == 2) {
         // lane owns entries 2*lane, 2*lane+1: one 64-bit + one 16-bit load
-        float2 f = __ldg(reinterpret_cast<const float2 *>(sp_data + base) + lane);
-        unsigned short u = __ldg(reinterpret_cast<const unsigned short *>(sp_index + base) + lane);
+        float2 f = fwd_ld<P>(reinterpret_cast<const float2 *>(sp_data + base) + lane);
+        unsigned short u = fwd_ld<P>(reinterpret_cast<const unsigned short *>(sp_index + base) + lane);
         sl.v[0] = f.x; sl.v[1] = f.y;
         sl.s[0] = (unsigned char)(u & 0xff); sl.s[1] = (unsigned char)(u >> 8);
     } else if constexpr (C::EXACT && C::EPL == 4) {
-        float4 f = ld_gather_f4(reinterpret_cast<const float4 *>(sp_data + base) + lane);
-        unsigned u = ld_gather_u32(reinterpret_cast<const unsigned *>(sp_index + base) + lane);
+        float4 f = fwd_ld<P>(reinterpret_cast<const float4 *>(sp_data + base) + lane);
+        unsigned u = fwd_ld<P>(reinterpret_cast<const unsigned *>(sp_index + base) + lane);
         sl.v[0] = f.x; sl.v[1] = f.y; sl.v[2] = f.z; sl.v[3] = f.w;
         sl.s[0] = u & 0xff; sl.s[1] = (u >> 8) & 0xff; sl.s[2] = (u >> 16) & 0xff; sl.s[3] = u >> 24;
     } else {
@@ -81,8 +97,8 @@ __device__ __forceinline__ void fwd_gather(Slice<C> &sl, const float *__restrict
         for (int i = 0; i < C::EPL; ++i) {
             const int l = lane + 32 * i;
             if (C::EXACT || l < k) {
-                sl.v[i] = ld_gather_f32(sp_data + base + l);
-                sl.s[i] = ld_gather_u8(sp_index + base + l);
+                sl.v[i] = fwd_ld<P>(sp_data + base + l);
+                sl.s[i] = fwd_ld<P>(sp_index + base + l);
             } else {
                 sl.v[i] = 0.f;
                 sl.s[i] = 0;
@@ -118,9 +134,8 @@ __device__ __forceinline__ void fwd_accumulate(const Slice<C> &sl, float *acc_la
 // staging reads, U gathers and U accumulates back to back.  profiles/r01_forward_pipeline.md)
 template <class C>
 __device__ __forceinline__ void fwd_process_batch(const int2 *stage, int len, float *acc_lane,
-                                                  const float *__restrict__ sp_data,
-                                                  const unsigned char *__restrict__ sp_index,
-                                                  int k, int lane)
+                                                  const float *sp_data,
+                                                  const unsigned char *sp_index, int k, int lane)
 {
     constexpr int U = C::U, E = C::E, STEP = U * E;
     const int e = lane & (E - 1);
@@ -266,18 +281,29 @@ spgemm_fwd_clear_shared_rows(const int4 *__restrict__ warp4, int64_t num_tasks, 
 template <class C>
 __global__ void __launch_bounds__(C::WPB * 32, C::MINB)
 spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *__restrict__ idx,
-                  const float *__restrict__ val, const float *__restrict__ sp_data,
-                  const unsigned char *__restrict__ sp_index, int k, float *__restrict__ out, int d,
-                  int tasks_per_warp, int accumulate, int64_t num_rows_out)
+                  const float *__restrict__ val, const float *sp_data,
+                  const unsigned char *sp_index, int k, float *__restrict__ out, int d,
+                  int tasks_per_warp, int accumulate, int64_t num_rows_out,
+                  typename PeerParam<C::PEER>::type peer)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t cta = blockIdx.x;
+    bool gathered = true;  // PEER: the other ranks' CBSR blocks have arrived
+    if constexpr (C::PEER) {
+        if (cta < peer.copy_ctas) {  // lowest block ids: resident before any waiting CTA
+            peer_push_block(peer, (int)cta, smem_raw);
+            return;
+        }
+        cta -= peer.copy_ctas;
+        gathered = false;
+    }
     float *acc = reinterpret_cast<float *>(smem_raw) + warp * d * C::R;
     int2 *stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + C::WPB * d * C::R) +
                   warp * FWD_STAGE;
     float *acc_lane = acc + (lane & (C::R - 1));
 
-    const int64_t t0 = ((int64_t)blockIdx.x * C::WPB + warp) * tasks_per_warp;
+    const int64_t t0 = (cta * C::WPB + warp) * tasks_per_warp;
     if (t0 >= num_tasks) return;  // no CTA-wide barrier below
     const int64_t t1 = min(t0 + (int64_t)tasks_per_warp, num_tasks);
 
@@ -315,6 +341,13 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
         }
         const int64_t loc = info.y;
         const int len = info.z;
+        if constexpr (C::PEER) {
+            // tasks from `wait_from_task` on read columns owned by other ranks
+            if (!gathered && t >= peer.wait_from_task) {
+                peer_wait_gathered(peer, lane);
+                gathered = true;
+            }
+        }
         fwd_stage_edges(pre, stage, lane);
         if (has_next)  // next task's CSR slice streams in while this task's gathers run
             fwd_fetch_edges(pre, idx, val, ninfo.y, min(ninfo.z, FWD_STAGE), lane);
@@ -349,13 +382,17 @@ struct FwdArgs {
     cudaStream_t st;
     int depth;
     int64_t num_rows_out;
+    const PeerArgs *peer;  // fused multi-GPU launch only
 };
 
 template <class C>
 static int launch_fwd(const FwdArgs &a)
 {
-    const size_t smem = (size_t)C::WPB * a.d * C::R * sizeof(float) +
-                        (size_t)C::WPB * FWD_STAGE * sizeof(int2);
+    size_t smem = (size_t)C::WPB * a.d * C::R * sizeof(float) +
+                  (size_t)C::WPB * FWD_STAGE * sizeof(int2);
+    if constexpr (C::PEER) {  // the copy CTAs stage their TMA chunks in the same dynamic smem
+        if (a.peer->use_tma && smem < PEER_TMA_SMEM + 128) smem = PEER_TMA_SMEM + 128;
+    }
     if (smem > 48 * 1024) {
         static bool opted_in = false;  // per variant; benign if raced
         if (!opted_in) {
@@ -365,14 +402,19 @@ static int launch_fwd(const FwdArgs &a)
         }
     }
     const int64_t chunks = ceil_div<int64_t>(a.W, a.tasks_per_warp);
-    const int64_t grid = ceil_div<int64_t>(chunks, C::WPB);
+    int64_t grid = ceil_div<int64_t>(chunks, C::WPB);
+    typename PeerParam<C::PEER>::type peer{};
+    if constexpr (C::PEER) {
+        peer = *a.peer;
+        grid += peer.copy_ctas;
+    }
     if (grid > 0x7fffffffLL) {
         set_error("maxk_spgemm_forward: grid too large");
         return MAXK_ERR_UNSUPPORTED;
     }
     spgemm_fwd_kernel<C><<<(unsigned)grid, C::WPB * 32, smem, a.st>>>(
         reinterpret_cast<const int4 *>(a.warp4), a.W, a.idx, a.val, a.sp_data, a.sp_index, a.k,
-        a.out, a.d, a.tasks_per_warp, a.accumulate, a.num_rows_out);
+        a.out, a.d, a.tasks_per_warp, a.accumulate, a.num_rows_out, peer);
     MAXK_LAUNCH_CHECK("spgemm_fwd_kernel");
     return MAXK_OK;
 }
@@ -489,7 +531,7 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
     int shape = g_fwd_depth;
     if (shape <= 0) shape = (num_tasks < 2 * num_rows_out) ? 2 : 1;
     FwdArgs a{warp4, num_tasks, indices, values, sp_data, sp_index, k, out, d,
-              tpw, accumulate, st, shape, num_rows_out};
+              tpw, accumulate, st, shape, num_rows_out, nullptr};
     // Output is DEFINED by this call without a memset of the whole of it: rows
     // shared between two runs are cleared here, rows without tasks inside the main kernel.
     if (!accumulate) {
@@ -530,5 +572,76 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
     }
 #undef MAXK_FWD_CASE
     set_error("maxk_spgemm_forward: unsupported k=%d", k);
+    return MAXK_ERR_UNSUPPORTED;
+}
+
+// ---- fused all-gather + forward over NVLink peer memory (peer.cuh) ---------------------------
+extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoch,
+                                         const int32_t *warp4, int64_t num_tasks,
+                                         int64_t wait_from_task, const int32_t *indices,
+                                         const float *values, float *out, int64_t num_rows_out,
+                                         int32_t d, int32_t copy_ctas, void *stream)
+{
+    MAXK_REQUIRE(ctx != nullptr, "maxk_spgemm_forward_fused: ctx is NULL");
+    const int world = ctx->world, rank = ctx->rank, k = ctx->k;
+    MAXK_REQUIRE(world >= 1 && world <= MAXK_PEER_MAX && rank >= 0 && rank < world,
+                 "maxk_spgemm_forward_fused: world=%d rank=%d out of range", world, rank);
+    MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0 && wait_from_task >= 0,
+                 "maxk_spgemm_forward_fused: negative size");
+    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
+                 "maxk_spgemm_forward_fused: d=%d must be a multiple of 4 in [4,256]", d);
+    MAXK_REQUIRE(k >= 1 && k <= d, "maxk_spgemm_forward_fused: k=%d must be in [1,d=%d]", k, d);
+    MAXK_REQUIRE(ctx->block_rows > 0 && ctx->block_rows % 16 == 0,
+                 "maxk_spgemm_forward_fused: block_rows must be a positive multiple of 16");
+    MAXK_REQUIRE(copy_ctas != 0 && copy_ctas >= -1024 && copy_ctas <= 1024,
+                 "maxk_spgemm_forward_fused: copy_ctas out of range");
+    MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "maxk_spgemm_forward_fused: out is NULL");
+    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
+                 "maxk_spgemm_forward_fused: out and warp4 must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PeerArgs pa{};
+    pa.copy_ctas = copy_ctas < 0 ? -copy_ctas : copy_ctas;
+    pa.use_tma = copy_ctas > 0 ? 1 : 0;  // negative count: plain load/store copy (measurement knob)
+    pa.world = world;
+    pa.rank = rank;
+    pa.k = k;
+    pa.epoch = epoch;
+    pa.block_rows = ctx->block_rows;
+    pa.wait_from_task = wait_from_task;
+    for (int r = 0; r < world; ++r) {
+        MAXK_REQUIRE(ctx->g_data[r] && ctx->g_index[r] && ctx->flags[r],
+                     "maxk_spgemm_forward_fused: buffers of rank %d are not mapped", r);
+        MAXK_REQUIRE(ctx->rows_of[r] >= 0 && ctx->rows_of[r] <= ctx->block_rows,
+                     "maxk_spgemm_forward_fused: rows_of[%d] exceeds block_rows", r);
+        pa.rows_of[r] = ctx->rows_of[r];
+        pa.g_data[r] = static_cast<float *>(ctx->g_data[r]);
+        pa.g_index[r] = static_cast<unsigned char *>(ctx->g_index[r]);
+        pa.flags[r] = static_cast<unsigned *>(ctx->flags[r]);
+    }
+    pa.local_sync = static_cast<unsigned *>(ctx->local_sync);
+    MAXK_REQUIRE(pa.local_sync != nullptr, "maxk_spgemm_forward_fused: local_sync is NULL");
+    MAXK_REQUIRE(warp4 || num_tasks == 0, "maxk_spgemm_forward_fused: warp4 is NULL");
+    // local-column and remote-column tasks of one row meet in `out` through reductions
+    if (num_rows_out > 0) {
+        MAXK_CUDA(cudaMemsetAsync(out, 0, (size_t)num_rows_out * d * sizeof(float), st));
+        count_launch();
+    }
+    int tpw = g_fwd_tasks_per_warp;
+    if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
+    FwdArgs a{warp4, num_tasks, indices, values, pa.g_data[rank], pa.g_index[rank], k, out, d,
+              tpw, /*accumulate=*/1, st, 1, num_rows_out, &pa};
+    // the copy CTAs must run even when this rank has no task at all: launch_fwd adds them
+    switch (k) {
+        case 8: return launch_fwd<FwdCfg<8, 1, true, 4, 8, 4, 4, true>>(a);
+        case 16: return launch_fwd<FwdCfg<16, 1, true, 2, 8, 4, 4, true>>(a);
+        case 32: return launch_fwd<FwdCfg<32, 1, true, 1, 8, 4, 4, true>>(a);
+        case 64: return launch_fwd<FwdCfg<32, 2, true, 1, 8, 2, 4, true>>(a);
+        case 96: return launch_fwd<FwdCfg<32, 3, true, 1, 8, 2, 2, true>>(a);
+        case 128: return launch_fwd<FwdCfg<32, 4, true, 1, 8, 2, 2, true>>(a);
+        case 256: return launch_fwd<FwdCfg<32, 8, true, 1, 8, 1, 2, true>>(a);
+        default: break;
+    }
+    set_error("maxk_spgemm_forward_fused: k=%d is not built for the fused path (8, 16, 32, 64, 96, 128, 256)", k);
     return MAXK_ERR_UNSUPPORTED;
 }

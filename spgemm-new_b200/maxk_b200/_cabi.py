@@ -43,6 +43,14 @@ PROTOTYPES = {
     "maxk_cbsr_record_bytes": (_i32, [_i32]),
     "maxk_cbsr_pack": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "maxk_cbsr_unpack": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "maxk_peer_alloc": (ctypes.c_int, [_i64, ctypes.POINTER(_vp), _vp]),
+    "maxk_peer_free": (ctypes.c_int, [_vp]),
+    "maxk_peer_open": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "maxk_peer_close": (ctypes.c_int, [_vp]),
+    "maxk_peer_publish": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp]),
+    "maxk_spgemm_forward_fused": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp, _i64, _i64, _vp, _vp, _vp,
+                                                 _i64, _i32, _i32, _vp]),
+    "maxk_reduce_scatter_pull": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp, _vp]),
     # reference-named shims (cuda_kernel_wrappers.cu:38-91); dim3 by value
     "spmm_kernel_opt2_sparse_v3_wrapper": (None, None),
     "spmm_kernel_opt2_sparse_backward_v3_wrapper": (None, None),

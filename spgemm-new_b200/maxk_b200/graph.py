@@ -85,8 +85,12 @@ class _DistAggregate(Function):
 class DistGraph:
     """Row block [bounds[rank], bounds[rank+1]) of a global CSR graph on this rank's GPU."""
 
-    def __init__(self, indptr, indices, bounds: List[int], rank: int, group=None, split: bool = True):
+    def __init__(self, indptr, indices, bounds: List[int], rank: int, group=None, split: bool = True,
+                 comm: str = "nccl"):
+        """comm: "nccl" (all-gather / reduce-scatter collectives, dist.DistAggregator) or "peer"
+        (fused kernels over NVLink peer memory, peer.PeerAggregator; k in 8, 16, 32*m)."""
         self.bounds, self.rank, self.group, self.split = list(bounds), rank, group, split
+        self.comm = comm
         lo, hi = bounds[rank], bounds[rank + 1]
         self.n_rows = hi - lo
         self.n_cols = indptr.numel() - 1
@@ -104,8 +108,13 @@ class DistGraph:
         key = (kind, k, feat_dim)
         if key not in self._aggs:
             vals = edge_values(self.indptr, self.indices, kind, self.n_cols, self._col_deg)
-            self._aggs[key] = DistAggregator(self.indptr, self.indices, vals, self.bounds, self.rank, k,
-                                             feat_dim, group=self.group, split=self.split)
+            if self.comm == "peer":
+                from .peer import PeerAggregator
+                self._aggs[key] = PeerAggregator(self.indptr, self.indices, vals, self.bounds, self.rank, k,
+                                                 feat_dim, group=self.group)
+            else:
+                self._aggs[key] = DistAggregator(self.indptr, self.indices, vals, self.bounds, self.rank, k,
+                                                 feat_dim, group=self.group, split=self.split)
         return self._aggs[key]
 
     def aggregate(self, sp_data, sp_index, kind: str, feat_dim: int):

@@ -1,0 +1,241 @@
+"""Multi-GPU MaxK aggregation over NVLink peer memory: the collectives are OUR kernels.
+
+Same partition and the same three calls as `dist.DistAggregator` (exchange / forward /
+backward), but nothing on the data path goes through NCCL:
+
+  * forward: ONE kernel (`maxk_spgemm_forward_fused`).  Its first CTAs push this rank's CBSR
+    block (k fp32 + k uint8 per node) straight into every peer's gathered buffer with 128-bit
+    stores over NVLink/NVSwitch, while the remaining CTAs already aggregate the edges whose
+    columns this rank owns; the tasks that read other ranks' columns start as soon as the
+    peers' blocks have arrived.  No separate all-gather launch, no second stream;
+  * backward: one SSpMM over all columns into a full-height CBSR-shaped partial gradient,
+    then a pull reduce-scatter kernel: every rank reads its own block out of all partials
+    (again over NVLink) and adds them in rank order -- deterministic, unlike a ring.
+
+Buffers that peers read are cudaMalloc'ed by the C library, exported as CUDA IPC handles and
+exchanged once through torch.distributed (host side only).  Step numbers ("epochs") published
+in flag words order producers and consumers; two sets of buffers alternate by epoch parity
+(see csrc/peer.cuh for the protocol and why no further handshake is needed).
+
+One process per GPU, all GPUs of one NVLink domain (<= 16 ranks).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi, ops
+from .dist import partition_rows_by_nnz, remap_columns  # noqa: F401  (re-exported)
+
+PEER_MAX = 16
+
+
+class PeerCtx(ctypes.Structure):
+    """Mirror of `maxk_peer_ctx` (include/maxk_b200.h)."""
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("k", ctypes.c_int32),
+                ("block_rows", ctypes.c_int32), ("rows_of", ctypes.c_int32 * PEER_MAX),
+                ("g_data", ctypes.c_void_p * PEER_MAX), ("g_index", ctypes.c_void_p * PEER_MAX),
+                ("partial", ctypes.c_void_p * PEER_MAX), ("flags", ctypes.c_void_p * PEER_MAX),
+                ("local_sync", ctypes.c_void_p)]
+
+
+class _RawCuda:
+    """A cudaMalloc'ed range seen through __cuda_array_interface__ (so torch can wrap it)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3}
+
+
+def _wrap(ptr: int, shape, dtype: torch.dtype, device) -> torch.Tensor:
+    typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_RawCuda(ptr, shape, typestr), device=device)
+
+
+class _Shared:
+    """One IPC-exported allocation of this rank plus the peers' mappings of theirs."""
+
+    def __init__(self, nbytes: int, rank: int, world: int, group):
+        lib = _cabi.load()
+        self.own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _cabi.check(lib.maxk_peer_alloc(int(nbytes), ctypes.byref(self.own), handle))
+        handles: List[bytes] = [b""] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs: List[int] = []
+        self._opened: List[int] = []
+        for r in range(world):
+            if r == rank:
+                self.ptrs.append(int(self.own.value))
+                continue
+            p = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+            _cabi.check(lib.maxk_peer_open(buf, ctypes.byref(p)))
+            self.ptrs.append(int(p.value))
+            self._opened.append(int(p.value))
+
+    def release(self):
+        lib = _cabi.load()
+        for p in self._opened:
+            lib.maxk_peer_close(ctypes.c_void_p(p))
+        self._opened = []
+        if self.own:
+            lib.maxk_peer_free(self.own)
+            self.own = ctypes.c_void_p()
+
+
+class PeerAggregator:
+    def __init__(self, indptr_loc, indices_glob, values_loc, bounds: List[int], rank: int, k: int,
+                 feat_dim: int = 256, group=None, copy_ctas: int = 32):
+        assert indptr_loc.is_cuda, "the peer-memory path is CUDA only"
+        self.group = group
+        self.rank, self.world = rank, len(bounds) - 1
+        assert self.world <= PEER_MAX, f"at most {PEER_MAX} ranks"
+        self.bounds = list(bounds)
+        self.k, self.d = int(k), int(feat_dim)
+        self.copy_ctas = int(copy_ctas)
+        self.n_local = bounds[rank + 1] - bounds[rank]
+        max_rows = max(bounds[i + 1] - bounds[i] for i in range(self.world))
+        self.block_rows = (max_rows + 15) // 16 * 16
+        self.max_rows = self.block_rows  # name used by DistAggregator's callers
+        self.n_pad = self.world * self.block_rows
+        dev = indptr_loc.device
+        self.device = dev
+        indptr_loc = indptr_loc.to(torch.int32).contiguous()
+        values_loc = values_loc.to(torch.float32).contiguous()
+        lo, hi = bounds[rank], bounds[rank + 1]
+        c = indices_glob.long()
+        pos = remap_columns(c, bounds, self.block_rows)  # row of the gathered buffer
+        # backward: one row-major list over all columns
+        self.b_indices = pos.contiguous()
+        self.b_values = values_loc
+        self.b_warp4 = ops.build_worklist(indptr_loc)
+        # forward: [tasks on own columns | tasks on other ranks' columns] over a concatenated CSR
+        is_loc = (c >= lo) & (c < hi)
+        rows = torch.repeat_interleave(torch.arange(self.n_local, device=dev),
+                                       (indptr_loc[1:] - indptr_loc[:-1]).long())
+        idx_parts, val_parts, w4_parts = [], [], []
+        edge_off = 0
+        for sel in (is_loc, ~is_loc):
+            deg = torch.bincount(rows[sel], minlength=self.n_local)
+            ip = torch.zeros(self.n_local + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(deg, 0, out=ip[1:])
+            w4 = ops.build_worklist(ip.to(torch.int32)).view(-1, 4).clone()
+            w4[:, 1] += edge_off
+            idx_parts.append(pos[sel])
+            val_parts.append(values_loc[sel])
+            w4_parts.append(w4)
+            edge_off += int(ip[-1])
+        self.f_indices = torch.cat(idx_parts).contiguous()
+        self.f_values = torch.cat(val_parts).contiguous()
+        self.f_warp4 = torch.cat(w4_parts).reshape(-1).contiguous()
+        self.wait_from_task = w4_parts[0].shape[0]
+        self.num_tasks = self.f_warp4.numel() // 4
+        self.num_edges = int(indices_glob.numel())
+        # peer-visible buffers, two sets alternating by epoch parity
+        self._shared = []
+        self._ctx = []
+        nb_data, nb_index = self.n_pad * self.k * 4, self.n_pad * self.k
+        flags = _Shared(256, rank, self.world, group)
+        self._shared.append(flags)
+        self.local_sync = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.g_data, self.g_index, self.partial = [], [], []
+        rows_of = [bounds[i + 1] - bounds[i] for i in range(self.world)]
+        for _ in range(2):
+            sd = _Shared(nb_data, rank, self.world, group)
+            si = _Shared(nb_index, rank, self.world, group)
+            sp = _Shared(nb_data, rank, self.world, group)
+            self._shared += [sd, si, sp]
+            ctx = PeerCtx()
+            ctx.world, ctx.rank, ctx.k, ctx.block_rows = self.world, rank, self.k, self.block_rows
+            for r in range(self.world):
+                ctx.rows_of[r] = rows_of[r]
+                ctx.g_data[r], ctx.g_index[r] = sd.ptrs[r], si.ptrs[r]
+                ctx.partial[r], ctx.flags[r] = sp.ptrs[r], flags.ptrs[r]
+            ctx.local_sync = self.local_sync.data_ptr()
+            self._ctx.append(ctx)
+            self.g_data.append(_wrap(sd.ptrs[rank], (self.n_pad, self.k), torch.float32, dev))
+            self.g_index.append(_wrap(si.ptrs[rank], (self.n_pad, self.k), torch.uint8, dev))
+            self.partial.append(_wrap(sp.ptrs[rank], (self.n_pad, self.k), torch.float32, dev))
+        self._flag_ptr = flags.ptrs[rank]
+        self.y = torch.zeros((self.n_local, self.d), dtype=torch.float32, device=dev)
+        self.rs_out = torch.zeros((max(self.n_local, 1), self.k), dtype=torch.float32, device=dev)
+        self._fwd_epoch = 0
+        self._bwd_epoch = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)  # every mapping exists before anybody launches
+
+    @classmethod
+    def from_global_csr(cls, indptr, indices, values, bounds, rank, k, feat_dim=256, **kw):
+        lo, hi = bounds[rank], bounds[rank + 1]
+        e0, e1 = int(indptr[lo]), int(indptr[hi])
+        ip = (indptr[lo:hi + 1] - indptr[lo]).to(torch.int32)
+        return cls(ip, indices[e0:e1].contiguous(), values[e0:e1].contiguous(), bounds, rank, k,
+                   feat_dim, **kw)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def own_block(self, parity: int):
+        """Views of this rank's rows inside the gathered buffers (TopK can write them in place)."""
+        r0 = self.rank * self.block_rows
+        return (self.g_data[parity][r0:r0 + self.n_local], self.g_index[parity][r0:r0 + self.n_local])
+
+    # ------------------------------------------------------------------------- forward
+    def topk_and_exchange(self, x_loc: torch.Tensor):
+        """TopK straight into the peer-visible buffer (no staging copy), then publish."""
+        par = (self._fwd_epoch + 1) & 1
+        ops.topk_cbsr(x_loc, self.k, out=self.own_block(par))
+        return self._publish_forward()
+
+    def exchange(self, sp_data_loc: torch.Tensor, sp_index_loc: torch.Tensor):
+        """Place this rank's CBSR block where the peers will pull it from and publish it.
+        Returns the gathered buffers of this step; the other ranks' blocks are only valid once
+        `forward` has run."""
+        par = (self._fwd_epoch + 1) & 1
+        d_own, i_own = self.own_block(par)
+        d_own.copy_(sp_data_loc)
+        i_own.copy_(sp_index_loc)
+        return self._publish_forward()
+
+    def _publish_forward(self):
+        # nothing to signal here: the fused forward kernel pushes the block itself and stream
+        # order already puts the TopK / copy above in front of it
+        self._fwd_epoch += 1
+        par = self._fwd_epoch & 1
+        return self.g_data[par], self.g_index[par]
+
+    def forward(self, g_data=None, g_index=None) -> torch.Tensor:
+        par = self._fwd_epoch & 1
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.load().maxk_spgemm_forward_fused(
+                ctypes.byref(self._ctx[par]), self._fwd_epoch, self.f_warp4.data_ptr(), self.num_tasks,
+                self.wait_from_task, self.f_indices.data_ptr(), self.f_values.data_ptr(),
+                self.y.data_ptr(), self.n_local, self.d, self.copy_ctas, self._stream()))
+        return self.y
+
+    # ------------------------------------------------------------------------ backward
+    def backward(self, dy_loc: torch.Tensor, g_index: torch.Tensor) -> torch.Tensor:
+        """-> dXc for the rows this rank owns, f32[n_local, k]."""
+        self._bwd_epoch += 1
+        par = self._bwd_epoch & 1
+        lib = _cabi.load()
+        ops.sspmm_backward(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index,
+                           out=self.partial[par])
+        with torch.cuda.device(self.device):
+            _cabi.check(lib.maxk_peer_publish(ctypes.c_void_p(self._flag_ptr + 4 * 1), self._bwd_epoch,
+                                              self._stream()))
+            _cabi.check(lib.maxk_reduce_scatter_pull(ctypes.byref(self._ctx[par]), self._bwd_epoch,
+                                                     self.rs_out.data_ptr(), self._stream()))
+        return self.rs_out[: self.n_local]
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody still reads our memory
+        self.g_data, self.g_index, self.partial = [], [], []
+        for s in self._shared:
+            s.release()
+        self._shared = []

@@ -382,6 +382,38 @@ def test_host_aggregator_pipelined_submit_result():
         host.result(0)
 
 
+@pytest.mark.parametrize("k,copy_ctas", [(32, 3), (16, -2), (64, 1), (8, 2)])
+def test_peer_memory_path_single_rank(ops, k, copy_ctas):
+    """The fused (push all-gather + SpGEMM) kernel and the pull reduce-scatter of maxk_b200.peer
+    on a one-rank job: IPC allocation, [own columns | other columns] task order, accumulate
+    flushes, epoch-parity buffers.  The multi-rank exchange itself is checked by
+    scripts/peer_check.py under torchrun (2 and 8 B200s, profiles/r01_peer_memory.md)."""
+    import socket
+    import torch.distributed as dist
+    from maxk_b200.peer import PeerAggregator
+    p = Problem(n=500, avg=70.0, k=k, seed=90 + k, empty_frac=0.1)
+    g = p.cuda()
+    own_pg = not dist.is_initialized()
+    if own_pg:
+        with socket.socket() as sk_:
+            sk_.bind(("127.0.0.1", 0))
+            port = sk_.getsockname()[1]
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        agg = PeerAggregator(g["indptr"], g["indices"], g["values"], [0, p.n], 0, k, 256,
+                             copy_ctas=copy_ctas)
+        for step in range(3):  # both buffer parities
+            gd, gi = agg.exchange(g["sp_data"], g["sp_index"]) if step else agg.topk_and_exchange(g["x"])
+            y = agg.forward(gd, gi)
+            dxc = agg.backward(g["dy"], gi)
+            assert_close(y, p.fwd_oracle(), f"fused forward step {step}")
+            assert_close(dxc, p.bwd_oracle(), f"pull reduce-scatter step {step}")
+        agg.close()
+    finally:
+        if own_pg:
+            dist.destroy_process_group()
+
+
 def test_reference_named_shims():
     """The reference's own extern "C" launch shims (cuda_kernel_wrappers.cu:38-91), same argument
     lists (dim3 by value), resolved from libmaxk_b200.so."""
