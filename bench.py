@@ -304,14 +304,14 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank))
-    sampler.start()
+    sampler.start()  # before the barrier: starting the sampler must not skew the ranks
     launches0 = _cabi.launch_count()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     t_start.record()
     for i in range(args.steps):
         if world == 1:
