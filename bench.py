@@ -237,7 +237,7 @@ def main():
 
     if world > 1:
         from maxk_b200.dist import DistAggregator, partition_rows_by_nnz
-        bounds = partition_rows_by_nnz(g["indptr"], world)
+        bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
         comm = args.comm
         agg = None
         if comm == "peer":

@@ -144,29 +144,44 @@ MAXK_API int maxk_cbsr_unpack(const void *records, int64_t n, int32_t k, float *
                      uint8_t *sp_index, void *stream);
 
 /* ---- multi-GPU over NVLink peer memory (new: the reference is single-GPU) -----
- * One process per GPU.  Buffers that peers read are allocated with maxk_peer_alloc, their
+ * One process per GPU.  Buffers that peers touch are allocated with maxk_peer_alloc, their
  * 64-byte CUDA IPC handles are exchanged by the host (torch.distributed in the Python layer)
- * and mapped with maxk_peer_open.  A maxk_peer_ctx lists, for every rank r of the job, this
- * process's mapping of r's buffers (entry [rank] = the process's own allocations):
- *   g_data / g_index  gathered CBSR operand, float32 / uint8 [world * block_rows, k]; rank r
- *                     writes rows [r * block_rows, r * block_rows + rows_of[r]) of its own
- *                     buffer itself (TopK in place) and the fused forward pushes them into
- *                     the same rows of every peer's buffer;
- *   partial           CBSR-shaped partial gradients, float32 [world * block_rows, k];
+ * and mapped with maxk_peer_open.  Rank r owns the node rows [row_start[r], row_start[r] +
+ * rows_of[r]) of the GLOBAL node numbering; every rank holds full-height buffers in that
+ * numbering, so CSR column ids need no remapping.  A maxk_peer_ctx lists, for every rank r of
+ * the job, this process's mapping of r's buffers (entry [rank] = the process's own):
+ *   g_data / g_index  gathered CBSR operand, float32 / uint8 [n_total, k]; rank r writes its own
+ *                     rows of its own buffer (TopK in place) and the fused forward pushes them
+ *                     into the same rows of the peers' buffers;
+ *   partial           CBSR-shaped partial gradients, float32 [n_total, k];
  *   flags             uint32[64] per rank, zero-initialised: [1] = last epoch whose partial
- *                     gradients are published, [16 + r] = last epoch whose CBSR block from
- *                     rank r has arrived in this rank's buffer (written by rank r);
+ *                     gradients are published, [16 + r] = last epoch whose CBSR rows from
+ *                     rank r have arrived in this rank's buffer (written by rank r);
  *   local_sync        uint32[4] in the process's own memory, zero-initialised.
+ * Exchange volume: per ordered pair (this rank -> peer p) either the whole block travels
+ * (send_rows[p] == NULL: "dense", TMA bulk copies) or only the rows p's edges reference
+ * (send_rows[p] = device int32 list of global row ids inside this rank's block, ascending;
+ * "halo" mode for sparse graphs, where an all-gather of everything would cost more than the
+ * aggregation itself).  recv_rows[p] / recv_count[p] is the mirror image: the rows of p's block
+ * that THIS rank's edges reference (NULL = treat the whole block as referenced).  The backward
+ * zeroes / the reduce-scatter pulls exactly those rows.  Both sides must take the dense/halo
+ * decision of a pair from the same numbers (list length vs rows_of).
  * Epochs are step numbers that only grow; buffers alternate between two contexts by epoch
- * parity so that nobody overwrites what a slower peer still reads.  block_rows % 16 == 0.
+ * parity so that nobody overwrites what a slower peer still reads.  row_start[r] * k % 16 == 0.
  * Every device-side wait is bounded (about 5 s) and traps instead of hanging.             */
 typedef struct maxk_peer_ctx {
-    int32_t world, rank, k, block_rows;
-    int32_t rows_of[MAXK_PEER_MAX];
+    int32_t world, rank, k, reserved;
+    int64_t n_total;
+    int64_t row_start[MAXK_PEER_MAX];
+    int64_t rows_of[MAXK_PEER_MAX];
     void *g_data[MAXK_PEER_MAX];
     void *g_index[MAXK_PEER_MAX];
     void *partial[MAXK_PEER_MAX];
     void *flags[MAXK_PEER_MAX];
+    const int32_t *send_rows[MAXK_PEER_MAX];
+    int64_t send_count[MAXK_PEER_MAX];
+    const int32_t *recv_rows[MAXK_PEER_MAX];
+    int64_t recv_count[MAXK_PEER_MAX];
     void *local_sync;
 } maxk_peer_ctx;
 
@@ -179,19 +194,23 @@ MAXK_API int maxk_peer_close(void *dev_ptr);
 /* Stream-ordered system-scope release store *flag_word = epoch (after the backward kernel on
  * the same stream: flags[rank] + 1). */
 MAXK_API int maxk_peer_publish(void *flag_word, uint32_t epoch, void *stream);
-/* Fused all-gather + forward SpGEMM: ONE kernel whose first copy_ctas CTAs push this rank's
- * CBSR block to the peers over NVLink while the others aggregate.  The work list / CSR is the
- * concatenation [tasks whose columns this rank owns | tasks reading other ranks' columns],
- * columns remapped to rows of the gathered buffer; tasks from wait_from_task on wait for the
- * peers' blocks to arrive.  out float32[num_rows_out, d] is defined by the call.  k = ctx->k must be
- * 8, 16 or a multiple of 32.                                                              */
+/* Fused all-gather + forward SpGEMM: ONE kernel whose first |copy_ctas| CTAs push this rank's
+ * CBSR rows to the peers over NVLink while the others aggregate (copy_ctas < 0: plain
+ * load/store copies instead of TMA bulk copies for dense pairs).  The work list / CSR is the
+ * concatenation [tasks whose columns this rank owns | tasks reading other ranks' columns];
+ * tasks from wait_from_task on wait for the peers' rows to arrive.  out float32[num_rows_out, d]
+ * is defined by the call.  k = ctx->k must be 8, 16 or a multiple of 32.                  */
 MAXK_API int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoch, const int32_t *warp4,
                               int64_t num_tasks, int64_t wait_from_task, const int32_t *indices,
                               const float *values, float *out, int64_t num_rows_out, int32_t d,
                               int32_t copy_ctas, void *stream);
+/* Before the backward SSpMM (called with accumulate != 0 on ctx->partial[rank]): zero the rows
+ * of this rank's partial buffer that its edges can touch -- its own block, and per peer the
+ * whole block (dense pair) or the recv_rows list (halo pair). */
+MAXK_API int maxk_peer_zero_partial(const maxk_peer_ctx *ctx, void *stream);
 /* Pull reduce-scatter: waits until every peer has published `epoch` in flags[.][1], then
- * out[i, :] = sum over ranks r (in rank order: deterministic) of partial_r[rank's block][i, :],
- * out float32[rows_of[rank], k].                                                          */
+ * out[i, :] = sum over ranks r of partial_r[row_start[rank] + i, :] (dense pairs: all rows, in
+ * rank order; halo pairs: only the send_rows, added with reductions), out float32[rows_of[rank], k]. */
 MAXK_API int maxk_reduce_scatter_pull(const maxk_peer_ctx *ctx, uint32_t epoch, float *out, void *stream);
 
 /* ---- reference-named launch shims (ref: cuda_kernel_wrappers.cu:38-91, declared in

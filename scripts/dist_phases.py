@@ -23,7 +23,7 @@ from maxk_b200.dist import DistAggregator, partition_rows_by_nnz  # noqa: E402
 shape = sys.argv[1] if len(sys.argv) > 1 else "reddit"
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 g = graphs.make_graph(shape, seed=0, device=dev, values="uniform")
-bounds = partition_rows_by_nnz(g["indptr"], world)
+bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
 agg = DistAggregator.from_global_csr(g["indptr"], g["indices"], g["values"], bounds, rank, k, 256)
 gen = torch.Generator(dev).manual_seed(123 + rank)
 x = torch.rand(agg.n_local, 256, device=dev, generator=gen)

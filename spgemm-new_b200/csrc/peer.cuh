@@ -2,15 +2,18 @@
 // buffers shared with CUDA IPC; the reference has no multi-GPU code at all).
 //
 // Protocol (all flags are monotonically increasing step numbers, "epochs"):
-//   * every rank owns a gathered CBSR buffer [world * block_rows, k] (values + selectors) that
-//     its peers have mapped.  TopK writes the rank's own block in place (stream order makes
-//     it visible to the fused forward kernel that follows);
+//   * every rank owns a gathered CBSR buffer [n_total, k] (values + selectors, global node
+//     numbering) that its peers have mapped.  TopK writes the rank's own rows in place (stream
+//     order makes them visible to the fused forward kernel that follows);
 //   * the fused forward kernel's first `copy_ctas` CTAs PUSH that block into every peer's
 //     buffer with 128-bit stores over NVLink -- posted writes stream at link speed from a few
 //     CTAs, whereas reads are capped by the outstanding requests one SM may have (measured:
 //     a pull delivered 1.7 GB/s per CTA whatever the unroll) -- and the last of them to finish
 //     raises flag word [16 + rank] = epoch in every peer's flag array (system-scope release
 //     after a system fence);
+//   * per peer either the whole block travels (dense pair, TMA path below) or only the rows
+//     that peer's edges reference (halo pair: a row list, 128-bit load/store copies) -- on
+//     sparse graphs an all-gather of everything costs more than the aggregation itself;
 //   * the other CTAs aggregate the tasks on this rank's own columns straight away and, before
 //     the first task that reads other ranks' columns, wait until the flag words of all peers
 //     in their OWN memory (local polling, nothing crosses NVLink) show the epoch;
@@ -30,9 +33,11 @@ struct PeerArgs {
     int copy_ctas, world, rank, k;
     int use_tma;  // push through cp.async.bulk (needs PEER_TMA_SMEM + 128 bytes of dynamic smem)
     unsigned epoch;
-    int block_rows;
     long long wait_from_task;
-    int rows_of[MAXK_PEER_MAX];
+    long long row_start[MAXK_PEER_MAX];
+    long long rows_of[MAXK_PEER_MAX];
+    const int *send_rows[MAXK_PEER_MAX];  // NULL: dense pair (whole block); else rows peer p needs
+    long long send_count[MAXK_PEER_MAX];
     float *g_data[MAXK_PEER_MAX];           // rank r's gathered value buffer ([rank] = own)
     unsigned char *g_index[MAXK_PEER_MAX];  // rank r's gathered selector buffer
     unsigned *flags[MAXK_PEER_MAX];         // rank r's flag words ([rank] = own)
@@ -210,7 +215,8 @@ __device__ __forceinline__ void peer_tma_fanout(const PeerArgs &a, unsigned char
         const long long off = byte_off + lo + c * PEER_TMA_CHUNK;
         for (int s = 1; s < a.world; ++s) {
             const int p = (a.rank + s) % a.world;
-            tma_store_chunk(dst_base[p] + off, stage_smem + st * PEER_TMA_CHUNK, nb);
+            if (a.send_rows[p] == nullptr)  // dense pair
+                tma_store_chunk(dst_base[p] + off, stage_smem + st * PEER_TMA_CHUNK, nb);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
@@ -219,12 +225,52 @@ __device__ __forceinline__ void peer_tma_fanout(const PeerArgs &a, unsigned char
 constexpr int PEER_FLAG_BWD = 1;       // flag word: partial gradients published
 constexpr int PEER_FLAG_ARRIVED = 16;  // flag words [16 + r]: CBSR block of rank r has arrived
 
-// copy CTAs of the fused forward kernel: push this rank's CBSR block to every other rank
+// halo pair: copy the listed rows (global ids) of the own block into the same rows of peer p's
+// buffers; a row is k*4 bytes of values + k bytes of selectors, moved in 16-byte units when
+// k % 16 == 0 (4-byte units otherwise).  All copy CTAs share every list.
+__device__ __forceinline__ void peer_push_rows(const PeerArgs &a, int p, int cta)
+{
+    const int *rows = a.send_rows[p];
+    const long long n = a.send_count[p];
+    const long long tid = (long long)cta * blockDim.x + threadIdx.x;
+    const long long nthr = (long long)a.copy_ctas * blockDim.x;
+    const int k = a.k;
+    if ((k & 15) == 0) {
+        const int uv = k >> 2, upr = uv + (k >> 4);  // 16-byte units: values, then selectors
+        for (long long i = tid; i < n * upr; i += nthr) {
+            const long long r = __ldg(rows + i / upr);
+            const int u = (int)(i % upr);
+            if (u < uv) {
+                const uint4 v = ld_peer_u4(reinterpret_cast<const uint4 *>(a.g_data[a.rank] + r * k) + u);
+                reinterpret_cast<uint4 *>(a.g_data[p] + r * k)[u] = v;
+            } else {
+                const uint4 v = ld_peer_u4(reinterpret_cast<const uint4 *>(a.g_index[a.rank] + r * k) + (u - uv));
+                reinterpret_cast<uint4 *>(a.g_index[p] + r * k)[u - uv] = v;
+            }
+        }
+    } else {
+        const int uv = k, upr = k + (k >> 2);  // 4-byte units (k % 4 == 0)
+        for (long long i = tid; i < n * upr; i += nthr) {
+            const long long r = __ldg(rows + i / upr);
+            const int u = (int)(i % upr);
+            if (u < uv)
+                reinterpret_cast<unsigned *>(a.g_data[p] + r * k)[u] =
+                    reinterpret_cast<const unsigned *>(a.g_data[a.rank] + r * k)[u];
+            else
+                reinterpret_cast<unsigned *>(a.g_index[p] + r * k)[u - uv] =
+                    reinterpret_cast<const unsigned *>(a.g_index[a.rank] + r * k)[u - uv];
+        }
+    }
+}
+
+// copy CTAs of the fused forward kernel: push this rank's CBSR rows to every other rank
 __device__ __forceinline__ void peer_push_block(const PeerArgs &a, int cta, unsigned char *smem)
 {
-    const long long row0 = (long long)a.rank * a.block_rows;
-    const long long nel = (long long)a.rows_of[a.rank] * a.k;
-    if (a.use_tma) {
+    const long long row0 = a.row_start[a.rank];
+    const long long nel = a.rows_of[a.rank] * a.k;
+    bool any_dense = false;
+    for (int r = 0; r < a.world; ++r) any_dense |= (r != a.rank && a.send_rows[r] == nullptr);
+    if (any_dense && a.use_tma) {
         __shared__ __align__(8) unsigned long long mbar[PEER_TMA_STAGES];
         if (threadIdx.x == 0) {
             const unsigned mbar0 = smem_u32(mbar);
@@ -249,19 +295,25 @@ __device__ __forceinline__ void peer_push_block(const PeerArgs &a, int cta, unsi
             const long long t0 = nel & ~15LL;
             for (int s = 1; s < a.world; ++s) {
                 const int p = (a.rank + s) % a.world;
+                if (a.send_rows[p] != nullptr) continue;
                 for (long long i = t0 + threadIdx.x; i < nel; i += blockDim.x)
                     a.g_index[p][row0 * a.k + i] = a.g_index[a.rank][row0 * a.k + i];
             }
         }
-    } else {
+    } else if (any_dense) {
         const unsigned char *own_d = reinterpret_cast<const unsigned char *>(a.g_data[a.rank] + row0 * a.k);
         const unsigned char *own_i = a.g_index[a.rank] + row0 * a.k;
         for (int s = 1; s < a.world; ++s) {
             const int p = (a.rank + s) % a.world;  // staggered: rank r writes to r+1 first
+            if (a.send_rows[p] != nullptr) continue;
             peer_copy_slice(reinterpret_cast<unsigned char *>(a.g_data[p] + row0 * a.k), own_d, nel * 4,
                             cta, a.copy_ctas);
             peer_copy_slice(a.g_index[p] + row0 * a.k, own_i, nel, cta, a.copy_ctas);
         }
+    }
+    for (int s = 1; s < a.world; ++s) {  // halo pairs
+        const int p = (a.rank + s) % a.world;
+        if (a.send_rows[p] != nullptr && a.send_count[p] > 0) peer_push_rows(a, p, cta);
     }
     __syncthreads();
     if (threadIdx.x == 0) {

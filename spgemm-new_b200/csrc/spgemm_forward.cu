@@ -591,8 +591,6 @@ extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoc
     MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
                  "maxk_spgemm_forward_fused: d=%d must be a multiple of 4 in [4,256]", d);
     MAXK_REQUIRE(k >= 1 && k <= d, "maxk_spgemm_forward_fused: k=%d must be in [1,d=%d]", k, d);
-    MAXK_REQUIRE(ctx->block_rows > 0 && ctx->block_rows % 16 == 0,
-                 "maxk_spgemm_forward_fused: block_rows must be a positive multiple of 16");
     MAXK_REQUIRE(copy_ctas != 0 && copy_ctas >= -1024 && copy_ctas <= 1024,
                  "maxk_spgemm_forward_fused: copy_ctas out of range");
     MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "maxk_spgemm_forward_fused: out is NULL");
@@ -607,18 +605,29 @@ extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoc
     pa.rank = rank;
     pa.k = k;
     pa.epoch = epoch;
-    pa.block_rows = ctx->block_rows;
     pa.wait_from_task = wait_from_task;
     for (int r = 0; r < world; ++r) {
         MAXK_REQUIRE(ctx->g_data[r] && ctx->g_index[r] && ctx->flags[r],
                      "maxk_spgemm_forward_fused: buffers of rank %d are not mapped", r);
-        MAXK_REQUIRE(ctx->rows_of[r] >= 0 && ctx->rows_of[r] <= ctx->block_rows,
-                     "maxk_spgemm_forward_fused: rows_of[%d] exceeds block_rows", r);
+        MAXK_REQUIRE(ctx->rows_of[r] >= 0 && ctx->row_start[r] >= 0 &&
+                         ctx->row_start[r] + ctx->rows_of[r] <= ctx->n_total,
+                     "maxk_spgemm_forward_fused: row range of rank %d is outside [0, n_total)", r);
+        MAXK_REQUIRE((ctx->row_start[r] * (int64_t)k) % 16 == 0,
+                     "maxk_spgemm_forward_fused: row_start[%d] * k must be a multiple of 16", r);
         pa.rows_of[r] = ctx->rows_of[r];
+        pa.row_start[r] = ctx->row_start[r];
+        pa.send_rows[r] = (r == rank) ? nullptr : ctx->send_rows[r];
+        pa.send_count[r] = ctx->send_count[r];
         pa.g_data[r] = static_cast<float *>(ctx->g_data[r]);
         pa.g_index[r] = static_cast<unsigned char *>(ctx->g_index[r]);
         pa.flags[r] = static_cast<unsigned *>(ctx->flags[r]);
     }
+    // halo pairs are moved row by row with ordinary loads and stores: that needs many threads in
+    // flight (a dependent list -> row -> store chain per 16 bytes), so the copy part of the grid
+    // grows to four CTAs per SM -- the aggregating CTAs mostly wait for those rows anyway
+    for (int r = 0; r < world; ++r)
+        if (r != rank && pa.send_rows[r] != nullptr && pa.send_count[r] > 0 && pa.copy_ctas < 4 * kNumSMs)
+            pa.copy_ctas = 4 * kNumSMs;
     pa.local_sync = static_cast<unsigned *>(ctx->local_sync);
     MAXK_REQUIRE(pa.local_sync != nullptr, "maxk_spgemm_forward_fused: local_sync is NULL");
     MAXK_REQUIRE(warp4 || num_tasks == 0, "maxk_spgemm_forward_fused: warp4 is NULL");

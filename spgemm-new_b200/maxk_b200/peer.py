@@ -10,7 +10,11 @@ backward), but nothing on the data path goes through NCCL:
     peers' blocks have arrived.  No separate all-gather launch, no second stream;
   * backward: one SSpMM over all columns into a full-height CBSR-shaped partial gradient,
     then a pull reduce-scatter kernel: every rank reads its own block out of all partials
-    (again over NVLink) and adds them in rank order -- deterministic, unlike a ring.
+    (again over NVLink) and adds them in rank order -- deterministic, unlike a ring;
+  * per (sender, receiver) pair either the whole block travels or -- "halo" mode, for sparse
+    graphs where an all-gather of every node's CBSR row would cost more than the aggregation --
+    only the rows the receiver's edges reference (row lists exchanged once at set-up).  The
+    buffers use the global node numbering, blocks need not be padded to equal size.
 
 Buffers that peers read are cudaMalloc'ed by the C library, exported as CUDA IPC handles and
 exchanged once through torch.distributed (host side only).  Step numbers ("epochs") published
@@ -36,9 +40,12 @@ PEER_MAX = 16
 class PeerCtx(ctypes.Structure):
     """Mirror of `maxk_peer_ctx` (include/maxk_b200.h)."""
     _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("k", ctypes.c_int32),
-                ("block_rows", ctypes.c_int32), ("rows_of", ctypes.c_int32 * PEER_MAX),
+                ("reserved", ctypes.c_int32), ("n_total", ctypes.c_int64),
+                ("row_start", ctypes.c_int64 * PEER_MAX), ("rows_of", ctypes.c_int64 * PEER_MAX),
                 ("g_data", ctypes.c_void_p * PEER_MAX), ("g_index", ctypes.c_void_p * PEER_MAX),
                 ("partial", ctypes.c_void_p * PEER_MAX), ("flags", ctypes.c_void_p * PEER_MAX),
+                ("send_rows", ctypes.c_void_p * PEER_MAX), ("send_count", ctypes.c_int64 * PEER_MAX),
+                ("recv_rows", ctypes.c_void_p * PEER_MAX), ("recv_count", ctypes.c_int64 * PEER_MAX),
                 ("local_sync", ctypes.c_void_p)]
 
 
@@ -89,30 +96,34 @@ class _Shared:
 
 class PeerAggregator:
     def __init__(self, indptr_loc, indices_glob, values_loc, bounds: List[int], rank: int, k: int,
-                 feat_dim: int = 256, group=None, copy_ctas: int = 32):
+                 feat_dim: int = 256, group=None, copy_ctas: int = 16, halo_threshold: float = 0.3):
+        """halo_threshold: a (sender, receiver) pair exchanges only the rows the receiver's edges
+        reference when those are fewer than this fraction of the sender's block, the whole block
+        otherwise (0 = always the whole block, > 1 = always row lists)."""
         assert indptr_loc.is_cuda, "the peer-memory path is CUDA only"
         self.group = group
         self.rank, self.world = rank, len(bounds) - 1
         assert self.world <= PEER_MAX, f"at most {PEER_MAX} ranks"
         self.bounds = list(bounds)
         self.k, self.d = int(k), int(feat_dim)
+        if any((b * self.k) % 16 for b in bounds[:-1]):
+            raise ValueError("row block starts must satisfy start * k % 16 == 0: use "
+                             "partition_rows_by_nnz(indptr, world, align=16)")
         self.copy_ctas = int(copy_ctas)
         self.n_local = bounds[rank + 1] - bounds[rank]
-        max_rows = max(bounds[i + 1] - bounds[i] for i in range(self.world))
-        self.block_rows = (max_rows + 15) // 16 * 16
-        self.max_rows = self.block_rows  # name used by DistAggregator's callers
-        self.n_pad = self.world * self.block_rows
+        self.n_total = int(bounds[-1])
         dev = indptr_loc.device
         self.device = dev
+        world = self.world
         indptr_loc = indptr_loc.to(torch.int32).contiguous()
         values_loc = values_loc.to(torch.float32).contiguous()
         lo, hi = bounds[rank], bounds[rank + 1]
+        rows_of = [bounds[i + 1] - bounds[i] for i in range(world)]
         c = indices_glob.long()
-        pos = remap_columns(c, bounds, self.block_rows)  # row of the gathered buffer
-        # backward: one row-major list over all columns
-        self.b_indices = pos.contiguous()
+        # the buffers use the global node numbering, so column ids need no remapping
+        self.b_indices = indices_glob.to(torch.int32).contiguous()
         self.b_values = values_loc
-        self.b_warp4 = ops.build_worklist(indptr_loc)
+        self.b_warp4 = ops.build_worklist(indptr_loc)  # backward: one row-major list, all columns
         # forward: [tasks on own columns | tasks on other ranks' columns] over a concatenated CSR
         is_loc = (c >= lo) & (c < hi)
         rows = torch.repeat_interleave(torch.arange(self.n_local, device=dev),
@@ -125,7 +136,7 @@ class PeerAggregator:
             torch.cumsum(deg, 0, out=ip[1:])
             w4 = ops.build_worklist(ip.to(torch.int32)).view(-1, 4).clone()
             w4[:, 1] += edge_off
-            idx_parts.append(pos[sel])
+            idx_parts.append(self.b_indices[sel])
             val_parts.append(values_loc[sel])
             w4_parts.append(w4)
             edge_off += int(ip[-1])
@@ -135,31 +146,64 @@ class PeerAggregator:
         self.wait_from_task = w4_parts[0].shape[0]
         self.num_tasks = self.f_warp4.numel() // 4
         self.num_edges = int(indices_glob.numel())
-        # peer-visible buffers, two sets alternating by epoch parity
+        del rows, is_loc
+        # ---- who needs which rows: recv[p] = rows of p's block my edges reference ----------
+        bt = torch.tensor(bounds, device=dev, dtype=torch.long)
+        uniq = torch.unique(c)  # sorted
+        owner = torch.searchsorted(bt, uniq, right=True) - 1
+        recv = [uniq[owner == p].to(torch.int32).contiguous() for p in range(world)]
+        recv[rank] = recv[rank][:0]
+        del uniq, owner, c
+        recv_counts = torch.tensor([r.numel() for r in recv], device=dev, dtype=torch.int64)
+        if world > 1:
+            all_counts = [torch.zeros_like(recv_counts) for _ in range(world)]
+            dist.all_gather(all_counts, recv_counts, group=group)
+            send_counts = [int(all_counts[p][rank]) for p in range(world)]  # what p needs from me
+            send_flat = torch.empty(sum(send_counts), dtype=torch.int32, device=dev)
+            dist.all_to_all_single(send_flat, torch.cat(recv), send_counts,
+                                   [int(x) for x in recv_counts.tolist()], group=group)
+            send = list(torch.split(send_flat, send_counts))
+        else:
+            send_counts, send = [0], [recv[0]]
+        thr = float(halo_threshold)
+        # same numbers on both sides of a pair -> same decision
+        self.send_dense = [p != rank and send_counts[p] >= thr * max(rows_of[rank], 1) for p in range(world)]
+        self.recv_dense = [p != rank and recv[p].numel() >= thr * max(rows_of[p], 1) for p in range(world)]
+        self._dummy = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._send = [s.contiguous() for s in send]
+        self._recv = recv
+        self.exchange_rows = sum(rows_of[rank] if self.send_dense[p] else send_counts[p]
+                                 for p in range(world) if p != rank)
+        # ---- peer-visible buffers, two sets alternating by epoch parity ---------------------
         self._shared = []
         self._ctx = []
-        nb_data, nb_index = self.n_pad * self.k * 4, self.n_pad * self.k
-        flags = _Shared(256, rank, self.world, group)
+        nb_data, nb_index = max(self.n_total * self.k * 4, 16), max(self.n_total * self.k, 16)
+        flags = _Shared(256, rank, world, group)
         self._shared.append(flags)
         self.local_sync = torch.zeros(4, dtype=torch.int32, device=dev)
         self.g_data, self.g_index, self.partial = [], [], []
-        rows_of = [bounds[i + 1] - bounds[i] for i in range(self.world)]
         for _ in range(2):
-            sd = _Shared(nb_data, rank, self.world, group)
-            si = _Shared(nb_index, rank, self.world, group)
-            sp = _Shared(nb_data, rank, self.world, group)
+            sd = _Shared(nb_data, rank, world, group)
+            si = _Shared(nb_index, rank, world, group)
+            sp = _Shared(nb_data, rank, world, group)
             self._shared += [sd, si, sp]
             ctx = PeerCtx()
-            ctx.world, ctx.rank, ctx.k, ctx.block_rows = self.world, rank, self.k, self.block_rows
-            for r in range(self.world):
-                ctx.rows_of[r] = rows_of[r]
+            ctx.world, ctx.rank, ctx.k, ctx.n_total = world, rank, self.k, self.n_total
+            for r in range(world):
+                ctx.row_start[r], ctx.rows_of[r] = bounds[r], rows_of[r]
                 ctx.g_data[r], ctx.g_index[r] = sd.ptrs[r], si.ptrs[r]
                 ctx.partial[r], ctx.flags[r] = sp.ptrs[r], flags.ptrs[r]
+                if r != rank:
+                    ctx.send_count[r], ctx.recv_count[r] = send_counts[r], recv[r].numel()
+                    ctx.send_rows[r] = None if self.send_dense[r] else (
+                        self._send[r].data_ptr() if send_counts[r] else self._dummy.data_ptr())
+                    ctx.recv_rows[r] = None if self.recv_dense[r] else (
+                        recv[r].data_ptr() if recv[r].numel() else self._dummy.data_ptr())
             ctx.local_sync = self.local_sync.data_ptr()
             self._ctx.append(ctx)
-            self.g_data.append(_wrap(sd.ptrs[rank], (self.n_pad, self.k), torch.float32, dev))
-            self.g_index.append(_wrap(si.ptrs[rank], (self.n_pad, self.k), torch.uint8, dev))
-            self.partial.append(_wrap(sp.ptrs[rank], (self.n_pad, self.k), torch.float32, dev))
+            self.g_data.append(_wrap(sd.ptrs[rank], (self.n_total, self.k), torch.float32, dev))
+            self.g_index.append(_wrap(si.ptrs[rank], (self.n_total, self.k), torch.uint8, dev))
+            self.partial.append(_wrap(sp.ptrs[rank], (self.n_total, self.k), torch.float32, dev))
         self._flag_ptr = flags.ptrs[rank]
         self.y = torch.zeros((self.n_local, self.d), dtype=torch.float32, device=dev)
         self.rs_out = torch.zeros((max(self.n_local, 1), self.k), dtype=torch.float32, device=dev)
@@ -181,7 +225,7 @@ class PeerAggregator:
 
     def own_block(self, parity: int):
         """Views of this rank's rows inside the gathered buffers (TopK can write them in place)."""
-        r0 = self.rank * self.block_rows
+        r0 = self.bounds[self.rank]
         return (self.g_data[parity][r0:r0 + self.n_local], self.g_index[parity][r0:r0 + self.n_local])
 
     # ------------------------------------------------------------------------- forward
@@ -223,8 +267,10 @@ class PeerAggregator:
         self._bwd_epoch += 1
         par = self._bwd_epoch & 1
         lib = _cabi.load()
+        with torch.cuda.device(self.device):
+            _cabi.check(lib.maxk_peer_zero_partial(ctypes.byref(self._ctx[par]), self._stream()))
         ops.sspmm_backward(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index,
-                           out=self.partial[par])
+                           out=self.partial[par], accumulate=True)
         with torch.cuda.device(self.device):
             _cabi.check(lib.maxk_peer_publish(ctypes.c_void_p(self._flag_ptr + 4 * 1), self._bwd_epoch,
                                               self._stream()))

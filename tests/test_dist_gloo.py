@@ -138,6 +138,17 @@ def test_partition_and_remap_helpers():
         b = partition_rows_by_nnz(indptr, world)
         assert len(b) == world + 1 and b[0] == 0 and b[-1] == 6
         assert all(b[i] <= b[i + 1] for i in range(world))
+    # alignment and the row-aware cost model (skewed graph: 4 hub rows, 4000 rows of degree 1)
+    from maxk_b200.dist import row_cost_in_edges
+    deg = torch.cat([torch.full((4,), 1000), torch.ones(4000)]).long()
+    skew = torch.zeros(4005, dtype=torch.int64)
+    torch.cumsum(deg, 0, out=skew[1:])
+    by_nnz = partition_rows_by_nnz(skew, 2, align=16)
+    by_cost = partition_rows_by_nnz(skew, 2, align=16, row_cost=row_cost_in_edges(16))
+    assert by_nnz[1] % 16 == 0 and by_cost[1] % 16 == 0
+    assert by_nnz[1] <= 16                      # edges only: one rank gets nearly every row
+    assert 1000 < by_cost[1] < 3000             # rows weigh 11.6 edges each at k=16
+    assert abs(row_cost_in_edges(32) - 2048 / 336) < 1e-9
     bounds = [0, 3, 4, 10]
     cols = torch.tensor([0, 2, 3, 4, 9], dtype=torch.int32)
     pos = remap_columns(cols, bounds, max_rows=6)
