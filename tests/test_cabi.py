@@ -62,6 +62,45 @@ def test_argument_errors_without_gpu(lib):
         _cabi.check(rc)
 
 
+def test_peer_ctx_struct_matches_header(tmp_path):
+    """The ctypes mirror of `maxk_peer_ctx` has the size and field offsets the C compiler gives
+    the struct in include/maxk_b200.h (the multi-GPU part of the ABI is a struct by pointer)."""
+    import subprocess
+    from maxk_b200.peer import PEER_MAX, PeerCtx
+    fields = [name for name, _ in PeerCtx._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "maxk_b200.h"', 'int main(void) {',
+            '  printf("%d %zu\\n", MAXK_PEER_MAX, sizeof(maxk_peer_ctx));']
+    prog += [f'  printf("{f} %zu\\n", offsetof(maxk_peer_ctx, {f}));' for f in fields]
+    prog += ['  return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    lines = subprocess.check_output([str(exe)], text=True).split("\n")
+    peer_max, size = (int(v) for v in lines[0].split())
+    assert peer_max == PEER_MAX and size == ctypes.sizeof(PeerCtx)
+    for line in lines[1:]:
+        if line:
+            name, off = line.split()
+            assert getattr(PeerCtx, name).offset == int(off), name
+
+
+def test_peer_argument_errors_without_gpu(lib):
+    from maxk_b200 import _cabi
+    from maxk_b200.peer import PeerCtx
+    h = _cabi.load()
+    ctx = PeerCtx()
+    ctx.world, ctx.rank, ctx.k, ctx.n_total = 99, 0, 32, 10
+    assert h.maxk_reduce_scatter_pull(ctypes.byref(ctx), 1, None, None) == 1
+    assert b"out of range" in h.maxk_last_error()
+    ctx.world, ctx.rows_of[0], ctx.row_start[0] = 1, 10, 1     # start * k not 16-byte aligned... 32 is
+    ctx.k = 4                                                   # ... with k = 4 it is not
+    assert h.maxk_peer_zero_partial(ctypes.byref(ctx), None) == 1
+    assert b"multiple of 16" in h.maxk_last_error() or b"outside" in h.maxk_last_error()
+    assert h.maxk_spgemm_forward_fused(None, 1, None, 0, 0, None, None, None, 0, 256, 1, None) == 1
+    assert h.maxk_peer_publish(None, 1, None) == 1
+
+
 def test_python_surface_rejects_cpu_tensors(lib):
     from maxk_b200 import ops
     x = torch.rand(4, 256)
