@@ -82,6 +82,17 @@ def load_warp4_metadata(graph_name: str, num_warps: int = 12, warp_max_nz: int =
     return torch.from_numpy(data).cuda()
 
 
+def save_warp4_metadata(warp4: torch.Tensor, graph_name: str, num_warps: int = 12,
+                        warp_max_nz: int = 64) -> str:
+    """Write a work list in the reference's on-disk format (raw little-endian int32 quadruples,
+    kernels/generate_meta.py:47-48) so that the reference's C++ bench (spmm_maxk.cu:117) and
+    load_warp4_metadata read exactly what the device generator produced.  Returns the path."""
+    path = warp4_path(graph_name, num_warps, warp_max_nz)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    warp4.detach().cpu().numpy().astype(np.int32).tofile(path)
+    return path
+
+
 def generate_warp4_metadata(indptr: torch.Tensor, warp_max_nz: int = 64) -> torch.Tensor:
     """On-device replacement for kernels/generate_meta.py: int32[4W] on indptr's device."""
     return ops.build_worklist(indptr, warp_max_nz)

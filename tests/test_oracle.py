@@ -207,3 +207,31 @@ def test_cpu_path_port_matches_oracle():
     want = np.zeros((400, 256))
     np.put_along_axis(want, sp_index.astype(np.int64), dxc, axis=1)
     np.testing.assert_allclose(dx.numpy(), want, rtol=1e-5, atol=1e-6)
+
+
+def test_warp4_file_round_trip(tmp_path, monkeypatch):
+    """The on-disk work-list format: what save_warp4_metadata writes is byte for
+    byte what kernels/generate_meta.py writes for the same indptr (np.int32 quadruples, row-major),
+    and GraphDataLoader reads back the raw CSR files it saved."""
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "spgemm-new_b200"))
+    import maxk_cuda_kernels as mk
+    from graph_loader import GraphDataLoader
+    monkeypatch.chdir(tmp_path)
+    indptr, idx = O.synth_graph(300, 40.0, seed=9, empty_frac=0.1)
+    w4 = O.worklist(indptr)
+    path = mk.save_warp4_metadata(torch.from_numpy(w4), "toy")
+    assert path.endswith(os.path.join("w12_nz64_warp_4", "toy.warp4"))
+    raw = np.fromfile(path, dtype=np.int32)
+    np.testing.assert_array_equal(raw, w4.reshape(-1))
+    assert raw.reshape(-1, 4)[:, 3].max() == 0 and raw.reshape(-1, 4)[:, 2].max() <= 64
+    g = {"indptr": torch.from_numpy(indptr), "indices": torch.from_numpy(idx)}
+    GraphDataLoader.save_graph(g, str(tmp_path / "graphs"), "toy")
+    loader = GraphDataLoader(str(tmp_path / "graphs"))
+    assert loader.get_available_graphs() == ["toy"]
+    back = loader.load_graph("toy")
+    np.testing.assert_array_equal(back["indptr"].numpy(), indptr)
+    np.testing.assert_array_equal(back["indices"].numpy(), idx)
+    assert back["v_num"] == 300 and back["e_num"] == idx.shape[0]
