@@ -100,8 +100,43 @@ class PeerAggregator:
         """halo_threshold: a (sender, receiver) pair exchanges only the rows the receiver's edges
         reference when those are fewer than this fraction of the sender's block, the whole block
         otherwise (0 = always the whole block, > 1 = always row lists)."""
-        assert indptr_loc.is_cuda, "the peer-memory path is CUDA only"
         self.group = group
+        self._plan(indptr_loc, indices_glob, values_loc, bounds, rank, k, feat_dim, copy_ctas,
+                   halo_threshold)
+        world, dev = self.world, self.device
+        # ---- tell every owner which of its rows this rank references -------------------------
+        recv = self._recv
+        recv_counts = torch.tensor([r.numel() for r in recv], device=dev, dtype=torch.int64)
+        if world > 1:
+            all_counts = [torch.zeros_like(recv_counts) for _ in range(world)]
+            dist.all_gather(all_counts, recv_counts, group=group)
+            send_counts = [int(all_counts[p][rank]) for p in range(world)]  # what p needs from me
+            send_flat = torch.empty(sum(send_counts), dtype=torch.int32, device=dev)
+            dist.all_to_all_single(send_flat, torch.cat(recv), send_counts,
+                                   [int(x) for x in recv_counts.tolist()], group=group)
+            send = list(torch.split(send_flat, send_counts))
+        else:
+            send = [recv[0]]
+        # ---- peer-visible buffers (CUDA IPC), two sets alternating by epoch parity -----------
+        nb_data, nb_index = max(self.n_total * self.k * 4, 16), max(self.n_total * self.k, 16)
+        flags = _Shared(256, rank, world, group)
+        self._shared = [flags]
+        tables = []
+        for _ in range(2):
+            sd = _Shared(nb_data, rank, world, group)
+            si = _Shared(nb_index, rank, world, group)
+            sp = _Shared(nb_data, rank, world, group)
+            self._shared += [sd, si, sp]
+            tables.append((sd.ptrs, si.ptrs, sp.ptrs))
+        self._wire(send, flags.ptrs, tables)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)  # every mapping exists before anybody launches
+
+    # -------------------------------------------------------------------------- set-up
+    def _plan(self, indptr_loc, indices_glob, values_loc, bounds, rank, k, feat_dim, copy_ctas,
+              halo_threshold):
+        """Everything a rank can work out alone: task lists and the rows it references."""
+        assert indptr_loc.is_cuda, "the peer-memory path is CUDA only"
         self.rank, self.world = rank, len(bounds) - 1
         assert self.world <= PEER_MAX, f"at most {PEER_MAX} ranks"
         self.bounds = list(bounds)
@@ -110,6 +145,7 @@ class PeerAggregator:
             raise ValueError("row block starts must satisfy start * k % 16 == 0: use "
                              "partition_rows_by_nnz(indptr, world, align=16)")
         self.copy_ctas = int(copy_ctas)
+        self.halo_threshold = float(halo_threshold)
         self.n_local = bounds[rank + 1] - bounds[rank]
         self.n_total = int(bounds[-1])
         dev = indptr_loc.device
@@ -118,7 +154,7 @@ class PeerAggregator:
         indptr_loc = indptr_loc.to(torch.int32).contiguous()
         values_loc = values_loc.to(torch.float32).contiguous()
         lo, hi = bounds[rank], bounds[rank + 1]
-        rows_of = [bounds[i + 1] - bounds[i] for i in range(world)]
+        self.rows_of = [bounds[i + 1] - bounds[i] for i in range(world)]
         c = indices_glob.long()
         # the buffers use the global node numbering, so column ids need no remapping
         self.b_indices = indices_glob.to(torch.int32).contiguous()
@@ -146,53 +182,38 @@ class PeerAggregator:
         self.wait_from_task = w4_parts[0].shape[0]
         self.num_tasks = self.f_warp4.numel() // 4
         self.num_edges = int(indices_glob.numel())
-        del rows, is_loc
-        # ---- who needs which rows: recv[p] = rows of p's block my edges reference ----------
+        # who needs which rows: recv[p] = rows of p's block this rank's edges reference
         bt = torch.tensor(bounds, device=dev, dtype=torch.long)
         uniq = torch.unique(c)  # sorted
         owner = torch.searchsorted(bt, uniq, right=True) - 1
         recv = [uniq[owner == p].to(torch.int32).contiguous() for p in range(world)]
         recv[rank] = recv[rank][:0]
-        del uniq, owner, c
-        recv_counts = torch.tensor([r.numel() for r in recv], device=dev, dtype=torch.int64)
-        if world > 1:
-            all_counts = [torch.zeros_like(recv_counts) for _ in range(world)]
-            dist.all_gather(all_counts, recv_counts, group=group)
-            send_counts = [int(all_counts[p][rank]) for p in range(world)]  # what p needs from me
-            send_flat = torch.empty(sum(send_counts), dtype=torch.int32, device=dev)
-            dist.all_to_all_single(send_flat, torch.cat(recv), send_counts,
-                                   [int(x) for x in recv_counts.tolist()], group=group)
-            send = list(torch.split(send_flat, send_counts))
-        else:
-            send_counts, send = [0], [recv[0]]
-        thr = float(halo_threshold)
+        self._recv = recv
+
+    def _wire(self, send, flag_ptrs, tables):
+        """send[p]: rows of this rank's block that rank p references; flag_ptrs[r]: rank r's flag
+        words; tables: per epoch parity (g_data, g_index, partial) pointer lists indexed by rank --
+        all as seen from THIS process."""
+        rank, world, dev, bounds, rows_of = self.rank, self.world, self.device, self.bounds, self.rows_of
+        recv = self._recv
+        send_counts = [int(s.numel()) for s in send]
+        thr = self.halo_threshold
         # same numbers on both sides of a pair -> same decision
         self.send_dense = [p != rank and send_counts[p] >= thr * max(rows_of[rank], 1) for p in range(world)]
         self.recv_dense = [p != rank and recv[p].numel() >= thr * max(rows_of[p], 1) for p in range(world)]
         self._dummy = torch.zeros(4, dtype=torch.int32, device=dev)
         self._send = [s.contiguous() for s in send]
-        self._recv = recv
         self.exchange_rows = sum(rows_of[rank] if self.send_dense[p] else send_counts[p]
                                  for p in range(world) if p != rank)
-        # ---- peer-visible buffers, two sets alternating by epoch parity ---------------------
-        self._shared = []
-        self._ctx = []
-        nb_data, nb_index = max(self.n_total * self.k * 4, 16), max(self.n_total * self.k, 16)
-        flags = _Shared(256, rank, world, group)
-        self._shared.append(flags)
         self.local_sync = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.g_data, self.g_index, self.partial = [], [], []
-        for _ in range(2):
-            sd = _Shared(nb_data, rank, world, group)
-            si = _Shared(nb_index, rank, world, group)
-            sp = _Shared(nb_data, rank, world, group)
-            self._shared += [sd, si, sp]
+        self._ctx, self.g_data, self.g_index, self.partial = [], [], [], []
+        for d_ptrs, i_ptrs, p_ptrs in tables:
             ctx = PeerCtx()
             ctx.world, ctx.rank, ctx.k, ctx.n_total = world, rank, self.k, self.n_total
             for r in range(world):
                 ctx.row_start[r], ctx.rows_of[r] = bounds[r], rows_of[r]
-                ctx.g_data[r], ctx.g_index[r] = sd.ptrs[r], si.ptrs[r]
-                ctx.partial[r], ctx.flags[r] = sp.ptrs[r], flags.ptrs[r]
+                ctx.g_data[r], ctx.g_index[r] = d_ptrs[r], i_ptrs[r]
+                ctx.partial[r], ctx.flags[r] = p_ptrs[r], flag_ptrs[r]
                 if r != rank:
                     ctx.send_count[r], ctx.recv_count[r] = send_counts[r], recv[r].numel()
                     ctx.send_rows[r] = None if self.send_dense[r] else (
@@ -201,16 +222,50 @@ class PeerAggregator:
                         recv[r].data_ptr() if recv[r].numel() else self._dummy.data_ptr())
             ctx.local_sync = self.local_sync.data_ptr()
             self._ctx.append(ctx)
-            self.g_data.append(_wrap(sd.ptrs[rank], (self.n_total, self.k), torch.float32, dev))
-            self.g_index.append(_wrap(si.ptrs[rank], (self.n_total, self.k), torch.uint8, dev))
-            self.partial.append(_wrap(sp.ptrs[rank], (self.n_total, self.k), torch.float32, dev))
-        self._flag_ptr = flags.ptrs[rank]
+            self.g_data.append(_wrap(d_ptrs[rank], (self.n_total, self.k), torch.float32, dev))
+            self.g_index.append(_wrap(i_ptrs[rank], (self.n_total, self.k), torch.uint8, dev))
+            self.partial.append(_wrap(p_ptrs[rank], (self.n_total, self.k), torch.float32, dev))
+        self._flag_ptr = flag_ptrs[rank]
         self.y = torch.zeros((self.n_local, self.d), dtype=torch.float32, device=dev)
         self.rs_out = torch.zeros((max(self.n_local, 1), self.k), dtype=torch.float32, device=dev)
         self._fwd_epoch = 0
         self._bwd_epoch = 0
+
+    @classmethod
+    def local_group(cls, indptr, indices, values, bounds, k, feat_dim=256, copy_ctas=2,
+                    halo_threshold=0.3):
+        """All ranks of a job inside ONE process on ONE GPU (plain device tensors instead of IPC
+        mappings, no torch.distributed): the kernels, flags and row lists are exactly those of
+        the multi-process job.  For tests and debugging on a single-GPU box -- the ranks' kernels
+        wait for each other, so every step must be ENQUEUED for all ranks (one stream each)
+        before anything synchronises, and the grids must be small enough to be co-resident."""
+        world = len(bounds) - 1
+        aggs = []
+        for r in range(world):
+            lo, hi = bounds[r], bounds[r + 1]
+            e0, e1 = int(indptr[lo]), int(indptr[hi])
+            a = cls.__new__(cls)
+            a.group = None
+            a._shared = []
+            a._plan((indptr[lo:hi + 1] - indptr[lo]).to(torch.int32), indices[e0:e1].contiguous(),
+                    values[e0:e1].contiguous(), list(bounds), r, k, feat_dim, copy_ctas, halo_threshold)
+            aggs.append(a)
+        dev = aggs[0].device
+        n_total = aggs[0].n_total
+        keep = []
+
+        def alloc(shape, dtype):
+            ts = [torch.zeros(shape, dtype=dtype, device=dev) for _ in range(world)]
+            keep.append(ts)
+            return [t.data_ptr() for t in ts]
+        flag_ptrs = alloc((64,), torch.int32)
+        tables = [(alloc((max(n_total, 1), k), torch.float32), alloc((max(n_total, 1), k), torch.uint8),
+                   alloc((max(n_total, 1), k), torch.float32)) for _ in range(2)]
+        for r, a in enumerate(aggs):
+            a._keepalive = keep
+            a._wire([aggs[p]._recv[r] for p in range(world)], flag_ptrs, tables)
         torch.cuda.synchronize(dev)
-        dist.barrier(group=group)  # every mapping exists before anybody launches
+        return aggs
 
     @classmethod
     def from_global_csr(cls, indptr, indices, values, bounds, rank, k, feat_dim=256, **kw):
@@ -280,7 +335,8 @@ class PeerAggregator:
 
     def close(self):
         torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)  # nobody still reads our memory
+        if self._shared:
+            dist.barrier(group=self.group)  # nobody still reads our memory
         self.g_data, self.g_index, self.partial = [], [], []
         for s in self._shared:
             s.release()
