@@ -64,7 +64,8 @@ MAXK_API int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp);
  * to an instantiated value and up to the edges-per-instruction count); 0 = automatic. */
 MAXK_API int maxk_set_forward_copies(int copies);
 /* Bench/test hook: launch shape of the forward kernel (1 = 8-warp CTAs, 2 = 2-warp CTAs,
- * 3 = 8-warp CTAs with twice the gathers in flight); 0 = automatic. */
+ * 3 = 8-warp CTAs with twice the gathers in flight; 4-7 = experimental double-buffered
+ * gather batches, never chosen automatically); 0 = automatic. */
 MAXK_API int maxk_set_forward_depth(int depth);
 
 /* ---- a4: work list (replaces kernels/generate_meta.py:8-48 and the disk round trip of

@@ -104,11 +104,11 @@ __device__ __forceinline__ void peer_spin_until(const unsigned *flag, unsigned e
     }
 }
 
-// this CTA's share (cta of nctas) of a `bytes`-long copy; 16 x 128 bits in flight per thread
+// this CTA's share (cta of nctas) of a `bytes`-long copy; 8 x 128 bits in flight per thread
 __device__ __forceinline__ void peer_copy_slice(unsigned char *dst, const unsigned char *src,
                                                 long long bytes, int cta, int nctas)
 {
-    constexpr int U = 16;
+    constexpr int U = 8;  // 16 would spill under the aggregation kernel's 64-register cap
     const long long n16 = bytes >> 4;
     const long long lo = n16 * cta / nctas, hi = n16 * (cta + 1) / nctas;
     const uint4 *s = reinterpret_cast<const uint4 *>(src);

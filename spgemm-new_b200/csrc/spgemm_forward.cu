@@ -38,8 +38,11 @@ constexpr int FWD_STAGE = 64;  // staged (idx,val) pairs per warp == MAXK_WARP_M
 // EPL entries per lane (k > 32), EXACT: k == KL*EPL with aligned operands (vector gathers),
 // R accumulator copies, WPB warps per CTA, U gather instructions in flight, MINB CTAs/SM
 // the register budget is capped for.
-template <int KL_, int EPL_, bool EXACT_, int R_, int WPB_, int U_, int MINB_, bool PEER_ = false>
+template <int KL_, int EPL_, bool EXACT_, int R_, int WPB_, int U_, int MINB_, bool PEER_ = false,
+          bool DB_ = false>
 struct FwdCfg {
+    // DB: double-buffered gather batches (experimental launch shapes 4-7, see launch_fwd_r)
+    static constexpr bool DB = DB_;
     static constexpr int KL = KL_, EPL = EPL_, R = R_, WPB = WPB_, U = U_, MINB = MINB_;
     static constexpr bool EXACT = EXACT_;
     // PEER: fused multi-GPU variant -- the first CTAs of the grid push this rank's CBSR block
@@ -167,6 +170,66 @@ __device__ __forceinline__ void fwd_process_batch(const int2 *stage, int len, fl
             if (j + u * E < len)  // warp-uniform: skip instructions no lane needs
                 fwd_accumulate<C>(sl[u], acc_lane, __int_as_float(ev[u].y), k, lane,
                                   j + u * E + e < len);
+        }
+    }
+}
+
+// EXPERIMENTAL (launch shapes 4-7; written at the end of round 1 when the GPU budget was spent:
+// compiled, NOT yet run -- not reachable unless maxk_set_forward_depth asks for it).
+// Double-buffered batches: the gathers of batch b+1 are issued BEFORE the accumulates of
+// batch b, so a warp always has U gathers in flight instead of alternating between a gather
+// phase and an accumulate phase.  Motivation (profiles/r01_forward_pipeline.md): on the
+// products shape the kernel delivers 104 M edges/s per SM where the DRAM random-row floor is
+// 187 M/s -- by Little's law only ~36 of the 128 possible gathers per SM are in flight on
+// average; the batch form spends the rest of the time in staging reads and read-modify-write
+// chains with nothing outstanding.  (The per-edge rolling pipeline tried earlier put the
+// staging read, the gather and the accumulate of a slot into one dependent chain; this form
+// keeps them batched.)
+template <class C>
+__device__ __forceinline__ void fwd_load_batch(int2 (&ev)[C::U], Slice<C> (&sl)[C::U], const int2 *stage,
+                                               int j, int len, const float *sp_data,
+                                               const unsigned char *sp_index, int k, int lane)
+{
+    constexpr int U = C::U, E = C::E;
+    const int e = lane & (E - 1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        ev[u] = make_int2(0, 0);
+        if (j + u * E + e < len) ev[u] = stage[j + u * E + e];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (j + u * E + e < len) fwd_gather<C>(sl[u], sp_data, sp_index, ev[u].x, k, lane);
+}
+template <class C>
+__device__ __forceinline__ void fwd_acc_batch(const int2 (&ev)[C::U], const Slice<C> (&sl)[C::U],
+                                              float *acc_lane, int j, int len, int k, int lane)
+{
+    constexpr int U = C::U, E = C::E;
+    const int e = lane & (E - 1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (j + u * E < len)  // warp-uniform: skip instructions no lane needs
+            fwd_accumulate<C>(sl[u], acc_lane, __int_as_float(ev[u].y), k, lane, j + u * E + e < len);
+    }
+}
+template <class C>
+__device__ __forceinline__ void fwd_process_batch_db(const int2 *stage, int len, float *acc_lane,
+                                                     const float *sp_data,
+                                                     const unsigned char *sp_index, int k, int lane)
+{
+    constexpr int STEP = C::U * C::E;
+    int2 eva[C::U], evb[C::U];
+    Slice<C> sla[C::U], slb[C::U];
+    fwd_load_batch<C>(eva, sla, stage, 0, len, sp_data, sp_index, k, lane);
+    for (int j = 0; j < len; j += 2 * STEP) {
+        const bool has_b = j + STEP < len;  // warp-uniform
+        if (has_b) fwd_load_batch<C>(evb, slb, stage, j + STEP, len, sp_data, sp_index, k, lane);
+        fwd_acc_batch<C>(eva, sla, acc_lane, j, len, k, lane);
+        if (has_b) {
+            if (j + 2 * STEP < len)
+                fwd_load_batch<C>(eva, sla, stage, j + 2 * STEP, len, sp_data, sp_index, k, lane);
+            fwd_acc_batch<C>(evb, slb, acc_lane, j + STEP, len, k, lane);
         }
     }
 }
@@ -351,13 +414,19 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
         fwd_stage_edges(pre, stage, lane);
         if (has_next)  // next task's CSR slice streams in while this task's gathers run
             fwd_fetch_edges(pre, idx, val, ninfo.y, min(ninfo.z, FWD_STAGE), lane);
-        fwd_process_batch<C>(stage, min(len, FWD_STAGE), acc_lane, sp_data, sp_index, k, lane);
+        if constexpr (C::DB)
+            fwd_process_batch_db<C>(stage, min(len, FWD_STAGE), acc_lane, sp_data, sp_index, k, lane);
+        else
+            fwd_process_batch<C>(stage, min(len, FWD_STAGE), acc_lane, sp_data, sp_index, k, lane);
         for (int off = FWD_STAGE; off < len; off += FWD_STAGE) {  // len > 64: foreign work lists
             EdgeRegs more;
             const int ln = min(len - off, FWD_STAGE);
             fwd_fetch_edges(more, idx, val, loc + off, ln, lane);
             fwd_stage_edges(more, stage, lane);
-            fwd_process_batch<C>(stage, ln, acc_lane, sp_data, sp_index, k, lane);
+            if constexpr (C::DB)
+                fwd_process_batch_db<C>(stage, ln, acc_lane, sp_data, sp_index, k, lane);
+            else
+                fwd_process_batch<C>(stage, ln, acc_lane, sp_data, sp_index, k, lane);
         }
         info = ninfo;
         ninfo = nninfo;
@@ -442,6 +511,11 @@ static int launch_fwd_r(const FwdArgs &a)
         switch (a.depth) {
             case 2: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16>>(a);     // 2-warp CTAs
             case 3: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, 2 * U1, 3>>(a);  // deeper
+            // experimental, never chosen automatically: double-buffered gather batches
+            case 4: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, (U1 > 1 ? U1 / 2 : 1), 4, false, true>>(a);
+            case 5: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, 3, false, true>>(a);
+            case 6: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, (U1 > 1 ? U1 / 2 : 1), 16, false, true>>(a);
+            case 7: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 12, false, true>>(a);
             default: break;
         }
     }

@@ -197,6 +197,28 @@ def test_forward_launch_shapes(ops, k, shape):
         ops.set_tuning(-1, -1)
 
 
+@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
+                    reason="launch shapes 4-7 (double-buffered gather batches) were written after round 1's "
+                           "GPU budget was spent: compiled, not yet run; opt in with MAXK_EXPERIMENTAL=1")
+@pytest.mark.parametrize("shape", [4, 5, 6, 7])
+@pytest.mark.parametrize("k", [32, 16, 64, 8])
+def test_forward_experimental_shapes(ops, k, shape):
+    p = Problem(n=400, avg=45.0, k=k, seed=13 * k + shape, empty_frac=0.2)
+    g = p.cuda()
+    want = p.fwd_oracle()
+    try:
+        ops.set_forward_depth(shape)
+        for tpw in (-1, 1, 5):
+            ops.set_tuning(tpw, 0)
+            y = torch.full((p.n, 256), float("nan"), device="cuda")
+            ops.spgemm_forward(g["warp4"], g["indices"], g["values"], g["sp_data"], g["sp_index"],
+                               num_rows=p.n, out=y)
+            assert_close(y, want, f"k={k} shape={shape} tpw={tpw}")
+    finally:
+        ops.set_forward_depth(0)
+        ops.set_tuning(-1, -1)
+
+
 def test_forward_gap_rows_are_zeroed(ops):
     """Leading, interior and trailing rows without edges (and an output taller than the last
     task row) come back as zeros from a poisoned buffer."""
