@@ -101,22 +101,11 @@ class PeerAggregator:
         reference when those are fewer than this fraction of the sender's block, the whole block
         otherwise (0 = always the whole block, > 1 = always row lists)."""
         self.group = group
+        assert indptr_loc.is_cuda, "the peer-memory path is CUDA only"
         self._plan(indptr_loc, indices_glob, values_loc, bounds, rank, k, feat_dim, copy_ctas,
                    halo_threshold)
         world, dev = self.world, self.device
-        # ---- tell every owner which of its rows this rank references -------------------------
-        recv = self._recv
-        recv_counts = torch.tensor([r.numel() for r in recv], device=dev, dtype=torch.int64)
-        if world > 1:
-            all_counts = [torch.zeros_like(recv_counts) for _ in range(world)]
-            dist.all_gather(all_counts, recv_counts, group=group)
-            send_counts = [int(all_counts[p][rank]) for p in range(world)]  # what p needs from me
-            send_flat = torch.empty(sum(send_counts), dtype=torch.int32, device=dev)
-            dist.all_to_all_single(send_flat, torch.cat(recv), send_counts,
-                                   [int(x) for x in recv_counts.tolist()], group=group)
-            send = list(torch.split(send_flat, send_counts))
-        else:
-            send = [recv[0]]
+        send = self._exchange_lists(group)
         # ---- peer-visible buffers (CUDA IPC), two sets alternating by epoch parity -----------
         nb_data, nb_index = max(self.n_total * self.k * 4, 16), max(self.n_total * self.k, 16)
         flags = _Shared(256, rank, world, group)
@@ -133,10 +122,28 @@ class PeerAggregator:
         dist.barrier(group=group)  # every mapping exists before anybody launches
 
     # -------------------------------------------------------------------------- set-up
+    def _exchange_lists(self, group):
+        """Tell every owner which of its rows this rank's edges reference.  Returns send[p] = the
+        rows of THIS rank's block that rank p references (ascending global ids, int32)."""
+        recv, rank, world, dev = self._recv, self.rank, self.world, self.device
+        if world == 1:
+            return [recv[0]]
+        recv_counts = torch.tensor([r.numel() for r in recv], device=dev, dtype=torch.int64)
+        all_counts = [torch.zeros_like(recv_counts) for _ in range(world)]
+        dist.all_gather(all_counts, recv_counts, group=group)
+        send_counts = [int(all_counts[p][rank]) for p in range(world)]  # what p needs from me
+        send_flat = torch.empty(sum(send_counts), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(send_flat, torch.cat(recv), send_counts,
+                               [int(x) for x in recv_counts.tolist()], group=group)
+        return list(torch.split(send_flat, send_counts))
+
     def _plan(self, indptr_loc, indices_glob, values_loc, bounds, rank, k, feat_dim, copy_ctas,
-              halo_threshold):
-        """Everything a rank can work out alone: task lists and the rows it references."""
-        assert indptr_loc.is_cuda, "the peer-memory path is CUDA only"
+              halo_threshold, backend=None):
+        """Everything a rank can work out alone: task lists and the rows it references.
+        `backend`: operator set providing build_worklist (maxk_b200.ops; a CPU stand-in in the
+        gloo tests of this host logic)."""
+        if backend is None:
+            backend = ops
         self.rank, self.world = rank, len(bounds) - 1
         assert self.world <= PEER_MAX, f"at most {PEER_MAX} ranks"
         self.bounds = list(bounds)
@@ -159,7 +166,7 @@ class PeerAggregator:
         # the buffers use the global node numbering, so column ids need no remapping
         self.b_indices = indices_glob.to(torch.int32).contiguous()
         self.b_values = values_loc
-        self.b_warp4 = ops.build_worklist(indptr_loc)  # backward: one row-major list, all columns
+        self.b_warp4 = backend.build_worklist(indptr_loc)  # backward: one row-major list, all columns
         # forward: [tasks on own columns | tasks on other ranks' columns] over a concatenated CSR
         is_loc = (c >= lo) & (c < hi)
         rows = torch.repeat_interleave(torch.arange(self.n_local, device=dev),
@@ -170,7 +177,7 @@ class PeerAggregator:
             deg = torch.bincount(rows[sel], minlength=self.n_local)
             ip = torch.zeros(self.n_local + 1, dtype=torch.int64, device=dev)
             torch.cumsum(deg, 0, out=ip[1:])
-            w4 = ops.build_worklist(ip.to(torch.int32)).view(-1, 4).clone()
+            w4 = backend.build_worklist(ip.to(torch.int32)).view(-1, 4).clone()
             w4[:, 1] += edge_off
             idx_parts.append(self.b_indices[sel])
             val_parts.append(values_loc[sel])
@@ -247,6 +254,7 @@ class PeerAggregator:
             a = cls.__new__(cls)
             a.group = None
             a._shared = []
+            assert indptr.is_cuda, "the peer-memory path is CUDA only"
             a._plan((indptr[lo:hi + 1] - indptr[lo]).to(torch.int32), indices[e0:e1].contiguous(),
                     values[e0:e1].contiguous(), list(bounds), r, k, feat_dim, copy_ctas, halo_threshold)
             aggs.append(a)

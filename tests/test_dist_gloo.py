@@ -131,6 +131,77 @@ def test_two_rank_partitioned_aggregation_matches_single_process(split):
     np.testing.assert_allclose(g, g_ref, rtol=1e-5, atol=1e-6)
 
 
+def _peer_plan_worker(rank, world, port, q):
+    """Host logic of maxk_b200.peer on CPU: the plan ([own | other] task order over a concatenated
+    CSR, rows referenced per owner) and the halo row-list exchange over gloo.  The kernels are
+    replaced by the oracle: executing the plan's forward list on the FULL operand must give this
+    rank's rows of A * X, and the lists must be exactly the rows the peers' edges reference."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from maxk_b200.dist import partition_rows_by_nnz
+        from maxk_b200.peer import PeerAggregator
+        n, k, d, indptr, idx, val, x, dy = _problem()
+        tip, tix, tv = torch.from_numpy(indptr), torch.from_numpy(idx), torch.from_numpy(val)
+        bounds = partition_rows_by_nnz(tip, world, align=16)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        e0, e1 = int(indptr[lo]), int(indptr[hi])
+        a = PeerAggregator.__new__(PeerAggregator)
+        a._plan((tip[lo:hi + 1] - tip[lo]).to(torch.int32), tix[e0:e1].contiguous(), tv[e0:e1].contiguous(),
+                bounds, rank, k, d, 2, 0.3, backend=OracleOps)
+        send = a._exchange_lists(None)
+        sp_data, sp_index = O.topk_cbsr(x, k)
+        y = O.spgemm_forward(a.f_warp4.numpy(), a.f_indices.numpy(), a.f_values.numpy(), sp_data, sp_index,
+                             d, n_out=hi - lo)
+        g = O.sspmm_backward(a.b_warp4.numpy(), a.b_indices.numpy(), a.b_values.numpy(), dy[lo:hi], sp_index)
+        own_tasks = a.f_warp4.view(-1, 4)[: a.wait_from_task]
+        own_cols_ok = True
+        for row, loc, ln, _ in own_tasks.tolist():
+            c = a.f_indices[loc:loc + ln]
+            own_cols_ok &= bool(((c >= lo) & (c < hi)).all())
+        q.put((rank, bounds, y, g, [s.numpy().copy() for s in send], [r.numpy().copy() for r in a._recv],
+               own_cols_ok, a.wait_from_task, a.num_tasks))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_plan_and_halo_lists_over_gloo(world):
+    from oracle import oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_plan_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n, k, d, indptr, idx, val, x, dy = _problem()
+    sp_data, sp_index = O.topk_cbsr(x, k)
+    w4 = O.worklist(indptr)
+    y_ref = O.spgemm_forward(w4, idx, val, sp_data, sp_index, d)
+    g_ref = O.sspmm_backward(w4, idx, val, dy, sp_index)
+    bounds = res[0][1]
+    assert all(b % 16 == 0 for b in bounds[:-1]) and bounds[-1] == n
+    y = np.concatenate([r[2] for r in res])
+    np.testing.assert_allclose(y, y_ref, rtol=1e-5, atol=1e-6)      # [own | other] order, global columns
+    g = sum(r[3] for r in res)                                       # partial gradients add up
+    np.testing.assert_allclose(g, g_ref, rtol=1e-5, atol=1e-6)
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        assert res[r][6] and 0 < res[r][7] < res[r][8]               # tasks before wait_from touch own columns only
+        for p in range(world):
+            e0, e1 = int(indptr[bounds[p]]), int(indptr[bounds[p + 1]])
+            cols_p = np.unique(idx[e0:e1])                           # what rank p's edges reference
+            want = cols_p[(cols_p >= lo) & (cols_p < hi)] if p != r else cols_p[:0]
+            np.testing.assert_array_equal(res[r][4][p], want.astype(np.int32), err_msg=f"send[{r}->{p}]")
+            np.testing.assert_array_equal(res[p][5][r], want.astype(np.int32), err_msg=f"recv[{p}<-{r}]")
+
+
 def test_partition_and_remap_helpers():
     from maxk_b200.dist import partition_rows_by_nnz, remap_columns
     indptr = torch.tensor([0, 10, 10, 11, 50, 90, 100], dtype=torch.int32)
