@@ -1,0 +1,80 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE: how sharp are the SIMT tests?  Each mutant below is a one-line change to
+a COPY of spgemm-new_b200/csrc (a dropped barrier, an off-by-one, a wrong mask ...); the copy is
+built for the interpreter and tests/test_simt_kernels.py must FAIL on it.  Prints one line per
+mutant; exit code 1 if a mutant survives.
+
+    python tests/simt/mutation_check.py [name ...]
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "spgemm-new_b200", "csrc")
+
+# name: (file, old, new, occurrence)
+MUTANTS = {
+    "fwd-stage-no-barrier-after-write": ("spgemm_forward.cu", "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));\n    __syncwarp();",
+                                         "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));", 0),
+    "fwd-batch-runs-past-the-task": ("spgemm_forward.cu", "for (; j + STEP <= len; j += STEP) {  // every lane has an edge",
+                                     "for (; j + STEP <= len + 1; j += STEP) {", 0),
+    "fwd-shared-row-as-plain-store": ("spgemm_forward.cu", "const bool first_shared = accumulate || (prev_row == first_row);", "const bool first_shared = accumulate;", 0),
+    "fwd-gap-rows-not-zeroed": ("spgemm_forward.cu", "if (!accumulate) fwd_zero_rows(out, (int64_t)cur_row + 1, info.x, d, lane);", "", 0),
+    "fwd-db-second-batch-dropped": ("spgemm_forward.cu", "fwd_acc_batch<C>(evb, slb, acc_lane, j + STEP, len, k, lane);", "", 0),
+    "bwd-stage-no-barrier": ("sspmm_backward.cu", "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));\n    __syncwarp();", "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));", 0),
+    "bwd-dy-restage-no-barrier": ("sspmm_backward.cu", "            cur_row = info.x;\n            __syncwarp();", "            cur_row = info.x;", 0),
+    "bwd-selector-of-wrong-node": ("sspmm_backward.cu", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + q[u]);", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + (q[u] ^ 1));", 0),
+    "topk-emit-no-barrier": ("topk_cbsr.cu", "    __syncwarp();\n    unsigned char *oi = out_idx + row * k + lane;", "    unsigned char *oi = out_idx + row * k + lane;", 0),
+    "topk-tie-order": ("topk_cbsr.cu", "if (r0 < need) sel |= (1u << i);", "if (r0 <= need) sel |= (1u << i);", 0),
+    "topk-row-bound": ("topk_cbsr.cu", "if (row >= n) return;  // warp-uniform; no CTA barrier below\n\n", "if (row > n) return;\n\n", 0),
+    "worklist-scan-no-barrier": ("worklist.cu", "    if (lane == 31) warp_sums[warp] = inc;\n    __syncthreads();", "    if (lane == 31) warp_sums[warp] = inc;", 0),
+    "worklist-last-chunk-length": ("worklist.cu", "rec.z = min(nz, deg - nz * c_in_row);", "rec.z = nz;", 0),
+}
+
+# Mutants that SURVIVE because the change does not alter behaviour (listed so nobody re-adds them):
+# with MAXK_FWD_SYNCWARP=1 every fwd_accumulate ends in a __syncwarp, which already orders the
+# previous batch's staging reads before the next fwd_stage_edges write and the last accumulate
+# before fwd_flush_row -- the leading barriers of those two functions are redundant (they stay:
+# they cost nothing measurable and keep the functions correct on their own).
+EQUIVALENT = {
+    "fwd-stage-no-barrier-before-write": ("spgemm_forward.cu", "    __syncwarp();  // everyone is done reading the previous batch\n", "", 0),
+    "fwd-flush-no-leading-barrier": ("spgemm_forward.cu", "    constexpr int R = C::R;\n    __syncwarp();", "    constexpr int R = C::R;", 0),
+    # ... and the trailing barrier of fwd_flush_row is followed by fwd_stage_edges' leading one
+    "fwd-flush-no-trailing-barrier": ("spgemm_forward.cu", "        }\n    }\n    __syncwarp();\n}\n\n// coalesced fetch", "        }\n    }\n}\n\n// coalesced fetch", 0),
+}
+
+
+def run(name, spec):
+    fname, old, new, _ = spec
+    tmp = tempfile.mkdtemp(prefix="simt_mut_")
+    try:
+        src = os.path.join(tmp, "csrc")
+        shutil.copytree(CSRC, src)
+        path = os.path.join(src, fname)
+        text = open(path).read()
+        if text.count(old) < 1:
+            return "PATTERN NOT FOUND (update the mutant)"
+        open(path, "w").write(text.replace(old, new, 1))
+        env = dict(os.environ, SIMT_CSRC=src, SIMT_OUT=os.path.join(tmp, "out"))
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_simt_kernels.py"), "-x", "-q",
+                            "-p", "no:cacheprovider"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=1800)
+        if r.returncode == 0:
+            return "SURVIVED"
+        last = [ln for ln in r.stdout.splitlines() if ln.startswith(("FAILED", "ERROR"))]
+        return "killed  (" + (last[0][:110] if last else "rc=%d" % r.returncode) + ")"
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or [n for n, s in MUTANTS.items() if s]
+    bad = 0
+    for n in names:
+        res = run(n, MUTANTS.get(n) or EQUIVALENT[n])
+        bad += not res.startswith("killed")
+        print(f"{n:40s} {res}", flush=True)
+    sys.exit(1 if bad else 0)

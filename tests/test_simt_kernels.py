@@ -1,0 +1,256 @@
+"""CPU-side logic and memory-safety tests of the CUDA kernel SOURCES (no GPU needed).
+
+tests/simt/ compiles spgemm-new_b200/csrc/*.cu for the host and runs every CUDA thread as a
+fibre (warp collectives and barriers are rendezvous points; lanes are NOT in lock step between
+them, the weakest schedule CUDA allows).  Inputs and outputs sit between guard pages.  The cases
+mirror tests/test_gpu_parity.py -- same oracle, same tolerances -- at sizes the interpreter
+finishes in seconds.  This is a check of indexing, masks, barriers, tails and buffer bounds; the
+parity tests proper are the `-m gpu` ones, which run the real library on a B200.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import simt_lib as S
+from helpers import ATOL, RTOL, Problem
+from oracle import oracle as O
+
+
+def close(got, want, what=""):
+    np.testing.assert_allclose(got.astype(np.float64), want, rtol=RTOL, atol=ATOL, err_msg=what)
+
+
+@pytest.fixture(autouse=True)
+def _reset_knobs():
+    yield
+    S.set_tuning(-1, -1)
+    S.set_forward_depth(0)
+    S.set_forward_copies(0)
+
+
+# ------------------------------------------------------------------------------ a4
+def test_simt_worklist(golden_dir):
+    z = np.load(os.path.join(golden_dir, "worklist_cases.npz"))
+    for key in z.files:
+        if key.endswith("__indptr"):
+            name = key[:-8]
+            np.testing.assert_array_equal(S.worklist(z[key]), np.asarray(z[name + "__warp4"]).reshape(-1), err_msg=name)
+    for n, avg, seed, ef in ((1, 3.0, 0, 0.0), (1023, 9.0, 1, 0.2), (1024, 70.0, 2, 0.0), (1025, 200.0, 3, 0.5),
+                             (3000, 33.0, 4, 0.1)):
+        indptr, _ = O.synth_graph(n, avg, seed=seed, empty_frac=ef)
+        for nz in (64, 1, 7, 100):
+            np.testing.assert_array_equal(S.worklist(indptr, nz), O.worklist(indptr, nz).reshape(-1),
+                                          err_msg=f"n={n} nz={nz}")
+    assert S.worklist(np.zeros(1, np.int32)).size == 0
+    assert S.worklist(np.zeros(3000, np.int32)).size == 0
+    hub = np.array([0, 0, 300000, 300001, 300001], np.int32)
+    np.testing.assert_array_equal(S.worklist(hub), O.worklist(hub).reshape(-1))
+
+
+# ------------------------------------------------------------------------------ a1
+@pytest.mark.parametrize("d", [256, 128, 64, 32, 4])
+def test_simt_topk_bit_exact(d):
+    rng = np.random.default_rng(d)
+    for n in (1, 7, 8, 61):
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        for k in sorted({1, 2, 8, 16, 18, 32, 64, d} & set(range(1, d + 1))):
+            want_v, want_i = O.topk_cbsr(x, k)
+            v, i, dense = S.topk_f32(x, k, want_dense=True)
+            np.testing.assert_array_equal(i, want_i, err_msg=f"n={n} d={d} k={k}")
+            np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
+            np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
+    (dense,) = S.topk_f32(x, min(3, d), want_dense=True, want_cbsr=False)  # MaxK.forward only
+    np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, min(3, d)).view(np.uint32))
+
+
+def test_simt_topk_ties_and_specials():
+    rng = np.random.default_rng(11)
+    x = np.zeros((64, 256), np.float32)
+    x[0, :] = 1.0
+    x[1, 10:20] = 5.0
+    x[2, :] = -1.0; x[2, 200] = np.nan; x[2, 7] = np.inf
+    x[3, 0] = -0.0
+    x[4, :] = -np.inf
+    x[5, ::2] = np.nan
+    x[6:] = rng.integers(0, 4, size=(58, 256)).astype(np.float32)
+    x[40:] -= 2.0
+    for k in (1, 8, 16, 31, 32, 33, 64, 200, 256):
+        want_v, want_i = O.topk_cbsr(x, k)
+        v, i = S.topk_f32(x, k)
+        np.testing.assert_array_equal(i, want_i, err_msg=f"k={k}")
+        np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
+
+
+def test_simt_topk_goldens_from_torch(golden_dir):
+    z = np.load(os.path.join(golden_dir, "topk_cases.npz"))
+    n = 0
+    for key in z.files:
+        if key.startswith("idx_d"):
+            d, k = key[4:].split("_k")
+            v, i = S.topk_f32(z[f"x_{d}"], int(k))
+            np.testing.assert_array_equal(i, z[key], err_msg=key)
+            np.testing.assert_array_equal(v, z[f"val_{d}_k{k}"])
+            n += 1
+    assert n >= 12
+
+
+def test_simt_topk_u8():
+    rng = np.random.default_rng(3)
+    for d in (256, 64):
+        x = rng.integers(0, 256, size=(40, d), dtype=np.uint8)
+        x[0] = 0; x[1] = 255
+        for k in (1, 8, 32, 64):
+            want_v, want_i = O.topk_cbsr(x, k)
+            v, i = S.topk_u8(x, k)
+            np.testing.assert_array_equal(i, want_i)
+            np.testing.assert_array_equal(v, want_v)
+
+
+# ------------------------------------------------------------------------------ a2 / a3
+CASES = [
+    dict(k=32), dict(k=64), dict(k=16), dict(k=8), dict(k=18), dict(k=96), dict(k=128),
+    dict(k=1), dict(k=4), dict(k=256), dict(k=160),
+    dict(k=32, d=128), dict(k=16, d=64), dict(k=32, selector="torch"), dict(k=64, selector="random"),
+    dict(k=32, kind="uniform", avg=300.0, n=40, empty_frac=0.0),
+    dict(k=32, avg=3.0, n=1500, empty_frac=0.4),
+    dict(k=32, n=20, avg=1500.0, empty_frac=0.0),
+    dict(k=32, n=200, n_cols=700, avg=25.0),
+    dict(k=32, warp_max_nz=100), dict(k=16, warp_max_nz=200),
+    dict(k=32, warp_max_nz=5),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
+def test_simt_forward_backward_vs_oracle(case):
+    case = dict(n=250, **case) if "n" not in case else case
+    p = Problem(seed=len(str(case)), **case)
+    y = S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n, d=p.d)
+    close(y, p.fwd_oracle(), "forward")
+    dxc = S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index)
+    assert dxc.shape == (p.n_cols, p.k)
+    close(dxc, p.bwd_oracle(), "backward")
+
+
+@pytest.mark.parametrize("tpw", [1, 2, 3, 7, 64, 1000])
+def test_simt_run_length_invariance(tpw):
+    p = Problem(n=120, avg=150.0, k=32, seed=5, empty_frac=0.1)
+    S.set_tuning(tpw, tpw)
+    close(S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n), p.fwd_oracle())
+    close(S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index), p.bwd_oracle())
+
+
+@pytest.mark.parametrize("copies", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("k", [32, 64, 16, 8, 4, 2, 1, 18])
+def test_simt_forward_accumulator_copies(k, copies):
+    p = Problem(n=60, avg=100.0, k=k, seed=7 * k + copies, empty_frac=0.1)
+    want = p.fwd_oracle()
+    S.set_forward_copies(copies)
+    for tpw in (16, 2):
+        S.set_tuning(tpw, 0)
+        y = S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n)
+        close(y, want, f"k={k} copies={copies} tpw={tpw}")
+    y2 = S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n, accumulate=True, out_init=y)
+    close(y2, 2 * want, "accumulate")
+
+
+@pytest.mark.parametrize("shape", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("k", [32, 16, 64, 8, 128])
+def test_simt_forward_launch_shapes(k, shape):
+    """All launch shapes, the experimental double-buffered ones (4-7) included, from a poisoned
+    output buffer."""
+    p = Problem(n=200, avg=35.0, k=k, seed=31 * k + shape, empty_frac=0.3)
+    want = p.fwd_oracle()
+    S.set_forward_depth(shape)
+    for tpw in (-1, 1, 5):
+        S.set_tuning(tpw, 0)
+        close(S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n), want, f"k={k} shape={shape} tpw={tpw}")
+
+
+@pytest.mark.parametrize("shape", [0, 4, 7])
+def test_simt_forward_gap_rows_are_zeroed(shape):
+    n = 97
+    deg = np.zeros(n, np.int64)
+    deg[[5, 6, 40, 41, 42, 80]] = [3, 200, 1, 70, 64, 129]
+    indptr = np.zeros(n + 1, np.int32)
+    indptr[1:] = np.cumsum(deg)
+    rng = np.random.default_rng(3)
+    e = int(indptr[-1])
+    indices = rng.integers(0, n, e).astype(np.int32)
+    values = rng.random(e, dtype=np.float32)
+    x = rng.standard_normal((n, 256)).astype(np.float32)
+    sp_data, sp_index = O.topk_cbsr(x, 32)
+    w4 = O.worklist(indptr)
+    want = O.spgemm_forward(w4, indices, values, sp_data, sp_index, d=256, n_out=n + 10)
+    S.set_forward_depth(shape)
+    for tpw in (-1, 1, 2, 16):
+        S.set_tuning(tpw, 0)
+        close(S.spgemm_forward(w4, indices, values, sp_data, sp_index, n + 10), want, f"tpw={tpw}")
+
+
+def test_simt_output_is_defined_not_accumulated():
+    p = Problem(n=200, avg=20.0, k=32, seed=8, empty_frac=0.3)
+    y = S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n, out_init=np.full((p.n, 256), 7.0, np.float32))
+    close(y, p.fwd_oracle())
+    dxc = S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index, out_init=np.full((p.n, 32), -3.0, np.float32))
+    close(dxc, p.bwd_oracle())
+    dxc2 = S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index, out_init=dxc, accumulate=True)
+    close(dxc2, 2 * p.bwd_oracle())
+
+
+def test_simt_unaligned_operands_take_the_scalar_paths():
+    """sp_data not 16-byte / sp_index not 4-byte / dxc not 16-byte aligned: the library must fall
+    back to its scalar variants instead of issuing misaligned vector accesses."""
+    for k in (32, 64, 16, 20):
+        p = Problem(n=90, avg=40.0, k=k, seed=k)
+        close(S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n, data_align=4, index_align=1),
+              p.fwd_oracle(), f"forward k={k}")
+        close(S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index, dxc_align=4, index_align=1),
+              p.bwd_oracle(), f"backward k={k}")
+
+
+def test_simt_empty_inputs():
+    z32 = np.zeros(0, np.int32)
+    sp_data = np.random.default_rng(0).random((10, 32), dtype=np.float32)
+    sp_index = np.tile(np.arange(32, dtype=np.uint8), (10, 1))
+    y = S.spgemm_forward(z32, z32, np.zeros(0, np.float32), sp_data, sp_index, 10)
+    assert y.shape == (10, 256) and float(np.abs(y).sum()) == 0.0
+    dxc = S.sspmm_backward(z32, z32, np.zeros(0, np.float32), np.ones((10, 256), np.float32), sp_index)
+    assert dxc.shape == (10, 32) and float(np.abs(dxc).sum()) == 0.0
+    v, i = S.topk_f32(np.zeros((0, 256), np.float32), 32)
+    assert v.shape == (0, 32)
+
+
+# ------------------------------------------------------------------------------ a5
+def test_simt_layout_kernels_exact():
+    for k, d in ((32, 256), (8, 64), (18, 128), (64, 256), (1, 4)):
+        p = Problem(n=67, avg=5.0, k=k, d=d, seed=k)
+        dense = S.cbsr_scatter(p.sp_data, p.sp_index, d)
+        np.testing.assert_array_equal(dense, O.cbsr_scatter(p.sp_data, p.sp_index, d))
+        np.testing.assert_array_equal(S.cbsr_gather(dense, p.sp_index), p.sp_data)
+        np.testing.assert_array_equal(S.cbsr_mask(p.x, p.sp_index), O.maxk_dense(p.x, k))
+        if k % 4 == 0:
+            rec = S.cbsr_pack(p.sp_data, p.sp_index)
+            d2, i2 = S.cbsr_unpack(rec, 67, k)
+            np.testing.assert_array_equal(d2, p.sp_data)
+            np.testing.assert_array_equal(i2, p.sp_index)
+
+
+# ---------------------------------------------------------------- the interpreter itself
+def test_simt_reports_out_of_bounds_accesses():
+    """The guard pages work: an index array that is one element short is reported (with the
+    buffer and the CUDA thread), and the next call runs normally."""
+    p = Problem(n=80, avg=20.0, k=32, seed=3)
+    with pytest.raises(S.SimtError, match="indices"):
+        S.spgemm_forward(p.w4, p.idx[:-1], p.val, p.sp_data, p.sp_index, p.n)
+    with pytest.raises(S.SimtError, match="dxc"):
+        S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index, n_cbsr=p.n - 1)
+    close(S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n), p.fwd_oracle())
+
+
+def test_simt_library_is_not_the_product():
+    """The interpreter build is test infrastructure: the product binds lib/libmaxk_b200.so only."""
+    from maxk_b200 import _cabi
+    src = open(_cabi.__file__).read()
+    assert "simt" not in src.lower()
+    assert os.path.basename(_cabi.LIB_PATH) == "libmaxk_b200.so"
