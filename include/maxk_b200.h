@@ -64,8 +64,10 @@ MAXK_API int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp);
  * to an instantiated value and up to the edges-per-instruction count); 0 = automatic. */
 MAXK_API int maxk_set_forward_copies(int copies);
 /* Bench/test hook: launch shape of the forward kernel (1 = 8-warp CTAs, 2 = 2-warp CTAs,
- * 3 = 8-warp CTAs with twice the gathers in flight; 4-7 = experimental double-buffered
- * gather batches, never chosen automatically); 0 = automatic. */
+ * 3 = 8-warp CTAs with twice the gathers in flight; experimental and never chosen automatically:
+ * 4-7 = double-buffered gather batches, 8-11 = gathers through cp.async into a shared-memory
+ * ring (k = 16, 32, 64 with 16-byte aligned operands, otherwise the automatic shape));
+ * 0 = automatic. */
 MAXK_API int maxk_set_forward_depth(int depth);
 
 /* ---- a4: work list (replaces kernels/generate_meta.py:8-48 and the disk round trip of

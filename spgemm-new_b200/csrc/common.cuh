@@ -70,6 +70,22 @@ __device__ __forceinline__ void red_add_f1(float *addr, float a)
     asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 
+// Asynchronous 16-byte global -> shared copy (LDGSTS, L2 only: gathered rows are not re-read
+// through the L1).  Loads in flight hold no registers.  Completion: cp_async_wait<N>() (all but
+// the N most recent groups of the calling thread) followed by a barrier among the readers.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"l"(__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 template <typename T>

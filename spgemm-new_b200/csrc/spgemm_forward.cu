@@ -39,10 +39,16 @@ constexpr int FWD_STAGE = 64;  // staged (idx,val) pairs per warp == MAXK_WARP_M
 // R accumulator copies, WPB warps per CTA, U gather instructions in flight, MINB CTAs/SM
 // the register budget is capped for.
 template <int KL_, int EPL_, bool EXACT_, int R_, int WPB_, int U_, int MINB_, bool PEER_ = false,
-          bool DB_ = false>
+          bool DB_ = false, int RING_ = 0>
 struct FwdCfg {
     // DB: double-buffered gather batches (experimental launch shapes 4-7, see launch_fwd_r)
     static constexpr bool DB = DB_;
+    // RING > 0: gathers go through cp.async into a per-warp shared-memory ring of 2 x RING rows
+    // (experimental launch shapes 8-11); K is the compile-time k of the EXACT variants
+    static constexpr int RING = RING_;
+    static constexpr int K = (KL_ == 32) ? 32 * EPL_ : KL_;
+    static constexpr int ROW_BYTES = 5 * K;  // k fp32 values followed by k selector bytes
+    static_assert(RING_ == 0 || (EXACT_ && K % 16 == 0 && !DB_ && !PEER_), "ring rows move in 16-byte chunks");
     static constexpr int KL = KL_, EPL = EPL_, R = R_, WPB = WPB_, U = U_, MINB = MINB_;
     static constexpr bool EXACT = EXACT_;
     // PEER: fused multi-GPU variant -- the first CTAs of the grid push this rank's CBSR block
@@ -234,6 +240,93 @@ __device__ __forceinline__ void fwd_process_batch_db(const int2 *stage, int len,
     }
 }
 
+// EXPERIMENTAL (launch shapes 8-11; written when round 1's GPU budget was spent: compiled and
+// checked under the SIMT interpreter of tests/simt, NOT yet run on a GPU -- not reachable unless
+// maxk_set_forward_depth asks for it).  Gathers through LDGSTS (cp.async, 16-byte chunks) into a
+// per-warp shared-memory ring of two groups of RING rows: loads in flight hold no registers, so a
+// warp keeps up to 2 x RING CBSR rows in flight (the register path: U = 4) and a task of <= 32
+// edges issues all its gathers before it waits once.  Aimed at operands that miss the L2
+// (products shape: the kernel waits on DRAM latency with ~36 gathers in flight per SM where 64+
+// saturate the memory system, profiles/r01_forward_pipeline.md).  Cost: the gathered row crosses
+// the L1 data pipe twice more (shared-memory write + read), about 14.5 instead of 11 wavefronts
+// per edge -- a loss where that pipe is the bound (L2-resident operands).
+template <class C>
+__device__ __forceinline__ void fwd_ring_issue(const int2 *stage, int e0, int cnt, unsigned char *half,
+                                               const float *sp_data, const unsigned char *sp_index,
+                                               int lane)
+{
+    constexpr int K = C::K, CH = 5 * K / 16, VCH = K / 4;  // 16-byte chunks per row: values, selectors
+    const int n = cnt * CH;
+    for (int c = lane; c < n; c += 32) {
+        const int e = c / CH, p = c - e * CH;
+        const int64_t col = stage[e0 + e].x;
+        const unsigned char *src =
+            (p < VCH) ? reinterpret_cast<const unsigned char *>(sp_data) + col * (4 * K) + 16 * p
+                      : sp_index + col * K + 16 * (p - VCH);
+        cp_async16(half + e * C::ROW_BYTES + 16 * p, src);
+    }
+    cp_async_commit();  // every lane, also those without a chunk: group counts stay warp-uniform
+}
+template <class C>
+__device__ __forceinline__ void fwd_ring_accumulate(const int2 *stage, int e0, int cnt,
+                                                    const unsigned char *half, float *acc_lane, int k,
+                                                    int lane)
+{
+    constexpr int U = C::U, E = C::E, K = C::K;
+    const int es = lane & (E - 1);
+    for (int j = 0; j < cnt; j += U * E) {
+        Slice<C> sl[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = j + u * E + es;
+            w[u] = 0.f;
+            if (e < cnt) {
+                w[u] = __int_as_float(stage[e0 + e].y);
+                const unsigned char *row = half + e * C::ROW_BYTES;
+                if constexpr (C::KL < 32) {
+                    const int entry = lane / E;
+                    sl[u].v[0] = reinterpret_cast<const float *>(row)[entry];
+                    sl[u].s[0] = row[4 * K + entry];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < C::EPL; ++i) {  // conflict-free: consecutive words / bytes
+                        sl[u].v[i] = reinterpret_cast<const float *>(row)[lane + 32 * i];
+                        sl[u].s[i] = row[4 * K + lane + 32 * i];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (j + u * E < cnt)  // warp-uniform
+                fwd_accumulate<C>(sl[u], acc_lane, w[u], k, lane, j + u * E + es < cnt);
+        }
+    }
+}
+template <class C>
+__device__ __forceinline__ void fwd_process_batch_ring(const int2 *stage, int len, float *acc_lane,
+                                                       unsigned char *ring, const float *sp_data,
+                                                       const unsigned char *sp_index, int k, int lane)
+{
+    constexpr int G = C::RING, HALF = G * C::ROW_BYTES;
+    const int ng = (len + G - 1) / G;
+    fwd_ring_issue<C>(stage, 0, min(G, len), ring, sp_data, sp_index, lane);
+    if (ng > 1) fwd_ring_issue<C>(stage, G, min(G, len - G), ring + HALF, sp_data, sp_index, lane);
+    for (int g = 0; g < ng; ++g) {
+        if (g + 1 < ng)
+            cp_async_wait<1>();  // this lane's chunks of group g have landed ...
+        else
+            cp_async_wait<0>();
+        __syncwarp();            // ... and so have the other lanes'
+        unsigned char *half = ring + (g & 1) * HALF;
+        fwd_ring_accumulate<C>(stage, g * G, min(G, len - g * G), half, acc_lane, k, lane);
+        __syncwarp();            // everyone is done reading this half
+        if (g + 2 < ng)
+            fwd_ring_issue<C>(stage, (g + 2) * G, min(G, len - (g + 2) * G), half, sp_data, sp_index, lane);
+    }
+}
+
 // Sum the R copies of the row, write it out (plain store or vector reduction) and clear
 // the accumulator.  Copies of one column are contiguous (acc[c*R + r]).
 template <class C>
@@ -365,6 +458,10 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
     int2 *stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + C::WPB * d * C::R) +
                   warp * FWD_STAGE;
     float *acc_lane = acc + (lane & (C::R - 1));
+    unsigned char *ring = nullptr;  // RING: 2 * RING gathered rows of this warp, behind the staging area
+    if constexpr (C::RING > 0)
+        ring = smem_raw + (size_t)C::WPB * d * C::R * sizeof(float) + (size_t)C::WPB * FWD_STAGE * sizeof(int2) +
+               (size_t)warp * 2 * C::RING * C::ROW_BYTES;
 
     const int64_t t0 = (cta * C::WPB + warp) * tasks_per_warp;
     if (t0 >= num_tasks) return;  // no CTA-wide barrier below
@@ -414,7 +511,9 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
         fwd_stage_edges(pre, stage, lane);
         if (has_next)  // next task's CSR slice streams in while this task's gathers run
             fwd_fetch_edges(pre, idx, val, ninfo.y, min(ninfo.z, FWD_STAGE), lane);
-        if constexpr (C::DB)
+        if constexpr (C::RING > 0)
+            fwd_process_batch_ring<C>(stage, min(len, FWD_STAGE), acc_lane, ring, sp_data, sp_index, k, lane);
+        else if constexpr (C::DB)
             fwd_process_batch_db<C>(stage, min(len, FWD_STAGE), acc_lane, sp_data, sp_index, k, lane);
         else
             fwd_process_batch<C>(stage, min(len, FWD_STAGE), acc_lane, sp_data, sp_index, k, lane);
@@ -423,7 +522,9 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
             const int ln = min(len - off, FWD_STAGE);
             fwd_fetch_edges(more, idx, val, loc + off, ln, lane);
             fwd_stage_edges(more, stage, lane);
-            if constexpr (C::DB)
+            if constexpr (C::RING > 0)
+                fwd_process_batch_ring<C>(stage, ln, acc_lane, ring, sp_data, sp_index, k, lane);
+            else if constexpr (C::DB)
                 fwd_process_batch_db<C>(stage, ln, acc_lane, sp_data, sp_index, k, lane);
             else
                 fwd_process_batch<C>(stage, ln, acc_lane, sp_data, sp_index, k, lane);
@@ -452,13 +553,15 @@ struct FwdArgs {
     int depth;
     int64_t num_rows_out;
     const PeerArgs *peer;  // fused multi-GPU launch only
+    bool ring_ok;          // operands 16-byte aligned: the cp.async ring variants may run
 };
 
 template <class C>
 static int launch_fwd(const FwdArgs &a)
 {
     size_t smem = (size_t)C::WPB * a.d * C::R * sizeof(float) +
-                  (size_t)C::WPB * FWD_STAGE * sizeof(int2);
+                  (size_t)C::WPB * FWD_STAGE * sizeof(int2) +
+                  (size_t)C::WPB * 2 * C::RING * C::ROW_BYTES;
     if constexpr (C::PEER) {  // the copy CTAs stage their TMA chunks in the same dynamic smem
         if (a.peer->use_tma && smem < PEER_TMA_SMEM + 128) smem = PEER_TMA_SMEM + 128;
     }
@@ -517,6 +620,22 @@ static int launch_fwd_r(const FwdArgs &a)
             case 6: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, (U1 > 1 ? U1 / 2 : 1), 16, false, true>>(a);
             case 7: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 12, false, true>>(a);
             default: break;
+        }
+        // experimental, never chosen automatically: cp.async gather ring (k = 16, 32, 64 with
+        // 16-byte aligned operands; anything else takes the default shapes)
+        if constexpr (EXACT && (KL == 32 ? 32 * EPL : KL) % 16 == 0) {
+            if (a.ring_ok) {
+                switch (a.depth) {
+                    case 8: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16, false, false, 16>>(a);
+                    case 9: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16, false, false, 8>>(a);
+                    case 10: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, 4, false, false, 16>>(a);
+                    case 11: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, 4, false, false, 8>>(a);
+                    default: break;
+                }
+            }
+        }
+        if (a.depth >= 8) {  // ring asked for but not applicable: the automatic CTA shape
+            if (a.W < 2 * a.num_rows_out) return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16>>(a);
         }
     }
     if constexpr (R <= 4)
@@ -604,8 +723,10 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
     // CTA shape: mostly single-task rows (W < 2N) -> 2-warp CTAs, see launch_fwd_r
     int shape = g_fwd_depth;
     if (shape <= 0) shape = (num_tasks < 2 * num_rows_out) ? 2 : 1;
+    const bool ring_ok = ((reinterpret_cast<uintptr_t>(sp_data) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(sp_index) & 15) == 0);
     FwdArgs a{warp4, num_tasks, indices, values, sp_data, sp_index, k, out, d,
-              tpw, accumulate, st, shape, num_rows_out, nullptr};
+              tpw, accumulate, st, shape, num_rows_out, nullptr, ring_ok};
     // Output is DEFINED by this call without a memset of the whole of it: rows
     // shared between two runs are cleared here, rows without tasks inside the main kernel.
     if (!accumulate) {
@@ -713,7 +834,7 @@ extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoc
     int tpw = g_fwd_tasks_per_warp;
     if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
     FwdArgs a{warp4, num_tasks, indices, values, pa.g_data[rank], pa.g_index[rank], k, out, d,
-              tpw, /*accumulate=*/1, st, 1, num_rows_out, &pa};
+              tpw, /*accumulate=*/1, st, 1, num_rows_out, &pa, false};
     // the copy CTAs must run even when this rank has no task at all: launch_fwd adds them
     switch (k) {
         case 8: return launch_fwd<FwdCfg<8, 1, true, 4, 8, 4, 4, true>>(a);

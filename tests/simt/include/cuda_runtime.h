@@ -100,6 +100,12 @@ void syncwarp(unsigned mask);
 enum Op { OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_ADD, OP_MIN, OP_MAX, OP_UMIN, OP_UMAX, OP_AND, OP_OR, OP_BALLOT };
 uint64_t collective(unsigned mask, Op op, uint64_t value, int arg, int width);
 
+// cp.async (LDGSTS): the copy is performed as LATE as the PTX model allows -- when the issuing
+// thread waits for its group (or returns) -- so a missing wait or barrier reads stale shared memory
+void cp_async(void *smem_dst, const void *gmem_src, int bytes);
+void cp_async_commit();
+void cp_async_wait(int all_but_newest);
+
 void yield_spin();  // a polite spin-wait iteration (__nanosleep)
 long long clock_ticks();
 [[noreturn]] void trap(const char *why);

@@ -25,6 +25,9 @@ MUTANTS = {
     "fwd-shared-row-as-plain-store": ("spgemm_forward.cu", "const bool first_shared = accumulate || (prev_row == first_row);", "const bool first_shared = accumulate;", 0),
     "fwd-gap-rows-not-zeroed": ("spgemm_forward.cu", "if (!accumulate) fwd_zero_rows(out, (int64_t)cur_row + 1, info.x, d, lane);", "", 0),
     "fwd-db-second-batch-dropped": ("spgemm_forward.cu", "fwd_acc_batch<C>(evb, slb, acc_lane, j + STEP, len, k, lane);", "", 0),
+    "ring-no-barrier-after-wait": ("spgemm_forward.cu", "        __syncwarp();            // ... and so have the other lanes'\n", "", 0),
+    "ring-waits-for-too-little": ("spgemm_forward.cu", "            cp_async_wait<1>();  // this lane's chunks of group g have landed ...", "            cp_async_wait<2>();", 0),
+    "ring-selector-chunk-offset": ("spgemm_forward.cu", ": sp_index + col * K + 16 * (p - VCH);", ": sp_index + col * K + 16 * (p - VCH + 1);", 0),
     "bwd-stage-no-barrier": ("sspmm_backward.cu", "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));\n    __syncwarp();", "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));", 0),
     "bwd-dy-restage-no-barrier": ("sspmm_backward.cu", "            cur_row = info.x;\n            __syncwarp();", "            cur_row = info.x;", 0),
     "bwd-selector-of-wrong-node": ("sspmm_backward.cu", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + q[u]);", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + (q[u] ^ 1));", 0),
@@ -43,6 +46,8 @@ MUTANTS = {
 EQUIVALENT = {
     "fwd-stage-no-barrier-before-write": ("spgemm_forward.cu", "    __syncwarp();  // everyone is done reading the previous batch\n", "", 0),
     "fwd-flush-no-leading-barrier": ("spgemm_forward.cu", "    constexpr int R = C::R;\n    __syncwarp();", "    constexpr int R = C::R;", 0),
+    # ... as is the barrier between the ring accumulate and the re-issue into the same half
+    "ring-no-barrier-before-reissue": ("spgemm_forward.cu", "        __syncwarp();            // everyone is done reading this half\n", "", 0),
     # ... and the trailing barrier of fwd_flush_row is followed by fwd_stage_edges' leading one
     "fwd-flush-no-trailing-barrier": ("spgemm_forward.cu", "        }\n    }\n    __syncwarp();\n}\n\n// coalesced fetch", "        }\n    }\n}\n\n// coalesced fetch", 0),
 }

@@ -45,8 +45,17 @@ struct Warp {
 
 enum Wait { RUN, WAIT_WARP, WAIT_BLOCK, WAIT_SPIN, DONE };
 
+struct AsyncCopy {
+    void *dst;
+    const void *src;
+    int bytes;
+    long group;
+};
+
 struct Fibre {
     Thread t;
+    std::vector<AsyncCopy> copies;  // cp.async issued, not yet performed
+    long cp_group = 0;              // the group new copies join (open until commit_group)
     void *sp = nullptr;
     Wait wait = RUN;
     unsigned wait_mask = 0;
@@ -104,9 +113,23 @@ simt_ctx_switch:
 
 void to_scheduler() { simt_ctx_switch(&g_cur->sp, g_sched_sp); }
 
+void drain_copies(Fibre *f, long below_group)
+{
+    size_t keep = 0;
+    for (size_t i = 0; i < f->copies.size(); ++i) {
+        const AsyncCopy &c = f->copies[i];
+        if (c.group < below_group)
+            memcpy(c.dst, c.src, (size_t)c.bytes);
+        else
+            f->copies[keep++] = c;
+    }
+    f->copies.resize(keep);
+}
+
 [[noreturn]] void fibre_exit()
 {
     Fibre *f = g_cur;
+    drain_copies(f, f->cp_group + 1);  // outstanding copies still land after the thread returns
     f->wait = DONE;
     f->w->exited |= 1u << f->t.lane;
     --g_blk.alive;
@@ -418,6 +441,26 @@ uint64_t collective(unsigned mask, Op op, uint64_t value, int arg, int width)
     return r;
 }
 
+bool g_cp_async_eager = false;  // tests run both: data lands at once / as late as PTX allows
+
+void cp_async(void *smem_dst, const void *gmem_src, int bytes)
+{
+    Fibre *f = g_cur;
+    if ((reinterpret_cast<uintptr_t>(smem_dst) | reinterpret_cast<uintptr_t>(gmem_src)) & (uintptr_t)(bytes - 1))
+        fail(where() + ": cp.async with a misaligned address");
+    volatile char probe = *static_cast<const volatile char *>(gmem_src);  // fault now, in the issuing thread
+    (void)probe;
+    probe = static_cast<const volatile char *>(gmem_src)[bytes - 1];
+    if (g_cp_async_eager)
+        memcpy(smem_dst, gmem_src, (size_t)bytes);
+    else
+        f->copies.push_back(AsyncCopy{smem_dst, gmem_src, bytes, f->cp_group});
+}
+
+void cp_async_commit() { ++g_cur->cp_group; }
+
+void cp_async_wait(int all_but_newest) { drain_copies(g_cur, g_cur->cp_group - all_but_newest); }
+
 void yield_spin()
 {
     Fibre *f = g_cur;
@@ -496,4 +539,5 @@ cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return
 cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
 
 // what the tests read back after a failed launch
+extern "C" __attribute__((visibility("default"))) void simt_set_cp_async_eager(int eager) { simt::g_cp_async_eager = eager != 0; }
 extern "C" __attribute__((visibility("default"))) const char *simt_last_failure(void) { return simt::g_fail_msg.c_str(); }

@@ -85,6 +85,9 @@ PTX = [
     (r"^st\.release\.(sys|gpu)\.global\.u32 ", "{{ *(volatile unsigned *)({0}) = ({1}); }}"),
     (r"^ld\.global\.L1::no_allocate\.v4\.u32 ",
      "{{ const unsigned *p_ = (const unsigned *)({4}); ({0}) = p_[0]; ({1}) = p_[1]; ({2}) = p_[2]; ({3}) = p_[3]; }}"),
+    (r"^cp\.async\.cg\.shared\.global ", "::simt::cp_async((void *)({0}), (const void *)({1}), 16)"),
+    (r"^cp\.async\.commit_group", "::simt::cp_async_commit()"),
+    (r"^cp\.async\.wait_group ", "::simt::cp_async_wait({0})"),
     (r"^atom\.acq_rel\.gpu\.global\.add\.u32 ",
      "{{ unsigned *p_ = (unsigned *)({1}); ({0}) = *p_; *p_ += 1; }}"),
 ]

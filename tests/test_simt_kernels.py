@@ -27,6 +27,7 @@ def _reset_knobs():
     S.set_tuning(-1, -1)
     S.set_forward_depth(0)
     S.set_forward_copies(0)
+    S.set_cp_async_eager(False)
 
 
 # ------------------------------------------------------------------------------ a4
@@ -154,11 +155,12 @@ def test_simt_forward_accumulator_copies(k, copies):
     close(y2, 2 * want, "accumulate")
 
 
-@pytest.mark.parametrize("shape", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("shape", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
 @pytest.mark.parametrize("k", [32, 16, 64, 8, 128])
 def test_simt_forward_launch_shapes(k, shape):
-    """All launch shapes, the experimental double-buffered ones (4-7) included, from a poisoned
-    output buffer."""
+    """All launch shapes, the experimental ones included (4-7: double-buffered gather batches,
+    8-11: cp.async gather ring -- the interpreter performs an asynchronous copy as late as PTX
+    allows, at the issuing thread's wait), from a poisoned output buffer."""
     p = Problem(n=200, avg=35.0, k=k, seed=31 * k + shape, empty_frac=0.3)
     want = p.fwd_oracle()
     S.set_forward_depth(shape)
@@ -167,7 +169,7 @@ def test_simt_forward_launch_shapes(k, shape):
         close(S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n), want, f"k={k} shape={shape} tpw={tpw}")
 
 
-@pytest.mark.parametrize("shape", [0, 4, 7])
+@pytest.mark.parametrize("shape", [0, 4, 7, 8, 11])
 def test_simt_forward_gap_rows_are_zeroed(shape):
     n = 97
     deg = np.zeros(n, np.int64)
@@ -207,6 +209,28 @@ def test_simt_unaligned_operands_take_the_scalar_paths():
               p.fwd_oracle(), f"forward k={k}")
         close(S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index, dxc_align=4, index_align=1),
               p.bwd_oracle(), f"backward k={k}")
+
+
+@pytest.mark.parametrize("eager", [False, True])
+@pytest.mark.parametrize("shape", [8, 10])
+def test_simt_ring_shapes_on_hard_cases(shape, eager):
+    """cp.async ring variants: tasks longer than one ring (hub rows), foreign work lists with
+    len > 64, single-edge rows, accumulate mode, and unaligned operands (falls back); with the
+    asynchronous copies landing as late and as early as PTX allows."""
+    S.set_forward_depth(shape)
+    S.set_cp_async_eager(eager)
+    for case in (dict(k=32, n=20, avg=1500.0, empty_frac=0.0), dict(k=16, warp_max_nz=200), dict(k=32, warp_max_nz=5),
+                 dict(k=64, avg=3.0, n=700, empty_frac=0.4), dict(k=32, n=200, n_cols=700, avg=25.0),
+                 dict(k=32, selector="random"), dict(k=64, d=128)):
+        case = dict(n=150, **case) if "n" not in case else case
+        p = Problem(seed=len(str(case)) + shape, **case)
+        want = p.fwd_oracle()
+        y = S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n, d=p.d)
+        close(y, want, str(case))
+        close(S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n, d=p.d, accumulate=True, out_init=y),
+              2 * want, "accumulate " + str(case))
+        close(S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n, d=p.d, data_align=4, index_align=1),
+              want, "unaligned " + str(case))
 
 
 def test_simt_empty_inputs():
