@@ -114,6 +114,21 @@ MAXK_API int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks, co
                             int32_t k, float *out, int64_t num_rows_out, int32_t d,
                             int32_t accumulate, void *stream);
 
+/* ---- a2, EXPERIMENTAL (round 1, after the GPU budget: checked under the SIMT interpreter of
+ * tests/simt only; nothing calls these by default): bank-planned forward.  The forward kernel is
+ * bound by shared-memory wavefronts of its scatter into the output row (32 random columns per
+ * edge collide in the 32 banks, ~3.3-way).  maxk_cbsr_bank_plan gives every entry of a CBSR row
+ * one of two homes for its column (word c of copy 0 or word 256 + (c%8)*32 + c/8 of copy 1) so
+ * that the 32 entries of one update spread over the banks (~2-way), once per row instead of
+ * once per edge; sp_addr uint16[n,k] holds the chosen accumulator words and replaces sp_index in
+ * maxk_spgemm_forward_planned (k % 32 == 0; same output contract as maxk_spgemm_forward_acc).  */
+MAXK_API int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, uint16_t *sp_addr,
+                        void *stream);
+MAXK_API int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
+                                const float *values, const float *sp_data, const uint16_t *sp_addr,
+                                int32_t k, float *out, int64_t num_rows_out, int32_t d,
+                                int32_t accumulate, void *stream);
+
 /* ---- a3: backward outer-product sampled SSpMM  dXc = sample(A^T dY, sp_index)
  * (replaces spmm_kernel_opt2_sparse_backward_v3, kernels/spmm_maxk_backward.cu:15-115;
  * spmm_maxk_backward, cuda_kernel_bindings.cpp:106-161) ----------------------------------

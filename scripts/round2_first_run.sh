@@ -1,14 +1,14 @@
 #!/bin/bash
 # First gpurun call of round 2 (1 GPU, ~3 minutes): validate and measure what round 1 wrote after
 # its GPU budget was spent -- the double-buffered (launch shapes 4-7) and cp.async-ring (8-11)
-# forward variants, both already checked under the SIMT interpreter (tests/test_simt_kernels.py) -- and
+# forward variants and the bank-planned forward (csrc/cbsr_plan.cu), all already checked under the SIMT interpreter (tests/test_simt_kernels.py) -- and
 # re-measure the one-GPU epoch that the scaling table still quotes from the first session.
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/round2_first_run.sh'
 mkdir -p gpurun_out
-MAXK_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -k "experimental_shapes" > gpurun_out/pytest_experimental.log 2>&1
+MAXK_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -k "experimental" > gpurun_out/pytest_experimental.log 2>&1
 echo "experimental shapes: rc=$? $(tail -1 gpurun_out/pytest_experimental.log)"
 for shape in products reddit flickr; do
-  python scripts/sweep_fwd.py --shape $shape --ks 32,16,64 --copies 0 --tpw=-1 --depth 0,1,2,4,5,6,7,8,9,10,11 2>/dev/null | tee gpurun_out/sweep_db_$shape.jsonl
+  python scripts/sweep_fwd.py --shape $shape --ks 32,16,64 --copies 0 --tpw=-1 --depth 0,1,2,4,5,6,7,8,9,10,11 --planned 2>/dev/null | tee gpurun_out/sweep_db_$shape.jsonl
 done
 python scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_n1_round2.json
 python scripts/topk_probe.py 2>/dev/null | tee gpurun_out/topk_probe_round2.log

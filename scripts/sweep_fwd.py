@@ -18,6 +18,7 @@ ap.add_argument("--copies", default="0,1,2,4,8,16")
 ap.add_argument("--tpw", default="16")
 ap.add_argument("--depth", default="0")
 ap.add_argument("--bwd-tpw", default="")
+ap.add_argument("--planned", action="store_true", help="also time the experimental bank-planned forward (k % 32 == 0)")
 ap.add_argument("--iters", type=int, default=10)
 a = ap.parse_args()
 
@@ -60,6 +61,23 @@ for k in [int(v) for v in a.ks.split(",")]:
                 print(json.dumps(r), flush=True)
     ops.set_forward_copies(0)
     ops.set_forward_depth(0)
+    if a.planned and k % 32 == 0:
+        # the plan is made once per TopK, the planned forward runs once per layer: both are timed
+        sa = ops.cbsr_bank_plan(si)
+        t_plan = timeit(lambda: ops.cbsr_bank_plan(si, out=sa), a.iters)
+        ref = ops.spgemm_forward(w4, g["indices"], g["values"], sd, si, num_rows=n)
+        for tpw in [int(v) for v in a.tpw.split(",")]:
+            for dep in (1, 2):
+                ops.set_forward_depth(dep)
+                ops.set_tuning(tpw, 0)
+                t = timeit(lambda: ops.spgemm_forward_planned(w4, g["indices"], g["values"], sd, sa, out=y, num_rows=n), a.iters)
+                err = float((y - ref).abs().max() / ref.abs().max())
+                r = {"kernel": "fwd_planned", "shape": a.shape, "k": k, "tpw": tpw, "depth": dep, "ms": round(t, 4),
+                     "plan_ms": round(t_plan, 4), "frac": round(b["fwd"] / t / 1e6 / peak, 3),
+                     "frac_with_plan": round(b["fwd"] / (t + t_plan) / 1e6 / peak, 3), "rel_err_vs_default": err}
+                res.append(r)
+                print(json.dumps(r), flush=True)
+        ops.set_forward_depth(0)
     if a.bwd_tpw:
         dxc = torch.empty(n, k, device="cuda")
         for tpw in [int(v) for v in a.bwd_tpw.split(",")]:

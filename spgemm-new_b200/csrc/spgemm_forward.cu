@@ -23,6 +23,8 @@
 //   * 64-bit row offsets (ref uses int: overflow beyond 8.39 M nodes).
 // HBM traffic is the CSR stream + one write of Y; the CBSR operand (5k B/node) lives in
 // the 126 MB L2.  No tensor cores: 2 flops per >= 5 bytes gathered.
+#include <type_traits>
+
 #include "common.cuh"
 #include "peer.cuh"
 
@@ -39,8 +41,14 @@ constexpr int FWD_STAGE = 64;  // staged (idx,val) pairs per warp == MAXK_WARP_M
 // R accumulator copies, WPB warps per CTA, U gather instructions in flight, MINB CTAs/SM
 // the register budget is capped for.
 template <int KL_, int EPL_, bool EXACT_, int R_, int WPB_, int U_, int MINB_, bool PEER_ = false,
-          bool DB_ = false, int RING_ = 0>
+          bool DB_ = false, int RING_ = 0, bool PLAN_ = false>
 struct FwdCfg {
+    // PLAN: the second operand is the bank plan sp_addr (uint16 accumulator words, cbsr_plan.cu)
+    // instead of sp_index; the output row lives in two 256-word copies (experimental, own entry point)
+    static constexpr bool PLAN = PLAN_;
+    static constexpr int PLAN_WORDS = 512;
+    static_assert(!PLAN_ || (EXACT_ && KL_ == 32 && R_ == 1 && !PEER_ && !DB_ && RING_ == 0),
+                  "the planned variant exists for k % 32 == 0, one accumulator set");
     // DB: double-buffered gather batches (experimental launch shapes 4-7, see launch_fwd_r)
     static constexpr bool DB = DB_;
     // RING > 0: gathers go through cp.async into a per-warp shared-memory ring of 2 x RING rows
@@ -63,7 +71,8 @@ struct FwdCfg {
 template <class C>
 struct Slice {
     float v[C::EPL];
-    unsigned char s[C::EPL];
+    // column id (uint8) -- or, PLAN, the accumulator word of the entry (uint16)
+    typename std::conditional<C::PLAN, unsigned short, unsigned char>::type s[C::EPL];
 };
 
 // read-only path for an operand that is constant during the kernel; plain (coherent) loads
@@ -83,7 +92,15 @@ __device__ __forceinline__ void fwd_gather(Slice<C> &sl, const float *sp_data,
 {
     constexpr bool P = C::PEER;
     const int64_t base = (int64_t)col * k;
-    if constexpr (C::KL < 32) {
+    if constexpr (C::PLAN) {
+        // entry 32*i + lane: the grouping the plan was made for; sp_index points at sp_addr
+        const unsigned short *sp_addr = reinterpret_cast<const unsigned short *>(sp_index);
+#pragma unroll
+        for (int i = 0; i < C::EPL; ++i) {
+            sl.v[i] = fwd_ld<P>(sp_data + base + lane + 32 * i);
+            sl.s[i] = fwd_ld<P>(sp_addr + base + lane + 32 * i);
+        }
+    } else if constexpr (C::KL < 32) {
         const int entry = lane / C::E;
         sl.v[0] = fwd_ld<P>(sp_data + base + entry);
         sl.s[0] = fwd_ld<P>(sp_index + base + entry);
@@ -379,6 +396,33 @@ __device__ __forceinline__ void fwd_flush_row(float *acc, float *__restrict__ ou
     __syncwarp();
 }
 
+// PLAN: out[row, c] = copy0[c] + copy1[(c mod 8)*32 + c/8]; both copies are cleared.
+template <class C>
+__device__ __forceinline__ void fwd_flush_row_planned(float *acc, float *__restrict__ out, int64_t row,
+                                                      int d, int lane, bool shared_row)
+{
+    __syncwarp();
+    float *dst = out + row * (int64_t)d;
+    const float *acc1 = acc + 256;
+    for (int c = lane * 4; c < d; c += 128) {
+        float4 v = *reinterpret_cast<float4 *>(acc + c);
+        // (c + i) mod 8 = (c mod 8) + i and (c + i) / 8 = c / 8 for i < 4, because c % 4 == 0
+        const float *p = acc1 + ((c & 7) << 5) + (c >> 3);
+        v.x += p[0];
+        v.y += p[32];
+        v.z += p[64];
+        v.w += p[96];
+        if (shared_row)
+            red_add_f4(dst + c, v.x, v.y, v.z, v.w);
+        else
+            st_stream_f4(reinterpret_cast<float4 *>(dst + c), v);
+    }
+    __syncwarp();  // every lane has read both copies before anybody clears a word of them
+    for (int i = lane * 4; i < C::PLAN_WORDS; i += 128)
+        *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+}
+
 // coalesced fetch of up to FWD_STAGE (idx,val) pairs of one task into registers
 struct EdgeRegs {
     int i0, i1;
@@ -454,9 +498,17 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
         cta -= peer.copy_ctas;
         gathered = false;
     }
-    float *acc = reinterpret_cast<float *>(smem_raw) + warp * d * C::R;
-    int2 *stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + C::WPB * d * C::R) +
-                  warp * FWD_STAGE;
+    float *acc;
+    int2 *stage;
+    if constexpr (C::PLAN) {  // two 256-word copies of the row per warp
+        acc = reinterpret_cast<float *>(smem_raw) + warp * C::PLAN_WORDS;
+        stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + C::WPB * C::PLAN_WORDS) +
+                warp * FWD_STAGE;
+    } else {
+        acc = reinterpret_cast<float *>(smem_raw) + warp * d * C::R;
+        stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + C::WPB * d * C::R) +
+                warp * FWD_STAGE;
+    }
     float *acc_lane = acc + (lane & (C::R - 1));
     unsigned char *ring = nullptr;  // RING: 2 * RING gathered rows of this warp, behind the staging area
     if constexpr (C::RING > 0)
@@ -467,8 +519,13 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
     if (t0 >= num_tasks) return;  // no CTA-wide barrier below
     const int64_t t1 = min(t0 + (int64_t)tasks_per_warp, num_tasks);
 
-    for (int i = lane * 4; i < d * C::R; i += 128)
-        *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (C::PLAN) {
+        for (int i = lane * 4; i < C::PLAN_WORDS; i += 128)
+            *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        for (int i = lane * 4; i < d * C::R; i += 128)
+            *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
     int4 info = ld_stream_int4(warp4 + t0);
     int4 ninfo = info;  // task t+1, loaded one task early so that its CSR slice can be
@@ -494,8 +551,12 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
         if (t + 2 < t1) nninfo = ld_stream_int4(warp4 + t + 2);
 
         if (info.x != cur_row) {
-            fwd_flush_row<C>(acc, out, cur_row, d, lane,
-                             accumulate || (first_shared && cur_row == first_row));
+            if constexpr (C::PLAN)
+                fwd_flush_row_planned<C>(acc, out, cur_row, d, lane,
+                                         accumulate || (first_shared && cur_row == first_row));
+            else
+                fwd_flush_row<C>(acc, out, cur_row, d, lane,
+                                 accumulate || (first_shared && cur_row == first_row));
             if (!accumulate) fwd_zero_rows(out, (int64_t)cur_row + 1, info.x, d, lane);
             cur_row = info.x;
         }
@@ -532,8 +593,12 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
         info = ninfo;
         ninfo = nninfo;
     }
-    fwd_flush_row<C>(acc, out, cur_row, d, lane,
-                     last_shared || (first_shared && cur_row == first_row));
+    if constexpr (C::PLAN)
+        fwd_flush_row_planned<C>(acc, out, cur_row, d, lane,
+                                 last_shared || (first_shared && cur_row == first_row));
+    else
+        fwd_flush_row<C>(acc, out, cur_row, d, lane,
+                         last_shared || (first_shared && cur_row == first_row));
     if (!accumulate && t1 == num_tasks) fwd_zero_rows(out, (int64_t)cur_row + 1, num_rows_out, d, lane);
 }
 
@@ -559,7 +624,7 @@ struct FwdArgs {
 template <class C>
 static int launch_fwd(const FwdArgs &a)
 {
-    size_t smem = (size_t)C::WPB * a.d * C::R * sizeof(float) +
+    size_t smem = (size_t)C::WPB * (C::PLAN ? C::PLAN_WORDS : a.d * C::R) * sizeof(float) +
                   (size_t)C::WPB * FWD_STAGE * sizeof(int2) +
                   (size_t)C::WPB * 2 * C::RING * C::ROW_BYTES;
     if constexpr (C::PEER) {  // the copy CTAs stage their TMA chunks in the same dynamic smem
@@ -767,6 +832,72 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
     }
 #undef MAXK_FWD_CASE
     set_error("maxk_spgemm_forward: unsupported k=%d", k);
+    return MAXK_ERR_UNSUPPORTED;
+}
+
+// ---- forward with a bank plan (cbsr_plan.cu): EXPERIMENTAL, own entry point ---------------------
+template <int EPL>
+static int launch_fwd_planned(const FwdArgs &a)
+{
+    constexpr int U1 = (EPL == 1) ? 4 : (EPL <= 4 ? 2 : 1);
+    if (a.depth == 2) return launch_fwd<FwdCfg<32, EPL, true, 1, 2, U1, (EPL <= 2 ? 16 : 8), false, false, 0, true>>(a);
+    return launch_fwd<FwdCfg<32, EPL, true, 1, 8, U1, (EPL <= 2 ? 4 : 2), false, false, 0, true>>(a);
+}
+
+extern "C" int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks,
+                                           const int32_t *indices, const float *values,
+                                           const float *sp_data, const uint16_t *sp_addr, int32_t k,
+                                           float *out, int64_t num_rows_out, int32_t d,
+                                           int32_t accumulate, void *stream)
+{
+    MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0, "maxk_spgemm_forward_planned: negative size");
+    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
+                 "maxk_spgemm_forward_planned: d=%d must be a multiple of 4 in [4,256]", d);
+    MAXK_REQUIRE(k >= 32 && k <= d && k % 32 == 0,
+                 "maxk_spgemm_forward_planned: k=%d must be a multiple of 32 in [32,d=%d]", k, d);
+    MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "maxk_spgemm_forward_planned: out is NULL");
+    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
+                 "maxk_spgemm_forward_planned: out and warp4 must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (num_rows_out == 0) return MAXK_OK;
+    if (num_tasks == 0) {
+        if (!accumulate) {
+            MAXK_CUDA(cudaMemsetAsync(out, 0, (size_t)num_rows_out * d * sizeof(float), st));
+            count_launch();
+        }
+        return MAXK_OK;
+    }
+    MAXK_REQUIRE(warp4 && indices && values && sp_data && sp_addr,
+                 "maxk_spgemm_forward_planned: NULL input pointer");
+    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(sp_data) & 3) == 0 && (reinterpret_cast<uintptr_t>(sp_addr) & 1) == 0,
+                 "maxk_spgemm_forward_planned: sp_data / sp_addr are misaligned");
+    int tpw = g_fwd_tasks_per_warp;
+    if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
+    int shape = g_fwd_depth;
+    if (shape != 1 && shape != 2) shape = (num_tasks < 2 * num_rows_out) ? 2 : 1;
+    FwdArgs a{warp4, num_tasks, indices, values, sp_data, reinterpret_cast<const uint8_t *>(sp_addr), k, out, d,
+              tpw, accumulate, st, shape, num_rows_out, nullptr, false};
+    if (!accumulate) {
+        const int64_t boundaries = (num_tasks - 1) / a.tasks_per_warp;
+        if (boundaries > 0) {
+            spgemm_fwd_clear_shared_rows<<<(unsigned)ceil_div<int64_t>(boundaries, 8), 256, 0, st>>>(
+                reinterpret_cast<const int4 *>(warp4), num_tasks, a.tasks_per_warp, out, d);
+            MAXK_LAUNCH_CHECK("spgemm_fwd_clear_shared_rows");
+        }
+    }
+    switch (k / 32) {
+        case 1: return launch_fwd_planned<1>(a);
+        case 2: return launch_fwd_planned<2>(a);
+        case 3: return launch_fwd_planned<3>(a);
+        case 4: return launch_fwd_planned<4>(a);
+        case 5: return launch_fwd_planned<5>(a);
+        case 6: return launch_fwd_planned<6>(a);
+        case 7: return launch_fwd_planned<7>(a);
+        case 8: return launch_fwd_planned<8>(a);
+        default: break;
+    }
+    set_error("maxk_spgemm_forward_planned: unsupported k=%d", k);
     return MAXK_ERR_UNSUPPORTED;
 }
 

@@ -221,6 +221,37 @@ def test_forward_experimental_shapes(ops, k, shape):
         ops.set_tuning(-1, -1)
 
 
+@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
+                    reason="bank-planned forward (csrc/cbsr_plan.cu): written after round 1's GPU budget was spent, "
+                           "checked under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
+@pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=128), dict(k=256), dict(k=32, d=128),
+                                  dict(k=32, selector="random"), dict(k=32, avg=3.0, n=3000, empty_frac=0.4),
+                                  dict(k=32, n=50, avg=2000.0, empty_frac=0.0), dict(k=32, warp_max_nz=100)],
+                         ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
+def test_forward_planned_experimental(ops, case):
+    p = Problem(seed=len(str(case)) + 2, **case)
+    g = p.cuda()
+    sp_addr = ops.cbsr_bank_plan(g["sp_index"])
+    c = g["sp_index"].long()
+    a = sp_addr.long()
+    assert bool(((a == c) | (a == 256 + (c % 8) * 32 + c // 8)).all())
+    want = p.fwd_oracle()
+    try:
+        for shape, tpw in ((0, -1), (1, 1), (2, 5)):
+            ops.set_forward_depth(shape)
+            ops.set_tuning(tpw, 0)
+            y = torch.full((p.n, p.d), float("nan"), device="cuda")
+            ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr,
+                                       feat_dim=p.d, num_rows=p.n, out=y)
+            assert_close(y, want, f"shape={shape} tpw={tpw}")
+        ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr,
+                                   feat_dim=p.d, num_rows=p.n, out=y, accumulate=True)
+        assert_close(y, 2 * want, "accumulate")
+    finally:
+        ops.set_forward_depth(0)
+        ops.set_tuning(-1, -1)
+
+
 def test_forward_gap_rows_are_zeroed(ops):
     """Leading, interior and trailing rows without edges (and an output taller than the last
     task row) come back as zeros from a poisoned buffer."""

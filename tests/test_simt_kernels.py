@@ -233,6 +233,84 @@ def test_simt_ring_shapes_on_hard_cases(shape, eager):
               want, "unaligned " + str(case))
 
 
+# ------------------------------------------------------- bank-planned forward (experimental)
+def _bank_loads(sp_addr):
+    """fullest bank of every 32-entry update instruction: [n, k/32]"""
+    n, k = sp_addr.shape
+    banks = (sp_addr.astype(np.int64) % 32).reshape(n, k // 32, 32)
+    return np.stack([np.bincount(b, minlength=32).max() for b in banks.reshape(-1, 32)]).reshape(n, k // 32)
+
+
+@pytest.mark.parametrize("k", [32, 64, 18, 96, 256])
+def test_simt_bank_plan_is_valid_and_spreads_the_banks(k):
+    rng = np.random.default_rng(k)
+    n = 300
+    sp_index = np.sort(np.argsort(rng.random((n, 256)), axis=1)[:, :k], axis=1).astype(np.uint8)
+    sp_addr = S.cbsr_bank_plan(sp_index)
+    c = sp_index.astype(np.int64)
+    home0, home1 = c, 256 + (c % 8) * 32 + c // 8
+    assert ((sp_addr == home0) | (sp_addr == home1)).all(), "every entry sits in one of its two homes"
+    if k % 32 == 0:
+        planned = _bank_loads(sp_addr)
+        plain = _bank_loads(sp_index.astype(np.uint16))
+        # 32 random columns: the fullest bank holds ~3.3 (k = 256: all columns -> 8); two homes: ~2
+        assert planned.max() <= 3 and planned.mean() < 2.2, (planned.mean(), planned.max())
+        assert planned.mean() <= plain.mean(), (planned.mean(), plain.mean())
+        if k == 32:
+            assert planned.mean() < plain.mean() - 0.9, (planned.mean(), plain.mean())
+    # rows that need no choice stay in copy 0
+    ident = np.tile(np.arange(32, dtype=np.uint8), (3, 1))
+    assert (S.cbsr_bank_plan(ident) == ident).all()
+
+
+PLANNED_CASES = [dict(k=32), dict(k=64), dict(k=96), dict(k=128), dict(k=256), dict(k=160),
+                 dict(k=32, d=128), dict(k=32, d=36), dict(k=32, selector="random"), dict(k=64, selector="torch"),
+                 dict(k=32, kind="uniform", avg=300.0, n=40, empty_frac=0.0), dict(k=32, avg=3.0, n=1500, empty_frac=0.4),
+                 dict(k=32, n=20, avg=1500.0, empty_frac=0.0), dict(k=32, n=200, n_cols=700, avg=25.0),
+                 dict(k=32, warp_max_nz=100), dict(k=32, warp_max_nz=5)]
+
+
+@pytest.mark.parametrize("case", PLANNED_CASES, ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
+def test_simt_planned_forward_vs_oracle(case):
+    case = dict(n=250, **case) if "n" not in case else case
+    p = Problem(seed=len(str(case)) + 1, **case)
+    sp_addr = S.cbsr_bank_plan(p.sp_index)
+    want = p.fwd_oracle()
+    for shape, tpw in ((0, -1), (1, 1), (2, 5), (1, 16)):
+        S.set_forward_depth(shape)
+        S.set_tuning(tpw, 0)
+        y = S.spgemm_forward_planned(p.w4, p.idx, p.val, p.sp_data, sp_addr, p.n, d=p.d)
+        close(y, want, f"shape={shape} tpw={tpw}")
+    y2 = S.spgemm_forward_planned(p.w4, p.idx, p.val, p.sp_data, sp_addr, p.n, d=p.d, accumulate=True, out_init=y)
+    close(y2, 2 * want, "accumulate")
+    y3 = S.spgemm_forward_planned(p.w4, p.idx, p.val, p.sp_data, sp_addr, p.n, d=p.d, data_align=4, addr_align=2)
+    close(y3, want, "operands aligned to their element size only")
+
+
+def test_simt_planned_forward_gap_rows_and_empty():
+    n = 97
+    deg = np.zeros(n, np.int64)
+    deg[[5, 6, 40, 41, 42, 80]] = [3, 200, 1, 70, 64, 129]
+    indptr = np.zeros(n + 1, np.int32)
+    indptr[1:] = np.cumsum(deg)
+    rng = np.random.default_rng(3)
+    e = int(indptr[-1])
+    indices = rng.integers(0, n, e).astype(np.int32)
+    values = rng.random(e, dtype=np.float32)
+    sp_data, sp_index = O.topk_cbsr(rng.standard_normal((n, 256)).astype(np.float32), 32)
+    sp_addr = S.cbsr_bank_plan(sp_index)
+    w4 = O.worklist(indptr)
+    want = O.spgemm_forward(w4, indices, values, sp_data, sp_index, d=256, n_out=n + 10)
+    for tpw in (-1, 1, 2, 16):
+        S.set_tuning(tpw, 0)
+        close(S.spgemm_forward_planned(w4, indices, values, sp_data, sp_addr, n + 10), want, f"tpw={tpw}")
+    z32 = np.zeros(0, np.int32)
+    y = S.spgemm_forward_planned(z32, z32, np.zeros(0, np.float32), sp_data, sp_addr, 10)
+    assert y.shape == (10, 256) and float(np.abs(y).sum()) == 0.0
+    with pytest.raises(S.SimtError, match="multiple of 32"):
+        S.spgemm_forward_planned(w4, indices, values, sp_data[:, :16], sp_addr[:, :16], n)
+
+
 def test_simt_empty_inputs():
     z32 = np.zeros(0, np.int32)
     sp_data = np.random.default_rng(0).random((10, 32), dtype=np.float32)
