@@ -121,7 +121,8 @@ MAXK_API int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks, co
  * one of two homes for its column (word c of copy 0 or word 256 + (c%8)*32 + c/8 of copy 1) so
  * that the 32 entries of one update spread over the banks (~2-way), once per row instead of
  * once per edge; sp_addr uint16[n,k] holds the chosen accumulator words and replaces sp_index in
- * maxk_spgemm_forward_planned (k % 32 == 0; same output contract as maxk_spgemm_forward_acc).  */
+ * maxk_spgemm_forward_planned (k = 8, 16 or a multiple of 32; same output contract as
+ * maxk_spgemm_forward_acc).  */
 MAXK_API int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, uint16_t *sp_addr,
                         void *stream);
 MAXK_API int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,

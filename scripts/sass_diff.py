@@ -1,0 +1,67 @@
+#!/usr/bin/env python3
+"""Compare the SASS of two builds of libmaxk_b200.so kernel by kernel (addresses stripped).
+
+    cuobjdump -sass old.so > old.sass; cuobjdump -sass new.so > new.sass
+    python scripts/sass_diff.py old.sass new.sass
+    python scripts/sass_diff.py --write-manifest profiles/rNN_sass_manifest.json build.sass   # keep a baseline
+    python scripts/sass_diff.py profiles/rNN_sass_manifest.json new.sass
+
+Used to show that a change which only ADDS template variants leaves every kernel that was
+validated on the GPU bit-for-bit the same program.  Template parameters appended to FwdCfg with
+a default show up as a suffix in the mangled names: pass it with --strip (e.g. ELi0ELb0E).
+"""
+import hashlib
+import json
+import re
+import sys
+
+
+def funcs(path):
+    if path.endswith(".json"):  # a manifest written with --write-manifest: kernel -> [n, sha1]
+        return {k: tuple(v) for k, v in json.load(open(path)).items()}
+    d = _funcs_sass(path)
+    return {k: (len(v), hashlib.sha1("\n".join(v).encode()).hexdigest()) for k, v in d.items()}
+
+
+def _funcs_sass(path):
+    d, name, body = {}, None, []
+    for ln in open(path):
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            if name:
+                d[name] = body
+            name, body = m.group(1), []
+        elif re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+            body.append(re.sub(r"/\*[0-9a-f]+\*/", "", ln).strip())
+    if name:
+        d[name] = body
+    return d
+
+
+if __name__ == "__main__":
+    strip = ""
+    args = sys.argv[1:]
+    if "--strip" in args:
+        i = args.index("--strip")
+        strip = args[i + 1]
+        del args[i:i + 2]
+    if "--write-manifest" in args:  # python scripts/sass_diff.py --write-manifest out.json build.sass
+        i = args.index("--write-manifest")
+        json.dump(funcs(args[i + 2]), open(args[i + 1], "w"), indent=0, sort_keys=True)
+        sys.exit(0)
+    a, b = funcs(args[0]), funcs(args[1])
+    same = diff = 0
+    new = []
+    for n, body in b.items():
+        o = n.replace(strip + "EEEE", "EEEE") if strip and "FwdCfg" in n else n
+        if o in a:
+            if a[o] == body:
+                same += 1
+            else:
+                diff += 1
+                print("DIFF", n, a[o][0], "->", body[0], "instructions")
+        else:
+            new.append(n)
+    gone = [n for n in a if n not in b and not any((m.replace(strip + "EEEE", "EEEE") if strip else m) == n for m in b)]
+    print(f"identical {same}, changed {diff}, new {len(new)}, removed {len(gone)} (old build: {len(a)} kernels)")
+    sys.exit(1 if diff or gone else 0)

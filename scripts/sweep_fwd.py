@@ -61,7 +61,7 @@ for k in [int(v) for v in a.ks.split(",")]:
                 print(json.dumps(r), flush=True)
     ops.set_forward_copies(0)
     ops.set_forward_depth(0)
-    if a.planned and k % 32 == 0:
+    if a.planned and (k % 32 == 0 or k in (8, 16)):
         # the plan is made once per TopK, the planned forward runs once per layer: both are timed
         sa = ops.cbsr_bank_plan(si)
         t_plan = timeit(lambda: ops.cbsr_bank_plan(si, out=sa), a.iters)

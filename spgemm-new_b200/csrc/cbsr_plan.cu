@@ -25,7 +25,9 @@
 // replaces sp_index as the forward kernel's second gather (64 instead of 32 bytes per row at
 // k = 32 -- still one wavefront, 6k instead of 5k bytes per node in the L2).  Entries are planned
 // in groups of 32 consecutive entries, which is how the planned forward kernel maps entries to
-// lanes (entry 32*i + lane in its i-th update instruction).
+// lanes (entry 32*i + lane in its i-th update instruction).  For k = 16 and k = 8 one instruction
+// carries 32/k edges, each with its own accumulator set on its own 1/E of the banks (word*E + slot),
+// so a row's k entries are planned over k banks (b mod k).
 #include "common.cuh"
 
 namespace maxk {
@@ -67,14 +69,14 @@ struct BankLoad {  // 32 four-bit counters (an instruction has at most 32 entrie
 // one thread per (row, group of 32 entries)
 __global__ void __launch_bounds__(128)
 cbsr_bank_plan_kernel(const unsigned char *__restrict__ sp_index, int64_t n, int k, int groups,
-                      unsigned short *__restrict__ sp_addr)
+                      int group_len, unsigned bank_mask, unsigned short *__restrict__ sp_addr)
 {
     const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= n * groups) return;
     const int64_t row = item / groups;
     const int g = (int)(item - row * groups);
-    const int j0 = g * PLAN_GROUP;
-    const int cnt = min(PLAN_GROUP, k - j0);
+    const int j0 = g * group_len;
+    const int cnt = min(group_len, k - j0);
     const unsigned char *src = sp_index + row * k + j0;
 
     unsigned char c[PLAN_GROUP];
@@ -86,7 +88,7 @@ cbsr_bank_plan_kernel(const unsigned char *__restrict__ sp_index, int64_t n, int
 #pragma unroll
     for (int i = 0; i < PLAN_GROUP; ++i) {
         if (i < cnt) {
-            const unsigned b0 = c[i] & 31u, b1 = c[i] >> 3;
+            const unsigned b0 = c[i] & bank_mask, b1 = (c[i] >> 3) & bank_mask;
             const bool second = load.get(b1) < load.get(b0);
             copy |= second ? (1u << i) : 0u;
             load.add(second ? b1 : b0, +1);
@@ -100,7 +102,7 @@ cbsr_bank_plan_kernel(const unsigned char *__restrict__ sp_index, int64_t n, int
 #pragma unroll
         for (int i = 0; i < PLAN_GROUP; ++i) {
             if (i < cnt) {
-                const unsigned b0 = c[i] & 31u, b1 = c[i] >> 3;
+                const unsigned b0 = c[i] & bank_mask, b1 = (c[i] >> 3) & bank_mask;
                 const bool second = (copy >> i) & 1u;
                 const unsigned cur = second ? b1 : b0, alt = second ? b0 : b1;
                 if (load.get(cur) == m && load.get(alt) + 1u < m) {
@@ -131,11 +133,16 @@ extern "C" int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k
     if (n == 0) return MAXK_OK;
     MAXK_REQUIRE(sp_index != nullptr && sp_addr != nullptr, "maxk_cbsr_bank_plan: NULL pointer");
     MAXK_REQUIRE((reinterpret_cast<uintptr_t>(sp_addr) & 1) == 0, "maxk_cbsr_bank_plan: sp_addr must be 2-byte aligned");
-    const int groups = ceil_div<int>(k, PLAN_GROUP);
+    // entries of one update instruction and the banks they share: k >= 32 -> 32 entries over 32
+    // banks; k = 16 / 8 -> the row's k entries over k banks (the other edges of the instruction
+    // use the other banks)
+    const int group_len = (k == 16 || k == 8) ? k : PLAN_GROUP;
+    const unsigned bank_mask = (unsigned)group_len - 1u;
+    const int groups = ceil_div<int>(k, group_len);
     const int64_t grid = ceil_div<int64_t>(n * groups, 128);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_cbsr_bank_plan: n too large");
     cbsr_bank_plan_kernel<<<(unsigned)grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        sp_index, n, k, groups, sp_addr);
+        sp_index, n, k, groups, group_len, bank_mask, sp_addr);
     MAXK_LAUNCH_CHECK("cbsr_bank_plan_kernel");
     return MAXK_OK;
 }

@@ -46,9 +46,9 @@ struct FwdCfg {
     // PLAN: the second operand is the bank plan sp_addr (uint16 accumulator words, cbsr_plan.cu)
     // instead of sp_index; the output row lives in two 256-word copies (experimental, own entry point)
     static constexpr bool PLAN = PLAN_;
-    static constexpr int PLAN_WORDS = 512;
-    static_assert(!PLAN_ || (EXACT_ && KL_ == 32 && R_ == 1 && !PEER_ && !DB_ && RING_ == 0),
-                  "the planned variant exists for k % 32 == 0, one accumulator set");
+    static constexpr int PLAN_WORDS = 512 * R_;  // two homes per column, one set per edge slot
+    static_assert(!PLAN_ || (EXACT_ && R_ == 32 / KL_ && !PEER_ && !DB_ && RING_ == 0),
+                  "the planned variant: k % 32 == 0 or k = 16, 8; one accumulator set per edge slot");
     // DB: double-buffered gather batches (experimental launch shapes 4-7, see launch_fwd_r)
     static constexpr bool DB = DB_;
     // RING > 0: gathers go through cp.async into a per-warp shared-memory ring of 2 x RING rows
@@ -93,12 +93,19 @@ __device__ __forceinline__ void fwd_gather(Slice<C> &sl, const float *sp_data,
     constexpr bool P = C::PEER;
     const int64_t base = (int64_t)col * k;
     if constexpr (C::PLAN) {
-        // entry 32*i + lane: the grouping the plan was made for; sp_index points at sp_addr
+        // entry 32*i + lane (k < 32: entry lane / E of edge slot lane % E): the grouping the plan
+        // was made for; sp_index points at sp_addr
         const unsigned short *sp_addr = reinterpret_cast<const unsigned short *>(sp_index);
+        if constexpr (C::KL < 32) {
+            const int entry = lane / C::E;
+            sl.v[0] = fwd_ld<P>(sp_data + base + entry);
+            sl.s[0] = fwd_ld<P>(sp_addr + base + entry);
+        } else {
 #pragma unroll
-        for (int i = 0; i < C::EPL; ++i) {
-            sl.v[i] = fwd_ld<P>(sp_data + base + lane + 32 * i);
-            sl.s[i] = fwd_ld<P>(sp_addr + base + lane + 32 * i);
+            for (int i = 0; i < C::EPL; ++i) {
+                sl.v[i] = fwd_ld<P>(sp_data + base + lane + 32 * i);
+                sl.s[i] = fwd_ld<P>(sp_addr + base + lane + 32 * i);
+            }
         }
     } else if constexpr (C::KL < 32) {
         const int entry = lane / C::E;
@@ -403,6 +410,24 @@ __device__ __forceinline__ void fwd_flush_row_planned(float *acc, float *__restr
 {
     __syncwarp();
     float *dst = out + row * (int64_t)d;
+    if constexpr (C::R > 1) {  // k = 16, 8: R sets, word * R + slot
+        constexpr int R = C::R;
+        for (int c = lane; c < d; c += 32) {
+            const float *p0 = acc + c * R, *p1 = acc + (256 + ((c & 7) << 5) + (c >> 3)) * R;
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) s += p0[r] + p1[r];
+            if (shared_row)
+                red_add_f1(dst + c, s);
+            else
+                __stcs(dst + c, s);
+        }
+        __syncwarp();
+        for (int i = lane * 4; i < C::PLAN_WORDS; i += 128)
+            *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        return;
+    }
     const float *acc1 = acc + 256;
     for (int c = lane * 4; c < d; c += 128) {
         float4 v = *reinterpret_cast<float4 *>(acc + c);
@@ -836,12 +861,12 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
 }
 
 // ---- forward with a bank plan (cbsr_plan.cu): EXPERIMENTAL, own entry point ---------------------
-template <int EPL>
+template <int KL, int EPL>
 static int launch_fwd_planned(const FwdArgs &a)
 {
-    constexpr int U1 = (EPL == 1) ? 4 : (EPL <= 4 ? 2 : 1);
-    if (a.depth == 2) return launch_fwd<FwdCfg<32, EPL, true, 1, 2, U1, (EPL <= 2 ? 16 : 8), false, false, 0, true>>(a);
-    return launch_fwd<FwdCfg<32, EPL, true, 1, 8, U1, (EPL <= 2 ? 4 : 2), false, false, 0, true>>(a);
+    constexpr int U1 = (EPL == 1) ? 4 : (EPL <= 4 ? 2 : 1), R = 32 / KL;
+    if (a.depth == 2) return launch_fwd<FwdCfg<KL, EPL, true, R, 2, U1, (EPL <= 2 ? 16 : 8), false, false, 0, true>>(a);
+    return launch_fwd<FwdCfg<KL, EPL, true, R, 8, U1, (EPL <= 2 ? (R <= 2 ? 4 : 3) : 2), false, false, 0, true>>(a);
 }
 
 extern "C" int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks,
@@ -853,8 +878,8 @@ extern "C" int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tas
     MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0, "maxk_spgemm_forward_planned: negative size");
     MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
                  "maxk_spgemm_forward_planned: d=%d must be a multiple of 4 in [4,256]", d);
-    MAXK_REQUIRE(k >= 32 && k <= d && k % 32 == 0,
-                 "maxk_spgemm_forward_planned: k=%d must be a multiple of 32 in [32,d=%d]", k, d);
+    MAXK_REQUIRE(k >= 8 && k <= d && (k % 32 == 0 || k == 16 || k == 8),
+                 "maxk_spgemm_forward_planned: k=%d must be 8, 16 or a multiple of 32, and <= d=%d", k, d);
     MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "maxk_spgemm_forward_planned: out is NULL");
     MAXK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
@@ -886,15 +911,17 @@ extern "C" int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tas
             MAXK_LAUNCH_CHECK("spgemm_fwd_clear_shared_rows");
         }
     }
+    if (k == 16) return launch_fwd_planned<16, 1>(a);
+    if (k == 8) return launch_fwd_planned<8, 1>(a);
     switch (k / 32) {
-        case 1: return launch_fwd_planned<1>(a);
-        case 2: return launch_fwd_planned<2>(a);
-        case 3: return launch_fwd_planned<3>(a);
-        case 4: return launch_fwd_planned<4>(a);
-        case 5: return launch_fwd_planned<5>(a);
-        case 6: return launch_fwd_planned<6>(a);
-        case 7: return launch_fwd_planned<7>(a);
-        case 8: return launch_fwd_planned<8>(a);
+        case 1: return launch_fwd_planned<32, 1>(a);
+        case 2: return launch_fwd_planned<32, 2>(a);
+        case 3: return launch_fwd_planned<32, 3>(a);
+        case 4: return launch_fwd_planned<32, 4>(a);
+        case 5: return launch_fwd_planned<32, 5>(a);
+        case 6: return launch_fwd_planned<32, 6>(a);
+        case 7: return launch_fwd_planned<32, 7>(a);
+        case 8: return launch_fwd_planned<32, 8>(a);
         default: break;
     }
     set_error("maxk_spgemm_forward_planned: unsupported k=%d", k);

@@ -224,7 +224,7 @@ def test_forward_experimental_shapes(ops, k, shape):
 @pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
                     reason="bank-planned forward (csrc/cbsr_plan.cu): written after round 1's GPU budget was spent, "
                            "checked under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
-@pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=128), dict(k=256), dict(k=32, d=128),
+@pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=16), dict(k=8), dict(k=128), dict(k=256), dict(k=32, d=128),
                                   dict(k=32, selector="random"), dict(k=32, avg=3.0, n=3000, empty_frac=0.4),
                                   dict(k=32, n=50, avg=2000.0, empty_frac=0.0), dict(k=32, warp_max_nz=100)],
                          ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))

@@ -241,6 +241,20 @@ def _bank_loads(sp_addr):
     return np.stack([np.bincount(b, minlength=32).max() for b in banks.reshape(-1, 32)]).reshape(n, k // 32)
 
 
+@pytest.mark.parametrize("k", [16, 8])
+def test_simt_bank_plan_small_k(k):
+    """k = 16 / 8: the row's k entries share k banks (the other edges of the instruction use the rest)."""
+    rng = np.random.default_rng(k)
+    n = 400
+    sp_index = np.sort(np.argsort(rng.random((n, 256)), axis=1)[:, :k], axis=1).astype(np.uint8)
+    sp_addr = S.cbsr_bank_plan(sp_index)
+    c = sp_index.astype(np.int64)
+    assert ((sp_addr == c) | (sp_addr == 256 + (c % 8) * 32 + c // 8)).all()
+    fullest = lambda a: np.array([np.bincount(r % k, minlength=k).max() for r in a.astype(np.int64)])  # noqa: E731
+    planned, plain = fullest(sp_addr), fullest(sp_index)
+    assert planned.max() <= 3 and planned.mean() < plain.mean() - 0.4, (planned.mean(), plain.mean())
+
+
 @pytest.mark.parametrize("k", [32, 64, 18, 96, 256])
 def test_simt_bank_plan_is_valid_and_spreads_the_banks(k):
     rng = np.random.default_rng(k)
@@ -263,7 +277,7 @@ def test_simt_bank_plan_is_valid_and_spreads_the_banks(k):
     assert (S.cbsr_bank_plan(ident) == ident).all()
 
 
-PLANNED_CASES = [dict(k=32), dict(k=64), dict(k=96), dict(k=128), dict(k=256), dict(k=160),
+PLANNED_CASES = [dict(k=16), dict(k=8), dict(k=16, d=64), dict(k=8, avg=200.0, n=40), dict(k=32), dict(k=64), dict(k=96), dict(k=128), dict(k=256), dict(k=160),
                  dict(k=32, d=128), dict(k=32, d=36), dict(k=32, selector="random"), dict(k=64, selector="torch"),
                  dict(k=32, kind="uniform", avg=300.0, n=40, empty_frac=0.0), dict(k=32, avg=3.0, n=1500, empty_frac=0.4),
                  dict(k=32, n=20, avg=1500.0, empty_frac=0.0), dict(k=32, n=200, n_cols=700, avg=25.0),
@@ -308,7 +322,7 @@ def test_simt_planned_forward_gap_rows_and_empty():
     y = S.spgemm_forward_planned(z32, z32, np.zeros(0, np.float32), sp_data, sp_addr, 10)
     assert y.shape == (10, 256) and float(np.abs(y).sum()) == 0.0
     with pytest.raises(S.SimtError, match="multiple of 32"):
-        S.spgemm_forward_planned(w4, indices, values, sp_data[:, :16], sp_addr[:, :16], n)
+        S.spgemm_forward_planned(w4, indices, values, sp_data[:, :20], sp_addr[:, :20], n)
 
 
 def test_simt_empty_inputs():
