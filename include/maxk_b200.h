@@ -118,16 +118,18 @@ MAXK_API int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks, co
  * tests/simt only; nothing calls these by default): bank-planned forward.  The forward kernel is
  * bound by shared-memory wavefronts of its scatter into the output row (32 random columns per
  * edge collide in the 32 banks, ~3.3-way).  maxk_cbsr_bank_plan gives every entry of a CBSR row
- * one of two homes for its column (word c of copy 0 or word 256 + (c%8)*32 + c/8 of copy 1) so
- * that the 32 entries of one update spread over the banks (~2-way), once per row instead of
- * once per edge; sp_addr uint16[n,k] holds the chosen accumulator words and replaces sp_index in
- * maxk_spgemm_forward_planned (k = 8, 16 or a multiple of 32; same output contract as
- * maxk_spgemm_forward_acc).  */
-MAXK_API int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, uint16_t *sp_addr,
-                        void *stream);
+ * one of `homes` (2, 4 or 8) homes for its column -- word c of copy 0 or a word of copy h in
+ * another bank -- by a maximum matching of the 32 entries of one update onto the 32 banks, once
+ * per row instead of once per edge (fullest bank ~2.0 / 1.5 / 1.0 instead of 3.3); sp_addr
+ * uint16[n,k] holds the chosen accumulator words and replaces sp_index in
+ * maxk_spgemm_forward_planned (k = 8, 16 or a multiple of 32; 4 homes for k = 16, 32, 64 and 8 homes
+ * for k = 32, 64 only; same
+ * homes as the plan was made with; same output contract as maxk_spgemm_forward_acc).           */
+MAXK_API int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, int32_t homes,
+                        uint16_t *sp_addr, void *stream);
 MAXK_API int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                                 const float *values, const float *sp_data, const uint16_t *sp_addr,
-                                int32_t k, float *out, int64_t num_rows_out, int32_t d,
+                                int32_t k, int32_t homes, float *out, int64_t num_rows_out, int32_t d,
                                 int32_t accumulate, void *stream);
 
 /* ---- a3: backward outer-product sampled SSpMM  dXc = sample(A^T dY, sp_index)

@@ -63,20 +63,22 @@ for k in [int(v) for v in a.ks.split(",")]:
     ops.set_forward_depth(0)
     if a.planned and (k % 32 == 0 or k in (8, 16)):
         # the plan is made once per TopK, the planned forward runs once per layer: both are timed
-        sa = ops.cbsr_bank_plan(si)
-        t_plan = timeit(lambda: ops.cbsr_bank_plan(si, out=sa), a.iters)
         ref = ops.spgemm_forward(w4, g["indices"], g["values"], sd, si, num_rows=n)
-        for tpw in [int(v) for v in a.tpw.split(",")]:
-            for dep in (1, 2):
-                ops.set_forward_depth(dep)
-                ops.set_tuning(tpw, 0)
-                t = timeit(lambda: ops.spgemm_forward_planned(w4, g["indices"], g["values"], sd, sa, out=y, num_rows=n), a.iters)
-                err = float((y - ref).abs().max() / ref.abs().max())
-                r = {"kernel": "fwd_planned", "shape": a.shape, "k": k, "tpw": tpw, "depth": dep, "ms": round(t, 4),
-                     "plan_ms": round(t_plan, 4), "frac": round(b["fwd"] / t / 1e6 / peak, 3),
-                     "frac_with_plan": round(b["fwd"] / (t + t_plan) / 1e6 / peak, 3), "rel_err_vs_default": err}
-                res.append(r)
-                print(json.dumps(r), flush=True)
+        for homes in ((2, 4, 8) if k in (32, 64) else (2, 4) if k == 16 else (2,)):
+            sa = ops.cbsr_bank_plan(si, homes)
+            t_plan = timeit(lambda: ops.cbsr_bank_plan(si, homes, out=sa), a.iters)
+            for tpw in [int(v) for v in a.tpw.split(",")]:
+                for dep in (1, 2):
+                    ops.set_forward_depth(dep)
+                    ops.set_tuning(tpw, 0)
+                    t = timeit(lambda: ops.spgemm_forward_planned(w4, g["indices"], g["values"], sd, sa, homes, out=y,
+                                                                  num_rows=n), a.iters)
+                    err = float((y - ref).abs().max() / ref.abs().max())
+                    r = {"kernel": "fwd_planned", "shape": a.shape, "k": k, "homes": homes, "tpw": tpw, "depth": dep,
+                         "ms": round(t, 4), "plan_ms": round(t_plan, 4), "frac": round(b["fwd"] / t / 1e6 / peak, 3),
+                         "frac_with_plan": round(b["fwd"] / (t + t_plan) / 1e6 / peak, 3), "rel_err_vs_default": err}
+                    res.append(r)
+                    print(json.dumps(r), flush=True)
         ops.set_forward_depth(0)
     if a.bwd_tpw:
         dxc = torch.empty(n, k, device="cuda")

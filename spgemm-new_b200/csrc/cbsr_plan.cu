@@ -11,17 +11,20 @@
 // banks collide: the fullest bank holds 3.3 of them on average, so the load and the store of that
 // update cost ~3.3 wavefronts each, more than everything else together.  No fixed column->bank
 // mapping helps (any mapping sees the same random sets).  What helps is a CHOICE: give every
-// column two homes in different banks,
-//       copy 0:  word  c                          bank  c mod 32
-//       copy 1:  word  256 + (c mod 8)*32 + c/8   bank  c / 8
+// column H homes in different banks (H copies of the output row, common.cuh: plan_home_word),
+//       home 0:  word  c                                            bank  c mod 32
+//       home h:  word  h*256 + (c mod 8)*32 + (c/8 + S_h*(c mod 8) + T_h) mod 32
 // and decide once per CBSR row -- not once per edge -- which home each of its entries uses so
-// that the 32 entries of one instruction spread over the banks.  Greedy two-choice placement plus
-// two repair passes brings the fullest bank to 2 in 98 % of random rows (mean 2.02 vs 3.27), i.e.
-// ~2.5 of ~10 wavefronts per edge go away; the row is summed over its two copies when it is
-// flushed.  A row is planned once per TopK and used once per incident edge (492 times on the Reddit
-// shape, 25 on the products shape).
+// that the 32 entries of one update instruction spread over the banks.  The plan is a maximum
+// bipartite matching entries -> banks (augmenting paths, one thread per row); entries it leaves
+// over go to their least loaded bank.  Fullest bank of 32 random columns (simulation, 500 rows):
+//       one home 3.27   H = 2: 2.0   H = 4: 1.46 (54 % of rows conflict-free)   H = 8: 1.01
+// i.e. of ~10.9 wavefronts per edge on the Reddit shape ~2.9 / ~4 / ~4.9 go away; the row is
+// summed over its homes when it is flushed (H x the flush work and shared memory, so H is a
+// trade: 8 for long rows, 2 for short ones).  A row is planned once per TopK and used once per
+// incident edge (492 times on the Reddit shape, 25 on the products shape).
 //
-// The plan is a uint16 array sp_addr[N,k] holding the accumulator WORD of every entry (0..511): it
+// The plan is a uint16 array sp_addr[N,k] holding the accumulator WORD of every entry (< H*256): it
 // replaces sp_index as the forward kernel's second gather (64 instead of 32 bytes per row at
 // k = 32 -- still one wavefront, 6k instead of 5k bytes per node in the L2).  Entries are planned
 // in groups of 32 consecutive entries, which is how the planned forward kernel maps entries to
@@ -34,42 +37,10 @@ namespace maxk {
 
 constexpr int PLAN_GROUP = 32;
 
-__device__ __forceinline__ unsigned plan_word(unsigned c, unsigned copy)
-{
-    return copy ? (256u + ((c & 7u) << 5) + (c >> 3)) : c;
-}
-
-struct BankLoad {  // 32 four-bit counters (an instruction has at most 32 entries)
-    unsigned long long lo = 0ull, hi = 0ull;
-    __device__ __forceinline__ unsigned get(unsigned b) const
-    {
-        return (unsigned)(((b < 16u) ? lo : hi) >> (4u * (b & 15u))) & 15u;
-    }
-    __device__ __forceinline__ void add(unsigned b, int delta)
-    {
-        const unsigned long long one = 1ull << (4u * (b & 15u));
-        if (b < 16u)
-            lo = delta > 0 ? lo + one : lo - one;
-        else
-            hi = delta > 0 ? hi + one : hi - one;
-    }
-    __device__ __forceinline__ unsigned fullest() const
-    {
-        unsigned m = 0u;
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {
-            const unsigned a = (unsigned)(lo >> (4 * b)) & 15u, c = (unsigned)(hi >> (4 * b)) & 15u;
-            m = a > m ? a : m;
-            m = c > m ? c : m;
-        }
-        return m;
-    }
-};
-
-// one thread per (row, group of 32 entries)
+// one thread per (row, group of entries that share an update instruction)
 __global__ void __launch_bounds__(128)
 cbsr_bank_plan_kernel(const unsigned char *__restrict__ sp_index, int64_t n, int k, int groups,
-                      int group_len, unsigned bank_mask, unsigned short *__restrict__ sp_addr)
+                      int group_len, unsigned bank_mask, int homes, unsigned short *__restrict__ sp_addr)
 {
     const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= n * groups) return;
@@ -79,57 +50,81 @@ cbsr_bank_plan_kernel(const unsigned char *__restrict__ sp_index, int64_t n, int
     const int cnt = min(group_len, k - j0);
     const unsigned char *src = sp_index + row * k + j0;
 
-    unsigned char c[PLAN_GROUP];
-#pragma unroll
-    for (int i = 0; i < PLAN_GROUP; ++i) c[i] = (i < cnt) ? __ldg(src + i) : (unsigned char)0;
-
-    BankLoad load;
-    unsigned copy = 0u;  // bit i: entry i lives in copy 1
-#pragma unroll
+    unsigned char c[PLAN_GROUP];       // columns of the entries
+    signed char owner[PLAN_GROUP];     // bank -> entry that holds it (-1: free)
+    signed char home[PLAN_GROUP];      // entry -> home it uses (-1: not placed yet)
+    unsigned char done[PLAN_GROUP];    // entry -> placed for good
     for (int i = 0; i < PLAN_GROUP; ++i) {
-        if (i < cnt) {
-            const unsigned b0 = c[i] & bank_mask, b1 = (c[i] >> 3) & bank_mask;
-            const bool second = load.get(b1) < load.get(b0);
-            copy |= second ? (1u << i) : 0u;
-            load.add(second ? b1 : b0, +1);
-        }
+        c[i] = (i < cnt) ? __ldg(src + i) : (unsigned char)0;
+        owner[i] = -1;
+        home[i] = -1;
+        done[i] = 0;
     }
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {  // repair: move entries out of the fullest banks
-        const unsigned m = load.fullest();
-        if (m <= 1u) break;
-        bool moved = false;
-#pragma unroll
-        for (int i = 0; i < PLAN_GROUP; ++i) {
-            if (i < cnt) {
-                const unsigned b0 = c[i] & bank_mask, b1 = (c[i] >> 3) & bank_mask;
-                const bool second = (copy >> i) & 1u;
-                const unsigned cur = second ? b1 : b0, alt = second ? b0 : b1;
-                if (load.get(cur) == m && load.get(alt) + 1u < m) {
-                    load.add(cur, -1);
-                    load.add(alt, +1);
-                    copy ^= 1u << i;
-                    moved = true;
+    auto bank = [&](int e, int h) -> unsigned { return plan_home_word(c[e], h) & bank_mask; };
+
+    // Layer 0: a maximum matching entries -> banks (Kuhn's augmenting paths, depth-first, explicit
+    // stack): every matched entry has a bank to itself.  Entries it leaves over are matched among
+    // themselves onto a second slot of every bank (layer 1), and so on: the fullest bank holds as
+    // many entries as layers were needed (1 for most rows with 8 homes, 2 with 2 homes).
+    int placed = 0;
+    for (int layer = 0; layer < PLAN_GROUP && placed < cnt; ++layer) {
+        for (int b = 0; b < PLAN_GROUP; ++b) owner[b] = -1;
+        for (int i = 0; i < cnt; ++i) {
+            if (done[i]) continue;  // placed by an earlier layer
+            unsigned visited = 0u;
+            signed char st_entry[PLAN_GROUP], st_next[PLAN_GROUP], st_bank[PLAN_GROUP], st_home[PLAN_GROUP];
+            int sp = 0;
+            st_entry[0] = (signed char)i;
+            st_next[0] = 0;
+            bool found = false;
+            while (sp >= 0) {
+                const int e = st_entry[sp], h = st_next[sp];
+                if (h == homes) {  // this entry cannot be re-homed: back up
+                    --sp;
+                    continue;
+                }
+                st_next[sp] = (signed char)(h + 1);
+                const unsigned b = bank(e, h);
+                if ((visited >> b) & 1u) continue;
+                visited |= 1u << b;
+                st_bank[sp] = (signed char)b;
+                st_home[sp] = (signed char)h;
+                if (owner[b] < 0) {
+                    found = true;
+                    break;
+                }
+                ++sp;  // ask the holder of bank b (an entry of this layer) to move
+                st_entry[sp] = owner[b];
+                st_next[sp] = 0;
+            }
+            if (found) {
+                for (int l = sp; l >= 0; --l) {  // every entry on the path takes the bank it asked for
+                    owner[st_bank[l]] = st_entry[l];
+                    home[st_entry[l]] = st_home[l];
                 }
             }
         }
-        if (!moved) break;
+        for (int b = 0; b < PLAN_GROUP; ++b) {  // what this layer matched is final
+            if (owner[b] >= 0 && !done[owner[b]]) {
+                done[owner[b]] = 1;
+                ++placed;
+            }
+        }
     }
     unsigned short *dst = sp_addr + row * k + j0;
-#pragma unroll
-    for (int i = 0; i < PLAN_GROUP; ++i)
-        if (i < cnt) dst[i] = (unsigned short)plan_word(c[i], (copy >> i) & 1u);
+    for (int i = 0; i < cnt; ++i) dst[i] = (unsigned short)plan_home_word(c[i], home[i]);
 }
 
 }  // namespace maxk
 
 using namespace maxk;
 
-extern "C" int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, uint16_t *sp_addr,
-                                   void *stream)
+extern "C" int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, int32_t homes,
+                                   uint16_t *sp_addr, void *stream)
 {
     MAXK_REQUIRE(n >= 0, "maxk_cbsr_bank_plan: negative n");
     MAXK_REQUIRE(k >= 1 && k <= MAXK_MAX_DIM, "maxk_cbsr_bank_plan: k=%d out of range", k);
+    MAXK_REQUIRE(homes == 2 || homes == 4 || homes == 8, "maxk_cbsr_bank_plan: homes=%d must be 2, 4 or 8", homes);
     if (n == 0) return MAXK_OK;
     MAXK_REQUIRE(sp_index != nullptr && sp_addr != nullptr, "maxk_cbsr_bank_plan: NULL pointer");
     MAXK_REQUIRE((reinterpret_cast<uintptr_t>(sp_addr) & 1) == 0, "maxk_cbsr_bank_plan: sp_addr must be 2-byte aligned");
@@ -142,7 +137,7 @@ extern "C" int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k
     const int64_t grid = ceil_div<int64_t>(n * groups, 128);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_cbsr_bank_plan: n too large");
     cbsr_bank_plan_kernel<<<(unsigned)grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        sp_index, n, k, groups, group_len, bank_mask, sp_addr);
+        sp_index, n, k, groups, group_len, bank_mask, homes, sp_addr);
     MAXK_LAUNCH_CHECK("cbsr_bank_plan_kernel");
     return MAXK_OK;
 }

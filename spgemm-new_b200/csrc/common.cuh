@@ -86,6 +86,21 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- bank plan (cbsr_plan.cu, planned forward): the homes of an output column ---------------------
+// Home 0 of column c is word c (bank c mod 32).  Home h >= 1 is word
+//   h*256 + (c mod 8)*32 + ((c/8 + S_h*(c mod 8) + T_h) mod 32)      bank (c/8 + S_h*(c mod 8) + T_h) mod 32
+// -- for fixed c mod 8 a rotation of c/8, hence a bijection of 0..255 for every h; different S_h
+// make two columns that share a bank in one home share it in few others.
+constexpr int PLAN_MAX_HOMES = 8;
+__host__ __device__ constexpr int plan_s(int h) { return h == 1 ? 0 : h == 2 ? 5 : h == 3 ? 11 : h == 4 ? 3 : h == 5 ? 7 : h == 6 ? 13 : 9; }
+__host__ __device__ constexpr int plan_t(int h) { return h == 1 ? 0 : h == 2 ? 7 : h == 3 ? 19 : h == 4 ? 3 : h == 5 ? 11 : h == 6 ? 23 : 29; }
+__host__ __device__ __forceinline__ unsigned plan_home_word(unsigned c, int h)
+{
+    if (h == 0) return c;
+    const unsigned lo = c & 7u;
+    return (unsigned)h * 256u + lo * 32u + (((c >> 3) + (unsigned)plan_s(h) * lo + (unsigned)plan_t(h)) & 31u);
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 template <typename T>

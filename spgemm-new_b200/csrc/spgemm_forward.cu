@@ -41,13 +41,16 @@ constexpr int FWD_STAGE = 64;  // staged (idx,val) pairs per warp == MAXK_WARP_M
 // R accumulator copies, WPB warps per CTA, U gather instructions in flight, MINB CTAs/SM
 // the register budget is capped for.
 template <int KL_, int EPL_, bool EXACT_, int R_, int WPB_, int U_, int MINB_, bool PEER_ = false,
-          bool DB_ = false, int RING_ = 0, bool PLAN_ = false>
+          bool DB_ = false, int RING_ = 0, int PLAN_ = 0>
 struct FwdCfg {
-    // PLAN: the second operand is the bank plan sp_addr (uint16 accumulator words, cbsr_plan.cu)
-    // instead of sp_index; the output row lives in two 256-word copies (experimental, own entry point)
-    static constexpr bool PLAN = PLAN_;
-    static constexpr int PLAN_WORDS = 512 * R_;  // two homes per column, one set per edge slot
-    static_assert(!PLAN_ || (EXACT_ && R_ == 32 / KL_ && !PEER_ && !DB_ && RING_ == 0),
+    // PLAN (= homes per column, 0 = off): the second operand is the bank plan sp_addr (uint16
+    // accumulator words, cbsr_plan.cu) instead of sp_index; the output row lives in HOMES
+    // 256-word copies (experimental, own entry point)
+    static constexpr bool PLAN = PLAN_ > 0;
+    static constexpr int HOMES = PLAN_;
+    static constexpr int PLAN_WORDS = PLAN_ * 256 * R_;  // HOMES homes per column, one set per edge slot
+    static_assert(PLAN_ == 0 || PLAN_ == 2 || PLAN_ == 4 || PLAN_ == 8, "homes");
+    static_assert(PLAN_ == 0 || (EXACT_ && R_ == 32 / KL_ && !PEER_ && !DB_ && RING_ == 0),
                   "the planned variant: k % 32 == 0 or k = 16, 8; one accumulator set per edge slot");
     // DB: double-buffered gather batches (experimental launch shapes 4-7, see launch_fwd_r)
     static constexpr bool DB = DB_;
@@ -403,46 +406,49 @@ __device__ __forceinline__ void fwd_flush_row(float *acc, float *__restrict__ ou
     __syncwarp();
 }
 
-// PLAN: out[row, c] = copy0[c] + copy1[(c mod 8)*32 + c/8]; both copies are cleared.
+// PLAN: out[row, c] = sum over the homes h of acc[plan_home_word(c, h)] (and over the R edge-slot
+// sets for k < 32); all homes are cleared.
 template <class C>
 __device__ __forceinline__ void fwd_flush_row_planned(float *acc, float *__restrict__ out, int64_t row,
                                                       int d, int lane, bool shared_row)
 {
+    constexpr int R = C::R, H = C::HOMES;
     __syncwarp();
     float *dst = out + row * (int64_t)d;
-    if constexpr (C::R > 1) {  // k = 16, 8: R sets, word * R + slot
-        constexpr int R = C::R;
+    if constexpr (R > 1) {  // k = 16, 8: word * R + slot
         for (int c = lane; c < d; c += 32) {
-            const float *p0 = acc + c * R, *p1 = acc + (256 + ((c & 7) << 5) + (c >> 3)) * R;
             float s = 0.f;
 #pragma unroll
-            for (int r = 0; r < R; ++r) s += p0[r] + p1[r];
+            for (int h = 0; h < H; ++h) {
+                const float *p = acc + plan_home_word((unsigned)c, h) * R;
+#pragma unroll
+                for (int r = 0; r < R; ++r) s += p[r];
+            }
             if (shared_row)
                 red_add_f1(dst + c, s);
             else
                 __stcs(dst + c, s);
         }
-        __syncwarp();
-        for (int i = lane * 4; i < C::PLAN_WORDS; i += 128)
-            *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
-        return;
+    } else {
+        for (int c = lane * 4; c < d; c += 128) {
+            float4 v = *reinterpret_cast<float4 *>(acc + c);  // home 0
+            // c % 4 == 0: columns c .. c+3 share c/8 and have c mod 8 = (c mod 8) + i
+            const unsigned lo = c & 7, hi = c >> 3;
+#pragma unroll
+            for (int h = 1; h < H; ++h) {
+                const float *p = acc + h * 256;
+                v.x += p[(lo + 0) * 32 + ((hi + plan_s(h) * (lo + 0) + plan_t(h)) & 31)];
+                v.y += p[(lo + 1) * 32 + ((hi + plan_s(h) * (lo + 1) + plan_t(h)) & 31)];
+                v.z += p[(lo + 2) * 32 + ((hi + plan_s(h) * (lo + 2) + plan_t(h)) & 31)];
+                v.w += p[(lo + 3) * 32 + ((hi + plan_s(h) * (lo + 3) + plan_t(h)) & 31)];
+            }
+            if (shared_row)
+                red_add_f4(dst + c, v.x, v.y, v.z, v.w);
+            else
+                st_stream_f4(reinterpret_cast<float4 *>(dst + c), v);
+        }
     }
-    const float *acc1 = acc + 256;
-    for (int c = lane * 4; c < d; c += 128) {
-        float4 v = *reinterpret_cast<float4 *>(acc + c);
-        // (c + i) mod 8 = (c mod 8) + i and (c + i) / 8 = c / 8 for i < 4, because c % 4 == 0
-        const float *p = acc1 + ((c & 7) << 5) + (c >> 3);
-        v.x += p[0];
-        v.y += p[32];
-        v.z += p[64];
-        v.w += p[96];
-        if (shared_row)
-            red_add_f4(dst + c, v.x, v.y, v.z, v.w);
-        else
-            st_stream_f4(reinterpret_cast<float4 *>(dst + c), v);
-    }
-    __syncwarp();  // every lane has read both copies before anybody clears a word of them
+    __syncwarp();  // every lane has read all homes before anybody clears a word of them
     for (int i = lane * 4; i < C::PLAN_WORDS; i += 128)
         *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
@@ -861,20 +867,41 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
 }
 
 // ---- forward with a bank plan (cbsr_plan.cu): EXPERIMENTAL, own entry point ---------------------
-template <int KL, int EPL>
-static int launch_fwd_planned(const FwdArgs &a)
+template <int KL, int EPL, int H>
+static int launch_fwd_planned_h(const FwdArgs &a)
 {
     constexpr int U1 = (EPL == 1) ? 4 : (EPL <= 4 ? 2 : 1), R = 32 / KL;
-    if (a.depth == 2) return launch_fwd<FwdCfg<KL, EPL, true, R, 2, U1, (EPL <= 2 ? 16 : 8), false, false, 0, true>>(a);
-    return launch_fwd<FwdCfg<KL, EPL, true, R, 8, U1, (EPL <= 2 ? (R <= 2 ? 4 : 3) : 2), false, false, 0, true>>(a);
+    if (a.depth == 2) return launch_fwd<FwdCfg<KL, EPL, true, R, 2, U1, (EPL <= 2 ? 16 : 8), false, false, 0, H>>(a);
+    return launch_fwd<FwdCfg<KL, EPL, true, R, 8, U1, (EPL <= 2 ? (R <= 2 ? 4 : 3) : 2), false, false, 0, H>>(a);
+}
+// 4 and 8 homes are built for k = 32 and 64, 4 homes also for k = 16 (the k of the BASELINE kernel
+// bench; shared memory per warp is homes * 32/min(k,32) KB); every other supported k has the
+// two-home variant
+template <int KL, int EPL>
+static int launch_fwd_planned(const FwdArgs &a, int homes)
+{
+    if constexpr (KL == 32 && EPL <= 2) {
+        if (homes == 4) return launch_fwd_planned_h<KL, EPL, 4>(a);
+        if (homes == 8) return launch_fwd_planned_h<KL, EPL, 8>(a);
+    }
+    if constexpr (KL == 16) {
+        if (homes == 4) return launch_fwd_planned_h<KL, EPL, 4>(a);
+    }
+    if (homes != 2) {
+        set_error("maxk_spgemm_forward_planned: homes=%d is not built for k=%d (4: k = 16, 32, 64; 8: k = 32, 64)",
+                  homes, a.k);
+        return MAXK_ERR_UNSUPPORTED;
+    }
+    return launch_fwd_planned_h<KL, EPL, 2>(a);
 }
 
 extern "C" int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks,
                                            const int32_t *indices, const float *values,
                                            const float *sp_data, const uint16_t *sp_addr, int32_t k,
-                                           float *out, int64_t num_rows_out, int32_t d,
+                                           int32_t homes, float *out, int64_t num_rows_out, int32_t d,
                                            int32_t accumulate, void *stream)
 {
+    MAXK_REQUIRE(homes == 2 || homes == 4 || homes == 8, "maxk_spgemm_forward_planned: homes=%d must be 2, 4 or 8", homes);
     MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0, "maxk_spgemm_forward_planned: negative size");
     MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
                  "maxk_spgemm_forward_planned: d=%d must be a multiple of 4 in [4,256]", d);
@@ -911,17 +938,17 @@ extern "C" int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tas
             MAXK_LAUNCH_CHECK("spgemm_fwd_clear_shared_rows");
         }
     }
-    if (k == 16) return launch_fwd_planned<16, 1>(a);
-    if (k == 8) return launch_fwd_planned<8, 1>(a);
+    if (k == 16) return launch_fwd_planned<16, 1>(a, homes);
+    if (k == 8) return launch_fwd_planned<8, 1>(a, homes);
     switch (k / 32) {
-        case 1: return launch_fwd_planned<32, 1>(a);
-        case 2: return launch_fwd_planned<32, 2>(a);
-        case 3: return launch_fwd_planned<32, 3>(a);
-        case 4: return launch_fwd_planned<32, 4>(a);
-        case 5: return launch_fwd_planned<32, 5>(a);
-        case 6: return launch_fwd_planned<32, 6>(a);
-        case 7: return launch_fwd_planned<32, 7>(a);
-        case 8: return launch_fwd_planned<32, 8>(a);
+        case 1: return launch_fwd_planned<32, 1>(a, homes);
+        case 2: return launch_fwd_planned<32, 2>(a, homes);
+        case 3: return launch_fwd_planned<32, 3>(a, homes);
+        case 4: return launch_fwd_planned<32, 4>(a, homes);
+        case 5: return launch_fwd_planned<32, 5>(a, homes);
+        case 6: return launch_fwd_planned<32, 6>(a, homes);
+        case 7: return launch_fwd_planned<32, 7>(a, homes);
+        case 8: return launch_fwd_planned<32, 8>(a, homes);
         default: break;
     }
     set_error("maxk_spgemm_forward_planned: unsupported k=%d", k);

@@ -142,10 +142,11 @@ def spgemm_forward(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Ten
 
 
 # ---------------------------------------------------- a2, experimental: bank-planned forward
-def cbsr_bank_plan(sp_index: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def cbsr_bank_plan(sp_index: torch.Tensor, homes: int = 2, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """EXPERIMENTAL (csrc/cbsr_plan.cu; not yet run on a GPU).  sp_index uint8 [N, k] -> sp_addr
     uint16 [N, k]: the shared-memory accumulator word each entry uses in `spgemm_forward_planned`,
-    chosen per row so that the 32 entries of one update spread over the 32 banks."""
+    chosen per row among `homes` (2, 4, 8) candidates so that the 32 entries of one update spread
+    over the 32 banks."""
     lib = _cabi.load()
     _cuda(sp_index, "sparse_selector", torch.uint8)
     _req(sp_index.dim() == 2, "sparse_selector must be [N, k]")
@@ -156,16 +157,16 @@ def cbsr_bank_plan(sp_index: torch.Tensor, out: Optional[torch.Tensor] = None) -
         else:
             _cuda(out, "out", torch.uint16)
             _req(tuple(out.shape) == (n, k), "out has the wrong shape")
-        _cabi.check(lib.maxk_cbsr_bank_plan(sp_index.data_ptr(), n, k, out.data_ptr(), _stream(sp_index)))
+        _cabi.check(lib.maxk_cbsr_bank_plan(sp_index.data_ptr(), n, k, int(homes), out.data_ptr(), _stream(sp_index)))
     return out
 
 
 def spgemm_forward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
-                           sp_data: torch.Tensor, sp_addr: torch.Tensor, feat_dim: int = FULL_DIM,
-                           num_rows: Optional[int] = None, out: Optional[torch.Tensor] = None,
-                           accumulate: bool = False) -> torch.Tensor:
-    """EXPERIMENTAL: `spgemm_forward` with the bank plan `sp_addr = cbsr_bank_plan(sp_index)` in
-    place of the selectors (k % 32 == 0).  Same output contract."""
+                           sp_data: torch.Tensor, sp_addr: torch.Tensor, homes: int = 2,
+                           feat_dim: int = FULL_DIM, num_rows: Optional[int] = None,
+                           out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """EXPERIMENTAL: `spgemm_forward` with the bank plan `sp_addr = cbsr_bank_plan(sp_index, homes)`
+    in place of the selectors (k = 8, 16 or a multiple of 32).  Same output contract."""
     lib = _cabi.load()
     _cuda(warp4, "warp4_metadata", torch.int32)
     _cuda(indices, "indices", torch.int32)
@@ -185,8 +186,9 @@ def spgemm_forward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: t
             _cuda(out, "out", torch.float32)
             _req(tuple(out.shape) == (n_out, feat_dim), "out has the wrong shape")
         _cabi.check(lib.maxk_spgemm_forward_planned(warp4.data_ptr(), w, indices.data_ptr(), values.data_ptr(),
-                                                    sp_data.data_ptr(), sp_addr.data_ptr(), k, out.data_ptr(),
-                                                    n_out, feat_dim, 1 if accumulate else 0, _stream(sp_data)))
+                                                    sp_data.data_ptr(), sp_addr.data_ptr(), k, int(homes),
+                                                    out.data_ptr(), n_out, feat_dim, 1 if accumulate else 0,
+                                                    _stream(sp_data)))
     return out
 
 

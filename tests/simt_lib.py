@@ -287,18 +287,18 @@ def cbsr_unpack(records, n, k):
     return r["sp_data"], r["sp_index"]
 
 
-def cbsr_bank_plan(sp_index):
+def cbsr_bank_plan(sp_index, homes=2):
     L = load()
     sp_index = np.ascontiguousarray(sp_index, np.uint8)
     n, k = sp_index.shape
     r = _run(L.maxk_cbsr_bank_plan, {"sp_index": Guarded(sp_index, name="sp_index", align=1)},
              {"sp_addr": Guarded(shape=(n, k), dtype=np.uint16, name="sp_addr", align=2)},
-             lambda p: (p["sp_index"], i64(n), i32(k), p["sp_addr"], None))
+             lambda p: (p["sp_index"], i64(n), i32(k), i32(homes), p["sp_addr"], None))
     return r["sp_addr"]
 
 
 def spgemm_forward_planned(w4, idx, val, sp_data, sp_addr, n_out, d=256, accumulate=False, out_init=None,
-                           data_align=16, addr_align=16):
+                           data_align=16, addr_align=16, homes=2):
     L = load()
     w4 = np.ascontiguousarray(w4, np.int32).reshape(-1)
     k = sp_data.shape[1]
@@ -309,5 +309,5 @@ def spgemm_forward_planned(w4, idx, val, sp_data, sp_addr, n_out, d=256, accumul
     out = Guarded(out_init, name="out") if out_init is not None else Guarded(shape=(n_out, d), dtype=np.float32, name="out")
     r = _run(L.maxk_spgemm_forward_planned, ins, {"out": out},
              lambda p: (p["warp4"], i64(w4.shape[0] // 4), p["idx"], p["val"], p["sp_data"], p["sp_addr"], i32(k),
-                        p["out"], i64(n_out), i32(d), i32(1 if accumulate else 0), None))
+                        i32(homes), p["out"], i64(n_out), i32(d), i32(1 if accumulate else 0), None))
     return r["out"]

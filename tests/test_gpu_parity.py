@@ -231,22 +231,21 @@ def test_forward_experimental_shapes(ops, k, shape):
 def test_forward_planned_experimental(ops, case):
     p = Problem(seed=len(str(case)) + 2, **case)
     g = p.cuda()
-    sp_addr = ops.cbsr_bank_plan(g["sp_index"])
-    c = g["sp_index"].long()
-    a = sp_addr.long()
-    assert bool(((a == c) | (a == 256 + (c % 8) * 32 + c // 8)).all())
     want = p.fwd_oracle()
     try:
-        for shape, tpw in ((0, -1), (1, 1), (2, 5)):
-            ops.set_forward_depth(shape)
-            ops.set_tuning(tpw, 0)
-            y = torch.full((p.n, p.d), float("nan"), device="cuda")
-            ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr,
-                                       feat_dim=p.d, num_rows=p.n, out=y)
-            assert_close(y, want, f"shape={shape} tpw={tpw}")
-        ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr,
-                                   feat_dim=p.d, num_rows=p.n, out=y, accumulate=True)
-        assert_close(y, 2 * want, "accumulate")
+        for homes in ((2, 4, 8) if p.k in (32, 64) else (2, 4) if p.k == 16 else (2,)):
+            sp_addr = ops.cbsr_bank_plan(g["sp_index"], homes)
+            assert int(sp_addr.long().max()) < homes * 256
+            for shape, tpw in ((0, -1), (1, 1), (2, 5)):
+                ops.set_forward_depth(shape)
+                ops.set_tuning(tpw, 0)
+                y = torch.full((p.n, p.d), float("nan"), device="cuda")
+                ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, homes,
+                                           feat_dim=p.d, num_rows=p.n, out=y)
+                assert_close(y, want, f"homes={homes} shape={shape} tpw={tpw}")
+            ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, homes,
+                                       feat_dim=p.d, num_rows=p.n, out=y, accumulate=True)
+            assert_close(y, 2 * want, "accumulate")
     finally:
         ops.set_forward_depth(0)
         ops.set_tuning(-1, -1)
