@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--sweep", action="store_true", help="also time k=8/16/64, TopK and the work list")
+    ap.add_argument("--planned", type=int, default=0, choices=(0, 2, 4, 8),
+                    help="EXPERIMENTAL (N=1): forward through the bank plan with this many homes per column "
+                         "(csrc/cbsr_plan.cu); the plan is made next to the TopK, outside the step, and timed separately")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--comm", choices=("peer", "nccl"), default="peer",
@@ -283,6 +286,7 @@ def main():
         x = torch.rand(n, FEAT_DIM, device=dev, generator=gen)
         dy = torch.rand(n, FEAT_DIM, device=dev, generator=gen)
         sp_data, sp_index = ops.topk_cbsr(x, k)
+        sp_addr = ops.cbsr_bank_plan(sp_index, args.planned) if args.planned else None
         y = torch.empty(n, FEAT_DIM, device=dev)
         dxc = torch.empty(n, k, device=dev)
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -292,7 +296,11 @@ def main():
             i = step_no[0]
             if i >= 0:
                 ev[i][0].record()
-            ops.spgemm_forward(warp4, g["indices"], g["values"], sp_data, sp_index, out=y, num_rows=n)
+            if sp_addr is not None:
+                ops.spgemm_forward_planned(warp4, g["indices"], g["values"], sp_data, sp_addr, args.planned,
+                                           out=y, num_rows=n)
+            else:
+                ops.spgemm_forward(warp4, g["indices"], g["values"], sp_data, sp_index, out=y, num_rows=n)
             if i >= 0:
                 ev[i][1].record()
             ops.sspmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dxc)
@@ -465,6 +473,16 @@ def main():
                                  "(37 MB) is L2-resident by design",
                            "step_algorithmic_bytes": step_bytes},
                 "clocks": clocks, "gpu_launches": launches}
+        if world == 1 and args.planned:
+            line["config"]["forward"] = (f"EXPERIMENTAL bank-planned forward, {args.planned} homes per column; the plan "
+                                         "kernel runs next to the TopK, outside the step (plan_ms)")
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(10):
+                ops.cbsr_bank_plan(sp_index, args.planned, out=sp_addr)
+            t1.record()
+            torch.cuda.synchronize()
+            line["plan_ms"] = t0.elapsed_time(t1) / 10
         if roofline:
             line["roofline"] = roofline
         if cpu_baseline:

@@ -98,16 +98,20 @@ __device__ __forceinline__ void fwd_gather(Slice<C> &sl, const float *sp_data,
     if constexpr (C::PLAN) {
         // entry 32*i + lane (k < 32: entry lane / E of edge slot lane % E): the grouping the plan
         // was made for; sp_index points at sp_addr
+        // k is the compile-time C::K here and column ids are non-negative: one unsigned 32x32->64
+        // multiply per edge instead of the sign-extended 64-bit product of the generic path (the
+        // planned kernel is close to issue-bound once the bank conflicts are gone)
         const unsigned short *sp_addr = reinterpret_cast<const unsigned short *>(sp_index);
+        const uint64_t ubase = (uint64_t)(uint32_t)col * (uint32_t)C::K;
         if constexpr (C::KL < 32) {
             const int entry = lane / C::E;
-            sl.v[0] = fwd_ld<P>(sp_data + base + entry);
-            sl.s[0] = fwd_ld<P>(sp_addr + base + entry);
+            sl.v[0] = fwd_ld<P>(sp_data + ubase + entry);
+            sl.s[0] = fwd_ld<P>(sp_addr + ubase + entry);
         } else {
 #pragma unroll
             for (int i = 0; i < C::EPL; ++i) {
-                sl.v[i] = fwd_ld<P>(sp_data + base + lane + 32 * i);
-                sl.s[i] = fwd_ld<P>(sp_addr + base + lane + 32 * i);
+                sl.v[i] = fwd_ld<P>(sp_data + ubase + lane + 32 * i);
+                sl.s[i] = fwd_ld<P>(sp_addr + ubase + lane + 32 * i);
             }
         }
     } else if constexpr (C::KL < 32) {
