@@ -303,7 +303,10 @@ def main():
                 ops.spgemm_forward(warp4, g["indices"], g["values"], sp_data, sp_index, out=y, num_rows=n)
             if i >= 0:
                 ev[i][1].record()
-            ops.sspmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dxc)
+            if sp_addr is not None and k % 32 == 0 and k <= 128:
+                ops.sspmm_backward_planned(warp4, g["indices"], g["values"], dy, sp_addr, args.planned, out=dxc)
+            else:
+                ops.sspmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dxc)
             if i >= 0:
                 ev[i][2].record()
 
@@ -474,8 +477,8 @@ def main():
                            "step_algorithmic_bytes": step_bytes},
                 "clocks": clocks, "gpu_launches": launches}
         if world == 1 and args.planned:
-            line["config"]["forward"] = (f"EXPERIMENTAL bank-planned forward, {args.planned} homes per column; the plan "
-                                         "kernel runs next to the TopK, outside the step (plan_ms)")
+            line["config"]["forward"] = (f"EXPERIMENTAL bank-planned forward and backward, {args.planned} homes per "
+                                         "column; the plan kernel runs next to the TopK, outside the step (plan_ms)")
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
             for _ in range(10):

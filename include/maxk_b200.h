@@ -131,6 +131,14 @@ MAXK_API int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks
                                 const float *values, const float *sp_data, const uint16_t *sp_addr,
                                 int32_t k, int32_t homes, float *out, int64_t num_rows_out, int32_t d,
                                 int32_t accumulate, void *stream);
+/* The backward through the same plan (k = 32, 64, 96, 128): dY rows are staged in all homes and
+ * entry l of CBSR row j looks its value up at word sp_addr[j,l]; one instruction covers the 32
+ * entries of one edge (ncu, round 1: 2.2 of the default kernel's 5.8 wavefronts per edge are bank
+ * conflicts of exactly these lookups).  Same output contract as maxk_sspmm_backward.          */
+MAXK_API int maxk_sspmm_backward_planned(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
+                                const float *values, const float *dy, const uint16_t *sp_addr,
+                                int32_t k, int32_t homes, int32_t d, float *dxc,
+                                int64_t num_cbsr_rows, int32_t accumulate, void *stream);
 
 /* ---- a3: backward outer-product sampled SSpMM  dXc = sample(A^T dY, sp_index)
  * (replaces spmm_kernel_opt2_sparse_backward_v3, kernels/spmm_maxk_backward.cu:15-115;

@@ -192,6 +192,35 @@ def spgemm_forward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: t
     return out
 
 
+def sspmm_backward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
+                           grad_output: torch.Tensor, sp_addr: torch.Tensor, homes: int = 2,
+                           out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """EXPERIMENTAL: `sspmm_backward` with the bank plan in place of the selectors (k = 32, 64, 96, 128;
+    the plan must have been made with the same `homes`).  Same output contract."""
+    lib = _cabi.load()
+    _cuda(warp4, "warp4_metadata", torch.int32)
+    _cuda(indices, "indices", torch.int32)
+    _cuda(values, "values", torch.float32)
+    _cuda(grad_output, "grad_output", torch.float32)
+    _cuda(sp_addr, "sp_addr", torch.uint16)
+    _req(grad_output.dim() == 2 and sp_addr.dim() == 2, "grad_output and sp_addr must be 2-D")
+    n_cbsr, k = sp_addr.shape
+    d = grad_output.shape[1]
+    w = warp4.numel() // 4
+    with torch.cuda.device(grad_output.device):
+        if out is None:
+            _req(not accumulate, "accumulate=True needs an `out` tensor")
+            out = torch.empty((n_cbsr, k), dtype=torch.float32, device=grad_output.device)
+        else:
+            _cuda(out, "out", torch.float32)
+            _req(tuple(out.shape) == (n_cbsr, k), "out has the wrong shape")
+        _cabi.check(lib.maxk_sspmm_backward_planned(warp4.data_ptr(), w, indices.data_ptr(), values.data_ptr(),
+                                                    grad_output.data_ptr(), sp_addr.data_ptr(), k, int(homes), d,
+                                                    out.data_ptr(), n_cbsr, 1 if accumulate else 0,
+                                                    _stream(grad_output)))
+    return out
+
+
 # ------------------------------------------------------------------------------ a3
 def sspmm_backward(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
                    grad_output: torch.Tensor, sp_index: torch.Tensor,

@@ -311,3 +311,22 @@ def spgemm_forward_planned(w4, idx, val, sp_data, sp_addr, n_out, d=256, accumul
              lambda p: (p["warp4"], i64(w4.shape[0] // 4), p["idx"], p["val"], p["sp_data"], p["sp_addr"], i32(k),
                         i32(homes), p["out"], i64(n_out), i32(d), i32(1 if accumulate else 0), None))
     return r["out"]
+
+
+def sspmm_backward_planned(w4, idx, val, dy, sp_addr, homes=2, n_cbsr=None, accumulate=False, out_init=None,
+                           dxc_align=16, addr_align=16):
+    L = load()
+    w4 = np.ascontiguousarray(w4, np.int32).reshape(-1)
+    sp_addr = np.asarray(sp_addr, np.uint16)
+    n_cbsr = sp_addr.shape[0] if n_cbsr is None else n_cbsr
+    k, d = sp_addr.shape[1], dy.shape[1]
+    ins = {"warp4": Guarded(w4, name="warp4"), "idx": Guarded(np.asarray(idx, np.int32), name="indices", align=4),
+           "val": Guarded(np.asarray(val, np.float32), name="values", align=4),
+           "dy": Guarded(np.asarray(dy, np.float32), name="dy"),
+           "sp_addr": Guarded(sp_addr, name="sp_addr", align=addr_align)}
+    out = (Guarded(out_init, name="dxc", align=dxc_align) if out_init is not None
+           else Guarded(shape=(n_cbsr, k), dtype=np.float32, name="dxc", align=dxc_align))
+    r = _run(L.maxk_sspmm_backward_planned, ins, {"dxc": out},
+             lambda p: (p["warp4"], i64(w4.shape[0] // 4), p["idx"], p["val"], p["dy"], p["sp_addr"], i32(k), i32(homes),
+                        i32(d), p["dxc"], i64(n_cbsr), i32(1 if accumulate else 0), None))
+    return r["dxc"]
