@@ -51,16 +51,20 @@ cbsr_bank_plan_kernel(const unsigned char *__restrict__ sp_index, int64_t n, int
     const unsigned char *src = sp_index + row * k + j0;
 
     unsigned char c[PLAN_GROUP];       // columns of the entries
+    unsigned char pos[PLAN_GROUP][PLAN_MAX_HOMES];  // entry, home -> word of the home modulo 32 (its bank)
     signed char owner[PLAN_GROUP];     // bank -> entry that holds it (-1: free)
     signed char home[PLAN_GROUP];      // entry -> home it uses (-1: not placed yet)
     unsigned char done[PLAN_GROUP];    // entry -> placed for good
     for (int i = 0; i < PLAN_GROUP; ++i) {
-        c[i] = (i < cnt) ? __ldg(src + i) : (unsigned char)0;
+        const unsigned ci = (i < cnt) ? __ldg(src + i) : 0u;
+        c[i] = (unsigned char)ci;
+#pragma unroll
+        for (int h = 0; h < PLAN_MAX_HOMES; ++h) pos[i][h] = (unsigned char)(plan_home_word(ci, h) & 31u);
         owner[i] = -1;
         home[i] = -1;
         done[i] = 0;
     }
-    auto bank = [&](int e, int h) -> unsigned { return plan_home_word(c[e], h) & bank_mask; };
+    auto bank = [&](int e, int h) -> unsigned { return pos[e][h] & bank_mask; };
 
     // Layer 0: a maximum matching entries -> banks (Kuhn's augmenting paths, depth-first, explicit
     // stack): every matched entry has a bank to itself.  Entries it leaves over are matched among
@@ -112,7 +116,10 @@ cbsr_bank_plan_kernel(const unsigned char *__restrict__ sp_index, int64_t n, int
         }
     }
     unsigned short *dst = sp_addr + row * k + j0;
-    for (int i = 0; i < cnt; ++i) dst[i] = (unsigned short)plan_home_word(c[i], home[i]);
+    for (int i = 0; i < cnt; ++i) {
+        const unsigned ci = c[i], h = (unsigned)home[i];
+        dst[i] = (unsigned short)(h == 0u ? ci : h * 256u + (ci & 7u) * 32u + pos[i][h]);
+    }
 }
 
 }  // namespace maxk
