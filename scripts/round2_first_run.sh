@@ -12,3 +12,9 @@ for shape in products reddit flickr; do
 done
 python scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_n1_round2.json
 python scripts/topk_probe.py 2>/dev/null | tee gpurun_out/topk_probe_round2.log
+# planned kernels end to end: the bench step and a dense-degree epoch (GIN k=64 on the proteins shape)
+for h in 2 4 8; do
+  python bench.py --planned $h --steps 20 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | tee gpurun_out/bench_planned_$h.json
+done
+python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_proteins_default.json
+MAXK_PLANNED_HOMES=8 python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_proteins_planned8.json

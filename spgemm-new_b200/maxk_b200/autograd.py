@@ -84,21 +84,45 @@ class SpGEMMFunction(Function):
         return ops.cbsr_scatter(dxc, sp_index, ctx.feat_dim), None, None
 
 
+def planned_homes() -> int:
+    """EXPERIMENTAL opt-in (unmeasured): MAXK_PLANNED_HOMES=2|4|8 routes the
+    CBSR-native aggregation through the bank plan (csrc/cbsr_plan.cu).  0 / unset = the default kernels."""
+    import os
+    try:
+        h = int(os.environ.get("MAXK_PLANNED_HOMES", "0"))
+    except ValueError:
+        return 0
+    return h if h in (2, 4, 8) else 0
+
+
 class CBSRAggregate(Function):
     """CBSR-native aggregation for layers that keep activations sparse end to end:
     Y = A @ scatter(sp_data, sp_index); gradient flows to sp_data only (CBSR layout)."""
 
     @staticmethod
     def forward(ctx, sp_data, sp_index, warp4, indices, values, feat_dim, num_rows):
+        k = sp_index.shape[1]
+        homes = planned_homes()
+        if homes and k % 32 == 0 and k <= 128 and (homes == 2 or k <= 64):
+            sp_addr = ops.cbsr_bank_plan(sp_index, homes)   # once per TopK, serves both directions
+            out = ops.spgemm_forward_planned(warp4, indices, values, sp_data.contiguous(), sp_addr, homes,
+                                             feat_dim=feat_dim, num_rows=num_rows)
+            ctx.save_for_backward(warp4, indices, values, sp_addr)
+            ctx.homes = homes
+            return out
         out = ops.spgemm_forward(warp4, indices, values, sp_data.contiguous(), sp_index,
                                  feat_dim=feat_dim, num_rows=num_rows)
         ctx.save_for_backward(warp4, indices, values, sp_index)
+        ctx.homes = 0
         return out
 
     @staticmethod
     def backward(ctx, grad_output):
-        warp4, indices, values, sp_index = ctx.saved_tensors
-        dxc = ops.sspmm_backward(warp4, indices, values, grad_output.contiguous(), sp_index)
+        warp4, indices, values, sel = ctx.saved_tensors
+        if ctx.homes:
+            dxc = ops.sspmm_backward_planned(warp4, indices, values, grad_output.contiguous(), sel, ctx.homes)
+        else:
+            dxc = ops.sspmm_backward(warp4, indices, values, grad_output.contiguous(), sel)
         return dxc, None, None, None, None, None, None
 
 
