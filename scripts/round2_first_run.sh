@@ -12,6 +12,11 @@ for shape in products reddit flickr; do
 done
 python scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_n1_round2.json
 python scripts/topk_probe.py 2>/dev/null | tee gpurun_out/topk_probe_round2.log
+# hardware questions the models had to guess (scalar vs vector reductions at the L2, conflict cost,
+# LDS vs SHFL broadcast, cp.async / cp.async.bulk gathers): one short probe, bounded
+mkdir -p scripts/probes/_bin
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a scripts/probes/pipe_probe.cu -o scripts/probes/_bin/pipe_probe \
+  && timeout 180 scripts/probes/_bin/pipe_probe | tee gpurun_out/pipe_probe.log
 # planned kernels end to end: the bench step and a dense-degree epoch (GIN k=64 on the proteins shape)
 for h in 2 4 8; do
   python bench.py --planned $h --steps 20 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | tee gpurun_out/bench_planned_$h.json
