@@ -1,0 +1,179 @@
+"""The Python host layer (maxk_b200.ops, the autograd Functions, the CBSR-native models) run on CPU
+tensors against the kernel sources under the SIMT interpreter.
+
+TEST DOUBLE, not a fallback: inside these tests only, `_cabi._lib` is pointed at
+tests/simt/_build/libmaxk_simt.so (same C ABI, host pointers for device pointers) and the three
+places where `ops` touches CUDA (`_cuda`, `_stream`, `torch.cuda.device`) are patched.  Outside the
+fixture nothing changes: `_cabi.load()` binds lib/libmaxk_b200.so and raises when it is missing.
+Purpose: the argument plumbing of code paths that have not yet run on a GPU (the planned kernels,
+MAXK_PLANNED_HOMES) and of the ones that have, checked against the oracle without a GPU.
+"""
+import contextlib
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import simt_lib as S
+from helpers import ATOL, RTOL, Problem
+from oracle import oracle as O
+
+
+@pytest.fixture()
+def ops(monkeypatch):
+    from maxk_b200 import _cabi
+    from maxk_b200 import ops as _ops
+
+    lib = S.load()
+    for name, (res, args) in _cabi.PROTOTYPES.items():
+        fn = getattr(lib, name)
+        if args is not None:
+            fn.restype, fn.argtypes = res, args
+    monkeypatch.setattr(_cabi, "_lib", lib)
+
+    def host_tensor(t, name, dtype=None, contiguous=True):
+        _ops._req(isinstance(t, torch.Tensor), f"{name} must be a tensor")
+        if dtype is not None:
+            _ops._req(t.dtype == dtype, f"{name} must be {str(dtype).replace('torch.', '')}")
+        if contiguous:
+            _ops._req(t.is_contiguous(), f"{name} must be contiguous")
+
+    monkeypatch.setattr(_ops, "_cuda", host_tensor)
+    monkeypatch.setattr(_ops, "_stream", lambda t: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda *_a, **_k: contextlib.nullcontext())
+    yield _ops
+    lib.maxk_set_tuning(-1, -1)
+    lib.maxk_set_forward_depth(0)
+    lib.maxk_set_forward_copies(0)
+    # restore what simt_lib expects of its own handle
+    lib.maxk_last_error.restype = ctypes.c_char_p
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def close(got, want, what=""):
+    np.testing.assert_allclose(got.detach().numpy().astype(np.float64), want, rtol=RTOL, atol=ATOL, err_msg=what)
+
+
+def _problem(**kw):
+    p = Problem(**kw)
+    return p, dict(indptr=_t(p.indptr), indices=_t(p.idx), values=_t(p.val), x=_t(p.x), sp_data=_t(p.sp_data),
+                   sp_index=_t(p.sp_index), warp4=_t(p.w4).reshape(-1), dy=_t(p.dy))
+
+
+def test_ops_default_kernels_through_python(ops):
+    p, g = _problem(n=150, avg=20.0, k=32, seed=4)
+    w4 = ops.build_worklist(g["indptr"])
+    assert torch.equal(w4, g["warp4"])
+    v, i, dense = ops.topk_cbsr(g["x"], 32, want_dense=True)
+    assert torch.equal(i, g["sp_index"]) and torch.equal(v, g["sp_data"])
+    np.testing.assert_array_equal(dense.numpy(), O.maxk_dense(p.x, 32))
+    y = ops.spgemm_forward(w4, g["indices"], g["values"], v, i, num_rows=p.n)
+    close(y, p.fwd_oracle())
+    dxc = ops.sspmm_backward(w4, g["indices"], g["values"], g["dy"], i)
+    close(dxc, p.bwd_oracle())
+    d = ops.cbsr_scatter(v, i, 256)
+    np.testing.assert_array_equal(d.numpy(), O.cbsr_scatter(p.sp_data, p.sp_index, 256))
+    assert torch.equal(ops.cbsr_gather(d, i), v)
+    rec = ops.cbsr_pack(v, i)
+    v2, i2 = ops.cbsr_unpack(rec, p.n, 32)
+    assert torch.equal(v2, v) and torch.equal(i2, i)
+    with pytest.raises(RuntimeError, match="accumulate=True needs"):
+        ops.spgemm_forward(w4, g["indices"], g["values"], v, i, accumulate=True)
+
+
+@pytest.mark.parametrize("homes", [2, 4, 8])
+@pytest.mark.parametrize("k", [32, 64])
+def test_ops_planned_kernels_through_python(ops, k, homes):
+    p, g = _problem(n=120, avg=30.0, k=k, seed=k + homes)
+    sp_addr = ops.cbsr_bank_plan(g["sp_index"], homes)
+    assert sp_addr.dtype == torch.uint16 and tuple(sp_addr.shape) == (p.n, k)
+    assert int(sp_addr.to(torch.int64).max()) < homes * 256
+    y = ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, homes, num_rows=p.n)
+    close(y, p.fwd_oracle(), "planned forward")
+    ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, homes, num_rows=p.n,
+                               out=y, accumulate=True)
+    close(y, 2 * p.fwd_oracle(), "planned forward, accumulate")
+    dxc = ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, homes)
+    close(dxc, p.bwd_oracle(), "planned backward")
+    out = torch.empty_like(sp_addr)
+    assert ops.cbsr_bank_plan(g["sp_index"], homes, out=out) is out and torch.equal(out, sp_addr)
+    with pytest.raises(RuntimeError, match="homes"):
+        ops.cbsr_bank_plan(g["sp_index"], 5)
+    with pytest.raises(RuntimeError, match="wrong shape"):
+        ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, homes,
+                                   out=torch.empty(3, 3))
+
+
+@pytest.mark.parametrize("homes", [0, 2, 8])
+def test_autograd_functions_with_and_without_the_plan(ops, monkeypatch, homes):
+    """CBSRAggregate / TopKCBSR / SpGEMMFunction: same values and gradients whether the aggregation
+    runs through the default kernels or, with MAXK_PLANNED_HOMES set, through the planned ones."""
+    from maxk_b200.autograd import CBSRAggregate, SpGEMMFunction, TopKCBSR, planned_homes
+    if homes:
+        monkeypatch.setenv("MAXK_PLANNED_HOMES", str(homes))
+    else:
+        monkeypatch.delenv("MAXK_PLANNED_HOMES", raising=False)
+    assert planned_homes() == homes
+    p, g = _problem(n=100, avg=15.0, k=32, seed=21)
+    x = g["x"].clone().requires_grad_(True)
+    sp_data, sp_index = TopKCBSR.apply(x, 32)
+    y = CBSRAggregate.apply(sp_data, sp_index, g["warp4"], g["indices"], g["values"], 256, p.n)
+    close(y, p.fwd_oracle())
+    y.backward(g["dy"])
+    want = O.cbsr_scatter(p.bwd_oracle().astype(np.float32), p.sp_index, 256)
+    np.testing.assert_allclose(x.grad.numpy(), want, rtol=RTOL, atol=ATOL)
+    x2 = g["x"].clone().requires_grad_(True)
+    y2 = SpGEMMFunction.apply(x2, (g["indptr"], g["indices"], g["values"]), 32)
+    close(y2, p.fwd_oracle())
+    y2.backward(g["dy"])
+    np.testing.assert_allclose(x2.grad.numpy(), want, rtol=RTOL, atol=ATOL)
+
+
+class _HostGraph:
+    """what maxk_b200.graph.Graph is to the models, on host tensors"""
+
+    def __init__(self, p, g):
+        from maxk_b200.graph import edge_values
+        self.g, self.n = g, p.n
+        self._vals = {kind: edge_values(g["indptr"], g["indices"], kind, p.n) for kind in ("sum", "mean", "gcn")}
+
+    def aggregate(self, sp_data, sp_index, kind, feat_dim):
+        from maxk_b200.autograd import CBSRAggregate
+        return CBSRAggregate.apply(sp_data, sp_index, self.g["warp4"], self.g["indices"], self._vals[kind].contiguous(),
+                                   feat_dim, self.n)
+
+
+@pytest.mark.parametrize("name", ["SAGE", "GCN", "GIN"])
+def test_models_train_step_same_with_and_without_the_plan(ops, monkeypatch, name):
+    """One forward + backward of each CBSR-native model (hidden 64, k = 32): the planned kernels
+    must give the loss and the parameter gradients of the default ones."""
+    import utils.models as M
+    p, g = _problem(n=80, avg=8.0, k=8, seed=5, empty_frac=0.0)
+    G = _HostGraph(p, g)
+    torch.manual_seed(0)
+    model = getattr(M, name)(16, 64, 2, 5, maxk=32, feat_drop=0.0, norm=True)
+    feats = torch.randn(p.n, 16)
+    target = torch.randint(0, 5, (p.n,))
+    results = []
+    for homes in (0, 8):
+        if homes:
+            monkeypatch.setenv("MAXK_PLANNED_HOMES", str(homes))
+        else:
+            monkeypatch.delenv("MAXK_PLANNED_HOMES", raising=False)
+        model.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(G, feats), target)
+        loss.backward()
+        results.append((float(loss.detach()), [q.grad.clone() for q in model.parameters()]))
+    assert np.isfinite(results[0][0])
+    assert abs(results[0][0] - results[1][0]) < 1e-5
+    for a, b in zip(results[0][1], results[1][1]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
+def test_the_double_is_gone_after_the_fixture():
+    from maxk_b200 import _cabi
+    assert _cabi._lib is None or "libmaxk_b200.so" in str(_cabi._lib._name)
