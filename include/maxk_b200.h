@@ -131,7 +131,7 @@ MAXK_API int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks
                                 const float *values, const float *sp_data, const uint16_t *sp_addr,
                                 int32_t k, int32_t homes, float *out, int64_t num_rows_out, int32_t d,
                                 int32_t accumulate, void *stream);
-/* The backward through the same plan (k = 32, 64, 96, 128): dY rows are staged in all homes and
+/* The backward through the same plan (k = 8, 16, 32, 64, 96, 128): dY rows are staged in all homes and
  * entry l of CBSR row j looks its value up at word sp_addr[j,l]; one instruction covers the 32
  * entries of one edge (ncu, round 1: 2.2 of the default kernel's 5.8 wavefronts per edge are bank
  * conflicts of exactly these lookups).  Same output contract as maxk_sspmm_backward.          */

@@ -23,7 +23,8 @@
 // Model (profiles/r01_static_forward_model.md): 0.5 (broadcast) + 1 (plan line) + fullest bank +
 // 1 (reduction) + 0.2 (streams) = 3.7 wavefronts per edge at H = 8 against 5.83 measured:
 // 2.58 -> ~1.7 ms on the Reddit shape if that pipe stays the bound -- the unknown is the L2, which
-// now sees 32 scalar reductions per 128-byte line instead of 8 vector ones.  k % 32 == 0.
+// now sees 32 scalar reductions per 128-byte line instead of 8 vector ones.
+// k = 32, 64, 96, 128; k = 16 and 8 carry 2 / 4 edges per instruction with one staged copy per edge slot.
 #include "common.cuh"
 
 namespace maxk {
@@ -117,7 +118,50 @@ __device__ __forceinline__ void bwp_process_batch(const int2 *stage, int len, co
     }
 }
 
-template <int EPL, int H>
+// ---- k = 16, 8: E = 32/k edges per lookup instruction, one copy of the staged row per edge slot on
+// its own 1/E of the banks (word * E + slot) -- the layout the plan of such a k was made for ----------
+template <int H, int E>
+__device__ __forceinline__ void bwp_stage_row_slots(float *dys, const float *__restrict__ src, int d, int lane)
+{
+    for (int c = lane; c < d; c += 32) {
+        const float v = ld_stream_f32(src + c);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float *p = dys + plan_home_word((unsigned)c, h) * E;
+#pragma unroll
+            for (int s = 0; s < E; ++s) p[s] = v;
+        }
+    }
+}
+
+template <int KL>
+__device__ __forceinline__ void bwp_process_batch_slots(const int2 *stage, int len, const float *dys,
+                                                        const unsigned short *__restrict__ sp_addr,
+                                                        float *__restrict__ dxc, int lane)
+{
+    constexpr int E = 32 / KL;
+    const int slot = lane & (E - 1), entry = lane / E;
+    for (int j = 0; j < len; j += BWP_U * E) {
+        int2 ev[BWP_U];
+        unsigned short a[BWP_U];
+#pragma unroll
+        for (int u = 0; u < BWP_U; ++u) {
+            ev[u] = make_int2(0, 0);
+            if (j + u * E + slot < len) ev[u] = stage[j + u * E + slot];
+        }
+#pragma unroll
+        for (int u = 0; u < BWP_U; ++u)
+            if (j + u * E + slot < len) a[u] = __ldg(sp_addr + (uint64_t)(uint32_t)ev[u].x * (uint32_t)KL + entry);
+#pragma unroll
+        for (int u = 0; u < BWP_U; ++u)
+            if (j + u * E + slot < len)
+                red_add_f1(dxc + (uint64_t)(uint32_t)ev[u].x * (uint32_t)KL + entry,
+                           __int_as_float(ev[u].y) * dys[a[u] * E + slot]);
+    }
+}
+
+// KL = 32: k = 32 * EPL;  KL = 16, 8: k = KL (EPL = 1)
+template <int KL, int EPL, int H>
 __global__ void __launch_bounds__(BWP_WPB * 32)
 sspmm_bwd_planned_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *__restrict__ idx,
                          const float *__restrict__ val, const float *__restrict__ dy,
@@ -126,8 +170,9 @@ sspmm_bwd_planned_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, cons
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *dys = reinterpret_cast<float *>(smem_raw) + warp * (H * 256);
-    int2 *stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + BWP_WPB * (H * 256)) +
+    constexpr int E = 32 / KL, ROW_WORDS = H * 256 * E;  // staged dY row: H homes x E edge slots
+    float *dys = reinterpret_cast<float *>(smem_raw) + warp * ROW_WORDS;
+    int2 *stage = reinterpret_cast<int2 *>(reinterpret_cast<float *>(smem_raw) + BWP_WPB * ROW_WORDS) +
                   warp * BWP_STAGE;
 
     const int64_t t0 = ((int64_t)blockIdx.x * BWP_WPB + warp) * tasks_per_warp;
@@ -147,35 +192,45 @@ sspmm_bwd_planned_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, cons
         if (info.x != cur_row) {  // stage dY[row,:] once per row, in every home
             cur_row = info.x;
             __syncwarp();  // lookups of the previous row are done
-            bwp_stage_row<H>(dys, dy + (int64_t)cur_row * d, d, lane);
+            if constexpr (KL == 32)
+                bwp_stage_row<H>(dys, dy + (int64_t)cur_row * d, d, lane);
+            else
+                bwp_stage_row_slots<H, E>(dys, dy + (int64_t)cur_row * d, d, lane);
             // visibility is ordered by the __syncwarp pair in bwp_stage_edges below
         }
         const int64_t loc = info.y;
         const int len = info.z;
         bwp_stage_edges(pre, stage, lane);
         if (has_next) bwp_fetch_edges(pre, idx, val, ninfo.y, min(ninfo.z, BWP_STAGE), lane);
-        bwp_process_batch<EPL>(stage, min(len, BWP_STAGE), dys, sp_addr, dxc, lane);
+        if constexpr (KL == 32)
+            bwp_process_batch<EPL>(stage, min(len, BWP_STAGE), dys, sp_addr, dxc, lane);
+        else
+            bwp_process_batch_slots<KL>(stage, min(len, BWP_STAGE), dys, sp_addr, dxc, lane);
         for (int off = BWP_STAGE; off < len; off += BWP_STAGE) {  // len > 64: foreign work lists
             BwpEdgeRegs more;
             const int ln = min(len - off, BWP_STAGE);
             bwp_fetch_edges(more, idx, val, loc + off, ln, lane);
             bwp_stage_edges(more, stage, lane);
-            bwp_process_batch<EPL>(stage, ln, dys, sp_addr, dxc, lane);
+            if constexpr (KL == 32)
+                bwp_process_batch<EPL>(stage, ln, dys, sp_addr, dxc, lane);
+            else
+                bwp_process_batch_slots<KL>(stage, ln, dys, sp_addr, dxc, lane);
         }
         info = ninfo;
     }
 }
 
-template <int EPL, int H>
+template <int KL, int EPL, int H>
 static int launch_bwp(const int32_t *warp4, int64_t W, const int32_t *idx, const float *val,
                       const float *dy, const uint16_t *sp_addr, int d, float *dxc, int tasks_per_warp,
                       cudaStream_t st)
 {
-    const size_t smem = (size_t)BWP_WPB * H * 256 * sizeof(float) + (size_t)BWP_WPB * BWP_STAGE * sizeof(int2);
+    const size_t smem = (size_t)BWP_WPB * H * 256 * (32 / KL) * sizeof(float) +
+                        (size_t)BWP_WPB * BWP_STAGE * sizeof(int2);
     if (smem > 48 * 1024) {
         static bool opted_in = false;  // per variant; benign if raced
         if (!opted_in) {
-            MAXK_CUDA(cudaFuncSetAttribute(sspmm_bwd_planned_kernel<EPL, H>,
+            MAXK_CUDA(cudaFuncSetAttribute(sspmm_bwd_planned_kernel<KL, EPL, H>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             opted_in = true;
         }
@@ -186,7 +241,7 @@ static int launch_bwp(const int32_t *warp4, int64_t W, const int32_t *idx, const
         set_error("maxk_sspmm_backward_planned: grid too large");
         return MAXK_ERR_UNSUPPORTED;
     }
-    sspmm_bwd_planned_kernel<EPL, H><<<(unsigned)grid, BWP_WPB * 32, smem, st>>>(
+    sspmm_bwd_planned_kernel<KL, EPL, H><<<(unsigned)grid, BWP_WPB * 32, smem, st>>>(
         reinterpret_cast<const int4 *>(warp4), W, idx, val, dy, sp_addr, d, dxc, tasks_per_warp);
     MAXK_LAUNCH_CHECK("sspmm_bwd_planned_kernel");
     return MAXK_OK;
@@ -206,8 +261,10 @@ extern "C" int maxk_sspmm_backward_planned(const int32_t *warp4, int64_t num_tas
     MAXK_REQUIRE(num_tasks >= 0 && num_cbsr_rows >= 0, "maxk_sspmm_backward_planned: negative size");
     MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
                  "maxk_sspmm_backward_planned: d=%d must be a multiple of 4 in [4,256]", d);
-    MAXK_REQUIRE(k >= 32 && k <= d && k % 32 == 0 && k <= 128,
-                 "maxk_sspmm_backward_planned: k=%d must be 32, 64, 96 or 128, and <= d=%d", k, d);
+    MAXK_REQUIRE(k <= d && (k == 8 || k == 16 || (k >= 32 && k % 32 == 0 && k <= 128)),
+                 "maxk_sspmm_backward_planned: k=%d must be 8, 16, 32, 64, 96 or 128, and <= d=%d", k, d);
+    MAXK_REQUIRE(k >= 32 || homes == 2 || (k == 16 && homes == 4),
+                 "maxk_sspmm_backward_planned: homes=%d is not built for k=%d (k = 16: 2, 4; k = 8: 2)", homes, k);
     MAXK_REQUIRE(homes == 2 || homes == 4 || homes == 8,
                  "maxk_sspmm_backward_planned: homes=%d must be 2, 4 or 8", homes);
     MAXK_REQUIRE(dxc != nullptr || num_cbsr_rows == 0, "maxk_sspmm_backward_planned: dxc is NULL");
@@ -226,7 +283,10 @@ extern "C" int maxk_sspmm_backward_planned(const int32_t *warp4, int64_t num_tas
     int tpw = g_bwd_tasks_per_warp;
     if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
 #define MAXK_BWP_GO(E, HH) \
-    return launch_bwp<E, HH>(warp4, num_tasks, indices, values, dy, sp_addr, d, dxc, tpw, st)
+    return launch_bwp<32, E, HH>(warp4, num_tasks, indices, values, dy, sp_addr, d, dxc, tpw, st)
+    if (k == 16 && homes == 2) return launch_bwp<16, 1, 2>(warp4, num_tasks, indices, values, dy, sp_addr, d, dxc, tpw, st);
+    if (k == 16) return launch_bwp<16, 1, 4>(warp4, num_tasks, indices, values, dy, sp_addr, d, dxc, tpw, st);
+    if (k == 8) return launch_bwp<8, 1, 2>(warp4, num_tasks, indices, values, dy, sp_addr, d, dxc, tpw, st);
 #define MAXK_BWP_H(E)                \
     switch (homes) {                 \
         case 2: MAXK_BWP_GO(E, 2);   \

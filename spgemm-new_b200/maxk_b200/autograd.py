@@ -103,7 +103,7 @@ class CBSRAggregate(Function):
     def forward(ctx, sp_data, sp_index, warp4, indices, values, feat_dim, num_rows):
         k = sp_index.shape[1]
         homes = planned_homes()
-        if homes and k % 32 == 0 and k <= 128 and (homes == 2 or k <= 64):
+        if homes and k % 32 == 0 and k <= 128 and (homes == 2 or k <= 64):  # both directions are built
             sp_addr = ops.cbsr_bank_plan(sp_index, homes)   # once per TopK, serves both directions
             out = ops.spgemm_forward_planned(warp4, indices, values, sp_data.contiguous(), sp_addr, homes,
                                              feat_dim=feat_dim, num_rows=num_rows)

@@ -195,7 +195,7 @@ def spgemm_forward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: t
 def sspmm_backward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
                            grad_output: torch.Tensor, sp_addr: torch.Tensor, homes: int = 2,
                            out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    """EXPERIMENTAL: `sspmm_backward` with the bank plan in place of the selectors (k = 32, 64, 96, 128;
+    """EXPERIMENTAL: `sspmm_backward` with the bank plan in place of the selectors (k = 8, 16, 32, 64, 96, 128;
     the plan must have been made with the same `homes`).  Same output contract."""
     lib = _cabi.load()
     _cuda(warp4, "warp4_metadata", torch.int32)
