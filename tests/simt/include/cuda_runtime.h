@@ -36,7 +36,7 @@
 #define SIMT_NOINLINE __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
-#define __shared__ static  // CTAs run one after another, so one copy per kernel is enough
+#define __shared__ static thread_local  // one CTA at a time per host thread: one copy per kernel and thread
 
 // ---- vector types ---------------------------------------------------------------------------
 struct uint3 { unsigned x, y, z; };
@@ -87,7 +87,7 @@ struct Thread {  // what a fibre knows about itself
     dim3 bdim, gdim;
     int lane, warp;
 };
-extern Thread *self_;  // the running fibre
+extern thread_local Thread *self_;  // the running fibre of this host thread
 inline Thread &self() { return *self_; }
 
 void launch(const void *kernel, const LaunchCfg &cfg, const std::function<void()> &body);

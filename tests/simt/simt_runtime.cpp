@@ -1,7 +1,10 @@
 // tests/simt/simt_runtime.cpp -- TEST INFRASTRUCTURE (see include/cuda_runtime.h).
 //
 // SIMT interpreter: every CUDA thread of a CTA is a fibre with its own stack; CTAs run one
-// after another on the calling host thread.  A fibre runs until it reaches a rendezvous
+// after another on the calling host thread.  All interpreter state is per host thread, so several
+// host threads can each run a kernel at the same time: that is how the tests run the ranks of the
+// NVLink peer-memory path, whose kernels wait for each other through flag words (one host thread
+// per rank, buffers shared; a kernel that only spins yields the CPU).  A fibre runs until it reaches a rendezvous
 // (__syncthreads, __syncwarp, a warp collective, __nanosleep) or returns; the scheduler then
 // runs the next one.  This is the weakest schedule CUDA allows inside a warp -- lanes are
 // NOT in lock step between rendezvous points -- so code that relies on implicit warp
@@ -19,16 +22,19 @@
 //   * launch configuration: block size <= 1024, dynamic shared memory <= 48 KB unless the kernel
 //     opted in with cudaFuncSetAttribute, <= 227 KB in any case.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <signal.h>
 #include <sys/mman.h>
+#include <time.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 namespace simt {
 
-Thread *self_ = nullptr;
+thread_local Thread *self_ = nullptr;
 
 namespace {
 
@@ -70,18 +76,19 @@ struct Block {
     std::vector<Warp> warps;
 };
 
-Block g_blk;
-Fibre *g_cur = nullptr;
-void *g_sched_sp = nullptr;
-char *g_stacks = nullptr;
-const std::function<void()> *g_body = nullptr;
-unsigned long long g_progress = 0;
-bool g_failed = false;
-std::string g_fail_msg;
-cudaError_t g_last_error = cudaSuccess;
-long long g_clock = 0;
+thread_local Block g_blk;
+thread_local Fibre *g_cur = nullptr;
+thread_local void *g_sched_sp = nullptr;
+thread_local char *g_stacks = nullptr;
+thread_local const std::function<void()> *g_body = nullptr;
+thread_local unsigned long long g_progress = 0;
+thread_local bool g_failed = false;
+thread_local std::string g_fail_msg;
+thread_local cudaError_t g_last_error = cudaSuccess;
 std::map<const void *, int> g_max_dyn_smem;
-alignas(128) unsigned char g_dyn_smem[227 * 1024 + 128];
+std::mutex g_max_dyn_smem_lock;
+constexpr size_t kDynSmem = 227 * 1024 + 128;
+thread_local unsigned char *g_dyn_smem = nullptr;
 
 extern "C" void simt_ctx_switch(void **save_sp, void *load_sp);
 #if defined(__x86_64__)
@@ -248,11 +255,13 @@ void warp_barrier(unsigned mask, int op)
 // A fibre touched unmapped memory (the tests surround every buffer with guard pages).  The handler
 // runs on the faulting fibre's stack; SA_NODEFER keeps the signal unblocked, so leaving through
 // the scheduler instead of returning is harmless.
-void on_segv(int, siginfo_t *si, void *)
+struct sigaction g_old_segv, g_old_bus;
+
+void on_segv(int sig, siginfo_t *si, void *)
 {
-    if (g_cur == nullptr) {  // not inside a kernel: not ours
-        signal(SIGSEGV, SIG_DFL);
-        raise(SIGSEGV);
+    if (g_cur == nullptr) {  // not inside a kernel of this thread: not ours
+        sigaction(sig, sig == SIGBUS ? &g_old_bus : &g_old_segv, nullptr);
+        raise(sig);
         return;
     }
     char b[96];
@@ -297,7 +306,10 @@ bool run_block(const LaunchCfg &cfg, unsigned bx, unsigned by, unsigned bz)
         }
         if (g_failed) break;
         if (!ran && g_progress == before) {
-            if (spun) continue;  // spin-waits end by themselves (bounded) or trap
+            if (spun) {  // only spin-waits are left: another host thread (rank) has to move first;
+                sched_yield();  // the waits are bounded and trap by themselves
+                continue;
+            }
             int stuck = -1;
             for (int i = 0; i < n; ++i)
                 if (b.f[i].wait != DONE) { stuck = i; break; }
@@ -326,8 +338,11 @@ void launch(const void *kernel, const LaunchCfg &cfg, const std::function<void()
         return;
     }
     size_t limit = 48 * 1024;
-    auto it = g_max_dyn_smem.find(kernel);
-    if (it != g_max_dyn_smem.end()) limit = std::max<size_t>(limit, (size_t)it->second);
+    {
+        std::lock_guard<std::mutex> hold(g_max_dyn_smem_lock);
+        auto it = g_max_dyn_smem.find(kernel);
+        if (it != g_max_dyn_smem.end()) limit = std::max<size_t>(limit, (size_t)it->second);
+    }
     if (cfg.smem > limit) {
         g_last_error = cudaErrorInvalidValue;
         return;
@@ -343,19 +358,21 @@ void launch(const void *kernel, const LaunchCfg &cfg, const std::function<void()
     }
     g_body = &body;
     g_failed = false;
-    struct sigaction sa, old_segv, old_bus;
-    memset(&sa, 0, sizeof sa);
-    sa.sa_sigaction = on_segv;
-    sa.sa_flags = SA_SIGINFO | SA_NODEFER;
-    sigaction(SIGSEGV, &sa, &old_segv);
-    sigaction(SIGBUS, &sa, &old_bus);
+    static std::once_flag handlers;  // process-wide and for good: kernels of several threads overlap
+    std::call_once(handlers, [] {
+        struct sigaction sa;
+        memset(&sa, 0, sizeof sa);
+        sa.sa_sigaction = on_segv;
+        sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+        sigaction(SIGSEGV, &sa, &g_old_segv);
+        sigaction(SIGBUS, &sa, &g_old_bus);
+    });
     // poison dynamic shared memory: kernels must not rely on zeroed shared memory
-    memset(g_dyn_smem, 0xcb, sizeof g_dyn_smem);
+    if (!g_dyn_smem) g_dyn_smem = static_cast<unsigned char *>(aligned_alloc(128, kDynSmem));
+    memset(g_dyn_smem, 0xcb, kDynSmem);
     for (unsigned z = 0; z < cfg.grid.z && !g_failed; ++z)
         for (unsigned y = 0; y < cfg.grid.y && !g_failed; ++y)
             for (unsigned x = 0; x < cfg.grid.x && !g_failed; ++x) run_block(cfg, x, y, z);
-    sigaction(SIGSEGV, &old_segv, nullptr);
-    sigaction(SIGBUS, &old_bus, nullptr);
     g_body = nullptr;
     if (g_failed) g_last_error = cudaErrorLaunchFailure;
 }
@@ -365,7 +382,11 @@ void *dynamic_smem()
     return reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(g_dyn_smem) + 127) & ~uintptr_t(127));
 }
 
-void set_func_max_dynamic_smem(const void *kernel, int bytes) { g_max_dyn_smem[kernel] = bytes; }
+void set_func_max_dynamic_smem(const void *kernel, int bytes)
+{
+    std::lock_guard<std::mutex> hold(g_max_dyn_smem_lock);
+    g_max_dyn_smem[kernel] = bytes;
+}
 
 void syncthreads()
 {
@@ -469,7 +490,12 @@ void yield_spin()
     f->wait = RUN;
 }
 
-long long clock_ticks() { return g_clock += 1000000; }  // spin limits expire after a few thousand polls
+long long clock_ticks()  // ~2 "cycles" per nanosecond of real time: spin limits expire after seconds
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ((long long)ts.tv_sec * 1000000000LL + ts.tv_nsec) * 2;
+}
 
 void trap(const char *why) { fail(where() + ": " + why); }
 

@@ -177,3 +177,91 @@ def test_models_train_step_same_with_and_without_the_plan(ops, monkeypatch, name
 def test_the_double_is_gone_after_the_fixture():
     from maxk_b200 import _cabi
     assert _cabi._lib is None or "libmaxk_b200.so" in str(_cabi._lib._name)
+
+
+# ------------------------------------------------------------------- NVLink peer-memory path, on the CPU
+@pytest.fixture()
+def peer_group(ops, monkeypatch):
+    """PeerAggregator.local_group on host tensors: every rank's fused forward / pull reduce-scatter
+    kernel runs in its own host thread under the interpreter (the kernels of different ranks wait
+    for each other through flag words, exactly as on the GPUs); dense pairs use the load/store
+    push (copy_ctas < 0), the TMA push needs the hardware."""
+    from concurrent.futures import ThreadPoolExecutor
+    from maxk_b200 import peer as P
+
+    registry = {}
+
+    def wrap(ptr, shape, dtype, device):
+        return registry[int(ptr)].view(*shape)
+
+    monkeypatch.setattr(P, "_wrap", wrap)
+    monkeypatch.setattr(P.PeerAggregator, "_stream", lambda self: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+
+    def make(p, g, bounds, k, halo_threshold):
+        world = len(bounds) - 1
+        indptr, indices, values = g["indptr"].long(), g["indices"], g["values"]
+        aggs = []
+        for r in range(world):
+            lo, hi = bounds[r], bounds[r + 1]
+            e0, e1 = int(indptr[lo]), int(indptr[hi])
+            a = P.PeerAggregator.__new__(P.PeerAggregator)
+            a.group, a._shared = None, []
+            a._plan((indptr[lo:hi + 1] - indptr[lo]).to(torch.int32), indices[e0:e1].contiguous(),
+                    values[e0:e1].contiguous(), list(bounds), r, k, p.d, -2, halo_threshold)
+            aggs.append(a)
+        n_total = aggs[0].n_total
+
+        def alloc(shape, dtype):
+            ts = [torch.zeros(shape, dtype=dtype) for _ in range(world)]
+            for t in ts:
+                registry[t.data_ptr()] = t
+            return [t.data_ptr() for t in ts]
+        flag_ptrs = alloc((64,), torch.int32)
+        tables = [(alloc((max(n_total, 1), k), torch.float32), alloc((max(n_total, 1), k), torch.uint8),
+                   alloc((max(n_total, 1), k), torch.float32)) for _ in range(2)]
+        for r, a in enumerate(aggs):
+            a._wire([aggs[q]._recv[r] for q in range(world)], flag_ptrs, tables)
+        return aggs
+
+    pool = ThreadPoolExecutor(max_workers=4)
+    yield make, pool
+    pool.shutdown()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,k,halo", [(2, 32, 0.0), (2, 16, 2.0), (3, 32, 0.3), (3, 64, 2.0), (2, 8, 2.0), (4, 32, 0.0)])
+def test_peer_kernels_multi_rank_under_the_interpreter(peer_group, world, k, halo):
+    """Fused push all-gather + SpGEMM and pull reduce-scatter of `world` ranks (dense pairs, halo row
+    lists, mixed) against the single-process oracle, three steps with fresh inputs (the buffer
+    sets alternate by step parity)."""
+    from maxk_b200.dist import partition_rows_by_nnz
+    make, pool = peer_group
+    p, g = _problem(n=96 * world, avg=14.0, k=k, seed=world * 100 + k, empty_frac=0.1)
+    bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
+    aggs = make(p, g, bounds, k, halo)
+    rng = np.random.default_rng(k)
+    for step in range(3):
+        x = rng.random((p.n, p.d), dtype=np.float32)
+        dy = rng.random((p.n, p.d), dtype=np.float32)
+        sd, si = O.topk_cbsr(x, k)
+        want_y = O.spgemm_forward(p.w4, p.idx, p.val, sd, si, p.d, n_out=p.n)
+        want_g = O.sspmm_backward(p.w4, p.idx, p.val, dy, si)
+
+        def fwd(r):
+            lo, hi = bounds[r], bounds[r + 1]
+            aggs[r].exchange(_t(sd[lo:hi]), _t(si[lo:hi]))
+            return aggs[r].forward().clone()
+
+        ys = list(pool.map(fwd, range(world)))
+        for r in range(world):
+            close(ys[r], want_y[bounds[r]:bounds[r + 1]], f"forward, step {step}, rank {r}")
+
+        def bwd(r):
+            lo, hi = bounds[r], bounds[r + 1]
+            par = aggs[r]._fwd_epoch & 1
+            return aggs[r].backward(_t(dy[lo:hi]), aggs[r].g_index[par]).clone()
+
+        gs = list(pool.map(bwd, range(world)))
+        for r in range(world):
+            close(gs[r], want_g[bounds[r]:bounds[r + 1]], f"backward, step {step}, rank {r}")
