@@ -106,6 +106,20 @@ void cp_async(void *smem_dst, const void *gmem_src, int bytes);
 void cp_async_commit();
 void cp_async_wait(int all_but_newest);
 
+// 32-bit shared-memory addresses (what `cvta.to.shared` gives the PTX of the TMA path): a token is
+// the low 32 bits of the host address; the pages around the object are remembered per host thread
+// so that token arithmetic (base + offset) resolves back to host addresses
+size_t smem_token(const void *p);
+void *smem_resolve(size_t token);
+// mbarrier + cp.async.bulk (TMA unit), as late as PTX allows: a bulk load lands when its mbarrier
+// is waited for, a bulk store when its bulk group is waited for (or the thread returns)
+void mbar_init(size_t mbar, int count);
+void mbar_expect_tx(size_t mbar, unsigned bytes);
+void mbar_wait(size_t mbar, unsigned parity);
+void bulk_load(size_t smem_dst, const void *gmem_src, unsigned bytes, size_t mbar);
+void bulk_store(void *gmem_dst, size_t smem_src, unsigned bytes);
+void bulk_wait();
+
 void yield_spin();  // a polite spin-wait iteration (__nanosleep)
 long long clock_ticks();
 [[noreturn]] void trap(const char *why);
@@ -224,7 +238,7 @@ inline int __float_as_int(float v) { return (int)(uint32_t)::simt::to_bits(v); }
 inline float __frcp_rn(float v) { return 1.0f / v; }
 inline float __fdividef(float a, float b) { return a / b; }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
-inline size_t __cvta_generic_to_shared(const void *p) { return reinterpret_cast<size_t>(p); }
+inline size_t __cvta_generic_to_shared(const void *p) { return ::simt::smem_token(p); }
 
 // atomics: fibres never preempt each other, so plain read-modify-write is atomic here
 template <typename T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }

@@ -34,6 +34,11 @@ MUTANTS = {
     "topk-emit-no-barrier": ("topk_cbsr.cu", "    __syncwarp();\n    unsigned char *oi = out_idx + row * k + lane;", "    unsigned char *oi = out_idx + row * k + lane;", 0),
     "topk-tie-order": ("topk_cbsr.cu", "if (r0 < need) sel |= (1u << i);", "if (r0 <= need) sel |= (1u << i);", 0),
     "topk-row-bound": ("topk_cbsr.cu", "if (row >= n) return;  // warp-uniform; no CTA barrier below\n\n", "if (row > n) return;\n\n", 0),
+    # NVLink peer path (tests/test_simt_python_layer.py -k peer): the stand-in for the TMA unit lands data late
+    "peer-tma-stage-reused-before-its-stores-read-it": ("peer.cuh", 'if (chunks_issued >= PEER_TMA_STAGES) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");', "", "peer"),
+    "peer-tma-store-before-the-load-landed": ("peer.cuh", "        mbar_wait(mbar0 + 8 * st, (phase >> st) & 1u);\n", "", "peer"),
+    "peer-flag-raised-for-the-wrong-rank": ("peer.cuh", "st_release_sys(a.flags[p] + PEER_FLAG_ARRIVED + a.rank, a.epoch);", "st_release_sys(a.flags[p] + PEER_FLAG_ARRIVED + p, a.epoch);", "peer"),
+    "peer-halo-rows-of-the-wrong-peer": ("peer.cuh", "    const int *rows = a.send_rows[p];\n    const long long n = a.send_count[p];", "    const int *rows = a.send_rows[p];\n    const long long n = a.send_count[p] - 1;", "peer"),
     "worklist-scan-no-barrier": ("worklist.cu", "    if (lane == 31) warp_sums[warp] = inc;\n    __syncthreads();", "    if (lane == 31) warp_sums[warp] = inc;", 0),
     "worklist-last-chunk-length": ("worklist.cu", "rec.z = min(nz, deg - nz * c_in_row);", "rec.z = nz;", 0),
 }
@@ -54,7 +59,10 @@ EQUIVALENT = {
 
 
 def run(name, spec):
-    fname, old, new, _ = spec
+    fname, old, new, where = spec
+    target = [os.path.join(ROOT, "tests", "test_simt_kernels.py")]
+    if where == "peer":
+        target = [os.path.join(ROOT, "tests", "test_simt_python_layer.py"), "-k", "peer"]
     tmp = tempfile.mkdtemp(prefix="simt_mut_")
     try:
         src = os.path.join(tmp, "csrc")
@@ -65,8 +73,8 @@ def run(name, spec):
             return "PATTERN NOT FOUND (update the mutant)"
         open(path, "w").write(text.replace(old, new, 1))
         env = dict(os.environ, SIMT_CSRC=src, SIMT_OUT=os.path.join(tmp, "out"))
-        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_simt_kernels.py"), "-x", "-q",
-                            "-p", "no:cacheprovider"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=1800)
+        r = subprocess.run([sys.executable, "-m", "pytest", *target, "-x", "-q", "-p", "no:cacheprovider"],
+                           env=env, cwd=ROOT, capture_output=True, text=True, timeout=1800)
         if r.returncode == 0:
             return "SURVIVED"
         last = [ln for ln in r.stdout.splitlines() if ln.startswith(("FAILED", "ERROR"))]

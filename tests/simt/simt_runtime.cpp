@@ -29,6 +29,7 @@
 
 #include <map>
 #include <mutex>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -58,8 +59,16 @@ struct AsyncCopy {
     long group;
 };
 
+struct BulkCopy {  // cp.async.bulk issued, not yet performed
+    void *dst;
+    const void *src;
+    unsigned bytes;
+    uint64_t *mbar;  // loads: the barrier that counts the bytes; stores: nullptr
+};
+
 struct Fibre {
     Thread t;
+    std::vector<BulkCopy> bulk;
     std::vector<AsyncCopy> copies;  // cp.async issued, not yet performed
     long cp_group = 0;              // the group new copies join (open until commit_group)
     void *sp = nullptr;
@@ -133,10 +142,24 @@ void drain_copies(Fibre *f, long below_group)
     f->copies.resize(keep);
 }
 
+void drain_bulk_stores(Fibre *f)
+{
+    size_t keep = 0;
+    for (size_t i = 0; i < f->bulk.size(); ++i) {
+        const BulkCopy &c = f->bulk[i];
+        if (c.mbar == nullptr)
+            memcpy(c.dst, c.src, c.bytes);
+        else
+            f->bulk[keep++] = c;
+    }
+    f->bulk.resize(keep);
+}
+
 [[noreturn]] void fibre_exit()
 {
     Fibre *f = g_cur;
     drain_copies(f, f->cp_group + 1);  // outstanding copies still land after the thread returns
+    drain_bulk_stores(f);
     f->wait = DONE;
     f->w->exited |= 1u << f->t.lane;
     --g_blk.alive;
@@ -481,6 +504,95 @@ void cp_async(void *smem_dst, const void *gmem_src, int bytes)
 void cp_async_commit() { ++g_cur->cp_group; }
 
 void cp_async_wait(int all_but_newest) { drain_copies(g_cur, g_cur->cp_group - all_but_newest); }
+
+// ---- shared-memory address tokens ------------------------------------------------------------------
+thread_local std::unordered_map<uint32_t, uintptr_t> g_smem_pages;  // low 20 bits of the page number -> page number
+
+size_t smem_token(const void *p)
+{
+    const uintptr_t page = reinterpret_cast<uintptr_t>(p) >> 12;
+    for (uintptr_t i = 0; i < 64; ++i) {  // the object and what follows it (dynamic shared memory: 227 KB)
+        const uint32_t key = (uint32_t)((page + i) & 0xfffffu);
+        auto it = g_smem_pages.find(key);
+        if (it == g_smem_pages.end())
+            g_smem_pages.emplace(key, page + i);
+        else if (it->second != page + i) {
+            fprintf(stderr, "simt: two shared-memory objects share the low 32 address bits; rerun\n");
+            abort();
+        }
+    }
+    return (size_t)(uint32_t)reinterpret_cast<uintptr_t>(p);
+}
+
+void *smem_resolve(size_t token)
+{
+    const uint32_t t = (uint32_t)token;
+    auto it = g_smem_pages.find(t >> 12);
+    if (it == g_smem_pages.end()) fail(where() + ": a 32-bit shared-memory address that no cvta produced");
+    return reinterpret_cast<void *>((it->second << 12) | (t & 4095u));
+}
+
+// ---- mbarrier: bit 63 phase, bits 32..62 pending arrivals, bits 0..31 pending bytes (count 1 only) -----
+void mbar_init(size_t mbar, int count)
+{
+    *static_cast<uint64_t *>(smem_resolve(mbar)) = (uint64_t)count << 32;
+}
+
+static void mbar_settle(uint64_t *m)
+{
+    if ((*m & 0x7fffffffffffffffull) == 0) *m = ((*m ^ (1ull << 63)) & (1ull << 63)) | (1ull << 32);
+}
+
+void mbar_expect_tx(size_t mbar, unsigned bytes)
+{
+    uint64_t *m = static_cast<uint64_t *>(smem_resolve(mbar));
+    if (((*m >> 32) & 0x7fffffffu) == 0) fail(where() + ": mbarrier arrival without a pending arrival count");
+    *m = *m - (1ull << 32) + bytes;  // one arrival, `bytes` more expected
+    mbar_settle(m);
+}
+
+void bulk_load(size_t smem_dst, const void *gmem_src, unsigned bytes, size_t mbar)
+{
+    void *dst = smem_resolve(smem_dst);
+    if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(gmem_src) | bytes) & 15u)
+        fail(where() + ": cp.async.bulk needs 16-byte aligned addresses and sizes");
+    volatile char probe = static_cast<const volatile char *>(gmem_src)[bytes - 1];  // fault in the issuing thread
+    (void)probe;
+    g_cur->bulk.push_back(BulkCopy{dst, gmem_src, bytes, static_cast<uint64_t *>(smem_resolve(mbar))});
+}
+
+void mbar_wait(size_t mbar, unsigned parity)
+{
+    Fibre *f = g_cur;
+    uint64_t *m = static_cast<uint64_t *>(smem_resolve(mbar));
+    size_t keep = 0;  // the loads counted by this barrier land now, the latest moment PTX allows
+    for (size_t i = 0; i < f->bulk.size(); ++i) {
+        const BulkCopy c = f->bulk[i];
+        if (c.mbar == m) {
+            memcpy(c.dst, c.src, c.bytes);
+            if ((uint32_t)*m < c.bytes) fail(where() + ": more bytes arrived at an mbarrier than it expected");
+            *m -= c.bytes;
+            mbar_settle(m);
+        } else {
+            f->bulk[keep++] = c;
+        }
+    }
+    f->bulk.resize(keep);
+    if ((unsigned)(*m >> 63) == (parity & 1u))
+        fail(where() + ": mbarrier wait that nothing in flight can complete (deadlock on the GPU)");
+}
+
+void bulk_store(void *gmem_dst, size_t smem_src, unsigned bytes)
+{
+    const void *src = smem_resolve(smem_src);
+    if ((reinterpret_cast<uintptr_t>(gmem_dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 15u)
+        fail(where() + ": cp.async.bulk needs 16-byte aligned addresses and sizes");
+    volatile char *q = static_cast<volatile char *>(gmem_dst);  // fault in the issuing thread
+    q[bytes - 1] = q[bytes - 1];
+    g_cur->bulk.push_back(BulkCopy{gmem_dst, src, bytes, nullptr});
+}
+
+void bulk_wait() { drain_bulk_stores(g_cur); }
 
 void yield_spin()
 {

@@ -85,7 +85,17 @@ PTX = [
     (r"^st\.release\.(sys|gpu)\.global\.u32 ", "{{ *(volatile unsigned *)({0}) = ({1}); }}"),
     (r"^ld\.global\.L1::no_allocate\.v4\.u32 ",
      "{{ const unsigned *p_ = (const unsigned *)({4}); ({0}) = p_[0]; ({1}) = p_[1]; ({2}) = p_[2]; ({3}) = p_[3]; }}"),
-    (r"^cp\.async\.cg\.shared\.global ", "::simt::cp_async((void *)({0}), (const void *)({1}), 16)"),
+    (r"^cp\.async\.cg\.shared\.global ", "::simt::cp_async(::simt::smem_resolve({0}), (const void *)({1}), 16)"),
+    # TMA unit: mbarrier + bulk copies (NVLink push of the peer path)
+    (r"^mbarrier\.init\.shared::cta\.b64 \[%0\], 1;", "::simt::mbar_init({0}, 1)"),
+    (r"^fence\.(mbarrier_init|proxy\.async)", "(void)0"),
+    (r"^mbarrier\.arrive\.expect_tx\.shared::cta\.b64 _, ", "::simt::mbar_expect_tx({0}, {1})"),
+    (r"^cp\.async\.bulk\.shared::cluster\.global\.mbarrier::complete_tx::bytes ",
+     "::simt::bulk_load({0}, (const void *)({1}), {2}, {3})"),
+    (r"mbarrier\.try_wait\.parity\.shared::cta\.b64 p, \[%0\], %1;", "::simt::mbar_wait({0}, {1})"),
+    (r"^cp\.async\.bulk\.global\.shared::cta\.bulk_group ", "::simt::bulk_store((void *)({0}), {1}, {2})"),
+    (r"^cp\.async\.bulk\.commit_group", "(void)0"),
+    (r"^cp\.async\.bulk\.wait_group", "::simt::bulk_wait()"),
     (r"^cp\.async\.commit_group", "::simt::cp_async_commit()"),
     (r"^cp\.async\.wait_group ", "::simt::cp_async_wait({0})"),
     (r"^atom\.acq_rel\.gpu\.global\.add\.u32 ",

@@ -184,8 +184,9 @@ def test_the_double_is_gone_after_the_fixture():
 def peer_group(ops, monkeypatch):
     """PeerAggregator.local_group on host tensors: every rank's fused forward / pull reduce-scatter
     kernel runs in its own host thread under the interpreter (the kernels of different ranks wait
-    for each other through flag words, exactly as on the GPUs); dense pairs use the load/store
-    push (copy_ctas < 0), the TMA push needs the hardware."""
+    for each other through flag words, exactly as on the GPUs); dense pairs are pushed with loads and
+    stores (copy_ctas < 0) or through the interpreter's stand-in for the TMA unit (mbarrier +
+    cp.async.bulk, data landing as late as PTX allows)."""
     from concurrent.futures import ThreadPoolExecutor
     from maxk_b200 import peer as P
 
@@ -198,7 +199,7 @@ def peer_group(ops, monkeypatch):
     monkeypatch.setattr(P.PeerAggregator, "_stream", lambda self: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
 
-    def make(p, g, bounds, k, halo_threshold):
+    def make(p, g, bounds, k, halo_threshold, copy_ctas):
         world = len(bounds) - 1
         indptr, indices, values = g["indptr"].long(), g["indices"], g["values"]
         aggs = []
@@ -208,7 +209,7 @@ def peer_group(ops, monkeypatch):
             a = P.PeerAggregator.__new__(P.PeerAggregator)
             a.group, a._shared = None, []
             a._plan((indptr[lo:hi + 1] - indptr[lo]).to(torch.int32), indices[e0:e1].contiguous(),
-                    values[e0:e1].contiguous(), list(bounds), r, k, p.d, -2, halo_threshold)
+                    values[e0:e1].contiguous(), list(bounds), r, k, p.d, copy_ctas, halo_threshold)
             aggs.append(a)
         n_total = aggs[0].n_total
 
@@ -230,8 +231,9 @@ def peer_group(ops, monkeypatch):
 
 
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("copy_ctas", [-2, 3])
 @pytest.mark.parametrize("world,k,halo", [(2, 32, 0.0), (2, 16, 2.0), (3, 32, 0.3), (3, 64, 2.0), (2, 8, 2.0), (4, 32, 0.0)])
-def test_peer_kernels_multi_rank_under_the_interpreter(peer_group, world, k, halo):
+def test_peer_kernels_multi_rank_under_the_interpreter(peer_group, world, k, halo, copy_ctas):
     """Fused push all-gather + SpGEMM and pull reduce-scatter of `world` ranks (dense pairs, halo row
     lists, mixed) against the single-process oracle, three steps with fresh inputs (the buffer
     sets alternate by step parity)."""
@@ -239,7 +241,7 @@ def test_peer_kernels_multi_rank_under_the_interpreter(peer_group, world, k, hal
     make, pool = peer_group
     p, g = _problem(n=96 * world, avg=14.0, k=k, seed=world * 100 + k, empty_frac=0.1)
     bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
-    aggs = make(p, g, bounds, k, halo)
+    aggs = make(p, g, bounds, k, halo, copy_ctas)
     rng = np.random.default_rng(k)
     for step in range(3):
         x = rng.random((p.n, p.d), dtype=np.float32)
@@ -265,3 +267,34 @@ def test_peer_kernels_multi_rank_under_the_interpreter(peer_group, world, k, hal
         gs = list(pool.map(bwd, range(world)))
         for r in range(world):
             close(gs[r], want_g[bounds[r]:bounds[r + 1]], f"backward, step {step}, rank {r}")
+
+
+@pytest.mark.timeout(600)
+def test_peer_tma_push_of_a_block_larger_than_the_staging_ring(peer_group):
+    """One copy CTA pushes 100 KB (values) + 25 KB (selectors) through two 16 KB stages: the stage
+    reuse (`cp.async.bulk.wait_group.read`) and the mbarrier phases of many chunks are exercised; the
+    interpreter performs a bulk store only when its group is waited for, so a stage that is
+    refilled too early pushes the wrong bytes."""
+    from maxk_b200.dist import partition_rows_by_nnz
+    make, pool = peer_group
+    world, k = 2, 64
+    p, g = _problem(n=800, avg=4.0, k=k, seed=77, empty_frac=0.0)
+    bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
+    aggs = make(p, g, bounds, k, 0.0, 1)
+    rng = np.random.default_rng(1)
+    for step in range(2):
+        x = rng.random((p.n, p.d), dtype=np.float32)
+        sd, si = O.topk_cbsr(x, k)
+        want_y = O.spgemm_forward(p.w4, p.idx, p.val, sd, si, p.d, n_out=p.n)
+
+        def fwd(r):
+            lo, hi = bounds[r], bounds[r + 1]
+            aggs[r].exchange(_t(sd[lo:hi]), _t(si[lo:hi]))
+            return aggs[r].forward().clone()
+
+        ys = list(pool.map(fwd, range(world)))
+        for r in range(world):
+            close(ys[r], want_y[bounds[r]:bounds[r + 1]], f"forward, step {step}, rank {r}")
+            par = aggs[r]._fwd_epoch & 1   # the whole gathered operand arrived intact
+            np.testing.assert_array_equal(aggs[r].g_index[par].numpy(), si)
+            np.testing.assert_array_equal(aggs[r].g_data[par].numpy(), sd)
