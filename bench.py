@@ -189,8 +189,9 @@ def main():
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--sweep", action="store_true", help="also time k=8/16/64, TopK and the work list")
     ap.add_argument("--planned", type=int, default=0, choices=(0, 2, 4, 8),
-                    help="EXPERIMENTAL (N=1): forward through the bank plan with this many homes per column "
-                         "(csrc/cbsr_plan.cu); the plan is made next to the TopK, outside the step, and timed separately")
+                    help="EXPERIMENTAL: forward and backward through the bank plan with this many homes per column "
+                         "(csrc/cbsr_plan.cu).  N=1: the plan is made next to the TopK, outside the step, and timed "
+                         "separately; N>1 (peer transport): the plan travels in place of the selectors")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--comm", choices=("peer", "nccl"), default="peer",
@@ -250,7 +251,7 @@ def main():
             from maxk_b200.peer import PeerAggregator
             try:
                 agg = PeerAggregator.from_global_csr(g["indptr"], g["indices"], g["values"], bounds,
-                                                     rank, k, FEAT_DIM, copy_ctas=16)
+                                                     rank, k, FEAT_DIM, copy_ctas=16, homes=args.planned)
                 ok = 1
             except Exception as exc:  # noqa: BLE001
                 log(f"[rank {rank}] peer-memory path unavailable: {exc}")
@@ -273,9 +274,14 @@ def main():
         w = int(w_total)
 
         sd_loc, si_loc = ops.topk_cbsr(x_loc, k)   # like N=1: TopK is outside the step
+        planned_peer = bool(args.planned) and comm == "peer"
+        sa_loc = ops.cbsr_bank_plan(si_loc, args.planned) if planned_peer else None  # ... and so is the plan
 
         def step():
-            gd, gi = agg.exchange(sd_loc, si_loc)   # CBSR all-gather (NCCL, async)
+            if planned_peer:
+                gd, gi = agg.exchange(sd_loc, si_loc, sa_loc)
+            else:
+                gd, gi = agg.exchange(sd_loc, si_loc)   # CBSR all-gather (NCCL, async)
             agg.forward(gd, gi)                      # local columns overlap the all-gather
             agg.backward(dy_loc, gi)                 # + reduce-scatter of the partial gradients
         fwd_ms = bwd_ms = None
@@ -476,6 +482,10 @@ def main():
                                  "(37 MB) is L2-resident by design",
                            "step_algorithmic_bytes": step_bytes},
                 "clocks": clocks, "gpu_launches": launches}
+        if world > 1 and args.planned and comm == "peer":
+            line["config"]["forward"] = (f"EXPERIMENTAL bank-planned kernels, {args.planned} homes per column; the plan is "
+                                         "made next to the TopK, outside the step, and travels over NVLink in place "
+                                         "of the selectors")
         if world == 1 and args.planned:
             line["config"]["forward"] = (f"EXPERIMENTAL bank-planned forward and backward, {args.planned} homes per "
                                          "column; the plan kernel runs next to the TopK, outside the step (plan_ms)")

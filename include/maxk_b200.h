@@ -233,6 +233,13 @@ MAXK_API int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoch,
                               int64_t num_tasks, int64_t wait_from_task, const int32_t *indices,
                               const float *values, float *out, int64_t num_rows_out, int32_t d,
                               int32_t copy_ctas, void *stream);
+/* EXPERIMENTAL (unmeasured): the same kernel with the bank plan of cbsr_plan.cu travelling in place
+ * of the selectors: ctx->g_index[r] are uint16[n_total, k] buffers holding sp_addr (made with the same
+ * `homes` on every rank).  k = 8 (homes 2), 16 (2, 4), 32 and 64 (2, 4, 8).                    */
+MAXK_API int maxk_spgemm_forward_fused_planned(const maxk_peer_ctx *ctx, uint32_t epoch, int32_t homes,
+                                      const int32_t *warp4, int64_t num_tasks, int64_t wait_from_task,
+                                      const int32_t *indices, const float *values, float *out,
+                                      int64_t num_rows_out, int32_t d, int32_t copy_ctas, void *stream);
 /* Before the backward SSpMM (called with accumulate != 0 on ctx->partial[rank]): zero the rows
  * of this rank's partial buffer that its edges can touch -- its own block, and per peer the
  * whole block (dense pair) or the recv_rows list (halo pair). */

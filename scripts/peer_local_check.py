@@ -5,7 +5,9 @@ CBSR rows (TMA bulk copies or row lists), arrival flags, [own | other columns] t
 zeroing, publish + pull reduce-scatter, epoch-parity buffers -- checked against the single-GPU
 kernels with fresh inputs every step.
 
-    python scripts/peer_local_check.py WORLD K HALO_THRESHOLD [STEPS]
+    python scripts/peer_local_check.py WORLD K HALO_THRESHOLD [STEPS [HOMES]]
+
+HOMES = 2, 4, 8: the EXPERIMENTAL planned kernels (the bank plan travels in place of the selectors).
 
 Run in its own process (tests/test_gpu_parity.py does): the ranks' kernels wait for each other,
 so every rank's step is enqueued on its own stream before anything synchronises, and a bounded
@@ -32,12 +34,13 @@ from maxk_b200.peer import PeerAggregator  # noqa: E402
 
 world, k, halo = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+homes = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 p = Problem(n=480, avg=35.0, k=k, seed=17 * world + k, empty_frac=0.1)
 g = p.cuda()
 w4 = g["warp4"]
 bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
 aggs = PeerAggregator.local_group(g["indptr"], g["indices"], g["values"], bounds, k, 256,
-                                  copy_ctas=2, halo_threshold=halo)
+                                  copy_ctas=2, halo_threshold=halo, homes=homes)
 if halo == 0.0:
     assert all(sum(a.send_dense) == world - 1 for a in aggs)
 if halo >= 2.0:
@@ -73,5 +76,5 @@ for step in range(steps):
         ok = ok and f and b
         if not (f and b):
             print(f"MISMATCH world={world} k={k} halo={halo} step={step} rank={r}: fwd {f} bwd {b}", flush=True)
-print(f"peer_local_check world={world} k={k} halo={halo} steps={steps}: {'ok' if ok else 'FAILED'}", flush=True)
+print(f"peer_local_check world={world} k={k} halo={halo} steps={steps} homes={homes}: {'ok' if ok else 'FAILED'}", flush=True)
 sys.exit(0 if ok else 1)

@@ -228,6 +228,9 @@ constexpr int PEER_FLAG_ARRIVED = 16;  // flag words [16 + r]: CBSR block of ran
 // halo pair: copy the listed rows (global ids) of the own block into the same rows of peer p's
 // buffers; a row is k*4 bytes of values + k bytes of selectors, moved in 16-byte units when
 // k % 16 == 0 (4-byte units otherwise).  All copy CTAs share every list.
+// IB: bytes per entry of the second buffer -- 1 = uint8 selectors, 2 = the uint16 bank plan of the
+// planned kernels (cbsr_plan.cu), which then travels in place of the selectors.
+template <int IB = 1>
 __device__ __forceinline__ void peer_push_rows(const PeerArgs &a, int p, int cta)
 {
     const int *rows = a.send_rows[p];
@@ -236,7 +239,7 @@ __device__ __forceinline__ void peer_push_rows(const PeerArgs &a, int p, int cta
     const long long nthr = (long long)a.copy_ctas * blockDim.x;
     const int k = a.k;
     if ((k & 15) == 0) {
-        const int uv = k >> 2, upr = uv + (k >> 4);  // 16-byte units: values, then selectors
+        const int uv = k >> 2, upr = uv + ((k * IB) >> 4);  // 16-byte units: values, then selectors
         for (long long i = tid; i < n * upr; i += nthr) {
             const long long r = __ldg(rows + i / upr);
             const int u = (int)(i % upr);
@@ -244,12 +247,12 @@ __device__ __forceinline__ void peer_push_rows(const PeerArgs &a, int p, int cta
                 const uint4 v = ld_peer_u4(reinterpret_cast<const uint4 *>(a.g_data[a.rank] + r * k) + u);
                 reinterpret_cast<uint4 *>(a.g_data[p] + r * k)[u] = v;
             } else {
-                const uint4 v = ld_peer_u4(reinterpret_cast<const uint4 *>(a.g_index[a.rank] + r * k) + (u - uv));
-                reinterpret_cast<uint4 *>(a.g_index[p] + r * k)[u - uv] = v;
+                const uint4 v = ld_peer_u4(reinterpret_cast<const uint4 *>(a.g_index[a.rank] + r * k * IB) + (u - uv));
+                reinterpret_cast<uint4 *>(a.g_index[p] + r * k * IB)[u - uv] = v;
             }
         }
     } else {
-        const int uv = k, upr = k + (k >> 2);  // 4-byte units (k % 4 == 0)
+        const int uv = k, upr = k + ((k * IB) >> 2);  // 4-byte units (k % 4 == 0)
         for (long long i = tid; i < n * upr; i += nthr) {
             const long long r = __ldg(rows + i / upr);
             const int u = (int)(i % upr);
@@ -257,17 +260,19 @@ __device__ __forceinline__ void peer_push_rows(const PeerArgs &a, int p, int cta
                 reinterpret_cast<unsigned *>(a.g_data[p] + r * k)[u] =
                     reinterpret_cast<const unsigned *>(a.g_data[a.rank] + r * k)[u];
             else
-                reinterpret_cast<unsigned *>(a.g_index[p] + r * k)[u - uv] =
-                    reinterpret_cast<const unsigned *>(a.g_index[a.rank] + r * k)[u - uv];
+                reinterpret_cast<unsigned *>(a.g_index[p] + r * k * IB)[u - uv] =
+                    reinterpret_cast<const unsigned *>(a.g_index[a.rank] + r * k * IB)[u - uv];
         }
     }
 }
 
 // copy CTAs of the fused forward kernel: push this rank's CBSR rows to every other rank
+template <int IB = 1>
 __device__ __forceinline__ void peer_push_block(const PeerArgs &a, int cta, unsigned char *smem)
 {
     const long long row0 = a.row_start[a.rank];
     const long long nel = a.rows_of[a.rank] * a.k;
+    const long long nib = nel * IB;  // bytes of the second buffer (selectors or plan)
     bool any_dense = false;
     for (int r = 0; r < a.world; ++r) any_dense |= (r != a.rank && a.send_rows[r] == nullptr);
     if (any_dense && a.use_tma) {
@@ -287,33 +292,33 @@ __device__ __forceinline__ void peer_push_block(const PeerArgs &a, int cta, unsi
             }
             const unsigned stage = (smem_u32(smem) + 127u) & ~127u;
             peer_tma_fanout(a, dd, dd[a.rank], row0 * a.k * 4, (nel * 4) & ~15LL, cta, stage, mbar0, phase, issued);
-            peer_tma_fanout(a, di, di[a.rank], row0 * a.k, nel & ~15LL, cta, stage, mbar0, phase, issued);
+            peer_tma_fanout(a, di, di[a.rank], row0 * a.k * IB, nib & ~15LL, cta, stage, mbar0, phase, issued);
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all remote writes performed
             asm volatile("fence.proxy.async;" ::: "memory");
         }
-        if (cta == 0 && (nel & 15)) {  // selector tail of a block whose byte count is not 16-aligned
-            const long long t0 = nel & ~15LL;
+        if (cta == 0 && (nib & 15)) {  // selector tail of a block whose byte count is not 16-aligned
+            const long long t0 = nib & ~15LL;
             for (int s = 1; s < a.world; ++s) {
                 const int p = (a.rank + s) % a.world;
                 if (a.send_rows[p] != nullptr) continue;
-                for (long long i = t0 + threadIdx.x; i < nel; i += blockDim.x)
-                    a.g_index[p][row0 * a.k + i] = a.g_index[a.rank][row0 * a.k + i];
+                for (long long i = t0 + threadIdx.x; i < nib; i += blockDim.x)
+                    a.g_index[p][row0 * a.k * IB + i] = a.g_index[a.rank][row0 * a.k * IB + i];
             }
         }
     } else if (any_dense) {
         const unsigned char *own_d = reinterpret_cast<const unsigned char *>(a.g_data[a.rank] + row0 * a.k);
-        const unsigned char *own_i = a.g_index[a.rank] + row0 * a.k;
+        const unsigned char *own_i = a.g_index[a.rank] + row0 * a.k * IB;
         for (int s = 1; s < a.world; ++s) {
             const int p = (a.rank + s) % a.world;  // staggered: rank r writes to r+1 first
             if (a.send_rows[p] != nullptr) continue;
             peer_copy_slice(reinterpret_cast<unsigned char *>(a.g_data[p] + row0 * a.k), own_d, nel * 4,
                             cta, a.copy_ctas);
-            peer_copy_slice(a.g_index[p] + row0 * a.k, own_i, nel, cta, a.copy_ctas);
+            peer_copy_slice(a.g_index[p] + row0 * a.k * IB, own_i, nib, cta, a.copy_ctas);
         }
     }
     for (int s = 1; s < a.world; ++s) {  // halo pairs
         const int p = (a.rank + s) % a.world;
-        if (a.send_rows[p] != nullptr && a.send_count[p] > 0) peer_push_rows(a, p, cta);
+        if (a.send_rows[p] != nullptr && a.send_count[p] > 0) peer_push_rows<IB>(a, p, cta);
     }
     __syncthreads();
     if (threadIdx.x == 0) {

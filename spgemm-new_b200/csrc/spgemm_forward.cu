@@ -50,7 +50,7 @@ struct FwdCfg {
     static constexpr int HOMES = PLAN_;
     static constexpr int PLAN_WORDS = PLAN_ * 256 * R_;  // HOMES homes per column, one set per edge slot
     static_assert(PLAN_ == 0 || PLAN_ == 2 || PLAN_ == 4 || PLAN_ == 8, "homes");
-    static_assert(PLAN_ == 0 || (EXACT_ && R_ == 32 / KL_ && !PEER_ && !DB_ && RING_ == 0),
+    static_assert(PLAN_ == 0 || (EXACT_ && R_ == 32 / KL_ && !DB_ && RING_ == 0),
                   "the planned variant: k % 32 == 0 or k = 16, 8; one accumulator set per edge slot");
     // DB: double-buffered gather batches (experimental launch shapes 4-7, see launch_fwd_r)
     static constexpr bool DB = DB_;
@@ -527,7 +527,7 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
     bool gathered = true;  // PEER: the other ranks' CBSR blocks have arrived
     if constexpr (C::PEER) {
         if (cta < peer.copy_ctas) {  // lowest block ids: resident before any waiting CTA
-            peer_push_block(peer, (int)cta, smem_raw);
+            peer_push_block<(C::PLAN ? 2 : 1)>(peer, (int)cta, smem_raw);
             return;
         }
         cta -= peer.copy_ctas;
@@ -1036,5 +1036,93 @@ extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoc
         default: break;
     }
     set_error("maxk_spgemm_forward_fused: k=%d is not built for the fused path (8, 16, 32, 64, 96, 128, 256)", k);
+    return MAXK_ERR_UNSUPPORTED;
+}
+
+// ---- the same with the bank plan travelling in place of the selectors (EXPERIMENTAL, unmeasured) ----
+extern "C" int maxk_spgemm_forward_fused_planned(const maxk_peer_ctx *ctx, uint32_t epoch, int32_t homes,
+                                         const int32_t *warp4, int64_t num_tasks,
+                                         int64_t wait_from_task, const int32_t *indices,
+                                         const float *values, float *out, int64_t num_rows_out,
+                                         int32_t d, int32_t copy_ctas, void *stream)
+{
+    MAXK_REQUIRE(ctx != nullptr, "maxk_spgemm_forward_fused_planned: ctx is NULL");
+    MAXK_REQUIRE(homes == 2 || homes == 4 || homes == 8, "maxk_spgemm_forward_fused_planned: homes=%d must be 2, 4 or 8", homes);
+    const int world = ctx->world, rank = ctx->rank, k = ctx->k;
+    MAXK_REQUIRE(world >= 1 && world <= MAXK_PEER_MAX && rank >= 0 && rank < world,
+                 "maxk_spgemm_forward_fused_planned: world=%d rank=%d out of range", world, rank);
+    MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0 && wait_from_task >= 0,
+                 "maxk_spgemm_forward_fused_planned: negative size");
+    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
+                 "maxk_spgemm_forward_fused_planned: d=%d must be a multiple of 4 in [4,256]", d);
+    MAXK_REQUIRE(k >= 1 && k <= d, "maxk_spgemm_forward_fused_planned: k=%d must be in [1,d=%d]", k, d);
+    MAXK_REQUIRE(copy_ctas != 0 && copy_ctas >= -1024 && copy_ctas <= 1024,
+                 "maxk_spgemm_forward_fused_planned: copy_ctas out of range");
+    MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "maxk_spgemm_forward_fused_planned: out is NULL");
+    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
+                 "maxk_spgemm_forward_fused_planned: out and warp4 must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PeerArgs pa{};
+    pa.copy_ctas = copy_ctas < 0 ? -copy_ctas : copy_ctas;
+    pa.use_tma = copy_ctas > 0 ? 1 : 0;  // negative count: plain load/store copy (measurement knob)
+    pa.world = world;
+    pa.rank = rank;
+    pa.k = k;
+    pa.epoch = epoch;
+    pa.wait_from_task = wait_from_task;
+    for (int r = 0; r < world; ++r) {
+        MAXK_REQUIRE(ctx->g_data[r] && ctx->g_index[r] && ctx->flags[r],
+                     "maxk_spgemm_forward_fused_planned: buffers of rank %d are not mapped", r);
+        MAXK_REQUIRE(ctx->rows_of[r] >= 0 && ctx->row_start[r] >= 0 &&
+                         ctx->row_start[r] + ctx->rows_of[r] <= ctx->n_total,
+                     "maxk_spgemm_forward_fused_planned: row range of rank %d is outside [0, n_total)", r);
+        MAXK_REQUIRE((ctx->row_start[r] * (int64_t)k) % 16 == 0,
+                     "maxk_spgemm_forward_fused_planned: row_start[%d] * k must be a multiple of 16", r);
+        pa.rows_of[r] = ctx->rows_of[r];
+        pa.row_start[r] = ctx->row_start[r];
+        pa.send_rows[r] = (r == rank) ? nullptr : ctx->send_rows[r];
+        pa.send_count[r] = ctx->send_count[r];
+        pa.g_data[r] = static_cast<float *>(ctx->g_data[r]);
+        pa.g_index[r] = static_cast<unsigned char *>(ctx->g_index[r]);
+        pa.flags[r] = static_cast<unsigned *>(ctx->flags[r]);
+    }
+    // halo pairs are moved row by row with ordinary loads and stores: that needs many threads in
+    // flight (a dependent list -> row -> store chain per 16 bytes), so the copy part of the grid
+    // grows to four CTAs per SM -- the aggregating CTAs mostly wait for those rows anyway
+    for (int r = 0; r < world; ++r)
+        if (r != rank && pa.send_rows[r] != nullptr && pa.send_count[r] > 0 && pa.copy_ctas < 4 * kNumSMs)
+            pa.copy_ctas = 4 * kNumSMs;
+    pa.local_sync = static_cast<unsigned *>(ctx->local_sync);
+    MAXK_REQUIRE(pa.local_sync != nullptr, "maxk_spgemm_forward_fused_planned: local_sync is NULL");
+    MAXK_REQUIRE(warp4 || num_tasks == 0, "maxk_spgemm_forward_fused_planned: warp4 is NULL");
+    // local-column and remote-column tasks of one row meet in `out` through reductions
+    if (num_rows_out > 0) {
+        MAXK_CUDA(cudaMemsetAsync(out, 0, (size_t)num_rows_out * d * sizeof(float), st));
+        count_launch();
+    }
+    int tpw = g_fwd_tasks_per_warp;
+    if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
+    FwdArgs a{warp4, num_tasks, indices, values, pa.g_data[rank], pa.g_index[rank], k, out, d,
+              tpw, /*accumulate=*/1, st, 1, num_rows_out, &pa, false};
+    // the copy CTAs must run even when this rank has no task at all: launch_fwd adds them.
+    // g_index[r] holds the uint16 bank plan (cbsr_plan.cu) of every row instead of its selectors
+#define MAXK_FUSED_PLANNED(KL, EPL, R, U, MINB, H) \
+    return launch_fwd<FwdCfg<KL, EPL, true, R, 8, U, MINB, true, false, 0, H>>(a)
+    switch (k * 16 + homes) {
+        case 8 * 16 + 2: MAXK_FUSED_PLANNED(8, 1, 4, 4, 3, 2);
+        case 16 * 16 + 2: MAXK_FUSED_PLANNED(16, 1, 2, 4, 4, 2);
+        case 16 * 16 + 4: MAXK_FUSED_PLANNED(16, 1, 2, 4, 4, 4);
+        case 32 * 16 + 2: MAXK_FUSED_PLANNED(32, 1, 1, 4, 4, 2);
+        case 32 * 16 + 4: MAXK_FUSED_PLANNED(32, 1, 1, 4, 4, 4);
+        case 32 * 16 + 8: MAXK_FUSED_PLANNED(32, 1, 1, 4, 4, 8);
+        case 64 * 16 + 2: MAXK_FUSED_PLANNED(32, 2, 1, 2, 4, 2);
+        case 64 * 16 + 4: MAXK_FUSED_PLANNED(32, 2, 1, 2, 4, 4);
+        case 64 * 16 + 8: MAXK_FUSED_PLANNED(32, 2, 1, 2, 4, 8);
+        default: break;
+    }
+#undef MAXK_FUSED_PLANNED
+    set_error("maxk_spgemm_forward_fused_planned: k=%d with %d homes is not built (k = 8: 2; 16: 2, 4; 32, 64: 2, 4, 8)",
+              k, homes);
     return MAXK_ERR_UNSUPPORTED;
 }

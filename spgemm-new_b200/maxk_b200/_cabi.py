@@ -55,6 +55,8 @@ PROTOTYPES = {
     "maxk_peer_publish": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp]),
     "maxk_spgemm_forward_fused": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp, _i64, _i64, _vp, _vp, _vp,
                                                  _i64, _i32, _i32, _vp]),
+    "maxk_spgemm_forward_fused_planned": (ctypes.c_int, [_vp, ctypes.c_uint32, _i32, _vp, _i64, _i64, _vp, _vp, _vp,
+                                                         _i64, _i32, _i32, _vp]),
     "maxk_peer_zero_partial": (ctypes.c_int, [_vp, _vp]),
     "maxk_reduce_scatter_pull": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp, _vp]),
     # reference-named shims (cuda_kernel_wrappers.cu:38-91); dim3 by value

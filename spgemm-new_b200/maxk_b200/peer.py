@@ -58,7 +58,7 @@ class _RawCuda:
 
 
 def _wrap(ptr: int, shape, dtype: torch.dtype, device) -> torch.Tensor:
-    typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+    typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4", torch.uint16: "<u2"}[dtype]
     return torch.as_tensor(_RawCuda(ptr, shape, typestr), device=device)
 
 
@@ -96,18 +96,23 @@ class _Shared:
 
 class PeerAggregator:
     def __init__(self, indptr_loc, indices_glob, values_loc, bounds: List[int], rank: int, k: int,
-                 feat_dim: int = 256, group=None, copy_ctas: int = 16, halo_threshold: float = 0.3):
+                 feat_dim: int = 256, group=None, copy_ctas: int = 16, halo_threshold: float = 0.3,
+                 homes: int = 0):
         """halo_threshold: a (sender, receiver) pair exchanges only the rows the receiver's edges
         reference when those are fewer than this fraction of the sender's block, the whole block
-        otherwise (0 = always the whole block, > 1 = always row lists)."""
+        otherwise (0 = always the whole block, > 1 = always row lists).
+        homes (EXPERIMENTAL, unmeasured): 2, 4 or 8 = the bank plan of csrc/cbsr_plan.cu (uint16 per
+        entry) travels in place of the selectors and both directions run the planned kernels."""
         self.group = group
         assert indptr_loc.is_cuda, "the peer-memory path is CUDA only"
+        self.homes = int(homes)
         self._plan(indptr_loc, indices_glob, values_loc, bounds, rank, k, feat_dim, copy_ctas,
                    halo_threshold)
         world, dev = self.world, self.device
         send = self._exchange_lists(group)
         # ---- peer-visible buffers (CUDA IPC), two sets alternating by epoch parity -----------
-        nb_data, nb_index = max(self.n_total * self.k * 4, 16), max(self.n_total * self.k, 16)
+        nb_data = max(self.n_total * self.k * 4, 16)
+        nb_index = max(self.n_total * self.k * (2 if self.homes else 1), 16)
         flags = _Shared(256, rank, world, group)
         self._shared = [flags]
         tables = []
@@ -230,7 +235,8 @@ class PeerAggregator:
             ctx.local_sync = self.local_sync.data_ptr()
             self._ctx.append(ctx)
             self.g_data.append(_wrap(d_ptrs[rank], (self.n_total, self.k), torch.float32, dev))
-            self.g_index.append(_wrap(i_ptrs[rank], (self.n_total, self.k), torch.uint8, dev))
+            self.g_index.append(_wrap(i_ptrs[rank], (self.n_total, self.k),
+                                      torch.uint16 if getattr(self, "homes", 0) else torch.uint8, dev))
             self.partial.append(_wrap(p_ptrs[rank], (self.n_total, self.k), torch.float32, dev))
         self._flag_ptr = flag_ptrs[rank]
         self.y = torch.zeros((self.n_local, self.d), dtype=torch.float32, device=dev)
@@ -240,7 +246,7 @@ class PeerAggregator:
 
     @classmethod
     def local_group(cls, indptr, indices, values, bounds, k, feat_dim=256, copy_ctas=2,
-                    halo_threshold=0.3):
+                    halo_threshold=0.3, homes=0):
         """All ranks of a job inside ONE process on ONE GPU (plain device tensors instead of IPC
         mappings, no torch.distributed): the kernels, flags and row lists are exactly those of
         the multi-process job.  For tests and debugging on a single-GPU box -- the ranks' kernels
@@ -254,6 +260,7 @@ class PeerAggregator:
             a = cls.__new__(cls)
             a.group = None
             a._shared = []
+            a.homes = int(homes)
             assert indptr.is_cuda, "the peer-memory path is CUDA only"
             a._plan((indptr[lo:hi + 1] - indptr[lo]).to(torch.int32), indices[e0:e1].contiguous(),
                     values[e0:e1].contiguous(), list(bounds), r, k, feat_dim, copy_ctas, halo_threshold)
@@ -267,7 +274,8 @@ class PeerAggregator:
             keep.append(ts)
             return [t.data_ptr() for t in ts]
         flag_ptrs = alloc((64,), torch.int32)
-        tables = [(alloc((max(n_total, 1), k), torch.float32), alloc((max(n_total, 1), k), torch.uint8),
+        tables = [(alloc((max(n_total, 1), k), torch.float32),
+                   alloc((max(n_total, 1), k), torch.uint16 if homes else torch.uint8),
                    alloc((max(n_total, 1), k), torch.float32)) for _ in range(2)]
         for r, a in enumerate(aggs):
             a._keepalive = keep
@@ -295,17 +303,29 @@ class PeerAggregator:
     def topk_and_exchange(self, x_loc: torch.Tensor):
         """TopK straight into the peer-visible buffer (no staging copy), then publish."""
         par = (self._fwd_epoch + 1) & 1
-        ops.topk_cbsr(x_loc, self.k, out=self.own_block(par))
+        if self.homes:
+            d_own, a_own = self.own_block(par)
+            if getattr(self, "_sel_tmp", None) is None:
+                self._sel_tmp = torch.empty((self.n_local, self.k), dtype=torch.uint8, device=self.device)
+            ops.topk_cbsr(x_loc, self.k, out=(d_own, self._sel_tmp))
+            ops.cbsr_bank_plan(self._sel_tmp, self.homes, out=a_own)
+        else:
+            ops.topk_cbsr(x_loc, self.k, out=self.own_block(par))
         return self._publish_forward()
 
-    def exchange(self, sp_data_loc: torch.Tensor, sp_index_loc: torch.Tensor):
+    def exchange(self, sp_data_loc: torch.Tensor, sp_index_loc: torch.Tensor, sp_addr_loc=None):
         """Place this rank's CBSR block where the peers will pull it from and publish it.
         Returns the gathered buffers of this step; the other ranks' blocks are only valid once
         `forward` has run."""
         par = (self._fwd_epoch + 1) & 1
         d_own, i_own = self.own_block(par)
         d_own.copy_(sp_data_loc)
-        i_own.copy_(sp_index_loc)
+        if self.homes and sp_addr_loc is not None:   # plan made by the caller (next to its TopK)
+            i_own.copy_(sp_addr_loc)
+        elif self.homes:   # the plan of this rank's rows travels in place of their selectors
+            ops.cbsr_bank_plan(sp_index_loc.contiguous(), self.homes, out=i_own)
+        else:
+            i_own.copy_(sp_index_loc)
         return self._publish_forward()
 
     def _publish_forward(self):
@@ -318,10 +338,16 @@ class PeerAggregator:
     def forward(self, g_data=None, g_index=None) -> torch.Tensor:
         par = self._fwd_epoch & 1
         with torch.cuda.device(self.device):
-            _cabi.check(_cabi.load().maxk_spgemm_forward_fused(
-                ctypes.byref(self._ctx[par]), self._fwd_epoch, self.f_warp4.data_ptr(), self.num_tasks,
-                self.wait_from_task, self.f_indices.data_ptr(), self.f_values.data_ptr(),
-                self.y.data_ptr(), self.n_local, self.d, self.copy_ctas, self._stream()))
+            if self.homes:
+                _cabi.check(_cabi.load().maxk_spgemm_forward_fused_planned(
+                    ctypes.byref(self._ctx[par]), self._fwd_epoch, self.homes, self.f_warp4.data_ptr(),
+                    self.num_tasks, self.wait_from_task, self.f_indices.data_ptr(), self.f_values.data_ptr(),
+                    self.y.data_ptr(), self.n_local, self.d, self.copy_ctas, self._stream()))
+            else:
+                _cabi.check(_cabi.load().maxk_spgemm_forward_fused(
+                    ctypes.byref(self._ctx[par]), self._fwd_epoch, self.f_warp4.data_ptr(), self.num_tasks,
+                    self.wait_from_task, self.f_indices.data_ptr(), self.f_values.data_ptr(),
+                    self.y.data_ptr(), self.n_local, self.d, self.copy_ctas, self._stream()))
         return self.y
 
     # ------------------------------------------------------------------------ backward
@@ -332,8 +358,12 @@ class PeerAggregator:
         lib = _cabi.load()
         with torch.cuda.device(self.device):
             _cabi.check(lib.maxk_peer_zero_partial(ctypes.byref(self._ctx[par]), self._stream()))
-        ops.sspmm_backward(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index,
-                           out=self.partial[par], accumulate=True)
+        if self.homes:
+            ops.sspmm_backward_planned(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index, self.homes,
+                                       out=self.partial[par], accumulate=True)
+        else:
+            ops.sspmm_backward(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index,
+                               out=self.partial[par], accumulate=True)
         with torch.cuda.device(self.device):
             _cabi.check(lib.maxk_peer_publish(ctypes.c_void_p(self._flag_ptr + 4 * 1), self._bwd_epoch,
                                               self._stream()))

@@ -512,6 +512,20 @@ def test_peer_kernels_multi_rank_on_one_gpu(world, k, halo):
     assert "ok" in r.stdout
 
 
+@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
+                    reason="planned kernels on the peer-memory path: written after round 1's GPU budget was spent, "
+                           "checked with 2-4 ranks under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
+@pytest.mark.parametrize("world,k,halo,homes", [(2, 32, 0.0, 8), (3, 32, 0.3, 2), (2, 64, 2.0, 4), (2, 16, 0.0, 4)])
+def test_peer_planned_kernels_multi_rank_on_one_gpu(world, k, halo, homes):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "peer_local_check.py"),
+                        str(world), str(k), str(halo), "4", str(homes)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout[-600:], r.stderr[-1200:])
+    assert "ok" in r.stdout
+
+
 def test_reference_named_shims():
     """The reference's own extern "C" launch shims (cuda_kernel_wrappers.cu:38-91), same argument
     lists (dim3 by value), resolved from libmaxk_b200.so."""

@@ -199,7 +199,7 @@ def peer_group(ops, monkeypatch):
     monkeypatch.setattr(P.PeerAggregator, "_stream", lambda self: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
 
-    def make(p, g, bounds, k, halo_threshold, copy_ctas):
+    def make(p, g, bounds, k, halo_threshold, copy_ctas, homes=0):
         world = len(bounds) - 1
         indptr, indices, values = g["indptr"].long(), g["indices"], g["values"]
         aggs = []
@@ -207,7 +207,7 @@ def peer_group(ops, monkeypatch):
             lo, hi = bounds[r], bounds[r + 1]
             e0, e1 = int(indptr[lo]), int(indptr[hi])
             a = P.PeerAggregator.__new__(P.PeerAggregator)
-            a.group, a._shared = None, []
+            a.group, a._shared, a.homes = None, [], homes
             a._plan((indptr[lo:hi + 1] - indptr[lo]).to(torch.int32), indices[e0:e1].contiguous(),
                     values[e0:e1].contiguous(), list(bounds), r, k, p.d, copy_ctas, halo_threshold)
             aggs.append(a)
@@ -219,7 +219,8 @@ def peer_group(ops, monkeypatch):
                 registry[t.data_ptr()] = t
             return [t.data_ptr() for t in ts]
         flag_ptrs = alloc((64,), torch.int32)
-        tables = [(alloc((max(n_total, 1), k), torch.float32), alloc((max(n_total, 1), k), torch.uint8),
+        tables = [(alloc((max(n_total, 1), k), torch.float32),
+                   alloc((max(n_total, 1), k), torch.uint16 if homes else torch.uint8),
                    alloc((max(n_total, 1), k), torch.float32)) for _ in range(2)]
         for r, a in enumerate(aggs):
             a._wire([aggs[q]._recv[r] for q in range(world)], flag_ptrs, tables)
@@ -253,6 +254,47 @@ def test_peer_kernels_multi_rank_under_the_interpreter(peer_group, world, k, hal
         def fwd(r):
             lo, hi = bounds[r], bounds[r + 1]
             aggs[r].exchange(_t(sd[lo:hi]), _t(si[lo:hi]))
+            return aggs[r].forward().clone()
+
+        ys = list(pool.map(fwd, range(world)))
+        for r in range(world):
+            close(ys[r], want_y[bounds[r]:bounds[r + 1]], f"forward, step {step}, rank {r}")
+
+        def bwd(r):
+            lo, hi = bounds[r], bounds[r + 1]
+            par = aggs[r]._fwd_epoch & 1
+            return aggs[r].backward(_t(dy[lo:hi]), aggs[r].g_index[par]).clone()
+
+        gs = list(pool.map(bwd, range(world)))
+        for r in range(world):
+            close(gs[r], want_g[bounds[r]:bounds[r + 1]], f"backward, step {step}, rank {r}")
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,k,halo,homes,copy_ctas", [(2, 32, 0.0, 8, 3), (3, 32, 0.3, 2, -2), (2, 64, 2.0, 4, 2),
+                                                          (2, 16, 0.0, 4, 2), (3, 8, 2.0, 2, -1), (4, 32, 0.0, 4, 1)])
+def test_peer_planned_kernels_multi_rank_under_the_interpreter(peer_group, world, k, halo, homes, copy_ctas):
+    """The bank plan travels in place of the selectors (EXPERIMENTAL fused planned forward + planned
+    backward): same oracle, dense / halo / mixed pairs, TMA and load/store push."""
+    from maxk_b200.dist import partition_rows_by_nnz
+    make, pool = peer_group
+    p, g = _problem(n=96 * world, avg=14.0, k=k, seed=world * 10 + k + homes, empty_frac=0.1)
+    bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
+    aggs = make(p, g, bounds, k, halo, copy_ctas, homes)
+    rng = np.random.default_rng(k + homes)
+    for step in range(3):
+        x = rng.random((p.n, p.d), dtype=np.float32)
+        dy = rng.random((p.n, p.d), dtype=np.float32)
+        sd, si = O.topk_cbsr(x, k)
+        want_y = O.spgemm_forward(p.w4, p.idx, p.val, sd, si, p.d, n_out=p.n)
+        want_g = O.sspmm_backward(p.w4, p.idx, p.val, dy, si)
+
+        def fwd(r):
+            lo, hi = bounds[r], bounds[r + 1]
+            if step == 1:   # TopK straight into the peer-visible buffer, then the plan
+                aggs[r].topk_and_exchange(_t(x[lo:hi]))
+            else:
+                aggs[r].exchange(_t(sd[lo:hi]), _t(si[lo:hi]))
             return aggs[r].forward().clone()
 
         ys = list(pool.map(fwd, range(world)))
