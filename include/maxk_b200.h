@@ -135,6 +135,9 @@ MAXK_API int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks
  * entry l of CBSR row j looks its value up at word sp_addr[j,l]; one instruction covers the 32
  * entries of one edge (ncu, round 1: 2.2 of the default kernel's 5.8 wavefronts per edge are bank
  * conflicts of exactly these lookups).  Same output contract as maxk_sspmm_backward.          */
+/* Bench/test hook: 1 = the planned backward keeps the default kernel's (edge, 4-entry group) items and
+ * 128-bit vector reductions (k = 32, 64); 0 = one edge per lookup instruction, scalar reductions. */
+MAXK_API int maxk_set_planned_backward_vector(int on);
 MAXK_API int maxk_sspmm_backward_planned(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                                 const float *values, const float *dy, const uint16_t *sp_addr,
                                 int32_t k, int32_t homes, int32_t d, float *dxc,

@@ -86,12 +86,16 @@ for k in [int(v) for v in a.ks.split(",")]:
             t_def = timeit(lambda: ops.sspmm_backward(w4, g["indices"], g["values"], dy, si, out=dxc), a.iters)
             for homes in ((2, 4, 8) if k >= 32 else (2, 4) if k == 16 else (2,)):
                 sa = ops.cbsr_bank_plan(si, homes)
-                t = timeit(lambda: ops.sspmm_backward_planned(w4, g["indices"], g["values"], dy, sa, homes, out=dxc), a.iters)
-                err = float((dxc - ref_b).abs().max() / ref_b.abs().max())
-                r = {"kernel": "bwd_planned", "shape": a.shape, "k": k, "homes": homes, "ms": round(t, 4),
-                     "default_ms": round(t_def, 4), "frac": round(b["bwd"] / t / 1e6 / peak, 3), "rel_err_vs_default": err}
-                res.append(r)
-                print(json.dumps(r), flush=True)
+                for vector in ((False, True) if k in (32, 64) else (False,)):
+                    ops.set_planned_backward_vector(vector)
+                    t = timeit(lambda: ops.sspmm_backward_planned(w4, g["indices"], g["values"], dy, sa, homes, out=dxc), a.iters)
+                    err = float((dxc - ref_b).abs().max() / ref_b.abs().max())
+                    r = {"kernel": "bwd_planned", "shape": a.shape, "k": k, "homes": homes,
+                         "reductions": "v4" if vector else "scalar", "ms": round(t, 4), "default_ms": round(t_def, 4),
+                         "frac": round(b["bwd"] / t / 1e6 / peak, 3), "rel_err_vs_default": err}
+                    res.append(r)
+                    print(json.dumps(r), flush=True)
+                ops.set_planned_backward_vector(False)
     if a.bwd_tpw:
         dxc = torch.empty(n, k, device="cuda")
         for tpw in [int(v) for v in a.bwd_tpw.split(",")]:

@@ -118,6 +118,47 @@ __device__ __forceinline__ void bwp_process_batch(const int2 *stage, int len, co
     }
 }
 
+// ---- variant that keeps the 128-bit vector reductions of the default kernel (knob: maxk_set_planned_
+// backward_vector): work items are (edge, 4-entry group) as there, so one lookup instruction reads 8
+// entries of each of 4 edges.  The plan still removes the conflicts INSIDE a row (its 8 entries sit in
+// 8 different banks at H = 8); entries of different rows can still meet: fullest bank ~2.4 instead of
+// 3.3.  The fallback if the L2 turns out to take 32 scalar reductions per line slower than 8 vector ones.
+template <int EPL>
+__device__ __forceinline__ void bwp_process_batch_vec(const int2 *stage, int len, const float *dys,
+                                                      const unsigned short *__restrict__ sp_addr,
+                                                      float *__restrict__ dxc, int lane)
+{
+    constexpr int K = 32 * EPL, GROUPS = K / 4;  // 4-entry groups per edge (a power of two times 1..4)
+    const int items = len * GROUPS;
+    for (int i0 = lane; i0 < items; i0 += 32 * BWP_U) {
+        int2 ev[BWP_U];
+        int q[BWP_U];
+        uint2 a4[BWP_U];
+#pragma unroll
+        for (int u = 0; u < BWP_U; ++u) {
+            const int i = i0 + 32 * u;
+            if (i < items) {
+                const int e = i / GROUPS;
+                q[u] = i - e * GROUPS;
+                ev[u] = stage[e];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BWP_U; ++u)
+            if (i0 + 32 * u < items)
+                a4[u] = __ldg(reinterpret_cast<const uint2 *>(sp_addr + (uint64_t)(uint32_t)ev[u].x * (uint32_t)K) + q[u]);
+#pragma unroll
+        for (int u = 0; u < BWP_U; ++u) {
+            if (i0 + 32 * u < items) {
+                const float w = __int_as_float(ev[u].y);
+                const float g0 = dys[a4[u].x & 0xffffu], g1 = dys[a4[u].x >> 16];
+                const float g2 = dys[a4[u].y & 0xffffu], g3 = dys[a4[u].y >> 16];
+                red_add_f4(dxc + (uint64_t)(uint32_t)ev[u].x * (uint32_t)K + 4 * q[u], w * g0, w * g1, w * g2, w * g3);
+            }
+        }
+    }
+}
+
 // ---- k = 16, 8: E = 32/k edges per lookup instruction, one copy of the staged row per edge slot on
 // its own 1/E of the banks (word * E + slot) -- the layout the plan of such a k was made for ----------
 template <int H, int E>
@@ -160,8 +201,8 @@ __device__ __forceinline__ void bwp_process_batch_slots(const int2 *stage, int l
     }
 }
 
-// KL = 32: k = 32 * EPL;  KL = 16, 8: k = KL (EPL = 1)
-template <int KL, int EPL, int H>
+// KL = 32: k = 32 * EPL;  KL = 16, 8: k = KL (EPL = 1);  VEC: the vector-reduction variant (KL = 32)
+template <int KL, int EPL, int H, bool VEC = false>
 __global__ void __launch_bounds__(BWP_WPB * 32)
 sspmm_bwd_planned_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *__restrict__ idx,
                          const float *__restrict__ val, const float *__restrict__ dy,
@@ -202,7 +243,9 @@ sspmm_bwd_planned_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, cons
         const int len = info.z;
         bwp_stage_edges(pre, stage, lane);
         if (has_next) bwp_fetch_edges(pre, idx, val, ninfo.y, min(ninfo.z, BWP_STAGE), lane);
-        if constexpr (KL == 32)
+        if constexpr (VEC)
+            bwp_process_batch_vec<EPL>(stage, min(len, BWP_STAGE), dys, sp_addr, dxc, lane);
+        else if constexpr (KL == 32)
             bwp_process_batch<EPL>(stage, min(len, BWP_STAGE), dys, sp_addr, dxc, lane);
         else
             bwp_process_batch_slots<KL>(stage, min(len, BWP_STAGE), dys, sp_addr, dxc, lane);
@@ -211,7 +254,9 @@ sspmm_bwd_planned_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, cons
             const int ln = min(len - off, BWP_STAGE);
             bwp_fetch_edges(more, idx, val, loc + off, ln, lane);
             bwp_stage_edges(more, stage, lane);
-            if constexpr (KL == 32)
+            if constexpr (VEC)
+                bwp_process_batch_vec<EPL>(stage, ln, dys, sp_addr, dxc, lane);
+            else if constexpr (KL == 32)
                 bwp_process_batch<EPL>(stage, ln, dys, sp_addr, dxc, lane);
             else
                 bwp_process_batch_slots<KL>(stage, ln, dys, sp_addr, dxc, lane);
@@ -220,7 +265,7 @@ sspmm_bwd_planned_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, cons
     }
 }
 
-template <int KL, int EPL, int H>
+template <int KL, int EPL, int H, bool VEC = false>
 static int launch_bwp(const int32_t *warp4, int64_t W, const int32_t *idx, const float *val,
                       const float *dy, const uint16_t *sp_addr, int d, float *dxc, int tasks_per_warp,
                       cudaStream_t st)
@@ -230,7 +275,7 @@ static int launch_bwp(const int32_t *warp4, int64_t W, const int32_t *idx, const
     if (smem > 48 * 1024) {
         static bool opted_in = false;  // per variant; benign if raced
         if (!opted_in) {
-            MAXK_CUDA(cudaFuncSetAttribute(sspmm_bwd_planned_kernel<KL, EPL, H>,
+            MAXK_CUDA(cudaFuncSetAttribute(sspmm_bwd_planned_kernel<KL, EPL, H, VEC>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             opted_in = true;
         }
@@ -241,17 +286,26 @@ static int launch_bwp(const int32_t *warp4, int64_t W, const int32_t *idx, const
         set_error("maxk_sspmm_backward_planned: grid too large");
         return MAXK_ERR_UNSUPPORTED;
     }
-    sspmm_bwd_planned_kernel<KL, EPL, H><<<(unsigned)grid, BWP_WPB * 32, smem, st>>>(
+    sspmm_bwd_planned_kernel<KL, EPL, H, VEC><<<(unsigned)grid, BWP_WPB * 32, smem, st>>>(
         reinterpret_cast<const int4 *>(warp4), W, idx, val, dy, sp_addr, d, dxc, tasks_per_warp);
     MAXK_LAUNCH_CHECK("sspmm_bwd_planned_kernel");
     return MAXK_OK;
 }
 
 extern int g_bwd_tasks_per_warp;
+int g_bwp_vector = 0;  // 1: keep the 128-bit vector reductions (k = 32, 64)
 
 }  // namespace maxk
 
 using namespace maxk;
+
+// Bench/test hook: 1 = the planned backward keeps 128-bit vector reductions (k = 32, 64), 0 = scalar
+// reductions with one edge per lookup instruction (default).
+extern "C" int maxk_set_planned_backward_vector(int on)
+{
+    g_bwp_vector = on ? 1 : 0;
+    return MAXK_OK;
+}
 
 extern "C" int maxk_sspmm_backward_planned(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                                            const float *values, const float *dy, const uint16_t *sp_addr,
@@ -282,6 +336,20 @@ extern "C" int maxk_sspmm_backward_planned(const int32_t *warp4, int64_t num_tas
                  "maxk_sspmm_backward_planned: sp_addr / dxc are misaligned");
     int tpw = g_bwd_tasks_per_warp;
     if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
+    if (g_bwp_vector && (k == 32 || k == 64) && (reinterpret_cast<uintptr_t>(sp_addr) & 7) == 0 &&
+        (reinterpret_cast<uintptr_t>(dxc) & 15) == 0) {
+#define MAXK_BWP_VEC(E, HH) \
+    return launch_bwp<32, E, HH, true>(warp4, num_tasks, indices, values, dy, sp_addr, d, dxc, tpw, st)
+        switch (k / 32 * 16 + homes) {
+            case 16 + 2: MAXK_BWP_VEC(1, 2);
+            case 16 + 4: MAXK_BWP_VEC(1, 4);
+            case 16 + 8: MAXK_BWP_VEC(1, 8);
+            case 32 + 2: MAXK_BWP_VEC(2, 2);
+            case 32 + 4: MAXK_BWP_VEC(2, 4);
+            default: MAXK_BWP_VEC(2, 8);
+        }
+#undef MAXK_BWP_VEC
+    }
 #define MAXK_BWP_GO(E, HH) \
     return launch_bwp<32, E, HH>(warp4, num_tasks, indices, values, dy, sp_addr, d, dxc, tpw, st)
     if (k == 16 && homes == 2) return launch_bwp<16, 1, 2>(warp4, num_tasks, indices, values, dy, sp_addr, d, dxc, tpw, st);

@@ -142,6 +142,10 @@ def set_forward_copies(copies=0):
     load().maxk_set_forward_copies(int(copies))
 
 
+def set_planned_backward_vector(on):
+    load().maxk_set_planned_backward_vector(1 if on else 0)
+
+
 def set_cp_async_eager(eager):
     """cp.async data lands immediately (True) or as late as PTX allows, at the issuer's wait (False, default)."""
     load().simt_set_cp_async_eager(1 if eager else 0)

@@ -266,16 +266,19 @@ def test_backward_planned_experimental(ops, case):
     try:
         for homes in ((2, 4, 8) if p.k >= 32 else (2, 4) if p.k == 16 else (2,)):
             sp_addr = ops.cbsr_bank_plan(g["sp_index"], homes)
-            for tpw in (-1, 1, 5):
+            for tpw, vector in ((-1, False), (1, False), (5, False), (-1, True), (2, True)):
                 ops.set_tuning(0, tpw)
+                ops.set_planned_backward_vector(vector)
                 dxc = torch.full((p.n_cols, p.k), float("nan"), device="cuda")
                 ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, homes, out=dxc)
-                assert_close(dxc, want, f"homes={homes} tpw={tpw}")
+                assert_close(dxc, want, f"homes={homes} tpw={tpw} vector={vector}")
+            ops.set_planned_backward_vector(False)
             ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, homes, out=dxc,
                                        accumulate=True)
             assert_close(dxc, 2 * want, "accumulate")
     finally:
         ops.set_tuning(-1, -1)
+        ops.set_planned_backward_vector(False)
 
 
 def test_forward_gap_rows_are_zeroed(ops):

@@ -28,6 +28,7 @@ def _reset_knobs():
     S.set_forward_depth(0)
     S.set_forward_copies(0)
     S.set_cp_async_eager(False)
+    S.set_planned_backward_vector(False)
 
 
 # ------------------------------------------------------------------------------ a4
@@ -352,8 +353,12 @@ BWD_PLANNED_CASES = [dict(k=16), dict(k=8), dict(k=16, d=64, avg=90.0), dict(k=8
                      dict(k=32, n=200, n_cols=700, avg=25.0), dict(k=32, warp_max_nz=100), dict(k=64, warp_max_nz=5)]
 
 
+@pytest.mark.parametrize("vector", [False, True])
 @pytest.mark.parametrize("case", BWD_PLANNED_CASES, ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
-def test_simt_planned_backward_vs_oracle(case):
+def test_simt_planned_backward_vs_oracle(case, vector):
+    """scalar reductions, one edge per lookup instruction / vector reductions, (edge, 4-entry group) items
+    (k = 32 and 64 with aligned operands; every other case takes the scalar form)"""
+    S.set_planned_backward_vector(vector)
     case = dict(n=250, **case) if "n" not in case else case
     p = Problem(seed=len(str(case)) + 3, **case)
     want = p.bwd_oracle()
