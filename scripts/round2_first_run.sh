@@ -24,3 +24,10 @@ done
 python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_proteins_default.json
 MAXK_PLANNED_HOMES=8 python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_proteins_planned8.json
 # (with 2 or 8 GPUs: `torchrun ... bench.py --gpus N --planned 8` runs the planned kernels on the peer transport)
+# ncu of the planned kernels (only after the runs above exited 0 without ncu): launch list + one full capture each
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_planned.csv \
+  python scripts/profile_step.py --planned 8 --iters 2 > gpurun_out/ncu_planned_list.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:spgemm_fwd_kernel -s 3 -c 1 -o gpurun_out/prof_fwd_planned8 \
+  python scripts/profile_step.py --planned 8 --iters 2 > gpurun_out/ncu_fwd_planned.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:sspmm_bwd_planned -s 1 -c 1 -o gpurun_out/prof_bwd_planned8 \
+  python scripts/profile_step.py --planned 8 --iters 2 > gpurun_out/ncu_bwd_planned.log 2>&1
