@@ -109,9 +109,13 @@ class DistGraph:
         if key not in self._aggs:
             vals = edge_values(self.indptr, self.indices, kind, self.n_cols, self._col_deg)
             if self.comm == "peer":
+                from .autograd import planned_homes
                 from .peer import PeerAggregator
+                homes = planned_homes()  # EXPERIMENTAL opt-in (MAXK_PLANNED_HOMES), where the fused kernel is built
+                if not ((k in (32, 64) and homes) or (k == 16 and homes in (2, 4)) or (k == 8 and homes == 2)):
+                    homes = 0
                 self._aggs[key] = PeerAggregator(self.indptr, self.indices, vals, self.bounds, self.rank, k,
-                                                 feat_dim, group=self.group)
+                                                 feat_dim, group=self.group, homes=homes)
             else:
                 self._aggs[key] = DistAggregator(self.indptr, self.indices, vals, self.bounds, self.rank, k,
                                                  feat_dim, group=self.group, split=self.split)
