@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     if not force and up_to_date():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
+    cmd = [nvcc_path(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "--threads", "0", "-shared", "-Xcompiler", "-fPIC",
            "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            "-DMAXK_BUILDING_LIB", *extra]
     if verbose:
