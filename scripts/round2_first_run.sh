@@ -23,6 +23,7 @@ for h in 2 4 8; do
 done
 python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_proteins_default.json
 MAXK_PLANNED_HOMES=8 python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_proteins_planned8.json
+MAXK_PLANNED_HOMES=auto python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_proteins_auto.json
 # (with 2 or 8 GPUs: `torchrun ... bench.py --gpus N --planned 8` runs the planned kernels on the peer transport)
 # ncu of the planned kernels (only after the runs above exited 0 without ncu): launch list + one full capture each
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_planned.csv \

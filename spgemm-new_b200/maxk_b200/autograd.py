@@ -86,13 +86,56 @@ class SpGEMMFunction(Function):
 
 def planned_homes() -> int:
     """EXPERIMENTAL opt-in (unmeasured): MAXK_PLANNED_HOMES=2|4|8 routes the
-    CBSR-native aggregation through the bank plan (csrc/cbsr_plan.cu).  0 / unset = the default kernels."""
+    CBSR-native aggregation through the bank plan (csrc/cbsr_plan.cu); MAXK_PLANNED_HOMES=auto times
+    the candidates once per (work list, k) on the first call and keeps the fastest (-1 is returned
+    for "auto").  0 / unset = the default kernels."""
     import os
+    v = os.environ.get("MAXK_PLANNED_HOMES", "0").strip().lower()
+    if v == "auto":
+        return -1
     try:
-        h = int(os.environ.get("MAXK_PLANNED_HOMES", "0"))
+        h = int(v)
     except ValueError:
         return 0
     return h if h in (2, 4, 8) else 0
+
+
+_PLAN_CHOICE: dict = {}
+
+
+def choose_planned_homes(warp4, indices, values, sp_data, sp_index, feat_dim, num_rows, iters: int = 3) -> int:
+    """Time forward + backward (+ plan) of the default kernels and of the planned ones with 2 / 4 / 8
+    homes on the caller's own operands (CUDA events, after one warm-up each) and return the fastest
+    (0 = default).  Cached per (work list, k, feature width): graphs differ -- long rows on an
+    L2-resident operand gain from the plan, short rows pay its flush."""
+    k = sp_index.shape[1]
+    key = (warp4.data_ptr(), warp4.numel(), k, feat_dim)
+    if key in _PLAN_CHOICE:
+        return _PLAN_CHOICE[key]
+    cands = [0] + [h for h in (2, 4, 8) if k % 32 == 0 and k <= 128 and (h == 2 or k <= 64)]
+    dy = torch.ones((num_rows, feat_dim), dtype=torch.float32, device=sp_data.device)
+    best, best_ms = 0, float("inf")
+    for h in cands:
+        def step():
+            if h:
+                sa = ops.cbsr_bank_plan(sp_index, h)
+                ops.spgemm_forward_planned(warp4, indices, values, sp_data, sa, h, feat_dim=feat_dim, num_rows=num_rows)
+                ops.sspmm_backward_planned(warp4, indices, values, dy, sa, h)
+            else:
+                ops.spgemm_forward(warp4, indices, values, sp_data, sp_index, feat_dim=feat_dim, num_rows=num_rows)
+                ops.sspmm_backward(warp4, indices, values, dy, sp_index)
+        step()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(iters):
+            step()
+        t1.record()
+        t1.synchronize()
+        ms = t0.elapsed_time(t1) / iters
+        if ms < best_ms:
+            best, best_ms = h, ms
+    _PLAN_CHOICE[key] = best
+    return best
 
 
 class CBSRAggregate(Function):
@@ -103,6 +146,9 @@ class CBSRAggregate(Function):
     def forward(ctx, sp_data, sp_index, warp4, indices, values, feat_dim, num_rows):
         k = sp_index.shape[1]
         homes = planned_homes()
+        if homes < 0:
+            homes = choose_planned_homes(warp4, indices, values, sp_data.detach().contiguous(), sp_index, feat_dim,
+                                         num_rows)
         if homes and k % 32 == 0 and k <= 128 and (homes == 2 or k <= 64):  # both directions are built
             sp_addr = ops.cbsr_bank_plan(sp_index, homes)   # once per TopK, serves both directions
             out = ops.spgemm_forward_planned(warp4, indices, values, sp_data.contiguous(), sp_addr, homes,
