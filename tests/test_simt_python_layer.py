@@ -340,3 +340,38 @@ def test_peer_tma_push_of_a_block_larger_than_the_staging_ring(peer_group):
             par = aggs[r]._fwd_epoch & 1   # the whole gathered operand arrived intact
             np.testing.assert_array_equal(aggs[r].g_index[par].numpy(), si)
             np.testing.assert_array_equal(aggs[r].g_data[par].numpy(), sd)
+
+
+def test_auto_choice_of_planned_homes_runs_every_candidate(ops, monkeypatch):
+    """MAXK_PLANNED_HOMES=auto: the chooser times default / 2 / 4 / 8 homes on the caller's operands
+    (CUDA events replaced by a host clock here) and the aggregation then uses its pick."""
+    import time
+    from maxk_b200 import autograd as A
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self):
+            self.t = time.perf_counter()
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setenv("MAXK_PLANNED_HOMES", "auto")
+    A._PLAN_CHOICE.clear()
+    assert A.planned_homes() == -1
+    p, g = _problem(n=60, avg=12.0, k=32, seed=9)
+    x = g["x"].clone().requires_grad_(True)
+    sp_data, sp_index = A.TopKCBSR.apply(x, 32)
+    y = A.CBSRAggregate.apply(sp_data, sp_index, g["warp4"], g["indices"], g["values"], 256, p.n)
+    close(y, p.fwd_oracle())
+    y.backward(g["dy"])
+    assert len(A._PLAN_CHOICE) == 1 and next(iter(A._PLAN_CHOICE.values())) in (0, 2, 4, 8)
+    np.testing.assert_allclose(x.grad.numpy(), O.cbsr_scatter(p.bwd_oracle().astype(np.float32), p.sp_index, 256),
+                               rtol=RTOL, atol=ATOL)
+    A._PLAN_CHOICE.clear()
