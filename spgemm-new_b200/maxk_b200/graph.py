@@ -112,6 +112,7 @@ class DistGraph:
                 from .autograd import planned_homes
                 from .peer import PeerAggregator
                 homes = planned_homes()  # EXPERIMENTAL opt-in (MAXK_PLANNED_HOMES), where the fused kernel is built
+                homes = 0 if homes < 0 else homes  # "auto" is a single-GPU notion (all ranks must agree)
                 if not ((k in (32, 64) and homes) or (k == 16 and homes in (2, 4)) or (k == 8 and homes == 2)):
                     homes = 0
                 self._aggs[key] = PeerAggregator(self.indptr, self.indices, vals, self.bounds, self.rank, k,
