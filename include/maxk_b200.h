@@ -65,7 +65,7 @@ MAXK_API int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp);
 MAXK_API int maxk_set_forward_copies(int copies);
 /* Bench/test hook: launch shape of the forward kernel (1 = 8-warp CTAs, 2 = 2-warp CTAs,
  * 3 = 8-warp CTAs with twice the gathers in flight; experimental and never chosen automatically:
- * 4-7 = double-buffered gather batches, 8-11 = gathers through cp.async into a shared-memory
+ * 4-7 = double-buffered gather batches, 8-12 = gathers through cp.async into a shared-memory
  * ring (k = 16, 32, 64 with 16-byte aligned operands, otherwise the automatic shape));
  * 0 = automatic. */
 MAXK_API int maxk_set_forward_depth(int depth);

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 MAXK_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -k "experimental" > gpurun_out/pytest_experimental.log 2>&1
 echo "experimental shapes: rc=$? $(tail -1 gpurun_out/pytest_experimental.log)"
 for shape in products reddit flickr; do
-  python scripts/sweep_fwd.py --shape $shape --ks 32,16,64 --copies 0 --tpw=-1 --depth 0,1,2,4,5,6,7,8,9,10,11 --planned 2>/dev/null | tee gpurun_out/sweep_db_$shape.jsonl
+  python scripts/sweep_fwd.py --shape $shape --ks 32,16,64 --copies 0 --tpw=-1 --depth 0,1,2,4,5,6,7,8,9,10,11,12 --planned 2>/dev/null | tee gpurun_out/sweep_db_$shape.jsonl
 done
 python scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_n1_round2.json
 python scripts/topk_probe.py 2>/dev/null | tee gpurun_out/topk_probe_round2.log

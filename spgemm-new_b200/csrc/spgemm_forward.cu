@@ -730,6 +730,8 @@ static int launch_fwd_r(const FwdArgs &a)
                     case 9: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16, false, false, 8>>(a);
                     case 10: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, 4, false, false, 16>>(a);
                     case 11: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, 4, false, false, 8>>(a);
+                    // loads in flight hold no registers here: cap at 48 registers for 40 warps per SM
+                    case 12: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, (U1 > 1 ? U1 / 2 : 1), 20, false, false, 8>>(a);
                     default: break;
                 }
             }

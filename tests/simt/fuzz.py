@@ -31,7 +31,7 @@ def one(rng, it):
     n_cols = n if rng.random() < 0.7 else int(rng.integers(1, 400))
     avg = float(rng.choice([0.5, 3.0, 20.0, 70.0, 300.0]))
     nz = int(rng.choice([64, 64, 64, 1, 5, 63, 65, 100, 200]))
-    shape = int(rng.choice([0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]))
+    shape = int(rng.choice([0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12]))
     copies = int(rng.choice([0, 0, 1, 2, 4, 8, 16]))
     tpw_f, tpw_b = int(rng.choice([-1, 1, 2, 3, 16, 100])), int(rng.choice([-1, 1, 2, 16]))
     extra_rows = int(rng.choice([0, 0, 1, 9]))

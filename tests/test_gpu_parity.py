@@ -202,7 +202,7 @@ def test_forward_launch_shapes(ops, k, shape):
                            "written after round 1's GPU budget was spent: compiled and checked under the SIMT "
                            "interpreter (tests/test_simt_kernels.py), not yet run on a GPU; opt in with "
                            "MAXK_EXPERIMENTAL=1")
-@pytest.mark.parametrize("shape", [4, 5, 6, 7, 8, 9, 10, 11])
+@pytest.mark.parametrize("shape", [4, 5, 6, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("k", [32, 16, 64, 8])
 def test_forward_experimental_shapes(ops, k, shape):
     p = Problem(n=400, avg=45.0, k=k, seed=13 * k + shape, empty_frac=0.2)

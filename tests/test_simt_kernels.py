@@ -156,7 +156,7 @@ def test_simt_forward_accumulator_copies(k, copies):
     close(y2, 2 * want, "accumulate")
 
 
-@pytest.mark.parametrize("shape", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
+@pytest.mark.parametrize("shape", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("k", [32, 16, 64, 8, 128])
 def test_simt_forward_launch_shapes(k, shape):
     """All launch shapes, the experimental ones included (4-7: double-buffered gather batches,
@@ -170,7 +170,7 @@ def test_simt_forward_launch_shapes(k, shape):
         close(S.spgemm_forward(p.w4, p.idx, p.val, p.sp_data, p.sp_index, p.n), want, f"k={k} shape={shape} tpw={tpw}")
 
 
-@pytest.mark.parametrize("shape", [0, 4, 7, 8, 11])
+@pytest.mark.parametrize("shape", [0, 4, 7, 8, 11, 12])
 def test_simt_forward_gap_rows_are_zeroed(shape):
     n = 97
     deg = np.zeros(n, np.int64)
