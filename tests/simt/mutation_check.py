@@ -34,6 +34,15 @@ MUTANTS = {
     "topk-emit-no-barrier": ("topk_cbsr.cu", "    __syncwarp();\n    unsigned char *oi = out_idx + row * k + lane;", "    unsigned char *oi = out_idx + row * k + lane;", 0),
     "topk-tie-order": ("topk_cbsr.cu", "if (r0 < need) sel |= (1u << i);", "if (r0 <= need) sel |= (1u << i);", 0),
     "topk-row-bound": ("topk_cbsr.cu", "if (row >= n) return;  // warp-uniform; no CTA barrier below\n\n", "if (row > n) return;\n\n", 0),
+    # bank plan and planned kernels
+    "plan-home-word-formula": ("common.cuh", "return (unsigned)h * 256u + lo * 32u + (((c >> 3) + (unsigned)plan_s(h) * lo + (unsigned)plan_t(h)) & 31u);",
+                               "return (unsigned)h * 256u + lo * 32u + (((c >> 3) + (unsigned)plan_s(h) * lo + (unsigned)plan_t(h) + 1u) & 31u);", 0),
+    "plan-augment-forgets-the-path": ("cbsr_plan.cu", "                    owner[st_bank[l]] = st_entry[l];\n                    home[st_entry[l]] = st_home[l];",
+                                      "                    owner[st_bank[l]] = st_entry[l];\n                    if (l == sp) home[st_entry[l]] = st_home[l];", 0),
+    "planned-flush-skips-a-home": ("spgemm_forward.cu", "            for (int h = 1; h < H; ++h) {\n                const float *p = acc + h * 256;", "            for (int h = 1; h < H - 1; ++h) {\n                const float *p = acc + h * 256;", 0),
+    "planned-flush-clears-before-all-lanes-read": ("spgemm_forward.cu", "    __syncwarp();  // every lane has read all homes before anybody clears a word of them\n", "", 0),
+    "planned-backward-row-staged-in-home-0-only": ("sspmm_backward_planned.cu", "        for (int h = 1; h < H; ++h) {\n            float *p = dys + h * 256;", "        for (int h = 1; h < 1; ++h) {\n            float *p = dys + h * 256;", 0),
+    "planned-backward-no-barrier-before-restaging": ("sspmm_backward_planned.cu", "            __syncwarp();  // lookups of the previous row are done\n", "", 0),
     # NVLink peer path (tests/test_simt_python_layer.py -k peer): the stand-in for the TMA unit lands data late
     "peer-tma-stage-reused-before-its-stores-read-it": ("peer.cuh", 'if (chunks_issued >= PEER_TMA_STAGES) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");', "", "peer"),
     "peer-tma-store-before-the-load-landed": ("peer.cuh", "        mbar_wait(mbar0 + 8 * st, (phase >> st) & 1u);\n", "", "peer"),
