@@ -602,11 +602,11 @@ void yield_spin()
     f->wait = RUN;
 }
 
-long long clock_ticks()  // ~2 "cycles" per nanosecond of real time: spin limits expire after seconds
-{
+long long clock_ticks()  // a "cycle" every 4 ns of real time: the kernels' 10^10-cycle spin limits expire
+{                        // after 40 s, generous enough for a loaded test machine
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ((long long)ts.tv_sec * 1000000000LL + ts.tv_nsec) * 2;
+    return ((long long)ts.tv_sec * 1000000000LL + ts.tv_nsec) / 4;
 }
 
 void trap(const char *why) { fail(where() + ": " + why); }
