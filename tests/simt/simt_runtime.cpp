@@ -88,7 +88,7 @@ struct Block {
 thread_local Block g_blk;
 thread_local Fibre *g_cur = nullptr;
 thread_local void *g_sched_sp = nullptr;
-thread_local char *g_stacks = nullptr;
+thread_local char *g_stacks = nullptr;  // fibre stacks of this host thread (released when it exits)
 thread_local const std::function<void()> *g_body = nullptr;
 thread_local unsigned long long g_progress = 0;
 thread_local bool g_failed = false;
@@ -98,6 +98,16 @@ std::map<const void *, int> g_max_dyn_smem;
 std::mutex g_max_dyn_smem_lock;
 constexpr size_t kDynSmem = 227 * 1024 + 128;
 thread_local unsigned char *g_dyn_smem = nullptr;
+struct ThreadResources {  // host threads come and go (one per rank in the peer tests)
+    ~ThreadResources()
+    {
+        if (g_stacks) munmap(g_stacks, kStack * kMaxThreads);
+        free(g_dyn_smem);
+        g_stacks = nullptr;
+        g_dyn_smem = nullptr;
+    }
+};
+thread_local ThreadResources g_thread_resources;
 
 extern "C" void simt_ctx_switch(void **save_sp, void *load_sp);
 #if defined(__x86_64__)
@@ -375,6 +385,7 @@ void launch(const void *kernel, const LaunchCfg &cfg, const std::function<void()
         abort();
     }
     if (!g_stacks) {
+        (void)&g_thread_resources;  // instantiate the releaser for this thread
         g_stacks = static_cast<char *>(mmap(nullptr, kStack * kMaxThreads, PROT_READ | PROT_WRITE,
                                             MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0));
         if (g_stacks == MAP_FAILED) abort();
