@@ -878,7 +878,9 @@ static int launch_fwd_planned_h(const FwdArgs &a)
 {
     constexpr int U1 = (EPL == 1) ? 4 : (EPL <= 4 ? 2 : 1), R = 32 / KL;
     if (a.depth == 2) return launch_fwd<FwdCfg<KL, EPL, true, R, 2, U1, (EPL <= 2 ? 16 : 8), false, false, 0, H>>(a);
-    return launch_fwd<FwdCfg<KL, EPL, true, R, 8, U1, (EPL <= 2 ? (R <= 2 ? 4 : 3) : 2), false, false, 0, H>>(a);
+    // CTAs per SM the register budget is capped for: what the shared memory (H * R KB per warp) admits
+    constexpr int MINB8 = (EPL > 2) ? 2 : (H * R >= 8 ? 3 : 4);
+    return launch_fwd<FwdCfg<KL, EPL, true, R, 8, U1, MINB8, false, false, 0, H>>(a);
 }
 // 4 and 8 homes are built for k = 32 and 64, 4 homes also for k = 16 (the k of the BASELINE kernel
 // bench; shared memory per warp is homes * 32/min(k,32) KB); every other supported k has the
