@@ -149,6 +149,9 @@ MAXK_API int maxk_sspmm_backward_planned(const int32_t *warp4, int64_t num_tasks
  * dxc float32[num_cbsr_rows, k].  accumulate == 0: dxc is zero-filled first (defined
  * output); accumulate != 0: contributions are added to the existing content (used by
  * the multi-GPU local/remote split).                                                   */
+/* Bench/test hook (EXPERIMENTAL, unmeasured): 1 = the backward kernel loads dY[next row,:] into registers
+ * while it processes the current task (graphs of short rows: the row changes with every task). */
+MAXK_API int maxk_set_backward_prefetch(int on);
 MAXK_API int maxk_sspmm_backward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                         const float *values, const float *dy, const uint8_t *sp_index,
                         int32_t k, int32_t d, float *dxc, int64_t num_cbsr_rows,

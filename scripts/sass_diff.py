@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Compare the SASS of two builds of libmaxk_b200.so kernel by kernel (addresses stripped).
+r"""Compare the SASS of two builds of libmaxk_b200.so kernel by kernel (addresses stripped).
 
     cuobjdump -sass old.so > old.sass; cuobjdump -sass new.so > new.sass
     python scripts/sass_diff.py old.sass new.sass
@@ -8,7 +8,8 @@
 
 Used to show that a change which only ADDS template variants leaves every kernel that was
 validated on the GPU bit-for-bit the same program.  Template parameters appended to FwdCfg with
-a default show up as a suffix in the mangled names: pass it with --strip (e.g. ELi0ELb0E).
+a default show up as a suffix in the mangled names: pass it with --strip (e.g. ELi0ELi0 for FwdCfg)
+or as --map 'REGEX=>REPLACEMENT' pairs (e.g. --map 'sspmm_bwd_kernelI(Lin?\d+)ELb0EEE=>sspmm_bwd_kernelI\1EEE').
 """
 import hashlib
 import json
@@ -41,6 +42,12 @@ def _funcs_sass(path):
 if __name__ == "__main__":
     strip = ""
     args = sys.argv[1:]
+    maps = []  # --map 'REGEX=>REPLACEMENT' (repeatable): rewrite a NEW kernel name into its OLD spelling
+    while "--map" in args:
+        i = args.index("--map")
+        pat, rep = args[i + 1].split("=>", 1)
+        maps.append((re.compile(pat), rep))
+        del args[i:i + 2]
     if "--strip" in args:
         i = args.index("--strip")
         strip = args[i + 1]
@@ -54,6 +61,8 @@ if __name__ == "__main__":
     new = []
     for n, body in b.items():
         o = n.replace(strip + "EEEE", "EEEE") if strip and "FwdCfg" in n else n
+        for rx, rep in maps:
+            o = rx.sub(rep, o)
         if o in a:
             if a[o] == body:
                 same += 1
@@ -62,6 +71,12 @@ if __name__ == "__main__":
                 print("DIFF", n, a[o][0], "->", body[0], "instructions")
         else:
             new.append(n)
-    gone = [n for n in a if n not in b and not any((m.replace(strip + "EEEE", "EEEE") if strip else m) == n for m in b)]
+    def old_name(m):
+        o = m.replace(strip + "EEEE", "EEEE") if strip and "FwdCfg" in m else m
+        for rx, rep in maps:
+            o = rx.sub(rep, o)
+        return o
+    old_names = {old_name(m) for m in b}
+    gone = [n for n in a if n not in b and n not in old_names]
     print(f"identical {same}, changed {diff}, new {len(new)}, removed {len(gone)} (old build: {len(a)} kernels)")
     sys.exit(1 if diff or gone else 0)

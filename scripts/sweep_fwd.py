@@ -96,6 +96,16 @@ for k in [int(v) for v in a.ks.split(",")]:
                     res.append(r)
                     print(json.dumps(r), flush=True)
                 ops.set_planned_backward_vector(False)
+    if a.planned:  # the default backward with and without the dY-row prefetch (experimental knob)
+        dxc = torch.empty(n, k, device="cuda")
+        for pf in (False, True):
+            ops.set_backward_prefetch(pf)
+            t = timeit(lambda: ops.sspmm_backward(w4, g["indices"], g["values"], dy, si, out=dxc), a.iters)
+            r = {"kernel": "bwd", "shape": a.shape, "k": k, "row_prefetch": pf, "ms": round(t, 4),
+                 "frac": round(b["bwd"] / t / 1e6 / peak, 3)}
+            res.append(r)
+            print(json.dumps(r), flush=True)
+        ops.set_backward_prefetch(False)
     if a.bwd_tpw:
         dxc = torch.empty(n, k, device="cuda")
         for tpw in [int(v) for v in a.bwd_tpw.split(",")]:

@@ -111,7 +111,11 @@ __device__ __forceinline__ void bwd_process_batch(const int2 *stage, int len, co
     }
 }
 
-template <int GLOG2>
+// PF (experimental, maxk_set_backward_prefetch): dY[next row,:] is loaded into registers while the
+// current task is processed.  On graphs of short rows the row changes with every task and the
+// kernel otherwise waits a full DRAM latency for it (ncu, products shape, round 1: 27 % of the
+// stall samples sit on the staging stores that consume this load).
+template <int GLOG2, bool PF = false>
 __global__ void __launch_bounds__(BWD_WPB * 32)
 sspmm_bwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *__restrict__ idx,
                  const float *__restrict__ val, const float *__restrict__ dy,
@@ -133,6 +137,12 @@ sspmm_bwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *_
     bwd_fetch_edges(pre, idx, val, info.y, min(info.z, BWD_STAGE), lane);
 
     int cur_row = -1;
+    float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f), pf1 = pf0;  // PF: the next row, columns 4*lane.. and 128+4*lane..
+    if constexpr (PF) {
+        const float *src = dy + (int64_t)info.x * d;
+        if (lane * 4 < d) pf0 = ld_stream_f4(reinterpret_cast<const float4 *>(src + lane * 4));
+        if (lane * 4 + 128 < d) pf1 = ld_stream_f4(reinterpret_cast<const float4 *>(src + lane * 4 + 128));
+    }
     for (int64_t t = t0; t < t1; ++t) {
         const bool has_next = (t + 1 < t1);
         int4 ninfo = info;
@@ -141,11 +151,23 @@ sspmm_bwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *_
         if (info.x != cur_row) {  // stage dY[row,:] once per row
             cur_row = info.x;
             __syncwarp();
-            const float *src = dy + (int64_t)cur_row * d;
-            for (int c = lane * 4; c < d; c += 128)
-                *reinterpret_cast<float4 *>(dys + c) =
-                    ld_stream_f4(reinterpret_cast<const float4 *>(src + c));
+            if constexpr (PF) {  // it is already here
+                if (lane * 4 < d) *reinterpret_cast<float4 *>(dys + lane * 4) = pf0;
+                if (lane * 4 + 128 < d) *reinterpret_cast<float4 *>(dys + lane * 4 + 128) = pf1;
+            } else {
+                const float *src = dy + (int64_t)cur_row * d;
+                for (int c = lane * 4; c < d; c += 128)
+                    *reinterpret_cast<float4 *>(dys + c) =
+                        ld_stream_f4(reinterpret_cast<const float4 *>(src + c));
+            }
             // visibility is ordered by the __syncwarp pair in bwd_stage_edges below
+        }
+        if constexpr (PF) {
+            if (has_next && ninfo.x != cur_row) {  // rows ascend: the next different row is the next task's
+                const float *src = dy + (int64_t)ninfo.x * d;
+                if (lane * 4 < d) pf0 = ld_stream_f4(reinterpret_cast<const float4 *>(src + lane * 4));
+                if (lane * 4 + 128 < d) pf1 = ld_stream_f4(reinterpret_cast<const float4 *>(src + lane * 4 + 128));
+            }
         }
         const int64_t loc = info.y;
         const int len = info.z;
@@ -163,6 +185,8 @@ sspmm_bwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *_
     }
 }
 
+int g_bwd_prefetch = 0;  // 1: the PF variant (bench/test hook maxk_set_backward_prefetch)
+
 template <int GLOG2>
 static int launch_bwd(const int32_t *warp4, int64_t W, const int32_t *idx, const float *val,
                       const float *dy, const uint8_t *sp_index, int k, int d, float *dxc,
@@ -175,6 +199,12 @@ static int launch_bwd(const int32_t *warp4, int64_t W, const int32_t *idx, const
         set_error("maxk_sspmm_backward: grid too large");
         return MAXK_ERR_UNSUPPORTED;
     }
+    if (g_bwd_prefetch) {
+        sspmm_bwd_kernel<GLOG2, true><<<(unsigned)grid, BWD_WPB * 32, smem, st>>>(
+            reinterpret_cast<const int4 *>(warp4), W, idx, val, dy, sp_index, k, d, dxc, tasks_per_warp);
+        MAXK_LAUNCH_CHECK("sspmm_bwd_kernel");
+        return MAXK_OK;
+    }
     sspmm_bwd_kernel<GLOG2><<<(unsigned)grid, BWD_WPB * 32, smem, st>>>(
         reinterpret_cast<const int4 *>(warp4), W, idx, val, dy, sp_index, k, d, dxc, tasks_per_warp);
     MAXK_LAUNCH_CHECK("sspmm_bwd_kernel");
@@ -186,6 +216,13 @@ int g_bwd_tasks_per_warp = 0;  // run length; 0 = automatic (as in the forward k
 }  // namespace maxk
 
 using namespace maxk;
+
+// Bench/test hook: 1 = prefetch the next dY row into registers (experimental), 0 = default.
+extern "C" int maxk_set_backward_prefetch(int on)
+{
+    g_bwd_prefetch = on ? 1 : 0;
+    return MAXK_OK;
+}
 
 extern "C" int maxk_sspmm_backward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                                    const float *values, const float *dy, const uint8_t *sp_index,

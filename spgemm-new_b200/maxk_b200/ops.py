@@ -333,6 +333,11 @@ def set_tuning(fwd_tasks_per_warp: int = 0, bwd_tasks_per_warp: int = 0) -> None
     _cabi.check(_cabi.load().maxk_set_tuning(fwd_tasks_per_warp, bwd_tasks_per_warp))
 
 
+def set_backward_prefetch(on: bool = False) -> None:
+    """EXPERIMENTAL knob: the backward kernel prefetches the next dY row into registers."""
+    _cabi.load().maxk_set_backward_prefetch(1 if on else 0)
+
+
 def set_planned_backward_vector(on: bool = False) -> None:
     """EXPERIMENTAL knob: the planned backward with 128-bit vector reductions (k = 32, 64)."""
     _cabi.load().maxk_set_planned_backward_vector(1 if on else 0)

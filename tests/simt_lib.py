@@ -142,6 +142,10 @@ def set_forward_copies(copies=0):
     load().maxk_set_forward_copies(int(copies))
 
 
+def set_backward_prefetch(on):
+    load().maxk_set_backward_prefetch(1 if on else 0)
+
+
 def set_planned_backward_vector(on):
     load().maxk_set_planned_backward_vector(1 if on else 0)
 

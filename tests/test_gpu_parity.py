@@ -281,6 +281,27 @@ def test_backward_planned_experimental(ops, case):
         ops.set_planned_backward_vector(False)
 
 
+@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
+                    reason="backward with dY-row prefetch: written after round 1's GPU budget was spent, checked under "
+                           "the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
+@pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=16), dict(k=18), dict(k=32, d=128),
+                                  dict(k=32, avg=3.0, n=3000, empty_frac=0.4), dict(k=32, warp_max_nz=100)],
+                         ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
+def test_backward_row_prefetch_experimental(ops, case):
+    p = Problem(seed=len(str(case)) + 6, **case)
+    g = p.cuda()
+    try:
+        ops.set_backward_prefetch(True)
+        for tpw in (-1, 1, 3):
+            ops.set_tuning(0, tpw)
+            dxc = torch.full((p.n_cols, p.k), float("nan"), device="cuda")
+            ops.sspmm_backward(g["warp4"], g["indices"], g["values"], g["dy"], g["sp_index"], out=dxc)
+            assert_close(dxc, p.bwd_oracle(), f"tpw={tpw}")
+    finally:
+        ops.set_backward_prefetch(False)
+        ops.set_tuning(-1, -1)
+
+
 def test_forward_gap_rows_are_zeroed(ops):
     """Leading, interior and trailing rows without edges (and an output taller than the last
     task row) come back as zeros from a poisoned buffer."""

@@ -29,6 +29,7 @@ def _reset_knobs():
     S.set_forward_copies(0)
     S.set_cp_async_eager(False)
     S.set_planned_backward_vector(False)
+    S.set_backward_prefetch(False)
 
 
 # ------------------------------------------------------------------------------ a4
@@ -132,6 +133,24 @@ def test_simt_forward_backward_vs_oracle(case):
     dxc = S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index)
     assert dxc.shape == (p.n_cols, p.k)
     close(dxc, p.bwd_oracle(), "backward")
+
+
+@pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=16), dict(k=18), dict(k=8, d=64), dict(k=32, d=128),
+                                  dict(k=32, d=36), dict(k=32, avg=3.0, n=1500, empty_frac=0.4),
+                                  dict(k=32, n=20, avg=1500.0, empty_frac=0.0), dict(k=32, warp_max_nz=100),
+                                  dict(k=32, warp_max_nz=5), dict(k=32, n=200, n_cols=700, avg=25.0)],
+                         ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
+def test_simt_backward_with_row_prefetch(case):
+    """EXPERIMENTAL backward variant that loads the next dY row into registers one task early."""
+    case = dict(n=250, **case) if "n" not in case else case
+    p = Problem(seed=len(str(case)) + 9, **case)
+    S.set_backward_prefetch(True)
+    for tpw in (-1, 1, 3):
+        S.set_tuning(0, tpw)
+        close(S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index), p.bwd_oracle(), f"tpw={tpw}")
+    g2 = S.sspmm_backward(p.w4, p.idx, p.val, p.dy, p.sp_index, accumulate=True,
+                          out_init=np.ones((p.n_cols, p.k), np.float32))
+    close(g2, p.bwd_oracle() + 1.0, "accumulate")
 
 
 @pytest.mark.parametrize("tpw", [1, 2, 3, 7, 64, 1000])
