@@ -33,7 +33,8 @@ def _funcs_sass(path):
                 d[name] = body
             name, body = m.group(1), []
         elif re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
-            body.append(re.sub(r"/\*[0-9a-f]+\*/", "", ln).strip())
+            # addresses stripped, runs of blanks collapsed (cuobjdump pads to the longest line of the FILE)
+            body.append(re.sub(r"\s+", " ", re.sub(r"/\*[0-9a-f]+\*/", "", ln)).strip())
     if name:
         d[name] = body
     return d

@@ -338,6 +338,12 @@ def set_backward_prefetch(on: bool = False) -> None:
     _cabi.load().maxk_set_backward_prefetch(1 if on else 0)
 
 
+def set_topk_rows_per_warp(rows: int = 0) -> None:
+    """EXPERIMENTAL knob: rows > 1 = the fp32 TopK handles `rows` consecutive rows per warp, loading the
+    next row while it works on the current one; 0 / 1 = the default kernel."""
+    _cabi.load().maxk_set_topk_rows_per_warp(int(rows))
+
+
 def set_planned_backward_vector(on: bool = False) -> None:
     """EXPERIMENTAL knob: the planned backward with 128-bit vector reductions (k = 32, 64)."""
     _cabi.load().maxk_set_planned_backward_vector(1 if on else 0)

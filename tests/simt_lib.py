@@ -146,6 +146,10 @@ def set_backward_prefetch(on):
     load().maxk_set_backward_prefetch(1 if on else 0)
 
 
+def set_topk_rows_per_warp(rows=0):
+    load().maxk_set_topk_rows_per_warp(int(rows))
+
+
 def set_planned_backward_vector(on):
     load().maxk_set_planned_backward_vector(1 if on else 0)
 

@@ -302,6 +302,26 @@ def test_backward_row_prefetch_experimental(ops, case):
         ops.set_tuning(-1, -1)
 
 
+@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
+                    reason="fp32 TopK with several rows per warp: written after round 1's GPU budget was spent, checked "
+                           "under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
+@pytest.mark.parametrize("rpw", [2, 4, 8])
+def test_topk_rows_per_warp_experimental(ops, rpw):
+    rng = np.random.default_rng(rpw)
+    try:
+        ops.set_topk_rows_per_warp(rpw)
+        for n, d in ((1, 256), (8 * rpw + 3, 256), (5000, 256), (777, 128), (100, 36)):
+            x = rng.standard_normal((n, d)).astype(np.float32)
+            x[::5] = rng.integers(0, 3, size=x[::5].shape).astype(np.float32)  # rows of ties
+            for k in (1, 8, 18, 32):
+                want_v, want_i = O.topk_cbsr(x, k)
+                v, i = ops.topk_cbsr(torch.from_numpy(x).cuda(), k)
+                np.testing.assert_array_equal(i.cpu().numpy(), want_i, err_msg=f"n={n} d={d} k={k}")
+                np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), want_v.view(np.uint32))
+    finally:
+        ops.set_topk_rows_per_warp(0)
+
+
 def test_forward_gap_rows_are_zeroed(ops):
     """Leading, interior and trailing rows without edges (and an output taller than the last
     task row) come back as zeros from a poisoned buffer."""

@@ -30,6 +30,7 @@ def _reset_knobs():
     S.set_cp_async_eager(False)
     S.set_planned_backward_vector(False)
     S.set_backward_prefetch(False)
+    S.set_topk_rows_per_warp(0)
 
 
 # ------------------------------------------------------------------------------ a4
@@ -83,6 +84,31 @@ def test_simt_topk_ties_and_specials():
         v, i = S.topk_f32(x, k)
         np.testing.assert_array_equal(i, want_i, err_msg=f"k={k}")
         np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
+
+
+@pytest.mark.parametrize("rpw", [2, 3, 4, 16, 64])
+def test_simt_topk_rows_per_warp(rpw):
+    """EXPERIMENTAL fp32 TopK that gives a warp `rpw` consecutive rows and loads the next one early: same
+    bits as the oracle for every n around the multiples of rpw * (warps per CTA), ties and specials included."""
+    S.set_topk_rows_per_warp(rpw)
+    rng = np.random.default_rng(rpw)
+    for d in (256, 128, 36, 4):
+        for n in sorted({1, rpw - 1, rpw, rpw + 1, 8 * rpw - 1, 8 * rpw, 8 * rpw + 1, 61} - {0}):
+            if n > 140:
+                continue
+            x = rng.standard_normal((n, d)).astype(np.float32)
+            x[::3] = rng.integers(0, 3, size=x[::3].shape).astype(np.float32)  # rows full of ties
+            if n > 2:
+                x[2, 0] = np.nan
+                x[1, :] = -np.inf
+            for k in sorted({1, 8, 18, 32, 64, d} & set(range(1, d + 1))):
+                want_v, want_i = O.topk_cbsr(x, k)
+                v, i, dense = S.topk_f32(x, k, want_dense=True)
+                np.testing.assert_array_equal(i, want_i, err_msg=f"n={n} d={d} k={k}")
+                np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
+                np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
+    (dense,) = S.topk_f32(x, 2, want_dense=True, want_cbsr=False)
+    np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, 2).view(np.uint32))
 
 
 def test_simt_topk_goldens_from_torch(golden_dir):
