@@ -9,7 +9,7 @@ kernels with fresh inputs every step.
 
 HOMES = 2, 4, 8: the EXPERIMENTAL planned kernels (the bank plan travels in place of the selectors).
 
-Run in its own process (tests/test_gpu_parity.py does): the ranks' kernels wait for each other,
+Run in its own process (tests/test_gpu_zz_peer_one_gpu.py does): the ranks' kernels wait for each other,
 so every rank's step is enqueued on its own stream before anything synchronises, and a bounded
 device-side wait that expires traps the whole CUDA context.  Exit code 0 = parity."""
 import os
