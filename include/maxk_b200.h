@@ -172,6 +172,22 @@ MAXK_API int maxk_cbsr_gather(const float *dense, const uint8_t *sp_index, int64
 MAXK_API int maxk_cbsr_mask(const float *in, const uint8_t *sp_index, int64_t n, int32_t k, int32_t d,
                    float *out, void *stream);
 
+/* ---- SURVEY 8(f) rank 3, EXPERIMENTAL (unmeasured): the dense layer next to the aggregation on
+ * the CBSR operand itself, without the dense [n, d] twin.  m is a dense float32 [d, c] matrix,
+ * row-major (for a Linear layer: the transposed weight), d <= 256, c % 4 == 0.
+ * matmul     : out[i, 0:c] (+)= bias[0:c] + sum_j sp_data[i,j] * m[sp_index[i,j], 0:c]
+ *              = fc_self(h) on the MaxK-sparsified h (utils/models_old.py:55-60; the reference runs
+ *              torch's dense Linear on the masked [n, d] tensor).  bias may be NULL.
+ * sampled_dot: out[i,j] (+)= sum_c g[i,c] * m[sp_index[i,j], c]   (float32 [n, k]; the gradient of
+ *              matmul with respect to sp_data, g = dL/d out).
+ * accumulate != 0 adds to the existing content of out.  Selectors >= d contribute nothing / 0.  */
+MAXK_API int maxk_cbsr_matmul(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k,
+                     const float *m, int32_t d, int32_t c, const float *bias, float *out,
+                     int32_t accumulate, void *stream);
+MAXK_API int maxk_cbsr_sampled_dot(const float *g, int64_t n, int32_t c, const float *m, int32_t d,
+                          const uint8_t *sp_index, int32_t k, float *out, int32_t accumulate,
+                          void *stream);
+
 /* ---- multi-GPU wire format ("new"): one record per node,
  * k*float32 followed by k*uint8, padded to a 16-byte multiple, so that one all-gather
  * moves both arrays.  record_bytes = maxk_cbsr_record_bytes(k).                         */

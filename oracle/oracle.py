@@ -150,6 +150,24 @@ def cbsr_gather(dense, sp_index) -> np.ndarray:
     return out
 
 
+# --------------------------------------------------------------------------- 8(f) rank 3
+def cbsr_linear(sp_data, sp_index, weight, bias=None) -> np.ndarray:
+    """fc_self on the MaxK-sparsified activations, the way the reference computes it: torch's dense
+    Linear  y = h @ W^T + b  on the masked dense h = scatter(sp_data, sp_index)  (upstream
+    utils/models_old.py:55-60, fork utils/models.py:242; W is [C, D] like nn.Linear.weight).  fp64."""
+    w = np.asarray(weight, np.float64)
+    h = cbsr_scatter(sp_data, sp_index, w.shape[1]).astype(np.float64)
+    y = h @ w.T
+    return y if bias is None else y + np.asarray(bias, np.float64)
+
+
+def cbsr_linear_grad_values(g, sp_index, weight) -> np.ndarray:
+    """d loss / d sp_data of cbsr_linear for g = d loss / d y:  gather(g @ W, sp_index)  -- autograd's
+    Linear backward followed by the CBSR gather of TopK's backward (utils/models.py:55-59).  fp64."""
+    gx = np.asarray(g, np.float64) @ np.asarray(weight, np.float64)
+    return np.take_along_axis(gx, np.asarray(sp_index).astype(np.int64), axis=1)
+
+
 # --------------------------------------------------------------------------- a2
 def spgemm_forward(warp4, idx, val, sp_data, sp_index, d: int = 256, n_out=None,
                    dtype=np.float64) -> np.ndarray:

@@ -11,7 +11,10 @@ for shape in products reddit flickr; do
   python scripts/sweep_fwd.py --shape $shape --ks 32,16,64 --copies 0 --tpw=-1 --depth 0,1,2,4,5,6,7,8,9,10,11,12 --planned 2>/dev/null | tee gpurun_out/sweep_db_$shape.jsonl
 done
 python scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_n1_round2.json
-python scripts/topk_probe.py 2>/dev/null | tee gpurun_out/topk_probe_round2.log
+python scripts/topk_probe.py 2>/dev/null | tee gpurun_out/topk_probe_round2.log   # default and 2/4/8 rows per warp
+# fc_self on the CBSR operand vs torch's dense fp32 Linear (products-sized), then the epoch with it
+python scripts/cbsr_linear_probe.py 2>/dev/null | tee gpurun_out/cbsr_linear_probe.jsonl
+MAXK_CBSR_LINEAR=1 python scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_n1_cbsr_linear.json
 # hardware questions the models had to guess (scalar vs vector reductions at the L2, conflict cost,
 # LDS vs SHFL broadcast, cp.async / cp.async.bulk gathers): one short probe, bounded
 mkdir -p scripts/probes/_bin

@@ -172,6 +172,40 @@ class CBSRAggregate(Function):
         return dxc, None, None, None, None, None, None
 
 
+def cbsr_linear_enabled() -> bool:
+    """EXPERIMENTAL opt-in (unmeasured): MAXK_CBSR_LINEAR=1 computes SAGE's fc_self on the
+    CBSR operand (csrc/cbsr_dense.cu) instead of torch's dense Linear on the scattered twin."""
+    import os
+    return os.environ.get("MAXK_CBSR_LINEAR", "0").strip() == "1"
+
+
+class CBSRLinear(Function):
+    """y = scatter(sp_data, sp_index) @ weight^T + bias computed from the CBSR pair (N*k*C multiply-adds, no
+    dense [N, D] twin in the forward or in the gradient of the values).  Same result as
+    `Linear(scatter(...))` -- upstream's fc_self on the MaxK-sparsified h, utils/models_old.py:55-60 -- up to
+    fp32 summation order.  The weight gradient is a dense library GEMM on the scattered twin."""
+
+    @staticmethod
+    def forward(ctx, sp_data, sp_index, weight, bias):
+        m = weight.detach().t().contiguous()          # [D, C]: rows of m are what the selectors pick
+        sp_data = sp_data.contiguous()
+        out = ops.cbsr_matmul(sp_data, sp_index, m, None if bias is None else bias.detach().contiguous())
+        ctx.save_for_backward(sp_data, sp_index, m)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        sp_data, sp_index, m = ctx.saved_tensors
+        g = grad_output.contiguous()
+        d_sp = ops.cbsr_sampled_dot(g, m, sp_index) if ctx.needs_input_grad[0] else None
+        d_w = None
+        if ctx.needs_input_grad[2]:
+            d_w = g.t() @ ops.cbsr_scatter(sp_data, sp_index, m.shape[0])   # [C, D]
+        d_b = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[3] else None
+        return d_sp, None, d_w, d_b
+
+
 class TopKCBSR(Function):
     """x -> (sp_data, sp_index) with gradient dX = scatter(d sp_data, sp_index)."""
 

@@ -282,6 +282,56 @@ def cbsr_gather(dense: torch.Tensor, sp_index: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def cbsr_matmul(sp_data: torch.Tensor, sp_index: torch.Tensor, m: torch.Tensor,
+                bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                accumulate: bool = False) -> torch.Tensor:
+    """EXPERIMENTAL: out[N, C] (+)= bias + scatter(sp_data, sp_index) @ m without the dense
+    twin; m float32 [D, C] row-major (a Linear's weight transposed), D <= 256, C % 4 == 0."""
+    lib = _cabi.load()
+    _cuda(sp_data, "sp_data", torch.float32)
+    _cuda(sp_index, "sp_index", torch.uint8)
+    _cuda(m, "m", torch.float32)
+    n, k = sp_index.shape
+    d, c = m.shape
+    _req(tuple(sp_data.shape) == (n, k), "sp_data / sp_index shape mismatch")
+    if bias is not None:
+        _cuda(bias, "bias", torch.float32)
+        _req(tuple(bias.shape) == (c,), "bias must be [C]")
+    with torch.cuda.device(m.device):
+        if out is None:
+            _req(not accumulate, "accumulate needs out=")
+            out = torch.empty((n, c), dtype=torch.float32, device=m.device)
+        else:
+            _cuda(out, "out", torch.float32)
+            _req(tuple(out.shape) == (n, c), "out must be [N, C]")
+        _cabi.check(lib.maxk_cbsr_matmul(sp_data.data_ptr(), sp_index.data_ptr(), n, k, m.data_ptr(), d, c,
+                                         _ptr(bias), out.data_ptr(), 1 if accumulate else 0, _stream(m)))
+    return out
+
+
+def cbsr_sampled_dot(g: torch.Tensor, m: torch.Tensor, sp_index: torch.Tensor,
+                     out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """EXPERIMENTAL: out[i, j] (+)= <g[i, :], m[sp_index[i, j], :]>  (float32 [N, k]) --
+    the gradient of cbsr_matmul with respect to sp_data."""
+    lib = _cabi.load()
+    _cuda(g, "g", torch.float32)
+    _cuda(m, "m", torch.float32)
+    _cuda(sp_index, "sp_index", torch.uint8)
+    n, k = sp_index.shape
+    d, c = m.shape
+    _req(tuple(g.shape) == (n, c), "g must be [N, C]")
+    with torch.cuda.device(m.device):
+        if out is None:
+            _req(not accumulate, "accumulate needs out=")
+            out = torch.empty((n, k), dtype=torch.float32, device=m.device)
+        else:
+            _cuda(out, "out", torch.float32)
+            _req(tuple(out.shape) == (n, k), "out must be [N, k]")
+        _cabi.check(lib.maxk_cbsr_sampled_dot(g.data_ptr(), n, c, m.data_ptr(), d, sp_index.data_ptr(), k,
+                                              out.data_ptr(), 1 if accumulate else 0, _stream(m)))
+    return out
+
+
 def cbsr_mask(dense: torch.Tensor, sp_index: torch.Tensor) -> torch.Tensor:
     """dense * mask(sp_index)  (MaxK.backward, utils/models.py:55-59)."""
     lib = _cabi.load()

@@ -21,7 +21,8 @@ import torch.nn.functional as F
 import torch.nn.init as init
 from torch.nn import Linear
 
-from maxk_b200.autograd import MaxK, SpGEMMFunction, TopKCBSR  # noqa: F401  (re-exported like the reference)
+from maxk_b200.autograd import (CBSRLinear, MaxK, SpGEMMFunction, TopKCBSR,  # noqa: F401  (re-exported like the reference)
+                                cbsr_linear_enabled)
 from maxk_b200 import ops
 from torch.autograd import Function
 
@@ -93,9 +94,12 @@ class SAGE(_Base):
                 x = F.dropout(x, self.p, self.training)
             else:                   # SAGEConv("mean", feat_drop): dropout(maxk(x)) feeds both branches
                 sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
-                h = _Scatter.apply(sp_data, sp_index, self.hid)
-                x = self.fc_self_layers[i](h) + self.fc_neigh_layers[i](
-                    g.aggregate(sp_data, sp_index, "mean", self.hid))
+                fc_self = self.fc_self_layers[i]
+                if self.nonlinear == "maxk" and cbsr_linear_enabled():   # EXPERIMENTAL: fc_self on the CBSR operand
+                    own = CBSRLinear.apply(sp_data, sp_index, fc_self.weight, fc_self.bias)
+                else:
+                    own = fc_self(_Scatter.apply(sp_data, sp_index, self.hid))
+                x = own + self.fc_neigh_layers[i](g.aggregate(sp_data, sp_index, "mean", self.hid))
             x = self.normlayers[i](x)
         return self.lin_out(x)
 

@@ -47,3 +47,13 @@ class Problem:
 def assert_close(got: torch.Tensor, want: np.ndarray, what=""):
     g = got.detach().cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(g, want, rtol=RTOL, atol=ATOL, err_msg=what)
+
+
+def assert_close_sum(got, want, abs_terms, n_terms, what=""):
+    """fp32 sums of `n_terms` products against an fp64 oracle: the north-star tolerance (rtol 1e-5 / atol 1e-6),
+    widened to the forward error bound of an fp32 sum, (n_terms + 2) * 2^-24 * sum|terms|, where a result is a
+    cancellation of much larger terms (the bound fp32 summation in ANY order -- torch's GEMM included -- obeys)."""
+    got = np.asarray(got, np.float64)
+    allowed = np.maximum(ATOL + RTOL * np.abs(want), (n_terms + 2) * 2.0 ** -24 * np.asarray(abs_terms, np.float64))
+    bad = np.abs(got - want) > allowed
+    assert not bad.any(), (what, int(bad.sum()), float(np.abs(got - want).max()))

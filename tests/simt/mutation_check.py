@@ -48,6 +48,14 @@ MUTANTS = {
     "peer-tma-store-before-the-load-landed": ("peer.cuh", "        mbar_wait(mbar0 + 8 * st, (phase >> st) & 1u);\n", "", "peer"),
     "peer-flag-raised-for-the-wrong-rank": ("peer.cuh", "st_release_sys(a.flags[p] + PEER_FLAG_ARRIVED + a.rank, a.epoch);", "st_release_sys(a.flags[p] + PEER_FLAG_ARRIVED + p, a.epoch);", "peer"),
     "peer-halo-rows-of-the-wrong-peer": ("peer.cuh", "    const int *rows = a.send_rows[p];\n    const long long n = a.send_count[p];", "    const int *rows = a.send_rows[p];\n    const long long n = a.send_count[p] - 1;", "peer"),
+    # CBSR x dense products (cbsr_dense.cu) and the rows-per-warp TopK
+    "cbsr-dense-no-barrier-after-staging": ("cbsr_dense.cu", "            __syncwarp();\n            float4 acc = b4;", "            float4 acc = b4;", 0),
+    "cbsr-dense-no-barrier-before-restaging": ("cbsr_dense.cu", "            __syncwarp();  // the staging area is rewritten for the next row\n", "", 0),
+    "cbsr-dense-tile-reload-no-barrier": ("cbsr_dense.cu", "        __syncthreads();  // everyone is done with the previous tile\n", "", 0),
+    "cbsr-dense-transpose-keeps-the-sent-half": ("cbsr_dense.cu", "const float keep = upper ? p[i + half] : p[i];", "const float keep = upper ? p[i] : p[i + half];", 0),
+    "cbsr-dense-later-tiles-overwrite": ("cbsr_dense.cu", "const bool first = (col0 == 0) && !accumulate;", "const bool first = !accumulate;", 0),
+    "topk-rows-no-barrier-between-rows": ("topk_cbsr.cu", "        __syncwarp();  // the staging area is reused by the next row\n", "", 0),
+    "topk-rows-prefetch-past-the-last-row": ("topk_cbsr.cu", "        if (row + 1 < r1) {", "        if (row + 1 <= r1) {", 0),
     "worklist-scan-no-barrier": ("worklist.cu", "    if (lane == 31) warp_sums[warp] = inc;\n    __syncthreads();", "    if (lane == 31) warp_sums[warp] = inc;", 0),
     "worklist-last-chunk-length": ("worklist.cu", "rec.z = min(nz, deg - nz * c_in_row);", "rec.z = nz;", 0),
 }

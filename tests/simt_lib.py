@@ -268,6 +268,38 @@ def cbsr_gather(dense, sp_index):
     return r["sp_data"]
 
 
+def cbsr_matmul(sp_data, sp_index, m, bias=None, accumulate=False, out_init=None):
+    L = load()
+    n, k = sp_index.shape
+    d, c = m.shape
+    ins = {"sp_data": Guarded(np.asarray(sp_data, np.float32), name="sp_data", align=4),
+           "sp_index": Guarded(np.asarray(sp_index, np.uint8), name="sp_index", align=1),
+           "m": Guarded(np.asarray(m, np.float32), name="m")}
+    if bias is not None:
+        ins["bias"] = Guarded(np.asarray(bias, np.float32), name="bias")
+    out = Guarded(np.asarray(out_init, np.float32), name="out") if out_init is not None else \
+        Guarded(shape=(n, c), dtype=np.float32, name="out")
+    r = _run(L.maxk_cbsr_matmul, ins, {"out": out},
+             lambda p: (p["sp_data"], p["sp_index"], i64(n), i32(k), p["m"], i32(d), i32(c), p.get("bias"), p["out"],
+                        i32(1 if accumulate else 0), None))
+    return r["out"]
+
+
+def cbsr_sampled_dot(g, m, sp_index, accumulate=False, out_init=None):
+    L = load()
+    n, k = sp_index.shape
+    d, c = m.shape
+    out = Guarded(np.asarray(out_init, np.float32), name="out", align=4) if out_init is not None else \
+        Guarded(shape=(n, k), dtype=np.float32, name="out", align=4)
+    r = _run(L.maxk_cbsr_sampled_dot, {"g": Guarded(np.asarray(g, np.float32), name="g"),
+                                       "m": Guarded(np.asarray(m, np.float32), name="m"),
+                                       "sp_index": Guarded(np.asarray(sp_index, np.uint8), name="sp_index", align=1)},
+             {"out": out},
+             lambda p: (p["g"], i64(n), i32(c), p["m"], i32(d), p["sp_index"], i32(k), p["out"],
+                        i32(1 if accumulate else 0), None))
+    return r["out"]
+
+
 def cbsr_mask(dense, sp_index):
     L = load()
     n, k = sp_index.shape

@@ -322,6 +322,49 @@ def test_topk_rows_per_warp_experimental(ops, rpw):
         ops.set_topk_rows_per_warp(0)
 
 
+@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
+                    reason="CBSR x dense products (csrc/cbsr_dense.cu): written after round 1's GPU budget was spent, "
+                           "checked under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
+@pytest.mark.parametrize("case", [dict(n=5000, d=256, k=32, c=256), dict(n=3333, d=256, k=64, c=132),
+                                  dict(n=40000, d=64, k=8, c=4), dict(n=700, d=36, k=18, c=260),
+                                  dict(n=300, d=256, k=256, c=128), dict(n=1, d=128, k=1, c=8)],
+                         ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
+def test_cbsr_linear_products_experimental(ops, case):
+    """fc_self on the CBSR operand and the gradient of its values against the dense Linear on the scattered
+    twin (fp64 oracle); then the autograd Function against torch's own Linear."""
+    from helpers import assert_close_sum
+    n, d, k, c = case["n"], case["d"], case["k"], case["c"]
+    rng = np.random.default_rng(n + d + k + c)
+    sd, si = O.topk_cbsr(rng.standard_normal((n, d)).astype(np.float32), k)
+    w = (rng.standard_normal((c, d)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(c).astype(np.float32)
+    m = _cu(np.ascontiguousarray(w.T))
+    y_terms = np.abs(O.cbsr_scatter(sd, si, d)).astype(np.float64) @ np.abs(w.T).astype(np.float64)
+    y = ops.cbsr_matmul(_cu(sd), _cu(si), m, _cu(b))
+    assert_close_sum(y.cpu().numpy(), O.cbsr_linear(sd, si, w, b), y_terms + np.abs(b), k + 1, "matmul + bias")
+    ops.cbsr_matmul(_cu(sd), _cu(si), m, out=y, accumulate=True)
+    assert_close_sum(y.cpu().numpy(), 2 * O.cbsr_linear(sd, si, w) + b, 2 * y_terms + np.abs(b), k + 2, "accumulate")
+    g = rng.standard_normal((n, c)).astype(np.float32)
+    g_terms = np.take_along_axis(np.abs(g).astype(np.float64) @ np.abs(w).astype(np.float64), si.astype(np.int64), axis=1)
+    dv = ops.cbsr_sampled_dot(_cu(g), m, _cu(si))
+    assert_close_sum(dv.cpu().numpy(), O.cbsr_linear_grad_values(g, si, w), g_terms, c, "sampled dot")
+    # autograd Function against torch's Linear on the scattered twin
+    from maxk_b200.autograd import CBSRLinear
+    lin = torch.nn.Linear(d, c).cuda()
+    outs = []
+    for sparse in (False, True):
+        v = _cu(sd).requires_grad_(True)
+        lin.zero_grad()
+        if sparse:
+            out = CBSRLinear.apply(v, _cu(si), lin.weight, lin.bias)
+        else:
+            out = lin(torch.zeros(n, d, device="cuda").scatter(1, _cu(si).long(), v))
+        out.backward(_cu(g))
+        outs.append((out.detach(), v.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone()))
+    for a, b2, what in zip(outs[0], outs[1], ("y", "d sp_data", "dW", "db")):
+        torch.testing.assert_close(b2, a, rtol=1e-4, atol=1e-4, msg=lambda s, w2=what: f"{w2}: {s}")
+
+
 def test_forward_gap_rows_are_zeroed(ops):
     """Leading, interior and trailing rows without edges (and an output taller than the last
     task row) come back as zeros from a poisoned buffer."""

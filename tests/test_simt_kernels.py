@@ -421,6 +421,56 @@ def test_simt_planned_backward_vs_oracle(case, vector):
         close(g3, want, "defined output, operands aligned to their element size only")
 
 
+# ------------------------------------------------------------------------------ 8(f) rank 3
+@pytest.mark.parametrize("case", [dict(n=70, d=256, k=32, c=256), dict(n=33, d=256, k=64, c=132), dict(n=17, d=64, k=8, c=4),
+                                  dict(n=50, d=36, k=18, c=260), dict(n=5, d=256, k=256, c=128), dict(n=1, d=128, k=1, c=8),
+                                  dict(n=40, d=256, k=16, c=48), dict(n=3000, d=32, k=4, c=8)],
+                         ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
+def test_simt_cbsr_linear_products(case):
+    """EXPERIMENTAL csrc/cbsr_dense.cu: fc_self on the CBSR operand and the gradient of its values, against
+    the dense Linear on the scattered twin (fp64 oracle)."""
+    from helpers import assert_close_sum
+    n, d, k, c = case["n"], case["d"], case["k"], case["c"]
+    rng = np.random.default_rng(n + d + k + c)
+    sd, si = O.topk_cbsr(rng.standard_normal((n, d)).astype(np.float32), k)
+    w = (rng.standard_normal((c, d)) * 0.2).astype(np.float32)   # nn.Linear.weight layout [C, D]
+    b = rng.standard_normal(c).astype(np.float32)
+    m = np.ascontiguousarray(w.T)
+    h_abs = np.abs(O.cbsr_scatter(sd, si, d)).astype(np.float64)
+    y_terms = h_abs @ np.abs(w.T).astype(np.float64)
+    y = S.cbsr_matmul(sd, si, m, bias=b)
+    assert_close_sum(y, O.cbsr_linear(sd, si, w, b), y_terms + np.abs(b), k + 1, "matmul + bias")
+    y0 = S.cbsr_matmul(sd, si, m)
+    assert_close_sum(y0, O.cbsr_linear(sd, si, w), y_terms, k, "matmul")
+    y2 = S.cbsr_matmul(sd, si, m, accumulate=True, out_init=y0)
+    assert_close_sum(y2, 2 * O.cbsr_linear(sd, si, w), 2 * y_terms, k + 1, "matmul, accumulate")
+    g = rng.standard_normal((n, c)).astype(np.float32)
+    want = O.cbsr_linear_grad_values(g, si, w)
+    g_terms = np.take_along_axis(np.abs(g).astype(np.float64) @ np.abs(w).astype(np.float64), si.astype(np.int64), axis=1)
+    dv = S.cbsr_sampled_dot(g, m, si)
+    assert dv.shape == (n, k)
+    assert_close_sum(dv, want, g_terms, c, "sampled dot")
+    dv2 = S.cbsr_sampled_dot(g, m, si, accumulate=True, out_init=np.ones((n, k), np.float32))
+    assert_close_sum(dv2, want + 1.0, g_terms + 1.0, c + 1, "sampled dot, accumulate")
+
+
+def test_simt_cbsr_linear_products_edge_cases():
+    rng = np.random.default_rng(3)
+    m = rng.standard_normal((20, 8)).astype(np.float32)
+    si = np.array([[0, 19, 20, 255]], np.uint8)               # two selectors outside [0, d): contribute nothing
+    sd = np.array([[1.0, 2.0, 5.0, 7.0]], np.float32)
+    np.testing.assert_allclose(S.cbsr_matmul(sd, si, m)[0], m[0] + 2 * m[19], rtol=1e-6)
+    g = rng.standard_normal((1, 8)).astype(np.float32)
+    dv = S.cbsr_sampled_dot(g, m, si)[0]
+    np.testing.assert_allclose(dv[:2], [g[0] @ m[0], g[0] @ m[19]], rtol=1e-5)
+    assert dv[2] == 0.0 and dv[3] == 0.0
+    assert S.cbsr_matmul(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.uint8), m).shape == (0, 8)
+    with pytest.raises(S.SimtError, match="multiple of 4"):
+        S.cbsr_matmul(sd, si, rng.standard_normal((20, 6)).astype(np.float32))
+    with pytest.raises(S.SimtError, match="d=300"):
+        S.cbsr_sampled_dot(np.zeros((1, 8), np.float32), np.zeros((300, 8), np.float32), si)
+
+
 def test_simt_planned_backward_edge_cases():
     z32 = np.zeros(0, np.int32)
     sp_addr = np.tile(np.arange(32, dtype=np.uint16), (10, 1))

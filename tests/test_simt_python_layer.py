@@ -174,6 +174,56 @@ def test_models_train_step_same_with_and_without_the_plan(ops, monkeypatch, name
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
 
 
+def test_cbsr_linear_function_matches_dense_linear(ops):
+    """EXPERIMENTAL CBSRLinear (fc_self on the CBSR operand): value and all three gradients equal those of
+    torch's Linear on the scattered twin."""
+    from maxk_b200.autograd import CBSRLinear, TopKCBSR
+    torch.manual_seed(3)
+    x = torch.randn(90, 256)
+    lin = torch.nn.Linear(256, 64)
+    gy = torch.randn(90, 64)
+    outs = []
+    for sparse in (False, True):
+        xs = x.clone().requires_grad_(True)
+        lin.zero_grad()
+        sp_data, sp_index = TopKCBSR.apply(xs, 32)
+        if sparse:
+            y = CBSRLinear.apply(sp_data, sp_index, lin.weight, lin.bias)
+        else:
+            y = lin(_scatter(ops, sp_data, sp_index))
+        y.backward(gy)
+        outs.append((y.detach(), xs.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone()))
+    for a, b, what in zip(outs[0], outs[1], ("y", "dx", "dW", "db")):
+        torch.testing.assert_close(b, a, rtol=1e-4, atol=2e-5, msg=lambda m, w=what: f"{w}: {m}")
+    y_nb = CBSRLinear.apply(sp_data.detach(), sp_index, lin.weight.detach(), None)
+    torch.testing.assert_close(y_nb, outs[0][0] - lin.bias.detach(), rtol=1e-4, atol=2e-5)
+
+
+def _scatter(ops, sp_data, sp_index):
+    import utils.models as M
+    return M._Scatter.apply(sp_data, sp_index, 256)
+
+
+def test_sage_train_step_same_with_fc_self_on_the_cbsr_operand(ops, monkeypatch):
+    import utils.models as M
+    p, g = _problem(n=80, avg=8.0, k=8, seed=5, empty_frac=0.0)
+    G = _HostGraph(p, g)
+    torch.manual_seed(0)
+    model = M.SAGE(16, 64, 2, 5, maxk=16, feat_drop=0.0, norm=True)
+    feats = torch.randn(p.n, 16)
+    target = torch.randint(0, 5, (p.n,))
+    results = []
+    for on in ("0", "1"):
+        monkeypatch.setenv("MAXK_CBSR_LINEAR", on)
+        model.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(G, feats), target)
+        loss.backward()
+        results.append((float(loss.detach()), [q.grad.clone() for q in model.parameters()]))
+    assert np.isfinite(results[0][0]) and abs(results[0][0] - results[1][0]) < 1e-5
+    for a, b in zip(results[0][1], results[1][1]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
 def test_the_double_is_gone_after_the_fixture():
     from maxk_b200 import _cabi
     assert _cabi._lib is None or "libmaxk_b200.so" in str(_cabi._lib._name)
