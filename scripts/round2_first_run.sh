@@ -1,5 +1,5 @@
 #!/bin/bash
-# First gpurun call of round 2 (1 GPU, ~3 minutes): validate and measure what round 1 wrote after
+# First gpurun call of round 2 (1 GPU, ~10 minutes): validate and measure what round 1 wrote after
 # its GPU budget was spent -- the double-buffered (launch shapes 4-7) and cp.async-ring (8-11)
 # forward variants and the bank-planned forward (csrc/cbsr_plan.cu), all already checked under the SIMT interpreter (tests/test_simt_kernels.py) -- and
 # re-measure the one-GPU epoch that the scaling table still quotes from the first session.

@@ -58,8 +58,26 @@ def one(rng, it):
         got_w4 = S.worklist(indptr, nz)
         assert np.array_equal(got_w4, w4.reshape(-1)), "worklist"
         ov, oi = O.topk_cbsr(x, k)
+        rpw = int(rng.choice([0, 0, 2, 3, 8]))  # > 1: the experimental rows-per-warp TopK
+        params["rpw"] = rpw
+        S.set_topk_rows_per_warp(rpw)
         v, i = S.topk_f32(x, k)
         assert np.array_equal(i, oi) and np.array_equal(v.view(np.uint32), ov.view(np.uint32)), "topk"
+        # fc_self on the CBSR operand (cbsr_dense.cu) against the dense Linear on the scattered twin
+        c = int(rng.choice([4, 8, 48, 128, 132, 256, 260]))
+        params["c"] = c
+        w = (r.standard_normal((c, d)) * 0.2).astype(np.float32)
+        bias = r.standard_normal(c).astype(np.float32) if r.random() < 0.5 else None
+        m = np.ascontiguousarray(w.T)
+        terms = np.abs(O.cbsr_scatter(ov, oi, d)).astype(np.float64) @ np.abs(m).astype(np.float64) + (0 if bias is None else np.abs(bias))
+        ylin = S.cbsr_matmul(ov, oi, m, bias=bias)
+        wl = O.cbsr_linear(ov, oi, w, bias)
+        assert (np.abs(ylin - wl) <= np.maximum(ATOL + RTOL * np.abs(wl), (k + 3) * 2.0 ** -24 * terms)).all(), "cbsr_matmul"
+        gl = r.standard_normal((n_cols, c)).astype(np.float32)
+        wg = O.cbsr_linear_grad_values(gl, oi, w)
+        gterms = np.take_along_axis(np.abs(gl).astype(np.float64) @ np.abs(w).astype(np.float64), oi.astype(np.int64), axis=1)
+        dvl = S.cbsr_sampled_dot(gl, m, oi)
+        assert (np.abs(dvl - wg) <= np.maximum(ATOL + RTOL * np.abs(wg), (c + 2) * 2.0 ** -24 * gterms)).all(), "cbsr_sampled_dot"
         ov = np.abs(ov)
         if selector == "random":
             oi = np.argsort(r.random((n_cols, d)), axis=1)[:, :k].astype(np.uint8)
@@ -111,6 +129,7 @@ def one(rng, it):
     finally:
         S.set_forward_depth(0); S.set_forward_copies(0); S.set_tuning(-1, -1); S.set_cp_async_eager(False)
         S.set_planned_backward_vector(False)
+        S.set_topk_rows_per_warp(0)
 
 
 if __name__ == "__main__":

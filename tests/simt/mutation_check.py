@@ -54,7 +54,6 @@ MUTANTS = {
     "cbsr-dense-tile-reload-no-barrier": ("cbsr_dense.cu", "        __syncthreads();  // everyone is done with the previous tile\n", "", 0),
     "cbsr-dense-transpose-keeps-the-sent-half": ("cbsr_dense.cu", "const float keep = upper ? p[i + half] : p[i];", "const float keep = upper ? p[i] : p[i + half];", 0),
     "cbsr-dense-later-tiles-overwrite": ("cbsr_dense.cu", "const bool first = (col0 == 0) && !accumulate;", "const bool first = !accumulate;", 0),
-    "topk-rows-no-barrier-between-rows": ("topk_cbsr.cu", "        __syncwarp();  // the staging area is reused by the next row\n", "", 0),
     "topk-rows-prefetch-past-the-last-row": ("topk_cbsr.cu", "        if (row + 1 < r1) {", "        if (row + 1 <= r1) {", 0),
     "worklist-scan-no-barrier": ("worklist.cu", "    if (lane == 31) warp_sums[warp] = inc;\n    __syncthreads();", "    if (lane == 31) warp_sums[warp] = inc;", 0),
     "worklist-last-chunk-length": ("worklist.cu", "rec.z = min(nz, deg - nz * c_in_row);", "rec.z = nz;", 0),
@@ -66,6 +65,10 @@ MUTANTS = {
 # before fwd_flush_row -- the leading barriers of those two functions are redundant (they stay:
 # they cost nothing measurable and keep the functions correct on their own).
 EQUIVALENT = {
+    # every row starts with warp-wide REDUX collectives (row minimum / maximum): all lanes have left the previous
+    # row's emission reads before any lane can reach the next row's staging writes; the barrier stays as
+    # documentation of the reuse
+    "topk-rows-no-barrier-between-rows": ("topk_cbsr.cu", "        __syncwarp();  // the staging area is reused by the next row\n", "", 0),
     "fwd-stage-no-barrier-before-write": ("spgemm_forward.cu", "    __syncwarp();  // everyone is done reading the previous batch\n", "", 0),
     "fwd-flush-no-leading-barrier": ("spgemm_forward.cu", "    constexpr int R = C::R;\n    __syncwarp();", "    constexpr int R = C::R;", 0),
     # ... as is the barrier between the ring accumulate and the re-issue into the same half
