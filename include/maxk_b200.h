@@ -184,6 +184,10 @@ MAXK_API int maxk_cbsr_mask(const float *in, const uint8_t *sp_index, int64_t n,
 MAXK_API int maxk_cbsr_matmul(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k,
                      const float *m, int32_t d, int32_t c, const float *bias, float *out,
                      int32_t accumulate, void *stream);
+/* axpy: y[i, sp_index[i,j]] += (alpha_host + *alpha_dev) * sp_data[i,j] in place (alpha_dev may be NULL) --
+ * GINConv's "(1 + eps) * h" (utils/models.py:361) added to the aggregate without the dense twin of h. */
+MAXK_API int maxk_cbsr_axpy(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k, int32_t d,
+                   const float *alpha_dev, float alpha_host, float *y, void *stream);
 MAXK_API int maxk_cbsr_sampled_dot(const float *g, int64_t n, int32_t c, const float *m, int32_t d,
                           const uint8_t *sp_index, int32_t k, float *out, int32_t accumulate,
                           void *stream);

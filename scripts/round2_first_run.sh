@@ -14,7 +14,10 @@ python scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 
 python scripts/topk_probe.py 2>/dev/null | tee gpurun_out/topk_probe_round2.log   # default and 2/4/8 rows per warp
 # fc_self on the CBSR operand vs torch's dense fp32 Linear (products-sized), then the epoch with it
 python scripts/cbsr_linear_probe.py 2>/dev/null | tee gpurun_out/cbsr_linear_probe.jsonl
-MAXK_CBSR_LINEAR=1 python scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_n1_cbsr_linear.json
+MAXK_CBSR_NATIVE=1 python scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_n1_cbsr_native_sage.json
+for v in 0 1; do
+  MAXK_CBSR_NATIVE=$v python scripts/train_epoch.py --shape products --model gin --epochs 5 --warmup 2 2>/dev/null | grep "^{" | tee gpurun_out/epoch_n1_gin_native$v.json
+done
 # hardware questions the models had to guess (scalar vs vector reductions at the L2, conflict cost,
 # LDS vs SHFL broadcast, cp.async / cp.async.bulk gathers): one short probe, bounded
 mkdir -p scripts/probes/_bin

@@ -164,6 +164,25 @@ cbsr_sampled_dot_kernel(const float *__restrict__ g, int64_t n, int c, const flo
     }
 }
 
+// y[i, sp_index[i,j]] += alpha * sp_data[i,j]  (GIN's "(1 + eps) * h" term added to the aggregate in place,
+// utils/models.py:361, without the dense twin h): one warp per row, k scattered read-modify-writes inside the
+// row's own 4d bytes.  alpha = alpha_host + *alpha_dev (the learnable eps stays on the device: no host sync).
+constexpr int AX_WPB = 8;
+__global__ void __launch_bounds__(AX_WPB * 32)
+cbsr_axpy_kernel(const float *__restrict__ sp_data, const unsigned char *__restrict__ sp_index, int64_t n, int k,
+                 int d, const float *__restrict__ alpha_dev, float alpha_host, float *__restrict__ y)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * AX_WPB + warp;
+    if (row >= n) return;
+    const float alpha = alpha_host + (alpha_dev != nullptr ? __ldg(alpha_dev) : 0.f);
+    float *yr = y + row * d;
+    for (int j = lane; j < k; j += 32) {
+        const int s = sp_index[row * k + j];
+        if (s < d) yr[s] = fmaf(alpha, __ldg(sp_data + row * k + j), yr[s]);  // selectors of a row are distinct
+    }
+}
+
 static int cd_check(const char *who, int64_t n, int k, int d, int c)
 {
     MAXK_REQUIRE(n >= 0, "%s: negative n", who);
@@ -224,5 +243,21 @@ extern "C" int maxk_cbsr_sampled_dot(const float *g, int64_t n, int32_t c, const
     cbsr_sampled_dot_kernel<<<cd_grid(n), CD_WARPS * 32, cd_smem_bytes(d, k), static_cast<cudaStream_t>(stream)>>>(
         g, n, c, m, d, sp_index, k, out, accumulate);
     MAXK_LAUNCH_CHECK("cbsr_sampled_dot_kernel");
+    return MAXK_OK;
+}
+
+extern "C" int maxk_cbsr_axpy(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k, int32_t d,
+                              const float *alpha_dev, float alpha_host, float *y, void *stream)
+{
+    MAXK_REQUIRE(n >= 0, "maxk_cbsr_axpy: negative n");
+    MAXK_REQUIRE(d >= 1 && d <= MAXK_MAX_DIM, "maxk_cbsr_axpy: d=%d out of range [1,256]", d);
+    MAXK_REQUIRE(k >= 1 && k <= 256, "maxk_cbsr_axpy: k=%d out of range", k);
+    if (n == 0) return MAXK_OK;
+    MAXK_REQUIRE(sp_data && sp_index && y, "maxk_cbsr_axpy: NULL pointer");
+    const int64_t grid = ceil_div<int64_t>(n, AX_WPB);
+    MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_cbsr_axpy: n too large");
+    cbsr_axpy_kernel<<<(unsigned)grid, AX_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        sp_data, sp_index, n, k, d, alpha_dev, alpha_host, y);
+    MAXK_LAUNCH_CHECK("cbsr_axpy_kernel");
     return MAXK_OK;
 }

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "maxk_set_backward_prefetch": (ctypes.c_int, [ctypes.c_int]),
     "maxk_set_topk_rows_per_warp": (ctypes.c_int, [ctypes.c_int]),
     "maxk_cbsr_matmul": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "maxk_cbsr_axpy": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, ctypes.c_float, _vp, _vp]),
     "maxk_cbsr_sampled_dot": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "maxk_sspmm_backward_planned": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _i32,
                                                    _vp]),

@@ -172,11 +172,12 @@ class CBSRAggregate(Function):
         return dxc, None, None, None, None, None, None
 
 
-def cbsr_linear_enabled() -> bool:
-    """EXPERIMENTAL opt-in (unmeasured): MAXK_CBSR_LINEAR=1 computes SAGE's fc_self on the
-    CBSR operand (csrc/cbsr_dense.cu) instead of torch's dense Linear on the scattered twin."""
+def cbsr_native_enabled() -> bool:
+    """EXPERIMENTAL opt-in (unmeasured): MAXK_CBSR_NATIVE=1 keeps the layers on the CBSR
+    operand (csrc/cbsr_dense.cu): SAGE's fc_self without torch's dense Linear on the scattered twin, GIN's
+    (1 + eps) * h added to the aggregate in place."""
     import os
-    return os.environ.get("MAXK_CBSR_LINEAR", "0").strip() == "1"
+    return os.environ.get("MAXK_CBSR_NATIVE", "0").strip() == "1"
 
 
 class CBSRLinear(Function):
@@ -204,6 +205,28 @@ class CBSRLinear(Function):
             d_w = g.t() @ ops.cbsr_scatter(sp_data, sp_index, m.shape[0])   # [C, D]
         d_b = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[3] else None
         return d_sp, None, d_w, d_b
+
+
+class CBSRAddScaled(Function):
+    """y + (1 + eps) * scatter(sp_data, sp_index), computed in place on y (GINConv's self term,
+    utils/models.py:361) without the dense twin.  `y` must be a tensor nobody else needs unchanged (the
+    output of CBSRAggregate is: its backward saves inputs only).  eps: a one-element parameter."""
+
+    @staticmethod
+    def forward(ctx, y, sp_data, sp_index, eps):
+        sp_data = sp_data.contiguous()
+        ops.cbsr_axpy_(y, sp_data, sp_index, 1.0, eps.detach().reshape(1).contiguous())
+        ctx.mark_dirty(y)
+        ctx.save_for_backward(sp_data, sp_index, eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        sp_data, sp_index, eps = ctx.saved_tensors
+        picked = ops.cbsr_gather(grad_output.contiguous(), sp_index)          # dL/dy at the kept columns
+        d_sp = picked * (1.0 + eps.detach().reshape(())) if ctx.needs_input_grad[1] else None
+        d_eps = (picked * sp_data).sum().reshape(eps.shape) if ctx.needs_input_grad[3] else None
+        return grad_output, d_sp, None, d_eps
 
 
 class TopKCBSR(Function):

@@ -309,6 +309,24 @@ def cbsr_matmul(sp_data: torch.Tensor, sp_index: torch.Tensor, m: torch.Tensor,
     return out
 
 
+def cbsr_axpy_(y: torch.Tensor, sp_data: torch.Tensor, sp_index: torch.Tensor, alpha: float = 1.0,
+               alpha_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """EXPERIMENTAL: y[i, sp_index[i,j]] += (alpha + alpha_dev[0]) * sp_data[i,j], in place."""
+    lib = _cabi.load()
+    _cuda(y, "y", torch.float32)
+    _cuda(sp_data, "sp_data", torch.float32)
+    _cuda(sp_index, "sp_index", torch.uint8)
+    n, k = sp_index.shape
+    _req(tuple(sp_data.shape) == (n, k) and y.dim() == 2 and y.shape[0] == n, "shape mismatch")
+    if alpha_dev is not None:
+        _cuda(alpha_dev, "alpha_dev", torch.float32)
+        _req(alpha_dev.numel() == 1, "alpha_dev must hold one float")
+    with torch.cuda.device(y.device):
+        _cabi.check(lib.maxk_cbsr_axpy(sp_data.data_ptr(), sp_index.data_ptr(), n, k, y.shape[1], _ptr(alpha_dev),
+                                       float(alpha), y.data_ptr(), _stream(y)))
+    return y
+
+
 def cbsr_sampled_dot(g: torch.Tensor, m: torch.Tensor, sp_index: torch.Tensor,
                      out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """EXPERIMENTAL: out[i, j] (+)= <g[i, :], m[sp_index[i, j], :]>  (float32 [N, k]) --

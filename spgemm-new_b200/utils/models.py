@@ -21,8 +21,8 @@ import torch.nn.functional as F
 import torch.nn.init as init
 from torch.nn import Linear
 
-from maxk_b200.autograd import (CBSRLinear, MaxK, SpGEMMFunction, TopKCBSR,  # noqa: F401  (re-exported like the reference)
-                                cbsr_linear_enabled)
+from maxk_b200.autograd import (CBSRAddScaled, CBSRLinear, MaxK, SpGEMMFunction, TopKCBSR,  # noqa: F401  (re-exported like the reference)
+                                cbsr_native_enabled)
 from maxk_b200 import ops
 from torch.autograd import Function
 
@@ -95,7 +95,7 @@ class SAGE(_Base):
             else:                   # SAGEConv("mean", feat_drop): dropout(maxk(x)) feeds both branches
                 sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
                 fc_self = self.fc_self_layers[i]
-                if self.nonlinear == "maxk" and cbsr_linear_enabled():   # EXPERIMENTAL: fc_self on the CBSR operand
+                if self.nonlinear == "maxk" and cbsr_native_enabled():   # EXPERIMENTAL: fc_self on the CBSR operand
                     own = CBSRLinear.apply(sp_data, sp_index, fc_self.weight, fc_self.bias)
                 else:
                     own = fc_self(_Scatter.apply(sp_data, sp_index, self.hid))
@@ -143,7 +143,10 @@ class GIN(_Base):
         for i in range(self.num_layers):
             x = self.linlayers[i](x)
             sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
-            h = _Scatter.apply(sp_data, sp_index, self.hid)
-            x = (1.0 + self.eps[i]) * h + g.aggregate(sp_data, sp_index, "sum", self.hid)
+            if cbsr_native_enabled():   # EXPERIMENTAL: self term added to the aggregate in place, no dense twin
+                x = CBSRAddScaled.apply(g.aggregate(sp_data, sp_index, "sum", self.hid), sp_data, sp_index, self.eps[i])
+            else:
+                h = _Scatter.apply(sp_data, sp_index, self.hid)
+                x = (1.0 + self.eps[i]) * h + g.aggregate(sp_data, sp_index, "sum", self.hid)
             x = self.normlayers[i](x)
         return self.lin_out(x)

@@ -285,6 +285,19 @@ def cbsr_matmul(sp_data, sp_index, m, bias=None, accumulate=False, out_init=None
     return r["out"]
 
 
+def cbsr_axpy(y, sp_data, sp_index, alpha=1.0, alpha_dev=None):
+    L = load()
+    n, k = sp_index.shape
+    ins = {"sp_data": Guarded(np.asarray(sp_data, np.float32), name="sp_data", align=4),
+           "sp_index": Guarded(np.asarray(sp_index, np.uint8), name="sp_index", align=1)}
+    if alpha_dev is not None:
+        ins["alpha"] = Guarded(np.asarray([alpha_dev], np.float32), name="alpha", align=4)
+    r = _run(L.maxk_cbsr_axpy, ins, {"y": Guarded(np.asarray(y, np.float32), name="y", align=4)},
+             lambda p: (p["sp_data"], p["sp_index"], i64(n), i32(k), i32(y.shape[1]), p.get("alpha"),
+                        ctypes.c_float(alpha), p["y"], None))
+    return r["y"]
+
+
 def cbsr_sampled_dot(g, m, sp_index, accumulate=False, out_init=None):
     L = load()
     n, k = sp_index.shape

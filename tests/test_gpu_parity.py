@@ -363,6 +363,11 @@ def test_cbsr_linear_products_experimental(ops, case):
         outs.append((out.detach(), v.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone()))
     for a, b2, what in zip(outs[0], outs[1], ("y", "d sp_data", "dW", "db")):
         torch.testing.assert_close(b2, a, rtol=1e-4, atol=1e-4, msg=lambda s, w2=what: f"{w2}: {s}")
+    # GIN's self term added in place: y += (1 + eps) * scatter(sp_data, sp_index)
+    y0 = rng.standard_normal((n, d)).astype(np.float32)
+    yt = _cu(y0)
+    ops.cbsr_axpy_(yt, _cu(sd), _cu(si), 1.0, torch.full((1,), 0.25, device="cuda"))
+    assert_close(yt, y0 + 1.25 * O.cbsr_scatter(sd, si, d).astype(np.float64), "axpy")
 
 
 def test_forward_gap_rows_are_zeroed(ops):

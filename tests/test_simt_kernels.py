@@ -454,6 +454,22 @@ def test_simt_cbsr_linear_products(case):
     assert_close_sum(dv2, want + 1.0, g_terms + 1.0, c + 1, "sampled dot, accumulate")
 
 
+@pytest.mark.parametrize("n,d,k", [(70, 256, 32), (9, 64, 64), (33, 36, 18), (1, 4, 1), (20, 256, 256)])
+def test_simt_cbsr_axpy_in_place(n, d, k):
+    """y += (alpha + *alpha_dev) * scatter(sp_data, sp_index): GIN's self term without the dense twin."""
+    rng = np.random.default_rng(n + d + k)
+    sd, si = O.topk_cbsr(rng.standard_normal((n, d)).astype(np.float32), k)
+    y = rng.standard_normal((n, d)).astype(np.float32)
+    h = O.cbsr_scatter(sd, si, d).astype(np.float64)
+    close(S.cbsr_axpy(y, sd, si, alpha=1.0, alpha_dev=0.25), y + 1.25 * h, "alpha on the device")
+    close(S.cbsr_axpy(y, sd, si, alpha=-2.0), y - 2.0 * h, "host alpha only")
+    if d < 256:   # a selector outside [0, d) contributes nothing
+        si_bad, h_bad = si.copy(), h.copy()
+        si_bad[0, 0] = 255
+        h_bad[0, si[0, 0]] = 0.0
+        close(S.cbsr_axpy(y, sd, si_bad, alpha=1.0), y + h_bad, "selector outside [0, d)")
+
+
 def test_simt_cbsr_linear_products_edge_cases():
     rng = np.random.default_rng(3)
     m = rng.standard_normal((20, 8)).astype(np.float32)

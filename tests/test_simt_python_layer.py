@@ -204,17 +204,38 @@ def _scatter(ops, sp_data, sp_index):
     return M._Scatter.apply(sp_data, sp_index, 256)
 
 
-def test_sage_train_step_same_with_fc_self_on_the_cbsr_operand(ops, monkeypatch):
+def test_cbsr_add_scaled_function_matches_the_dense_expression(ops):
+    """EXPERIMENTAL CBSRAddScaled (GIN's (1 + eps) * h added in place): value and the gradients of y, sp_data, eps."""
+    from maxk_b200.autograd import CBSRAddScaled, TopKCBSR
+    torch.manual_seed(5)
+    x, base, gy = torch.randn(60, 256), torch.randn(60, 256), torch.randn(60, 256)
+    outs = []
+    for fused in (False, True):
+        xs, ys = x.clone().requires_grad_(True), base.clone().requires_grad_(True)
+        eps = torch.nn.Parameter(torch.full((1,), 0.3))
+        sp_data, sp_index = TopKCBSR.apply(xs, 32)
+        if fused:
+            out = CBSRAddScaled.apply(ys * 1.0, sp_data, sp_index, eps)
+        else:
+            out = (1.0 + eps) * _scatter(ops, sp_data, sp_index) + ys
+        out.backward(gy)
+        outs.append((out.detach(), xs.grad.clone(), ys.grad.clone(), eps.grad.clone()))
+    for a, b, what in zip(outs[0], outs[1], ("value", "dx", "dy", "d eps")):
+        torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-5, msg=lambda m, w=what: f"{w}: {m}")
+
+
+@pytest.mark.parametrize("name", ["SAGE", "GIN"])
+def test_train_step_same_with_layers_on_the_cbsr_operand(ops, monkeypatch, name):
     import utils.models as M
     p, g = _problem(n=80, avg=8.0, k=8, seed=5, empty_frac=0.0)
     G = _HostGraph(p, g)
     torch.manual_seed(0)
-    model = M.SAGE(16, 64, 2, 5, maxk=16, feat_drop=0.0, norm=True)
+    model = getattr(M, name)(16, 64, 2, 5, maxk=16, feat_drop=0.0, norm=True)
     feats = torch.randn(p.n, 16)
     target = torch.randint(0, 5, (p.n,))
     results = []
     for on in ("0", "1"):
-        monkeypatch.setenv("MAXK_CBSR_LINEAR", on)
+        monkeypatch.setenv("MAXK_CBSR_NATIVE", on)
         model.zero_grad()
         loss = torch.nn.functional.cross_entropy(model(G, feats), target)
         loss.backward()
