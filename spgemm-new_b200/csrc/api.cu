@@ -3,6 +3,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -31,6 +34,22 @@ int cuda_fail(cudaError_t e, const char *what)
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, device): a process that drives
+// several GPUs has to raise it on each of them, once.
+int opt_in_dynamic_smem(const void *kernel, const char *what)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    MAXK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({kernel, dev})) return MAXK_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    done.insert({kernel, dev});
+    return MAXK_OK;
+}
 
 }  // namespace maxk
 

@@ -214,11 +214,7 @@ extern "C" int maxk_cbsr_matmul(const float *sp_data, const uint8_t *sp_index, i
     MAXK_REQUIRE(((reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(out) |
                    reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
                  "maxk_cbsr_matmul: m, bias and out must be 16-byte aligned");
-    static bool opted_in = false;  // benign if raced
-    if (!opted_in) {
-        MAXK_CUDA(cudaFuncSetAttribute(cbsr_matmul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        opted_in = true;
-    }
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void *>(&cbsr_matmul_kernel), "cbsr_matmul_kernel")) return rc;
     cbsr_matmul_kernel<<<cd_grid(n), CD_WARPS * 32, cd_smem_bytes(d, k), static_cast<cudaStream_t>(stream)>>>(
         sp_data, sp_index, n, k, m, d, c, bias, out, accumulate);
     MAXK_LAUNCH_CHECK("cbsr_matmul_kernel");
@@ -234,12 +230,8 @@ extern "C" int maxk_cbsr_sampled_dot(const float *g, int64_t n, int32_t c, const
     MAXK_REQUIRE(g && sp_index && m && out, "maxk_cbsr_sampled_dot: NULL pointer");
     MAXK_REQUIRE(((reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(g)) & 15) == 0,
                  "maxk_cbsr_sampled_dot: m and g must be 16-byte aligned");
-    static bool opted_in = false;  // benign if raced
-    if (!opted_in) {
-        MAXK_CUDA(cudaFuncSetAttribute(cbsr_sampled_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024));
-        opted_in = true;
-    }
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void *>(&cbsr_sampled_dot_kernel), "cbsr_sampled_dot_kernel"))
+        return rc;
     cbsr_sampled_dot_kernel<<<cd_grid(n), CD_WARPS * 32, cd_smem_bytes(d, k), static_cast<cudaStream_t>(stream)>>>(
         g, n, c, m, d, sp_index, k, out, accumulate);
     MAXK_LAUNCH_CHECK("cbsr_sampled_dot_kernel");

@@ -20,6 +20,7 @@ constexpr int kNumSMs = 148;  // B200
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 void count_launch(int n = 1);
+int opt_in_dynamic_smem(const void *kernel, const char *what);  // up to 200 KB, once per (kernel, device)
 
 #define MAXK_REQUIRE(cond, ...)                    \
     do {                                           \

@@ -665,14 +665,8 @@ static int launch_fwd(const FwdArgs &a)
     if constexpr (C::PEER) {  // the copy CTAs stage their TMA chunks in the same dynamic smem
         if (a.peer->use_tma && smem < PEER_TMA_SMEM + 128) smem = PEER_TMA_SMEM + 128;
     }
-    if (smem > 48 * 1024) {
-        static bool opted_in = false;  // per variant; benign if raced
-        if (!opted_in) {
-            MAXK_CUDA(cudaFuncSetAttribute(spgemm_fwd_kernel<C>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            opted_in = true;
-        }
-    }
+    if (smem > 48 * 1024)
+        if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void *>(&spgemm_fwd_kernel<C>), "spgemm_fwd_kernel")) return rc;
     const int64_t chunks = ceil_div<int64_t>(a.W, a.tasks_per_warp);
     int64_t grid = ceil_div<int64_t>(chunks, C::WPB);
     typename PeerParam<C::PEER>::type peer{};

@@ -272,14 +272,10 @@ static int launch_bwp(const int32_t *warp4, int64_t W, const int32_t *idx, const
 {
     const size_t smem = (size_t)BWP_WPB * H * 256 * (32 / KL) * sizeof(float) +
                         (size_t)BWP_WPB * BWP_STAGE * sizeof(int2);
-    if (smem > 48 * 1024) {
-        static bool opted_in = false;  // per variant; benign if raced
-        if (!opted_in) {
-            MAXK_CUDA(cudaFuncSetAttribute(sspmm_bwd_planned_kernel<KL, EPL, H, VEC>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            opted_in = true;
-        }
-    }
+    if (smem > 48 * 1024)
+        if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void *>(&sspmm_bwd_planned_kernel<KL, EPL, H, VEC>),
+                                         "sspmm_bwd_planned_kernel"))
+            return rc;
     const int64_t chunks = ceil_div<int64_t>(W, tasks_per_warp);
     const int64_t grid = ceil_div<int64_t>(chunks, BWP_WPB);
     if (grid > 0x7fffffffLL) {

@@ -163,6 +163,7 @@ const char *cudaGetErrorName(cudaError_t e);
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p);
 cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags);
 cudaError_t cudaIpcCloseMemHandle(void *p);
+inline cudaError_t cudaGetDevice(int *dev) { *dev = 0; return cudaSuccess; }
 template <typename F>
 inline cudaError_t cudaFuncSetAttribute(F *kernel, cudaFuncAttribute attr, int value)
 {
