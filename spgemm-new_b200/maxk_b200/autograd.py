@@ -26,15 +26,13 @@ _WL_CACHE_MAX = 16
 def worklist_for(indptr: torch.Tensor) -> torch.Tensor:
     """Work list of a CSR graph, cached per indptr tensor (the cache holds a reference to the
     tensor, so its storage -- and therefore the key -- cannot be recycled while cached)."""
-    if indptr.dtype != torch.int32:
-        indptr = indptr.int()
-    indptr = indptr.contiguous()
-    key = (indptr.data_ptr(), indptr.numel(), str(indptr.device), indptr._version)
+    # keyed on the CALLER's tensor: an int64 or strided indptr is converted once, not on every call
+    key = (indptr.data_ptr(), indptr.numel(), str(indptr.device), indptr._version, indptr.dtype, indptr.stride())
     hit = _WL_CACHE.get(key)
     if hit is not None:
         _WL_CACHE.move_to_end(key)
         return hit[1]
-    warp4 = ops.build_worklist(indptr)
+    warp4 = ops.build_worklist(indptr.to(torch.int32).contiguous())
     _WL_CACHE[key] = (indptr, warp4)
     while len(_WL_CACHE) > _WL_CACHE_MAX:
         _WL_CACHE.popitem(last=False)

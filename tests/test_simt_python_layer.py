@@ -245,6 +245,23 @@ def test_train_step_same_with_layers_on_the_cbsr_operand(ops, monkeypatch, name)
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
 
 
+def test_worklist_cache_is_keyed_on_the_callers_tensor(ops):
+    """An int64 indptr (what DGL / torch hand over) is converted once: the second call is a cache hit,
+    an in-place change of the tensor is not."""
+    from maxk_b200 import autograd as A
+    p, g = _problem(n=50, avg=10.0, k=8, seed=2)
+    A._WL_CACHE.clear()
+    ip64 = g["indptr"].long()
+    w1 = A.worklist_for(ip64)
+    assert torch.equal(w1, g["warp4"]) and len(A._WL_CACHE) == 1
+    assert A.worklist_for(ip64) is w1 and len(A._WL_CACHE) == 1
+    assert A.worklist_for(g["indptr"]) is not w1 and len(A._WL_CACHE) == 2
+    ip64[-1] -= 1   # bumps the version counter: a different graph
+    w2 = A.worklist_for(ip64)
+    assert w2 is not w1 and int(w2.reshape(-1, 4)[:, 2].sum()) == int(ip64[-1])
+    A._WL_CACHE.clear()
+
+
 def test_the_double_is_gone_after_the_fixture():
     from maxk_b200 import _cabi
     assert _cabi._lib is None or "libmaxk_b200.so" in str(_cabi._lib._name)
