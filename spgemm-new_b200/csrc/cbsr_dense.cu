@@ -102,12 +102,14 @@ cbsr_matmul_kernel(const float *__restrict__ sp_data, const unsigned char *__res
     }
 }
 
-// 32 per-lane partial sums p[0..31] -> lane t ends with the warp total of p[t]
-// (halving exchange: 31 shuffles for 32 sums instead of 32 x 5)
-__device__ __forceinline__ float cd_transpose_reduce(float (&p)[32], int lane)
+// NB per-lane partial sums p[0..NB) -> every lane t ends with the warp total of p[t mod NB]
+// (halving exchange over the low lane bits: NB - 1 shuffles for NB sums instead of NB x 5; plain butterfly
+// adds over the remaining lane bits)
+template <int NB>
+__device__ __forceinline__ float cd_transpose_reduce(float (&p)[NB], int lane)
 {
 #pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
+    for (int half = NB / 2; half >= 1; half >>= 1) {
         const bool upper = (lane & half) != 0;
 #pragma unroll
         for (int i = 0; i < half; ++i) {
@@ -116,9 +118,15 @@ __device__ __forceinline__ float cd_transpose_reduce(float (&p)[32], int lane)
             p[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
         }
     }
-    return p[0];
+    float v = p[0];
+#pragma unroll
+    for (int bit = NB; bit < 32; bit <<= 1) v += __shfl_xor_sync(0xffffffffu, v, bit);
+    return v;
 }
 
+// NB = entries handled per exchange: 8 / 16 for k <= 8 / 16, else 32; the staged row is padded to a
+// multiple of NB with entries that contribute nothing, so the inner loop has no bounds test.
+template <int NB>
 __global__ void __launch_bounds__(CD_WARPS * 32, 1)
 cbsr_sampled_dot_kernel(const float *__restrict__ g, int64_t n, int c, const float *__restrict__ m, int d,
                         const unsigned char *__restrict__ sp_index, int k, float *__restrict__ out,
@@ -127,8 +135,10 @@ cbsr_sampled_dot_kernel(const float *__restrict__ g, int64_t n, int c, const flo
     extern __shared__ __align__(16) float cd_smem[];
     float *ms = cd_smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 *pr = reinterpret_cast<float2 *>(cd_smem + d * CD_TILE) + warp * k;
+    const int kpad = (k + NB - 1) / NB * NB;
+    float2 *pr = reinterpret_cast<float2 *>(cd_smem + d * CD_TILE) + warp * kpad;
     const int64_t gw = (int64_t)blockIdx.x * CD_WARPS + warp, stride = (int64_t)gridDim.x * CD_WARPS;
+    for (int j = k + lane; j < kpad; j += 32) pr[j] = make_float2(0.f, 0.f);  // padding, written once
 
     for (int col0 = 0; col0 < c; col0 += CD_TILE) {
         __syncthreads();
@@ -136,26 +146,24 @@ cbsr_sampled_dot_kernel(const float *__restrict__ g, int64_t n, int c, const flo
         __syncthreads();
         const int col = col0 + 4 * lane;
         const char *mt = reinterpret_cast<const char *>(ms + 4 * lane);
-        const bool first = (col0 == 0) && !accumulate;  // later tiles add to what the same warp wrote
+        const bool first = (col0 == 0) && !accumulate;  // later tiles add to what the same lane wrote
         for (int64_t row = gw; row < n; row += stride) {
             cd_stage_row(pr, nullptr, sp_index, row, k, d, lane, false);
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (col < c) g4 = __ldg(reinterpret_cast<const float4 *>(g + row * c + col));
             __syncwarp();
-            for (int j0 = 0; j0 < k; j0 += 32) {
-                float p[32];
+            for (int j0 = 0; j0 < kpad; j0 += NB) {
+                float p[NB];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    p[i] = 0.f;
-                    if (j0 + i < k) {  // warp-uniform
-                        const float4 w = *reinterpret_cast<const float4 *>(mt + __float_as_uint(pr[j0 + i].y));
-                        p[i] = fmaf(g4.x, w.x, fmaf(g4.y, w.y, fmaf(g4.z, w.z, g4.w * w.w)));
-                    }
+                for (int i = 0; i < NB; ++i) {
+                    const float4 w = *reinterpret_cast<const float4 *>(mt + __float_as_uint(pr[j0 + i].y));
+                    p[i] = fmaf(g4.x, w.x, fmaf(g4.y, w.y, fmaf(g4.z, w.z, g4.w * w.w)));
                 }
-                float tot = cd_transpose_reduce(p, lane);
-                if (j0 + lane < k) {
-                    if (pr[j0 + lane].x == 0.f) tot = 0.f;  // selector outside [0, d)
-                    float *o = out + row * k + j0 + lane;
+                float tot = cd_transpose_reduce<NB>(p, lane);
+                const int j = j0 + lane;
+                if (lane < NB && j < k) {
+                    if (pr[j].x == 0.f) tot = 0.f;  // selector outside [0, d)
+                    float *o = out + row * k + j;
                     *o = first ? tot : *o + tot;
                 }
             }
@@ -192,12 +200,28 @@ static int cd_check(const char *who, int64_t n, int k, int d, int c)
     return MAXK_OK;
 }
 
-static size_t cd_smem_bytes(int d, int k) { return (size_t)d * CD_TILE * 4 + (size_t)CD_WARPS * k * 8; }
+static size_t cd_smem_bytes(int d, int k, int nb = 1)
+{
+    return (size_t)d * CD_TILE * 4 + (size_t)CD_WARPS * ((k + nb - 1) / nb * nb) * 8;
+}
 
 static unsigned cd_grid(int64_t n)
 {
     const int64_t g = ceil_div<int64_t>(n, CD_WARPS);
     return (unsigned)(g < kNumSMs ? g : kNumSMs);
+}
+
+template <int NB>
+static int launch_sampled_dot(const float *g, int64_t n, int c, const float *m, int d, const uint8_t *sp_index, int k,
+                              float *out, int accumulate, void *stream)
+{
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void *>(&cbsr_sampled_dot_kernel<NB>),
+                                     "cbsr_sampled_dot_kernel"))
+        return rc;
+    cbsr_sampled_dot_kernel<NB><<<cd_grid(n), CD_WARPS * 32, cd_smem_bytes(d, k, NB), static_cast<cudaStream_t>(stream)>>>(
+        g, n, c, m, d, sp_index, k, out, accumulate);
+    MAXK_LAUNCH_CHECK("cbsr_sampled_dot_kernel");
+    return MAXK_OK;
 }
 
 }  // namespace maxk
@@ -230,12 +254,9 @@ extern "C" int maxk_cbsr_sampled_dot(const float *g, int64_t n, int32_t c, const
     MAXK_REQUIRE(g && sp_index && m && out, "maxk_cbsr_sampled_dot: NULL pointer");
     MAXK_REQUIRE(((reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(g)) & 15) == 0,
                  "maxk_cbsr_sampled_dot: m and g must be 16-byte aligned");
-    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void *>(&cbsr_sampled_dot_kernel), "cbsr_sampled_dot_kernel"))
-        return rc;
-    cbsr_sampled_dot_kernel<<<cd_grid(n), CD_WARPS * 32, cd_smem_bytes(d, k), static_cast<cudaStream_t>(stream)>>>(
-        g, n, c, m, d, sp_index, k, out, accumulate);
-    MAXK_LAUNCH_CHECK("cbsr_sampled_dot_kernel");
-    return MAXK_OK;
+    return k <= 8 ? launch_sampled_dot<8>(g, n, c, m, d, sp_index, k, out, accumulate, stream)
+           : k <= 16 ? launch_sampled_dot<16>(g, n, c, m, d, sp_index, k, out, accumulate, stream)
+                     : launch_sampled_dot<32>(g, n, c, m, d, sp_index, k, out, accumulate, stream);
 }
 
 extern "C" int maxk_cbsr_axpy(const float *sp_data, const uint8_t *sp_index, int64_t n, int32_t k, int32_t d,
