@@ -27,7 +27,6 @@ step 120 topk_probe_round2.log python scripts/topk_probe.py
 step 180 cbsr_linear_probe.jsonl python scripts/cbsr_linear_probe.py
 for model in sage gin gcn; do
   for v in 0 1; do
-    [ $model = gcn ] && [ $v = 1 ] && continue   # GCN has no dense twin to remove
     MAXK_CBSR_NATIVE=$v step 240 epoch_n1_${model}_native$v.json python scripts/train_epoch.py --shape products \
         --model $model --epochs 5 --warmup 2
   done

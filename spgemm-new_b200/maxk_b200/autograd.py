@@ -227,6 +227,41 @@ class CBSRAddScaled(Function):
         return grad_output, d_sp, None, d_eps
 
 
+class LinearTopKCBSR(Function):
+    """(sp_data, sp_index) = TopK_k(x @ weight^T + bias): the Linear in front of the MaxK of the GCN / GIN layers
+    (utils/models.py:318-322, 365-369) together with the selection.  The forward is the dense library GEMM
+    followed by the TopK kernel; what changes is the backward: the gradient that reaches the Linear's output is
+    k-sparse per row, so dX = scatter(g) @ weight is computed on the CBSR pair (N*k*in multiply-adds,
+    csrc/cbsr_dense.cu) instead of as a dense [N, D] x [D, in] GEMM.  dW and db use the scattered twin."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k):
+        y = torch.nn.functional.linear(x, weight, bias)
+        sp_data, sp_index = ops.topk_cbsr(y.contiguous(), k)
+        ctx.save_for_backward(x, weight, sp_index)
+        ctx.has_bias = bias is not None
+        ctx.mark_non_differentiable(sp_index)
+        return sp_data, sp_index
+
+    @staticmethod
+    def backward(ctx, g_data, _g_index):
+        x, weight, sp_index = ctx.saved_tensors
+        g_data = g_data.contiguous()
+        d_x = d_w = d_b = None
+        if ctx.needs_input_grad[0]:
+            if weight.shape[1] % 4 == 0:
+                d_x = ops.cbsr_matmul(g_data, sp_index, weight.detach().contiguous())   # rows of W picked by sel
+            else:
+                d_x = ops.cbsr_scatter(g_data, sp_index, weight.shape[0]) @ weight
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dense = ops.cbsr_scatter(g_data, sp_index, weight.shape[0])
+            if ctx.needs_input_grad[1]:
+                d_w = dense.t() @ x
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                d_b = dense.sum(0)
+        return d_x, d_w, d_b, None
+
+
 class TopKCBSR(Function):
     """x -> (sp_data, sp_index) with gradient dX = scatter(d sp_data, sp_index)."""
 

@@ -21,7 +21,7 @@ import torch.nn.functional as F
 import torch.nn.init as init
 from torch.nn import Linear
 
-from maxk_b200.autograd import (CBSRAddScaled, CBSRLinear, MaxK, SpGEMMFunction, TopKCBSR,  # noqa: F401  (re-exported like the reference)
+from maxk_b200.autograd import (CBSRAddScaled, CBSRLinear, LinearTopKCBSR, MaxK, SpGEMMFunction, TopKCBSR,  # noqa: F401  (re-exported like the reference)
                                 cbsr_native_enabled)
 from maxk_b200 import ops
 from torch.autograd import Function
@@ -52,6 +52,17 @@ def _sparsify(x, k, nonlinear, p, training):
     if p > 0 and training:
         sp_data = F.dropout(sp_data, p, True)
     return sp_data, sp_index
+
+
+def _linear_sparsify(lin, x, k, nonlinear, p, training):
+    """Linear -> MaxK -> dropout as CBSR; with MAXK_CBSR_NATIVE=1 (EXPERIMENTAL) the pair is one autograd
+    node whose backward computes dX on the CBSR gradient instead of as a dense GEMM."""
+    if nonlinear == "maxk" and cbsr_native_enabled():
+        sp_data, sp_index = LinearTopKCBSR.apply(x, lin.weight, lin.bias, k)
+        if p > 0 and training:
+            sp_data = F.dropout(sp_data, p, True)
+        return sp_data, sp_index
+    return _sparsify(lin(x), k, nonlinear, p, training)
 
 
 class _Base(nn.Module):
@@ -119,8 +130,7 @@ class GCN(_Base):
     def forward(self, g, x):
         x = self.lin_in(x).relu()
         for i in range(self.num_layers):
-            x = self.linlayers[i](x)
-            sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
+            sp_data, sp_index = _linear_sparsify(self.linlayers[i], x, self.maxk, self.nonlinear, self.p, self.training)
             x = g.aggregate(sp_data, sp_index, "gcn", self.hid) + self.conv_bias[i]
             x = self.normlayers[i](x)
         return self.lin_out(x)
@@ -141,8 +151,7 @@ class GIN(_Base):
     def forward(self, g, x):
         x = self.lin_in(x).relu()
         for i in range(self.num_layers):
-            x = self.linlayers[i](x)
-            sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
+            sp_data, sp_index = _linear_sparsify(self.linlayers[i], x, self.maxk, self.nonlinear, self.p, self.training)
             if cbsr_native_enabled():   # EXPERIMENTAL: self term added to the aggregate in place, no dense twin
                 x = CBSRAddScaled.apply(g.aggregate(sp_data, sp_index, "sum", self.hid), sp_data, sp_index, self.eps[i])
             else:

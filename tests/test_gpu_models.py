@@ -56,7 +56,7 @@ def _ref_forward(model, kind, A, x, k):
 @pytest.mark.skipif(__import__("os").environ.get("MAXK_EXPERIMENTAL") != "1",
                     reason="layers on the CBSR operand (MAXK_CBSR_NATIVE, csrc/cbsr_dense.cu): written after round 1's GPU "
                            "budget was spent, checked under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
-@pytest.mark.parametrize("name", ["SAGE", "GIN"])
+@pytest.mark.parametrize("name", ["SAGE", "GIN", "GCN"])
 def test_models_on_the_cbsr_operand_experimental(name, monkeypatch):
     monkeypatch.setenv("MAXK_CBSR_NATIVE", "1")
     test_models_match_dense_restatement(name, 2, True)

@@ -224,7 +224,29 @@ def test_cbsr_add_scaled_function_matches_the_dense_expression(ops):
         torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-5, msg=lambda m, w=what: f"{w}: {m}")
 
 
-@pytest.mark.parametrize("name", ["SAGE", "GIN"])
+def test_linear_topk_function_matches_linear_then_topk(ops):
+    """EXPERIMENTAL LinearTopKCBSR: same CBSR pair and same gradients of x, W, b as Linear followed by TopKCBSR."""
+    from maxk_b200.autograd import LinearTopKCBSR, TopKCBSR
+    torch.manual_seed(9)
+    x0 = torch.randn(70, 48)
+    lin = torch.nn.Linear(48, 256)
+    g = torch.randn(70, 32)
+    outs = []
+    for fused in (False, True):
+        x = x0.clone().requires_grad_(True)
+        lin.zero_grad()
+        if fused:
+            sp_data, sp_index = LinearTopKCBSR.apply(x, lin.weight, lin.bias, 32)
+        else:
+            sp_data, sp_index = TopKCBSR.apply(lin(x), 32)
+        sp_data.backward(g)
+        outs.append((sp_data.detach(), sp_index, x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone()))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+    for a, b, what in zip(outs[0][2:], outs[1][2:], ("dx", "dW", "db")):
+        torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5, msg=lambda m, w=what: f"{w}: {m}")
+
+
+@pytest.mark.parametrize("name", ["SAGE", "GIN", "GCN"])
 def test_train_step_same_with_layers_on_the_cbsr_operand(ops, monkeypatch, name):
     import utils.models as M
     p, g = _problem(n=80, avg=8.0, k=8, seed=5, empty_frac=0.0)
