@@ -9,13 +9,15 @@ graph (N = 232 965, E = 114 615 892, hidden 256, k = 32): one STEP = one forward
 SpGEMM  Y = A * X_cbsr  plus one backward sampled SSpMM  dXc = sample(A^T dY).
    value    = (B_fwd + B_bwd) / device time, inputs resident in HBM   
    e2e      = same bytes / time of HostAggregator.step() on pinned HOST buffers
-              (H2D X and dY, TopK, both kernels, D2H Y and dXc inside the timed region)
+              (H2D X and dY, TopK, both kernels, D2H Y and dXc inside the timed region); at N > 1 every rank
+              does that for its own rows through ShardHostAggregator.step() (max over ranks)
    roofline = dominant kernel's algorithmic GB/s against MEASURED_PEAKS.json's HBM figure
    cpu_baseline = the reference's CPU path (torch.topk + CSR SpMM, oracle/cpu_path.py) on a
               bounded row-sample of the same graph, on this box's host cores
 N > 1: the adjacency is 1-D row-partitioned (balanced by nnz) over the ranks; every step
-all-gathers the CBSR features and reduce-scatters the CBSR-shaped partial gradients with
-NCCL (strong scaling: the graph is fixed).
+exchanges the CBSR features and reduce-scatters the CBSR-shaped partial gradients -- with our own
+kernels over NVLink peer memory (--comm peer, default) or NCCL collectives (--comm nccl); strong
+scaling: the graph is fixed.
 `--impl reference` times the reference's CPU implementation of the same step on a bounded
 sample (rank 0 only).  One JSON line on stdout; everything else goes to stderr.
 """
@@ -454,8 +456,46 @@ def main():
                            "(ms_per_step_synchronous = HostAggregator.step, one at a time)"}
         log(f"[e2e] pipelined {e_ms:.2f} ms/step  {e2e['value']:.0f} GB/s   synchronous {sync_ms:.2f} ms/step")
         del host, xh, dyh
-    elif world > 1:
-        e2e = None
+    elif world > 1 and not args.no_e2e:
+        # every rank: its own rows from pinned host memory in, its own rows of Y and dXc back out, through
+        # maxk_b200.host.ShardHostAggregator (upload, TopK in place, exchange, forward, backward + reduce-scatter,
+        # download; results valid on return).  Set-up is agreed on by all ranks before anybody enters a step.
+        ok = 1
+        try:
+            from maxk_b200.host import ShardHostAggregator
+            shard = ShardHostAggregator(agg)
+            xh = x_loc.cpu().pin_memory()
+            dyh = dy_loc.cpu().pin_memory()
+        except Exception as exc:  # noqa: BLE001
+            log(f"[rank {rank}] e2e set-up failed: {exc}")
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 1:
+            e_steps = max(3, min(args.steps, 10))
+            for _ in range(2):
+                shard.step(xh, dyh)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                shard.step(xh, dyh)
+            torch.cuda.synchronize()
+            e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+            tmax = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            nbytes = torch.tensor([shard.h2d_bytes, shard.d2h_bytes], device=dev, dtype=torch.int64)
+            dist.all_reduce(nbytes)
+            e_ms = float(tmax)
+            e2e = {"value": step_bytes / (e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_ms,
+                   "h2d_bytes_per_step": int(nbytes[0]), "d2h_bytes_per_step": int(nbytes[1]), "steps": e_steps,
+                   "includes": f"per step and rank (max over {world} ranks, wall clock between synchronisations): H2D of "
+                               "the rank's X and dY rows (pinned), TopK->CBSR in place, exchange, forward, backward + "
+                               "reduce-scatter, D2H of its Y and dXc rows; ShardHostAggregator.step, one step at a time; "
+                               "bytes are summed over the ranks"}
+            log(f"[e2e] {e_ms:.2f} ms/step  {e2e['value']:.0f} GB/s over {world} ranks")
+            del shard, xh, dyh
 
     # ------------------------------------------------------------------ CPU baseline leg
     cpu_baseline = None

@@ -8,7 +8,7 @@ first operator call does, and fails loudly if it is missing.
 from . import _cabi, ops  # noqa: F401
 from .autograd import CBSRAddScaled, CBSRAggregate, CBSRLinear, LinearTopKCBSR, MaxK, SpGEMMFunction, TopKCBSR, worklist_for  # noqa: F401
 
-from .host import HostAggregator  # noqa: F401,E402
+from .host import HostAggregator, ShardHostAggregator  # noqa: F401,E402
 
 __all__ = ["ops", "MaxK", "SpGEMMFunction", "CBSRAggregate", "CBSRLinear", "CBSRAddScaled", "LinearTopKCBSR", "TopKCBSR", "worklist_for",
-           "HostAggregator"]
+           "HostAggregator", "ShardHostAggregator"]

@@ -150,3 +150,44 @@ class HostAggregator:
     def step(self, x_host: torch.Tensor, dy_host: torch.Tensor):
         """Synchronous form: results are valid on return."""
         return self.result(self.submit(x_host, dy_host))
+
+
+class ShardHostAggregator:
+    """Host-buffer entry point of ONE RANK of a row-partitioned job (one process per GPU): wraps a
+    `peer.PeerAggregator` or `dist.DistAggregator` and runs one forward + backward of the MaxK aggregation
+    on this rank's HOST rows:
+
+        y_host_loc, dxc_host_loc = shard.step(x_host_loc, dy_host_loc)
+
+    Per step: upload of the rank's X and dY rows (pinned buffers for full speed), TopK -> CBSR in place,
+    exchange with the other ranks, forward, download of Y behind the backward's launch, backward +
+    reduce-scatter, download of dXc; results are valid on return.  Every GPU uses its own PCIe link, so
+    the host traffic of the job (the same bytes as on one GPU) is spread over all of them.
+    This is what bench.py reports as `e2e` at N > 1."""
+
+    def __init__(self, agg):
+        self.agg = agg
+        dev = agg.y.device
+        self.device = dev
+        n_loc, d, k = int(agg.n_local), int(agg.d), int(agg.k)
+        pin = dev.type == "cuda"
+        self.x_d = torch.empty((n_loc, d), dtype=torch.float32, device=dev)
+        self.dy_d = torch.empty((n_loc, d), dtype=torch.float32, device=dev)
+        self.y_h = torch.empty((n_loc, d), dtype=torch.float32, pin_memory=pin)
+        self.dxc_h = torch.empty((n_loc, k), dtype=torch.float32, pin_memory=pin)
+        self.h2d_bytes = 2 * n_loc * d * 4
+        self.d2h_bytes = n_loc * (d + k) * 4
+
+    def step(self, x_host: torch.Tensor, dy_host: torch.Tensor):
+        """x_host, dy_host: f32[n_local, d] host tensors (this rank's rows).  Returns (y f32[n_local, d],
+        dxc f32[n_local, k]) in pinned host buffers owned by the object, valid until the next step."""
+        self.x_d.copy_(x_host, non_blocking=True)
+        self.dy_d.copy_(dy_host, non_blocking=True)
+        g_data, g_index = self.agg.topk_and_exchange(self.x_d)
+        y = self.agg.forward(g_data, g_index)
+        self.y_h.copy_(y, non_blocking=True)
+        dxc = self.agg.backward(self.dy_d, g_index)
+        self.dxc_h.copy_(dxc, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        return self.y_h, self.dxc_h

@@ -89,6 +89,13 @@ def _worker(rank, world, port, split, q):
         g_data, g_index = agg.topk_and_exchange(torch.from_numpy(x[lo:hi]))
         y = agg.forward(g_data, g_index).clone()
         dxc = agg.backward(torch.from_numpy(dy[lo:hi]), g_index).clone()
+        # the per-rank host-buffer entry point (what bench.py times as e2e at N > 1): same results, twice
+        from maxk_b200.host import ShardHostAggregator
+        shard = ShardHostAggregator(agg)
+        assert shard.h2d_bytes == 2 * (hi - lo) * d * 4 and shard.d2h_bytes == (hi - lo) * (d + k) * 4
+        for _ in range(2):
+            y_h, dxc_h = shard.step(torch.from_numpy(x[lo:hi]), torch.from_numpy(dy[lo:hi]))
+            assert torch.equal(y_h, y) and torch.equal(dxc_h, dxc)
         q.put((rank, bounds, y.numpy(), dxc.numpy(), agg.num_tasks))
     finally:
         dist.destroy_process_group()

@@ -381,6 +381,39 @@ def test_peer_kernels_multi_rank_under_the_interpreter(peer_group, world, k, hal
 
 
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,k,halo", [(2, 32, 0.0), (3, 16, 2.0)])
+def test_shard_host_aggregator_over_the_peer_path(peer_group, world, k, halo):
+    """ShardHostAggregator.step (host rows in, host rows out; what bench.py times as e2e at N > 1): every rank
+    runs its whole step -- TopK in place, push, fused forward, backward, pull reduce-scatter -- in its own
+    thread, three steps in a row."""
+    from maxk_b200.dist import partition_rows_by_nnz
+    from maxk_b200.host import ShardHostAggregator
+    make, pool = peer_group
+    p, g = _problem(n=96 * world, avg=14.0, k=k, seed=world * 7 + k, empty_frac=0.1)
+    bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
+    shards = [ShardHostAggregator(a) for a in make(p, g, bounds, k, halo, 2)]
+    assert sum(s.h2d_bytes for s in shards) == 2 * p.n * p.d * 4
+    assert sum(s.d2h_bytes for s in shards) == p.n * (p.d + k) * 4
+    rng = np.random.default_rng(k)
+    for step in range(3):
+        x = rng.random((p.n, p.d), dtype=np.float32)
+        dy = rng.random((p.n, p.d), dtype=np.float32)
+        sd, si = O.topk_cbsr(x, k)
+        want_y = O.spgemm_forward(p.w4, p.idx, p.val, sd, si, p.d, n_out=p.n)
+        want_g = O.sspmm_backward(p.w4, p.idx, p.val, dy, si)
+
+        def run(r):
+            lo, hi = bounds[r], bounds[r + 1]
+            y, gr = shards[r].step(_t(x[lo:hi]), _t(dy[lo:hi]))
+            return y.clone(), gr.clone()
+
+        outs = list(pool.map(run, range(world)))
+        for r in range(world):
+            close(outs[r][0], want_y[bounds[r]:bounds[r + 1]], f"Y, step {step}, rank {r}")
+            close(outs[r][1], want_g[bounds[r]:bounds[r + 1]], f"dXc, step {step}, rank {r}")
+
+
+@pytest.mark.timeout(600)
 @pytest.mark.parametrize("world,k,halo,homes,copy_ctas", [(2, 32, 0.0, 8, 3), (3, 32, 0.3, 2, -2), (2, 64, 2.0, 4, 2),
                                                           (2, 16, 0.0, 4, 2), (3, 8, 2.0, 2, -1), (4, 32, 0.0, 4, 1)])
 def test_peer_planned_kernels_multi_rank_under_the_interpreter(peer_group, world, k, halo, homes, copy_ctas):
