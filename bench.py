@@ -217,8 +217,11 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "reddit-shaped SpGEMM+SSpMM k=%d hidden 256 (bounded row sample on CPU)" % args.k,
-                           "k": args.k, "feat_dim": FEAT_DIM, "graph_scale": scale},
+                # the own arm's workload, word for word; what the CPU actually ran per step is in `sample`
+                "config": {"workload": f"reddit-shaped graph N={g['v_num']} E={g['e_num']}: forward SpGEMM + backward "
+                                       f"SSpMM, k={args.k}, hidden {FEAT_DIM}",
+                           "k": args.k, "feat_dim": FEAT_DIM, "graph_scale": scale,
+                           "sample": "bounded row sample of that graph on the host cores: " + info["sample"]},
                 "cpu_baseline": info,
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
