@@ -377,6 +377,33 @@ def main():
                           "edges_per_s": e / (bwd_ms * 1e-3)}}
         log(f"[own] fwd {fwd_ms:.3f} ms  bwd {bwd_ms:.3f} ms  step {ms_per_step:.3f} ms  "
             f"{value:.0f} GB/s  roofline {dom} {roofline['frac']:.3f} of {peak_src} peak")
+    elif not args.no_e2e:
+        # N > 1: forward and backward of a few extra steps timed apart (CUDA events on every rank, max over
+        # ranks); the roofline is PER GPU -- each rank's share of the algorithmic bytes against one GPU's peak
+        reps, f_ms, b_ms = 5, 0.0, 0.0
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for _ in range(reps):
+            gd, gi = agg.exchange(sd_loc, si_loc, sa_loc) if planned_peer else agg.exchange(sd_loc, si_loc)
+            evs[0].record()
+            agg.forward(gd, gi)
+            evs[1].record()
+            agg.backward(dy_loc, gi)
+            evs[2].record()
+            torch.cuda.synchronize()
+            f_ms += evs[0].elapsed_time(evs[1]) / reps
+            b_ms += evs[1].elapsed_time(evs[2]) / reps
+        tt = torch.tensor([f_ms, b_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        fwd_ms, bwd_ms = float(tt[0]), float(tt[1])
+        dom, dom_ms, dom_bytes = (("spgemm_fwd_fused" if comm == "peer" else "spgemm_fwd", fwd_ms, bytes_["fwd"] / world)
+                                  if fwd_ms >= bwd_ms else ("sspmm_bwd+reduce_scatter", bwd_ms, bytes_["bwd"] / world))
+        ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "peak_source": f"of {peak_src}", "traffic": None, "algorithmic_bytes": dom_bytes, "ms": dom_ms,
+                    "per_gpu": True, "note": "per GPU: 1/N of the job's algorithmic bytes over the slowest rank's phase "
+                                             "(exchange waits included), against one GPU's peak"}
+        extra["kernels"] = {"forward_phase_ms": fwd_ms, "backward_phase_ms": bwd_ms}
+        log(f"[own] N={world}: forward phase {fwd_ms:.3f} ms  backward phase {bwd_ms:.3f} ms  (max over ranks)")
     extra["edges_per_s"] = 2 * e / (ms_per_step * 1e-3)
     extra["num_tasks"] = w
 
