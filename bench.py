@@ -498,7 +498,7 @@ def main():
         ok = 1
         try:
             from maxk_b200.host import ShardHostAggregator
-            shard = ShardHostAggregator(agg)
+            shard = ShardHostAggregator(agg, overlap=os.environ.get("MAXK_SHARD_OVERLAP", "0") == "1")
             xh = x_loc.cpu().pin_memory()
             dyh = dy_loc.cpu().pin_memory()
         except Exception as exc:  # noqa: BLE001
@@ -528,8 +528,9 @@ def main():
                        "h2d_bytes_per_step": int(nbytes[0]), "d2h_bytes_per_step": int(nbytes[1]), "steps": e_steps,
                        "includes": f"per step and rank (max over {world} ranks, wall clock between synchronisations): H2D of "
                                    "the rank's X and dY rows (pinned), TopK->CBSR in place, exchange, forward, backward + "
-                                   "reduce-scatter, D2H of its Y and dXc rows; ShardHostAggregator.step, one step at a time; "
-                                   "bytes are summed over the ranks"}
+                                   "reduce-scatter, D2H of its Y and dXc rows; ShardHostAggregator.step, one step at a time"
+                                   + (" (EXPERIMENTAL overlap of the dY upload / Y download with the kernels)" if shard.overlap else "")
+                                   + "; bytes are summed over the ranks"}
                 log(f"[e2e] {e_ms:.2f} ms/step  {e2e['value']:.0f} GB/s over {world} ranks")
                 del shard, xh, dyh
             except Exception as exc:  # noqa: BLE001

@@ -43,7 +43,8 @@ done
 step 240 epoch_proteins_default.json python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2
 MAXK_PLANNED_HOMES=8 step 240 epoch_proteins_planned8.json python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2
 MAXK_PLANNED_HOMES=auto step 240 epoch_proteins_auto.json python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2
-# (with 2 or 8 GPUs: `torchrun ... bench.py --gpus N --planned 8` runs the planned kernels on the peer transport)
+# (with 2 or 8 GPUs: `torchrun ... bench.py --gpus N --planned 8` runs the planned kernels on the peer transport;
+#  `MAXK_SHARD_OVERLAP=1 torchrun ... bench.py --gpus N` times the e2e leg with the overlapped ShardHostAggregator)
 # 7. ncu of the planned kernels (only after the runs above exited without ncu): launch list + one full capture each
 step 300 ncu_planned_list.log ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
      --log-file $O/launches_planned.csv python scripts/profile_step.py --planned 8 --iters 2

@@ -163,9 +163,12 @@ class ShardHostAggregator:
     exchange with the other ranks, forward, download of Y behind the backward's launch, backward +
     reduce-scatter, download of dXc; results are valid on return.  Every GPU uses its own PCIe link, so
     the host traffic of the job (the same bytes as on one GPU) is spread over all of them.
-    This is what bench.py reports as `e2e` at N > 1."""
+    This is what bench.py reports as `e2e` at N > 1.
+    overlap=True (EXPERIMENTAL, unmeasured; CUDA only): the dY upload runs on a copy stream behind the forward and
+    the Y download on another one behind the backward, like HostAggregator does on one GPU; the aggregator's
+    own work stays on the caller's stream."""
 
-    def __init__(self, agg):
+    def __init__(self, agg, overlap: bool = False):
         self.agg = agg
         dev = agg.y.device
         self.device = dev
@@ -177,10 +180,40 @@ class ShardHostAggregator:
         self.dxc_h = torch.empty((n_loc, k), dtype=torch.float32, pin_memory=pin)
         self.h2d_bytes = 2 * n_loc * d * 4
         self.d2h_bytes = n_loc * (d + k) * 4
+        self.overlap = bool(overlap) and pin
+        if self.overlap:
+            self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def _step_overlapped(self, x_host, dy_host):
+        cur = torch.cuda.current_stream(self.device)
+        self.s_in.wait_stream(cur)   # whatever read x_d / dy_d before (it ran on the caller's stream) is done
+        with torch.cuda.stream(self.s_in):
+            self.x_d.copy_(x_host, non_blocking=True)
+            ev_x = torch.cuda.Event()
+            ev_x.record(self.s_in)
+            self.dy_d.copy_(dy_host, non_blocking=True)
+            ev_dy = torch.cuda.Event()
+            ev_dy.record(self.s_in)
+        cur.wait_event(ev_x)
+        g_data, g_index = self.agg.topk_and_exchange(self.x_d)
+        y = self.agg.forward(g_data, g_index)
+        ev_y = torch.cuda.Event()
+        ev_y.record(cur)
+        with torch.cuda.stream(self.s_out):   # Y goes home while the backward runs (the backward does not touch y)
+            self.s_out.wait_event(ev_y)
+            self.y_h.copy_(y, non_blocking=True)
+        cur.wait_event(ev_dy)
+        dxc = self.agg.backward(self.dy_d, g_index)
+        self.dxc_h.copy_(dxc, non_blocking=True)
+        cur.synchronize()
+        self.s_out.synchronize()
+        return self.y_h, self.dxc_h
 
     def step(self, x_host: torch.Tensor, dy_host: torch.Tensor):
         """x_host, dy_host: f32[n_local, d] host tensors (this rank's rows).  Returns (y f32[n_local, d],
         dxc f32[n_local, k]) in pinned host buffers owned by the object, valid until the next step."""
+        if self.overlap:
+            return self._step_overlapped(x_host, dy_host)
         self.x_d.copy_(x_host, non_blocking=True)
         self.dy_d.copy_(dy_host, non_blocking=True)
         g_data, g_index = self.agg.topk_and_exchange(self.x_d)
