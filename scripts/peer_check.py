@@ -60,6 +60,26 @@ for shape, scale, k, halo in cases:
             print(f"peer {shape} k={k} world={world} step {step}: fwd {e1} bwd {e2} all-ranks {bool(flag.item())}",
                   flush=True)
         ok = ok and bool(flag.item())
+    # the host-buffer entry point of a rank (bench.py's e2e at N > 1): one stream, then with the copy overlap
+    from maxk_b200.host import ShardHostAggregator
+    for overlap in (False, True):
+        shard = ShardHostAggregator(agg, overlap=overlap)
+        for step in range(3):
+            x = torch.rand(n, 256, device=dev, generator=torch.Generator(dev).manual_seed(70 + step))
+            dy = torch.rand(n, 256, device=dev, generator=torch.Generator(dev).manual_seed(80 + step))
+            sd, si = ops.topk_cbsr(x, k)
+            y_ref = ops.spgemm_forward(w4, g["indices"], g["values"], sd, si, num_rows=n)
+            g_ref = ops.sspmm_backward(w4, g["indices"], g["values"], dy, si)
+            y_h, dxc_h = shard.step(x[lo:hi].cpu().pin_memory(), dy[lo:hi].cpu().pin_memory())
+            e1 = torch.allclose(y_h, y_ref[lo:hi].cpu(), rtol=1e-5, atol=1e-6)
+            e2 = torch.allclose(dxc_h, g_ref[lo:hi].cpu(), rtol=1e-5, atol=1e-6)
+            flag = torch.tensor([int(e1 and e2)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(f"shard-host {shape} k={k} world={world} overlap={overlap} step {step}: fwd {e1} bwd {e2} "
+                      f"all-ranks {bool(flag.item())}", flush=True)
+            ok = ok and bool(flag.item())
+        del shard
     agg.close()
     del agg
 
