@@ -19,6 +19,11 @@ run 300 29704 bench.py --gpus $N --steps 40 --warmup 5 --comm nccl > $O/scale_nc
 echo "bench nccl rc=$?"
 run 300 29705 bench.py --gpus $N --steps 40 --warmup 5 --planned 8 > $O/scale_peer_planned8_n$N.json 2> $O/bench_planned_$N.err
 echo "bench peer planned rc=$?"
+for v in 0 1; do
+  MAXK_CBSR_NATIVE=$v run 400 2971$v scripts/train_epoch.py --shape products --model sage --epochs 5 --warmup 2 --comm peer \
+      2> $O/epoch_n${N}_native$v.err | grep "^{" > $O/epoch_n${N}_sage_native$v.json
+  echo "epoch N=$N MAXK_CBSR_NATIVE=$v: $(cut -c1-160 $O/epoch_n${N}_sage_native$v.json)"
+done
 python - <<'PY'
 import glob, json
 for p in sorted(glob.glob("gpurun_out/scale_*_n*.json")):
