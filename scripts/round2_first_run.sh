@@ -52,3 +52,10 @@ step 400 ncu_fwd_planned.log ncu --set full --clock-control none --import-source
      -f -o $O/prof_fwd_planned8 python scripts/profile_step.py --planned 8 --iters 2
 step 400 ncu_bwd_planned.log ncu --set full --clock-control none --import-source on -k regex:sspmm_bwd_planned -s 1 -c 1 \
      -f -o $O/prof_bwd_planned8 python scripts/profile_step.py --planned 8 --iters 2
+# ... and of the other new kernels: the CBSR x dense products and the rows-per-warp TopK
+step 400 ncu_cbsr_matmul.log ncu --set full --clock-control none --import-source on -k regex:cbsr_matmul_kernel -s 2 -c 1 \
+     -f -o $O/prof_cbsr_matmul python scripts/cbsr_linear_probe.py --ks 32 --iters 2
+step 400 ncu_cbsr_sampled_dot.log ncu --set full --clock-control none --import-source on -k regex:cbsr_sampled_dot_kernel -s 2 -c 1 \
+     -f -o $O/prof_cbsr_sampled_dot python scripts/cbsr_linear_probe.py --ks 32 --iters 2
+TOPK_RPW=4 step 300 ncu_topk_rows.log ncu --set full --clock-control none --import-source on -k regex:topk_cbsr_f32_rows_kernel -s 1 -c 1 \
+     -f -o $O/prof_topk_rows4 python scripts/topk_probe.py quick

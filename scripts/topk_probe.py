@@ -21,7 +21,8 @@ dists = (("uniform", torch.rand(n, 256, device="cuda", generator=g)),
          ("quantised", (torch.rand(n, 256, device="cuda", generator=g) * 8).floor()))
 for name, x in dists:
     for k in (8, 32, 64):
-        if quick:
+        if quick:   # for ncu: one launch per (distribution, k); TOPK_RPW=4 selects the rows-per-warp kernel
+            ops.set_topk_rows_per_warp(int(os.environ.get("TOPK_RPW", "0")))
             ops.topk_cbsr(x, k); continue
         b = 4 * n * 256 + 5 * n * k
         for rpw in (0, 2, 4, 8):  # 0 = default kernel; > 1 = experimental rows-per-warp kernel
