@@ -25,7 +25,7 @@ done
 step 120 topk_probe_round2.log python scripts/topk_probe.py
 # 4. SURVEY 8(f) rank 3: fc_self / GIN self term on the CBSR operand vs torch's dense fp32 path
 step 180 cbsr_linear_probe.jsonl python scripts/cbsr_linear_probe.py
-for model in sage gin gcn; do
+for model in sage; do
   for v in 0 1; do
     MAXK_CBSR_NATIVE=$v step 240 epoch_n1_${model}_native$v.json python scripts/train_epoch.py --shape products \
         --model $model --epochs 5 --warmup 2
@@ -42,7 +42,6 @@ for h in 2 4 8; do
 done
 step 240 epoch_proteins_default.json python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2
 MAXK_PLANNED_HOMES=8 step 240 epoch_proteins_planned8.json python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2
-MAXK_PLANNED_HOMES=auto step 240 epoch_proteins_auto.json python scripts/train_epoch.py --shape proteins --model gin --k 64 --epochs 5 --warmup 2
 # (with 2 or 8 GPUs: `torchrun ... bench.py --gpus N --planned 8` runs the planned kernels on the peer transport;
 #  `MAXK_SHARD_OVERLAP=1 torchrun ... bench.py --gpus N` times the e2e leg with the overlapped ShardHostAggregator)
 # 7. ncu of the planned kernels (only after the runs above exited without ncu): launch list + one full capture each
