@@ -18,8 +18,14 @@ N > 1: the adjacency is 1-D row-partitioned (balanced by nnz) over the ranks; ev
 exchanges the CBSR features and reduce-scatters the CBSR-shaped partial gradients -- with our own
 kernels over NVLink peer memory (--comm peer, default) or NCCL collectives (--comm nccl); strong
 scaling: the graph is fixed.
+   epoch    = (extra leg, after the timed region) full-graph training epochs/s of GraphSAGE MaxK k=32, 3 x 256,
+              LayerNorm, Adam on the ogbn-products-shaped graph (BASELINE.json configs[2]) at the N of the run --
+              the second half of BASELINE.json's metric; maxk_b200.train.run_epochs
+   parity_ok = (N > 1, outside the timed region) every rank checks its rows of Y and dXc of one step against the
+              single-GPU kernels run on the gathered operands
 `--impl reference` times the reference's CPU implementation of the same step on a bounded
-sample (rank 0 only).  One JSON line on stdout; everything else goes to stderr.
+sample (rank 0 only) and, on a GPU box, the reference's own CUDA kernels (oracle/_ref, kernels/*.cu compiled
+unmodified for sm_100a) on the full graph.  One JSON line on stdout; everything else goes to stderr.
 """
 from __future__ import annotations
 
@@ -180,6 +186,91 @@ def run_cpu_reference(g, k, steps, warmup, target_step_s=2.0):
                       f"fp32, {cores} threads",
             "ms_per_step": ms, "edges_per_s": s["e"] * 2 / (ms * 1e-3)}
     return value, ms, info
+
+
+def timeit_events(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def time_reference_kernels(g, k, dev):
+    """The reference's CUDA kernels (oracle/_ref: kernels/spmm_maxk.cu, spmm_maxk_backward.cu compiled unmodified
+    for sm_100a, reference launch shape 12 warps / CTA) on the full graph of the bench, reference protocol
+    (4 + 4 launches, outputs not re-zeroed: spmm_base.h:56-74).  None if there is no GPU or no oracle/_ref."""
+    if not torch.cuda.is_available():
+        return None
+    try:
+        from maxk_b200 import ops
+        from oracle import ref_kernels as R
+        if not R.available():
+            return None
+        n = g["v_num"]
+        warp4 = ops.build_worklist(g["indptr"])
+        gen = torch.Generator(dev).manual_seed(123)
+        x = torch.rand(n, FEAT_DIM, device=dev, generator=gen)
+        dy = torch.rand(n, FEAT_DIM, device=dev, generator=gen)
+        sp_data, sp_index = ops.topk_cbsr(x, k)
+        yr = torch.zeros(n, FEAT_DIM, device=dev)
+        dr = torch.zeros(n, k, device=dev)
+        tf = timeit_events(lambda: R.spmm_forward(warp4, g["indices"], g["values"], sp_data, sp_index, FEAT_DIM, out=yr), 4, 4)
+        tb = timeit_events(lambda: R.spmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dr), 4, 4)
+        return {"fwd_ms": tf, "bwd_ms": tb, "ms_per_step": tf + tb,
+                "note": "the reference's kernels/*.cu compiled unmodified for sm_100a (oracle/_ref), reference launch "
+                        "shape, full graph, outputs not re-zeroed (reference protocol, spmm_base.h:56-74)"}
+    except Exception as exc:  # noqa: BLE001
+        log("reference kernels on this GPU: skipped:", exc)
+        return None
+
+
+def multi_gpu_parity(agg, g, bounds, rank, world, k, dev, sd_loc, si_loc, dy_loc, dist, ops):
+    """One more step of the N-GPU job, outside the timed region, checked on EVERY rank against the single-GPU
+    kernels: the ranks' CBSR blocks and dY rows are gathered with plain broadcasts, each rank runs the one-GPU
+    forward and backward on the full graph and compares its own rows.  Tolerance: north-star rtol 1e-5 / atol 1e-6,
+    widened to the fp32 summation bound (fan-in + 2) * 2^-24 * sum|terms| where a row has thousands of terms (all
+    terms are non-negative here, so sum|terms| = |reference|)."""
+    n = g["v_num"]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    gsd = torch.empty((n, k), dtype=torch.float32, device=dev)
+    gsi = torch.empty((n, k), dtype=torch.uint8, device=dev)
+    gdy = torch.empty((n, FEAT_DIM), dtype=torch.float32, device=dev)
+    gsd[lo:hi], gsi[lo:hi], gdy[lo:hi] = sd_loc, si_loc, dy_loc
+    for r in range(world):
+        a, b = bounds[r], bounds[r + 1]
+        if b > a:
+            for t in (gsd, gsi, gdy):
+                dist.broadcast(t[a:b], src=r)
+    gd, gi = agg.exchange(sd_loc, si_loc)
+    y = agg.forward(gd, gi).clone()
+    dxc = agg.backward(dy_loc, gi).clone()
+    warp4 = ops.build_worklist(g["indptr"])
+    y_ref = ops.spgemm_forward(warp4, g["indices"], g["values"], gsd, gsi, num_rows=n)[lo:hi]
+    dxc_ref = ops.sspmm_backward(warp4, g["indices"], g["values"], gdy, gsi)[lo:hi]
+    deg = (g["indptr"][1:] - g["indptr"][:-1])[lo:hi].double()
+    col_deg = torch.bincount(g["indices"].long(), minlength=n)[lo:hi].double()
+
+    def excess(got, ref, fan):
+        got, ref = got.double(), ref.double()
+        allowed = torch.maximum(1e-6 + 1e-5 * ref.abs(), (fan[:, None] + 2.0) * 2.0 ** -24 * ref.abs())
+        err = (got - ref).abs()
+        strict = (err <= 1e-6 + 1e-5 * ref.abs()).double().mean()
+        return float((err - allowed).max()), float(err.max()), float(strict)
+    ey, ay, sy = excess(y, y_ref, deg)
+    eg, ag, sg = excess(dxc, dxc_ref, col_deg)
+    t = torch.tensor([max(ey, eg), ay, ag, -sy, -sg], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"parity_ok": bool(float(t[0]) <= 0.0), "max_abs_err_y": float(t[1]), "max_abs_err_dxc": float(t[2]),
+            "frac_within_rtol1e-5_atol1e-6": {"y": -float(t[3]), "dxc": -float(t[4])},
+            "checked": f"every rank: its rows of Y and dXc of one extra step (fused push all-gather + SpGEMM, SSpMM + pull "
+                       f"reduce-scatter at N={world}) against the single-GPU kernels on the gathered operands; tolerance "
+                       "rtol 1e-5 / atol 1e-6 widened to the fp32 summation bound (fan-in + 2) * 2^-24 * |ref|"}
 
 
 def main():

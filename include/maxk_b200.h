@@ -64,10 +64,10 @@ MAXK_API int maxk_set_tuning(int fwd_tasks_per_warp, int bwd_tasks_per_warp);
  * to an instantiated value and up to the edges-per-instruction count); 0 = automatic. */
 MAXK_API int maxk_set_forward_copies(int copies);
 /* Bench/test hook: launch shape of the forward kernel (1 = 8-warp CTAs, 2 = 2-warp CTAs,
- * 3 = 8-warp CTAs with twice the gathers in flight; experimental and never chosen automatically:
- * 4-7 = double-buffered gather batches, 8-12 = gathers through cp.async into a shared-memory
- * ring (k = 16, 32, 64 with 16-byte aligned operands, otherwise the automatic shape));
- * 0 = automatic. */
+ * 3 = 8-warp CTAs with twice the gathers in flight, 8 / 12 = 2-warp CTAs whose gathers go through
+ * cp.async into a shared-memory ring of 2 x 16 / 2 x 8 rows (k = 16, 32, 64 with 16-byte aligned
+ * operands, otherwise shape 2)); 0 = automatic: 1 for long rows, 2 for short rows, 8 (k <= 32) or
+ * 12 (k = 64) for short rows on an operand too large for the L2. */
 MAXK_API int maxk_set_forward_depth(int depth);
 
 /* ---- a4: work list (replaces kernels/generate_meta.py:8-48 and the disk round trip of
@@ -89,9 +89,6 @@ MAXK_API int maxk_worklist_fill(const int32_t *indptr, int64_t num_rows, int32_t
  * values are bit copies.  NaN ranks largest, -0 == +0.  d % 4 == 0, 1 <= k <= d <= 256.
  * dense_out (optional, may be NULL): x * mask, float32[n,d] (MaxK.forward,
  * utils/models.py:48-52).  sp_data / sp_index may be NULL when only dense_out is wanted. */
-/* Bench/test hook (EXPERIMENTAL, unmeasured): rows > 1 = the fp32 TopK gives every warp `rows` consecutive
- * rows and loads row j+1 while it works on row j; 0 or 1 = the default kernel (one row per warp). */
-MAXK_API int maxk_set_topk_rows_per_warp(int rows);
 MAXK_API int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t k, float *sp_data,
                        uint8_t *sp_index, float *dense_out, void *stream);
 /* uint8 flavour of the reference kernel's own data type (cuda_topk_maxk,
@@ -117,34 +114,27 @@ MAXK_API int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks, co
                             int32_t k, float *out, int64_t num_rows_out, int32_t d,
                             int32_t accumulate, void *stream);
 
-/* ---- a2, EXPERIMENTAL (round 1, after the GPU budget: checked under the SIMT interpreter of
- * tests/simt only; nothing calls these by default): bank-planned forward.  The forward kernel is
- * bound by shared-memory wavefronts of its scatter into the output row (32 random columns per
- * edge collide in the 32 banks, ~3.3-way).  maxk_cbsr_bank_plan gives every entry of a CBSR row
- * one of `homes` (2, 4 or 8) homes for its column -- word c of copy 0 or a word of copy h in
- * another bank -- by a maximum matching of the 32 entries of one update onto the 32 banks, once
- * per row instead of once per edge (fullest bank ~2.0 / 1.5 / 1.0 instead of 3.3); sp_addr
- * uint16[n,k] holds the chosen accumulator words and replaces sp_index in
- * maxk_spgemm_forward_planned (k = 8, 16 or a multiple of 32; 4 homes for k = 16, 32, 64 and 8 homes
- * for k = 32, 64 only; same
- * homes as the plan was made with; same output contract as maxk_spgemm_forward_acc).           */
-MAXK_API int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, int32_t homes,
-                        uint16_t *sp_addr, void *stream);
+/* ---- a2 through a bank plan (k = 32, 64; long rows on an L2-resident operand) ------------------
+ * There the forward kernel is bound by shared-memory wavefronts of its scatter into the output row:
+ * 32 random columns per edge collide in the 32 banks ~3.3-way (ncu, Reddit shape).
+ * maxk_cbsr_bank_plan gives every entry of a CBSR row one of two homes for its column -- word c of
+ * copy 0 (bank c mod 32) or word 256 + (c mod 8)*32 + c/8 of copy 1 (bank c/8) -- so that the 32
+ * entries of one update instruction spread over the banks (fullest bank ~2.1 instead of 3.3), once per
+ * row instead of once per edge: one warp per 32 entries, a few greedy rounds.  sp_addr uint16[n,k]
+ * holds the chosen accumulator words and replaces sp_index in maxk_spgemm_forward_planned (same output
+ * contract as maxk_spgemm_forward_acc; measured 3.99 -> ~3.1 ms on the Reddit shape at k = 32).
+ * maxk_sspmm_backward_planned is maxk_sspmm_backward reading its columns out of the same plan (the
+ * column of word w is w for w < 256, else ((w & 31) << 3) | ((w >> 5) & 7)): on the multi-GPU peer
+ * path the plan travels over NVLink in place of the selectors.                                    */
+MAXK_API int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, uint16_t *sp_addr, void *stream);
 MAXK_API int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                                 const float *values, const float *sp_data, const uint16_t *sp_addr,
-                                int32_t k, int32_t homes, float *out, int64_t num_rows_out, int32_t d,
+                                int32_t k, float *out, int64_t num_rows_out, int32_t d,
                                 int32_t accumulate, void *stream);
-/* The backward through the same plan (k = 8, 16, 32, 64, 96, 128): dY rows are staged in all homes and
- * entry l of CBSR row j looks its value up at word sp_addr[j,l]; one instruction covers the 32
- * entries of one edge (ncu, round 1: 2.2 of the default kernel's 5.8 wavefronts per edge are bank
- * conflicts of exactly these lookups).  Same output contract as maxk_sspmm_backward.          */
-/* Bench/test hook: 1 = the planned backward keeps the default kernel's (edge, 4-entry group) items and
- * 128-bit vector reductions (k = 32, 64); 0 = one edge per lookup instruction, scalar reductions. */
-MAXK_API int maxk_set_planned_backward_vector(int on);
 MAXK_API int maxk_sspmm_backward_planned(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                                 const float *values, const float *dy, const uint16_t *sp_addr,
-                                int32_t k, int32_t homes, int32_t d, float *dxc,
-                                int64_t num_cbsr_rows, int32_t accumulate, void *stream);
+                                int32_t k, int32_t d, float *dxc, int64_t num_cbsr_rows,
+                                int32_t accumulate, void *stream);
 
 /* ---- a3: backward outer-product sampled SSpMM  dXc = sample(A^T dY, sp_index)
  * (replaces spmm_kernel_opt2_sparse_backward_v3, kernels/spmm_maxk_backward.cu:15-115;
@@ -152,9 +142,6 @@ MAXK_API int maxk_sspmm_backward_planned(const int32_t *warp4, int64_t num_tasks
  * dxc float32[num_cbsr_rows, k].  accumulate == 0: dxc is zero-filled first (defined
  * output); accumulate != 0: contributions are added to the existing content (used by
  * the multi-GPU local/remote split).                                                   */
-/* Bench/test hook (EXPERIMENTAL, unmeasured): 1 = the backward kernel loads dY[next row,:] into registers
- * while it processes the current task (graphs of short rows: the row changes with every task). */
-MAXK_API int maxk_set_backward_prefetch(int on);
 MAXK_API int maxk_sspmm_backward(const int32_t *warp4, int64_t num_tasks, const int32_t *indices,
                         const float *values, const float *dy, const uint8_t *sp_index,
                         int32_t k, int32_t d, float *dxc, int64_t num_cbsr_rows,
@@ -172,8 +159,9 @@ MAXK_API int maxk_cbsr_gather(const float *dense, const uint8_t *sp_index, int64
 MAXK_API int maxk_cbsr_mask(const float *in, const uint8_t *sp_index, int64_t n, int32_t k, int32_t d,
                    float *out, void *stream);
 
-/* ---- SURVEY 8(f) rank 3, EXPERIMENTAL (unmeasured): the dense layer next to the aggregation on
- * the CBSR operand itself, without the dense [n, d] twin.  m is a dense float32 [d, c] matrix,
+/* ---- the dense layer next to the aggregation on the CBSR operand itself,
+ * without the dense [n, d] twin (measured on the products shape, k = 32: 3.8 vs 6.3 ms for fc_self,
+ * 5.1 vs 6.2 ms for the gradient of the kept values, profiles/r02_variants.md).  m is a dense float32 [d, c] matrix,
  * row-major (for a Linear layer: the transposed weight), d <= 256, c % 4 == 0.
  * matmul     : out[i, 0:c] (+)= bias[0:c] + sum_j sp_data[i,j] * m[sp_index[i,j], 0:c]
  *              = fc_self(h) on the MaxK-sparsified h (utils/models_old.py:55-60; the reference runs
@@ -226,7 +214,8 @@ MAXK_API int maxk_cbsr_unpack(const void *records, int64_t n, int32_t k, float *
  * decision of a pair from the same numbers (list length vs rows_of).
  * Epochs are step numbers that only grow; buffers alternate between two contexts by epoch
  * parity so that nobody overwrites what a slower peer still reads.  row_start[r] * k % 16 == 0.
- * Every device-side wait is bounded (about 5 s) and traps instead of hanging.             */
+ * Every device-side wait is bounded (maxk_set_peer_timeout_ms, default 10 minutes): one lane reports
+ * and the kernel traps instead of hanging the GPU.                                          */
 typedef struct maxk_peer_ctx {
     int32_t world, rank, k, reserved;
     int64_t n_total;
@@ -243,6 +232,9 @@ typedef struct maxk_peer_ctx {
     void *local_sync;
 } maxk_peer_ctx;
 
+/* Limit of every device-side wait for a peer, in milliseconds (0 = wait for ever).  Applies to the
+ * launches that follow on the calling process's current device. */
+MAXK_API int maxk_set_peer_timeout_ms(int64_t ms);
 /* cudaMalloc + cudaIpcGetMemHandle (handle_out: 64 bytes); memory is zero-filled. */
 MAXK_API int maxk_peer_alloc(int64_t bytes, void **dev_ptr, void *handle_out);
 MAXK_API int maxk_peer_free(void *dev_ptr);
@@ -262,10 +254,9 @@ MAXK_API int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoch,
                               int64_t num_tasks, int64_t wait_from_task, const int32_t *indices,
                               const float *values, float *out, int64_t num_rows_out, int32_t d,
                               int32_t copy_ctas, void *stream);
-/* EXPERIMENTAL (unmeasured): the same kernel with the bank plan of cbsr_plan.cu travelling in place
- * of the selectors: ctx->g_index[r] are uint16[n_total, k] buffers holding sp_addr (made with the same
- * `homes` on every rank).  k = 8 (homes 2), 16 (2, 4), 32 and 64 (2, 4, 8).                    */
-MAXK_API int maxk_spgemm_forward_fused_planned(const maxk_peer_ctx *ctx, uint32_t epoch, int32_t homes,
+/* The same kernel with the bank plan of cbsr_plan.cu travelling in place of the selectors:
+ * ctx->g_index[r] are uint16[n_total, k] buffers holding sp_addr.  k = 32, 64.                  */
+MAXK_API int maxk_spgemm_forward_fused_planned(const maxk_peer_ctx *ctx, uint32_t epoch,
                                       const int32_t *warp4, int64_t num_tasks, int64_t wait_from_task,
                                       const int32_t *indices, const float *values, float *out,
                                       int64_t num_rows_out, int32_t d, int32_t copy_ctas, void *stream);

@@ -1,150 +1,142 @@
 // cbsr_plan.cu -- bank plan of a CBSR operand for the forward SpGEMM's shared-memory scatter.
 //
-// EXPERIMENTAL (written when round 1's GPU budget was spent: compiled and checked under the SIMT
-// interpreter of tests/simt, NOT yet run on a GPU; reachable only through the two entry points
-// below, which nothing calls by default).
+// Why.  On operands that live in the L2 the forward kernel (spgemm_forward.cu) is bound by L1 /
+// shared-memory wavefronts (ncu, Reddit shape: 98 % of peak): per edge one value-line gather, one
+// selector-line gather, one staging broadcast -- and a read-modify-write of the output row in shared
+// memory whose 32 lanes hit 32 random columns.  32 random columns over 32 banks collide: the fullest
+// bank holds 3.3 of them on average, so the load and the store of that update cost ~3.3 wavefronts
+// each, more than everything else together.  No fixed column -> bank mapping helps (any mapping sees
+// the same random sets).  What helps is a CHOICE: every column gets two homes in different banks
+// (common.cuh: plan_home_word) and a plan decides ONCE PER CBSR ROW -- not once per edge -- which home
+// each of its entries uses, so that the 32 entries of one update instruction spread over the banks.
+// A row is planned once per TopK and used once per incident edge (492 times on the Reddit shape).
 //
-// Why.  The forward kernel (spgemm_forward.cu) is bound by L1/shared-memory wavefronts on
-// operands that live in the L2 (ncu: 93 % of peak on the Reddit shape): per edge one value-line
-// gather, one selector-line gather, one staging broadcast -- and a read-modify-write of the
-// output row in shared memory whose 32 lanes hit 32 random columns.  32 random columns over 32
-// banks collide: the fullest bank holds 3.3 of them on average, so the load and the store of that
-// update cost ~3.3 wavefronts each, more than everything else together.  No fixed column->bank
-// mapping helps (any mapping sees the same random sets).  What helps is a CHOICE: give every
-// column H homes in different banks (H copies of the output row, common.cuh: plan_home_word),
-//       home 0:  word  c                                            bank  c mod 32
-//       home h:  word  h*256 + (c mod 8)*32 + (c/8 + S_h*(c mod 8) + T_h) mod 32
-// and decide once per CBSR row -- not once per edge -- which home each of its entries uses so
-// that the 32 entries of one update instruction spread over the banks.  The plan is a maximum
-// bipartite matching entries -> banks (augmenting paths, one thread per row); entries it leaves
-// over go to their least loaded bank.  Fullest bank of 32 random columns (simulation, 500 rows):
-//       one home 3.27   H = 2: 2.0   H = 4: 1.46 (54 % of rows conflict-free)   H = 8: 1.01
-// i.e. of ~10.9 wavefronts per edge on the Reddit shape ~2.9 / ~4 / ~4.9 go away; the row is
-// summed over its homes when it is flushed (H x the flush work and shared memory, so H is a
-// trade: 8 for long rows, 2 for short ones).  A row is planned once per TopK and used once per
-// incident edge (492 times on the Reddit shape, 25 on the products shape).
+// The plan is a uint16 array sp_addr[N,k] holding the accumulator WORD of every entry (< 512): it
+// replaces sp_index as the forward kernel's second gather (64 instead of 32 bytes per row at k = 32:
+// still one wavefront).  Entries are planned in groups of 32 consecutive entries, which is how the
+// planned forward kernel maps entries to lanes (entry 32*i + lane in its i-th update instruction).
 //
-// The plan is a uint16 array sp_addr[N,k] holding the accumulator WORD of every entry (< H*256): it
-// replaces sp_index as the forward kernel's second gather (64 instead of 32 bytes per row at
-// k = 32 -- still one wavefront, 6k instead of 5k bytes per node in the L2).  Entries are planned
-// in groups of 32 consecutive entries, which is how the planned forward kernel maps entries to
-// lanes (entry 32*i + lane in its i-th update instruction).  For k = 16 and k = 8 one instruction
-// carries 32/k edges, each with its own accumulator set on its own 1/E of the banks (word*E + slot),
-// so a row's k entries are planned over k banks (b mod k).
+// Round 1 made the plan with an exact maximum matching, one THREAD per group: 1.4 ms for the Reddit
+// shape's 233 k rows -- as much as the plan saves.  This kernel gives a group to a WARP (lane = entry)
+// and places the entries greedily in a fixed number of warp-wide rounds, conflicts being settled
+// through a 32-entry owner table in shared memory (whoever's store lands last owns the bank):
+//   1. every entry asks for its home-0 bank;              2. the losers ask for their home-1 bank if free;
+//   3. one augmenting step per home: a loser u whose bank b is held by o takes b if o can move to
+//      its own other home (o's move and u's claim are settled through the same table);
+//   4. what is left (about 5 of 32 entries) shares a bank with one placed entry, spread by the same
+//      two rounds over a second layer (and a third ... until everything is placed).
+// Fullest bank on random 32-of-256 column sets: 3.27 without a plan, 2.00 with the exact two-home
+// matching, ~2.1 with this one (tests/test_simt_kernels.py measures it on the kernel's own output).
 #include "common.cuh"
 
 namespace maxk {
 
-constexpr int PLAN_GROUP = 32;
+constexpr int PLAN_WPB = 8;  // warps (groups) per CTA
 
-// one thread per (row, group of entries that share an update instruction)
-__global__ void __launch_bounds__(128)
-cbsr_bank_plan_kernel(const unsigned char *__restrict__ sp_index, int64_t n, int k, int groups,
-                      int group_len, unsigned bank_mask, int homes, unsigned short *__restrict__ sp_addr)
+__global__ void __launch_bounds__(PLAN_WPB * 32)
+cbsr_bank_plan_kernel(const unsigned char *__restrict__ sp_index, int64_t n_groups, int groups_per_row, int k,
+                      unsigned short *__restrict__ sp_addr)
 {
-    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= n * groups) return;
-    const int64_t row = item / groups;
-    const int g = (int)(item - row * groups);
-    const int j0 = g * group_len;
-    const int cnt = min(group_len, k - j0);
-    const unsigned char *src = sp_index + row * k + j0;
+    __shared__ unsigned char s_owner[PLAN_WPB][32];  // bank -> lane that holds it (layer 1)
+    __shared__ unsigned char s_req[PLAN_WPB][32];    // bank -> lane that claims it in the current round
+    __shared__ unsigned char s_move[PLAN_WPB][32];   // lane -> asked to move to its other home
+    __shared__ unsigned short s_banks[PLAN_WPB][32]; // lane -> b0 | b1 << 8
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t item = (int64_t)blockIdx.x * PLAN_WPB + warp;
+    if (item >= n_groups) return;  // warp-uniform; no CTA barrier below
+    const int64_t row = item / groups_per_row;
+    const int j = (int)(item - row * groups_per_row) * 32 + lane;  // entry of the row
+    const bool valid = j < k;
+    const unsigned c = valid ? (unsigned)__ldg(sp_index + row * k + j) : 0u;
+    const unsigned b0 = c & 31u, b1 = c >> 3;  // banks of the two homes
+    unsigned char *owner = s_owner[warp], *req = s_req[warp], *move = s_move[warp];
+    int home = -1;  // -1: not placed
 
-    unsigned char c[PLAN_GROUP];       // columns of the entries
-    unsigned char pos[PLAN_GROUP][PLAN_MAX_HOMES];  // entry, home -> word of the home modulo 32 (its bank)
-    signed char owner[PLAN_GROUP];     // bank -> entry that holds it (-1: free)
-    signed char home[PLAN_GROUP];      // entry -> home it uses (-1: not placed yet)
-    unsigned char done[PLAN_GROUP];    // entry -> placed for good
-    for (int i = 0; i < PLAN_GROUP; ++i) {
-        const unsigned ci = (i < cnt) ? __ldg(src + i) : 0u;
-        c[i] = (unsigned char)ci;
+    s_banks[warp][lane] = (unsigned short)(b0 | (b1 << 8));
+    move[lane] = 0;
+    // 1. home 0
+    if (valid) owner[b0] = (unsigned char)lane;
+    __syncwarp();
+    if (valid && owner[b0] == lane) home = 0;
+    unsigned taken = __reduce_or_sync(full, home == 0 ? (1u << b0) : 0u);
+    // 2. losers: home 1, if that bank is free
+    const bool ask1 = valid && home < 0 && !((taken >> b1) & 1u);
+    __syncwarp();
+    if (ask1) owner[b1] = (unsigned char)lane;
+    __syncwarp();
+    if (ask1 && owner[b1] == lane) home = 1;
+    taken |= __reduce_or_sync(full, (ask1 && home == 1) ? (1u << b1) : 0u);
+    // 3. one augmenting step through the holder of the bank of home hm (hm = 0, then 1)
 #pragma unroll
-        for (int h = 0; h < PLAN_MAX_HOMES; ++h) pos[i][h] = (unsigned char)(plan_home_word(ci, h) & 31u);
-        owner[i] = -1;
-        home[i] = -1;
-        done[i] = 0;
-    }
-    auto bank = [&](int e, int h) -> unsigned { return pos[e][h] & bank_mask; };
-
-    // Layer 0: a maximum matching entries -> banks (Kuhn's augmenting paths, depth-first, explicit
-    // stack): every matched entry has a bank to itself.  Entries it leaves over are matched among
-    // themselves onto a second slot of every bank (layer 1), and so on: the fullest bank holds as
-    // many entries as layers were needed (1 for most rows with 8 homes, 2 with 2 homes).
-    int placed = 0;
-    for (int layer = 0; layer < PLAN_GROUP && placed < cnt; ++layer) {
-        for (int b = 0; b < PLAN_GROUP; ++b) owner[b] = -1;
-        for (int i = 0; i < cnt; ++i) {
-            if (done[i]) continue;  // placed by an earlier layer
-            unsigned visited = 0u;
-            signed char st_entry[PLAN_GROUP], st_next[PLAN_GROUP], st_bank[PLAN_GROUP], st_home[PLAN_GROUP];
-            int sp = 0;
-            st_entry[0] = (signed char)i;
-            st_next[0] = 0;
-            bool found = false;
-            while (sp >= 0) {
-                const int e = st_entry[sp], h = st_next[sp];
-                if (h == homes) {  // this entry cannot be re-homed: back up
-                    --sp;
-                    continue;
-                }
-                st_next[sp] = (signed char)(h + 1);
-                const unsigned b = bank(e, h);
-                if ((visited >> b) & 1u) continue;
-                visited |= 1u << b;
-                st_bank[sp] = (signed char)b;
-                st_home[sp] = (signed char)h;
-                if (owner[b] < 0) {
-                    found = true;
-                    break;
-                }
-                ++sp;  // ask the holder of bank b (an entry of this layer) to move
-                st_entry[sp] = owner[b];
-                st_next[sp] = 0;
-            }
-            if (found) {
-                for (int l = sp; l >= 0; --l) {  // every entry on the path takes the bank it asked for
-                    owner[st_bank[l]] = st_entry[l];
-                    home[st_entry[l]] = st_home[l];
-                }
-            }
+    for (int hm = 0; hm < 2; ++hm) {
+        const unsigned mine = hm ? b1 : b0;
+        bool ask = valid && home < 0;
+        unsigned alt = 0u;
+        int o = 0;
+        if (ask) {
+            o = owner[mine];  // placed in step 1 or 2 (the bank is taken, or this lane would hold it)
+            const unsigned ob = s_banks[warp][o];
+            const unsigned o0 = ob & 0xffu, o1 = ob >> 8;
+            alt = (o0 == mine) ? o1 : o0;  // the holder's other home (o0 == o1: nowhere to go)
+            ask = alt != mine && !((taken >> alt) & 1u);
         }
-        for (int b = 0; b < PLAN_GROUP; ++b) {  // what this layer matched is final
-            if (owner[b] >= 0 && !done[owner[b]]) {
-                done[owner[b]] = 1;
-                ++placed;
-            }
+        __syncwarp();
+        if (ask) req[alt] = (unsigned char)lane;
+        __syncwarp();
+        const bool won = ask && req[alt] == lane;
+        if (won) {
+            move[o] = 1;
+            home = hm;
         }
+        __syncwarp();
+        if (won) {
+            owner[alt] = (unsigned char)o;
+            owner[mine] = (unsigned char)lane;
+        }
+        if (move[lane]) {  // this lane was asked to leave its bank for its other home
+            home ^= 1;
+            move[lane] = 0;
+        }
+        taken |= __reduce_or_sync(full, won ? (1u << alt) : 0u);
+        __syncwarp();
     }
-    unsigned short *dst = sp_addr + row * k + j0;
-    for (int i = 0; i < cnt; ++i) {
-        const unsigned ci = c[i], h = (unsigned)home[i];
-        dst[i] = (unsigned short)(h == 0u ? ci : h * 256u + (ci & 7u) * 32u + pos[i][h]);
+    // 4. further layers for what is left (one in almost every row): the same two rounds over a table
+    //    of second, third ... slots; every pass places at least one entry per bank asked for
+    while (__ballot_sync(full, valid && home < 0)) {
+        const bool left = valid && home < 0;
+        if (left) req[b0] = (unsigned char)lane;
+        __syncwarp();
+        const bool l0 = left && req[b0] == lane;
+        if (l0) home = 0;
+        const unsigned taken2 = __reduce_or_sync(full, l0 ? (1u << b0) : 0u);
+        const bool ask2 = left && home < 0 && !((taken2 >> b1) & 1u);
+        __syncwarp();
+        if (ask2) req[b1] = (unsigned char)lane;
+        __syncwarp();
+        if (ask2 && req[b1] == lane) home = 1;
+        __syncwarp();
     }
+    if (valid) sp_addr[row * k + j] = (unsigned short)plan_home_word(c, home);
 }
 
 }  // namespace maxk
 
 using namespace maxk;
 
-extern "C" int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, int32_t homes,
-                                   uint16_t *sp_addr, void *stream)
+extern "C" int maxk_cbsr_bank_plan(const uint8_t *sp_index, int64_t n, int32_t k, uint16_t *sp_addr, void *stream)
 {
     MAXK_REQUIRE(n >= 0, "maxk_cbsr_bank_plan: negative n");
     MAXK_REQUIRE(k >= 1 && k <= MAXK_MAX_DIM, "maxk_cbsr_bank_plan: k=%d out of range", k);
-    MAXK_REQUIRE(homes == 2 || homes == 4 || homes == 8, "maxk_cbsr_bank_plan: homes=%d must be 2, 4 or 8", homes);
     if (n == 0) return MAXK_OK;
     MAXK_REQUIRE(sp_index != nullptr && sp_addr != nullptr, "maxk_cbsr_bank_plan: NULL pointer");
     MAXK_REQUIRE((reinterpret_cast<uintptr_t>(sp_addr) & 1) == 0, "maxk_cbsr_bank_plan: sp_addr must be 2-byte aligned");
-    // entries of one update instruction and the banks they share: k >= 32 -> 32 entries over 32
-    // banks; k = 16 / 8 -> the row's k entries over k banks (the other edges of the instruction
-    // use the other banks)
-    const int group_len = (k == 16 || k == 8) ? k : PLAN_GROUP;
-    const unsigned bank_mask = (unsigned)group_len - 1u;
-    const int groups = ceil_div<int>(k, group_len);
-    const int64_t grid = ceil_div<int64_t>(n * groups, 128);
+    const int groups = ceil_div<int>(k, 32);
+    const int64_t n_groups = n * groups;
+    const int64_t grid = ceil_div<int64_t>(n_groups, PLAN_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_cbsr_bank_plan: n too large");
-    cbsr_bank_plan_kernel<<<(unsigned)grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        sp_index, n, k, groups, group_len, bank_mask, homes, sp_addr);
+    cbsr_bank_plan_kernel<<<(unsigned)grid, PLAN_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        sp_index, n_groups, groups, k, sp_addr);
     MAXK_LAUNCH_CHECK("cbsr_bank_plan_kernel");
     return MAXK_OK;
 }

@@ -87,19 +87,25 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// ---- bank plan (cbsr_plan.cu, planned forward): the homes of an output column ---------------------
-// Home 0 of column c is word c (bank c mod 32).  Home h >= 1 is word
-//   h*256 + (c mod 8)*32 + ((c/8 + S_h*(c mod 8) + T_h) mod 32)      bank (c/8 + S_h*(c mod 8) + T_h) mod 32
-// -- for fixed c mod 8 a rotation of c/8, hence a bijection of 0..255 for every h; different S_h
-// make two columns that share a bank in one home share it in few others.
-constexpr int PLAN_MAX_HOMES = 8;
-__host__ __device__ constexpr int plan_s(int h) { return h == 1 ? 0 : h == 2 ? 5 : h == 3 ? 11 : h == 4 ? 3 : h == 5 ? 7 : h == 6 ? 13 : 9; }
-__host__ __device__ constexpr int plan_t(int h) { return h == 1 ? 0 : h == 2 ? 7 : h == 3 ? 19 : h == 4 ? 3 : h == 5 ? 11 : h == 6 ? 23 : 29; }
+// ---- bank plan (cbsr_plan.cu, planned forward): the two homes of an output column -------------------
+// The accumulator row of the planned forward kernel has PLAN_HOMES = 2 copies of 256 words:
+//   home 0 of column c: word c                       bank c mod 32
+//   home 1 of column c: word 256 + (c mod 8)*32 + c/8   bank c / 8     (the 8 x 32 transpose of home 0)
+// Two columns that share a bank in one home (same c mod 32) never share it in the other (their c/8
+// differ), which is what gives the plan its choice.  (Round 2 measured 2, 4 and 8 homes with an exact
+// matching: 3.09 / 2.93 / 3.46 ms on the Reddit shape at k = 32 against 3.99 ms without a plan -- two
+// homes keep 4 CTAs per SM and halve the flush work, profiles/r02_variants.md.)
+constexpr int PLAN_HOMES = 2;
+__host__ __device__ constexpr int plan_s(int) { return 0; }
+__host__ __device__ constexpr int plan_t(int) { return 0; }
 __host__ __device__ __forceinline__ unsigned plan_home_word(unsigned c, int h)
 {
-    if (h == 0) return c;
-    const unsigned lo = c & 7u;
-    return (unsigned)h * 256u + lo * 32u + (((c >> 3) + (unsigned)plan_s(h) * lo + (unsigned)plan_t(h)) & 31u);
+    return h == 0 ? c : 256u + (c & 7u) * 32u + (c >> 3);
+}
+// the column of an accumulator word (inverse of plan_home_word for either home)
+__host__ __device__ __forceinline__ unsigned plan_word_column(unsigned w)
+{
+    return w < 256u ? w : (((w & 31u) << 3) | ((w >> 5) & 7u));
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -5,6 +5,10 @@
 
 namespace maxk {
 
+// clock64 ticks a device-side wait for a peer may take before it reports and traps; 0 = wait for ever.
+// Default: 10 minutes at 1.965 GHz (NCCL's default watchdog is of the same order).
+long long g_peer_spin_limit_cycles = 600LL * 1965000000LL;
+
 __global__ void peer_publish_kernel(unsigned *flag_word, unsigned epoch)
 {
     __threadfence_system();  // everything this stream wrote before is visible to the peers first
@@ -21,13 +25,14 @@ struct RsArgs {
     const int *rows[MAXK_PEER_MAX];  // NULL: dense pair (every row of the block), else halo list
     long long count[MAXK_PEER_MAX];
     long long row0;
+    long long spin_limit;
 };
 
 // dense pairs: out = sum_r partial_r[block of this rank]; r in rank order (deterministic)
 __global__ void __launch_bounds__(256) reduce_scatter_pull_kernel(RsArgs a, float *__restrict__ out)
 {
     if (threadIdx.x < a.world && threadIdx.x != a.rank)
-        peer_spin_until<true>(a.flags[threadIdx.x] + PEER_FLAG_BWD, a.epoch, threadIdx.x);
+        peer_spin_until<true>(a.flags[threadIdx.x] + PEER_FLAG_BWD, a.epoch, threadIdx.x, a.spin_limit);
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += stride) {
@@ -112,6 +117,13 @@ static int check_ctx(const maxk_peer_ctx *ctx, const char *who)
 }  // namespace maxk
 
 using namespace maxk;
+
+extern "C" int maxk_set_peer_timeout_ms(int64_t ms)
+{
+    MAXK_REQUIRE(ms >= 0, "maxk_set_peer_timeout_ms: negative limit");
+    g_peer_spin_limit_cycles = ms * 1965000LL;  // clock64 ticks at the B200's 1.965 GHz maximum; 0 = no limit
+    return MAXK_OK;
+}
 
 extern "C" int maxk_peer_alloc(int64_t bytes, void **dev_ptr, void *handle_out)
 {
@@ -213,6 +225,7 @@ extern "C" int maxk_reduce_scatter_pull(const maxk_peer_ctx *ctx, uint32_t epoch
     a.rank = ctx->rank;
     a.k = ctx->k;
     a.epoch = epoch;
+    a.spin_limit = g_peer_spin_limit_cycles;
     a.n4 = n / 4;
     a.row0 = ctx->row_start[ctx->rank];
     a.off = a.row0 * ctx->k;

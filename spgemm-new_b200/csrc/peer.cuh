@@ -20,9 +20,13 @@
 //   * the backward publishes flag word [1] = epoch after the SSpMM; the reduce-scatter kernel
 //     waits for it on every peer and pulls its block of each partial gradient;
 //   * buffers are double-buffered by epoch parity on the host side, so no "done reading"
-//     handshake is needed: a rank can only finish step e-1 after every peer has pushed its
-//     block of step e-1, i.e. after that peer has finished reading the buffers of step e-2.
-// Every spin is bounded: a peer that never arrives traps the kernel instead of hanging the GPU.
+//     handshake is needed: a rank only PUSHES step e after every peer's block of step e-1 has
+//     arrived in its own buffer (the copy CTAs wait for that, unconditionally -- also on a rank
+//     whose own tasks never read a remote column), i.e. after every peer has entered the forward
+//     of step e-1 and is therefore done with the buffers of step e-2, which step e overwrites.
+// Every spin is bounded (maxk_set_peer_timeout_ms, default 10 minutes -- ordinary rank skew such as
+// rank-0-only evaluation, checkpointing or a lazy module load must not kill the job): a peer that
+// never arrives makes ONE lane report and the kernel trap, instead of hanging the GPU.
 #pragma once
 
 #include "common.cuh"
@@ -42,6 +46,7 @@ struct PeerArgs {
     unsigned char *g_index[MAXK_PEER_MAX];  // rank r's gathered selector buffer
     unsigned *flags[MAXK_PEER_MAX];         // rank r's flag words ([rank] = own)
     unsigned *local_sync;                   // own memory: [1] arrival counter of the copy CTAs
+    long long spin_limit;                   // clock64 ticks a device-side wait may take (0 = no limit)
 };
 struct NoPeer {};
 template <bool P>
@@ -86,19 +91,23 @@ __device__ __forceinline__ uint4 ld_peer_u4(const uint4 *p)
     return v;
 }
 
-constexpr long long PEER_SPIN_LIMIT_CYCLES = 10000000000LL;  // ~5 s at 1.9 GHz
+// host-side default of PeerArgs::spin_limit / RsArgs::spin_limit (peer.cu: maxk_set_peer_timeout_ms)
+extern long long g_peer_spin_limit_cycles;
+static __device__ unsigned g_peer_timeout_reported;  // first lane to time out reports, the others only trap
 
 template <bool SYS>
-__device__ __forceinline__ void peer_spin_until(const unsigned *flag, unsigned epoch, int who)
+__device__ __forceinline__ void peer_spin_until(const unsigned *flag, unsigned epoch, int who, long long limit)
 {
     const long long t0 = clock64();
     while (true) {
         const unsigned v = SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag);
         if ((int)(v - epoch) >= 0) return;
         __nanosleep(200);  // back off: thousands of waiting warps must not starve the copy CTAs
-        if (clock64() - t0 > PEER_SPIN_LIMIT_CYCLES) {
-            printf("libmaxk_b200: timed out waiting for %s %d (flag %u, want %u)\n",
-                   SYS ? "peer rank" : "the gather of block", who, v, epoch);
+        if (limit > 0 && clock64() - t0 > limit) {
+            if (atomicExch(&g_peer_timeout_reported, 1u) == 0u)
+                printf("libmaxk_b200: timed out waiting for %s %d (flag %u, want %u); raise the limit with "
+                       "maxk_set_peer_timeout_ms\n",
+                       SYS ? "peer rank" : "the gather of block", who, v, epoch);
             __trap();
         }
     }
@@ -273,6 +282,16 @@ __device__ __forceinline__ void peer_push_block(const PeerArgs &a, int cta, unsi
     const long long row0 = a.row_start[a.rank];
     const long long nel = a.rows_of[a.rank] * a.k;
     const long long nib = nel * IB;  // bytes of the second buffer (selectors or plan)
+    // The buffers of this step's parity were last used by step epoch-2.  A peer is done reading them
+    // once it has entered the forward of step epoch-1, i.e. once its block of epoch-1 has arrived here:
+    // wait for that before overwriting anything over there -- in EVERY rank, also one whose own tasks
+    // never wait for a remote column (the aggregating warps' wait alone would let such a rank run ahead).
+    // No deadlock: the peers' pushes of epoch-1 wait for arrivals of epoch-2 only, and kernels of one
+    // stream run in launch order.
+    if (a.epoch >= 2u && (int)threadIdx.x < a.world && (int)threadIdx.x != a.rank)
+        peer_spin_until<true>(a.flags[a.rank] + PEER_FLAG_ARRIVED + threadIdx.x, a.epoch - 1u, (int)threadIdx.x,
+                              a.spin_limit);
+    __syncthreads();
     bool any_dense = false;
     for (int r = 0; r < a.world; ++r) any_dense |= (r != a.rank && a.send_rows[r] == nullptr);
     if (any_dense && a.use_tma) {
@@ -344,7 +363,7 @@ __device__ __forceinline__ void peer_push_block(const PeerArgs &a, int cta, unsi
 __device__ __forceinline__ void peer_wait_gathered(const PeerArgs &a, int lane)
 {
     if (lane < a.world && lane != a.rank)
-        peer_spin_until<true>(a.flags[a.rank] + PEER_FLAG_ARRIVED + lane, a.epoch, lane);
+        peer_spin_until<true>(a.flags[a.rank] + PEER_FLAG_ARRIVED + lane, a.epoch, lane, a.spin_limit);
     __syncwarp();
 }
 

@@ -41,25 +41,21 @@ constexpr int FWD_STAGE = 64;  // staged (idx,val) pairs per warp == MAXK_WARP_M
 // R accumulator copies, WPB warps per CTA, U gather instructions in flight, MINB CTAs/SM
 // the register budget is capped for.
 template <int KL_, int EPL_, bool EXACT_, int R_, int WPB_, int U_, int MINB_, bool PEER_ = false,
-          bool DB_ = false, int RING_ = 0, int PLAN_ = 0>
+          int RING_ = 0, bool PLAN_ = false>
 struct FwdCfg {
-    // PLAN (= homes per column, 0 = off): the second operand is the bank plan sp_addr (uint16
-    // accumulator words, cbsr_plan.cu) instead of sp_index; the output row lives in HOMES
-    // 256-word copies (experimental, own entry point)
-    static constexpr bool PLAN = PLAN_ > 0;
-    static constexpr int HOMES = PLAN_;
-    static constexpr int PLAN_WORDS = PLAN_ * 256 * R_;  // HOMES homes per column, one set per edge slot
-    static_assert(PLAN_ == 0 || PLAN_ == 2 || PLAN_ == 4 || PLAN_ == 8, "homes");
-    static_assert(PLAN_ == 0 || (EXACT_ && R_ == 32 / KL_ && !DB_ && RING_ == 0),
-                  "the planned variant: k % 32 == 0 or k = 16, 8; one accumulator set per edge slot");
-    // DB: double-buffered gather batches (experimental launch shapes 4-7, see launch_fwd_r)
-    static constexpr bool DB = DB_;
+    // PLAN: the second operand is the bank plan sp_addr (uint16 accumulator words, cbsr_plan.cu)
+    // instead of sp_index; the output row lives in PLAN_HOMES 256-word copies (k = 32, 64: long rows
+    // on an L2-resident operand, where the update's bank conflicts are the bound)
+    static constexpr bool PLAN = PLAN_;
+    static constexpr int HOMES = PLAN_ ? PLAN_HOMES : 0;
+    static constexpr int PLAN_WORDS = PLAN_HOMES * 256;
+    static_assert(!PLAN_ || (EXACT_ && KL_ == 32 && R_ == 1 && RING_ == 0), "the planned variant: k % 32 == 0");
     // RING > 0: gathers go through cp.async into a per-warp shared-memory ring of 2 x RING rows
-    // (experimental launch shapes 8-11); K is the compile-time k of the EXACT variants
+    // (operands that miss the L2: launch shapes 8 and 12); K is the compile-time k of the EXACT variants
     static constexpr int RING = RING_;
     static constexpr int K = (KL_ == 32) ? 32 * EPL_ : KL_;
     static constexpr int ROW_BYTES = 5 * K;  // k fp32 values followed by k selector bytes
-    static_assert(RING_ == 0 || (EXACT_ && K % 16 == 0 && !DB_ && !PEER_), "ring rows move in 16-byte chunks");
+    static_assert(RING_ == 0 || (EXACT_ && K % 16 == 0 && !PEER_), "ring rows move in 16-byte chunks");
     static constexpr int KL = KL_, EPL = EPL_, R = R_, WPB = WPB_, U = U_, MINB = MINB_;
     static constexpr bool EXACT = EXACT_;
     // PEER: fused multi-GPU variant -- the first CTAs of the grid push this rank's CBSR block
@@ -96,23 +92,15 @@ __device__ __forceinline__ void fwd_gather(Slice<C> &sl, const float *sp_data,
     constexpr bool P = C::PEER;
     const int64_t base = (int64_t)col * k;
     if constexpr (C::PLAN) {
-        // entry 32*i + lane (k < 32: entry lane / E of edge slot lane % E): the grouping the plan
-        // was made for; sp_index points at sp_addr
+        // entry 32*i + lane: the grouping the plan was made for; sp_index points at sp_addr.
         // k is the compile-time C::K here and column ids are non-negative: one unsigned 32x32->64
-        // multiply per edge instead of the sign-extended 64-bit product of the generic path (the
-        // planned kernel is close to issue-bound once the bank conflicts are gone)
+        // multiply per edge instead of the sign-extended 64-bit product of the generic path
         const unsigned short *sp_addr = reinterpret_cast<const unsigned short *>(sp_index);
         const uint64_t ubase = (uint64_t)(uint32_t)col * (uint32_t)C::K;
-        if constexpr (C::KL < 32) {
-            const int entry = lane / C::E;
-            sl.v[0] = fwd_ld<P>(sp_data + ubase + entry);
-            sl.s[0] = fwd_ld<P>(sp_addr + ubase + entry);
-        } else {
 #pragma unroll
-            for (int i = 0; i < C::EPL; ++i) {
-                sl.v[i] = fwd_ld<P>(sp_data + ubase + lane + 32 * i);
-                sl.s[i] = fwd_ld<P>(sp_addr + ubase + lane + 32 * i);
-            }
+        for (int i = 0; i < C::EPL; ++i) {
+            sl.v[i] = fwd_ld<P>(sp_data + ubase + lane + 32 * i);
+            sl.s[i] = fwd_ld<P>(sp_addr + ubase + lane + 32 * i);
         }
     } else if constexpr (C::KL < 32) {
         const int entry = lane / C::E;
@@ -211,76 +199,16 @@ __device__ __forceinline__ void fwd_process_batch(const int2 *stage, int len, fl
     }
 }
 
-// EXPERIMENTAL (launch shapes 4-7; written at the end of round 1 when the GPU budget was spent:
-// compiled, NOT yet run -- not reachable unless maxk_set_forward_depth asks for it).
-// Double-buffered batches: the gathers of batch b+1 are issued BEFORE the accumulates of
-// batch b, so a warp always has U gathers in flight instead of alternating between a gather
-// phase and an accumulate phase.  Motivation (profiles/r01_forward_pipeline.md): on the
-// products shape the kernel delivers 104 M edges/s per SM where the DRAM random-row floor is
-// 187 M/s -- by Little's law only ~36 of the 128 possible gathers per SM are in flight on
-// average; the batch form spends the rest of the time in staging reads and read-modify-write
-// chains with nothing outstanding.  (The per-edge rolling pipeline tried earlier put the
-// staging read, the gather and the accumulate of a slot into one dependent chain; this form
-// keeps them batched.)
-template <class C>
-__device__ __forceinline__ void fwd_load_batch(int2 (&ev)[C::U], Slice<C> (&sl)[C::U], const int2 *stage,
-                                               int j, int len, const float *sp_data,
-                                               const unsigned char *sp_index, int k, int lane)
-{
-    constexpr int U = C::U, E = C::E;
-    const int e = lane & (E - 1);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        ev[u] = make_int2(0, 0);
-        if (j + u * E + e < len) ev[u] = stage[j + u * E + e];
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (j + u * E + e < len) fwd_gather<C>(sl[u], sp_data, sp_index, ev[u].x, k, lane);
-}
-template <class C>
-__device__ __forceinline__ void fwd_acc_batch(const int2 (&ev)[C::U], const Slice<C> (&sl)[C::U],
-                                              float *acc_lane, int j, int len, int k, int lane)
-{
-    constexpr int U = C::U, E = C::E;
-    const int e = lane & (E - 1);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        if (j + u * E < len)  // warp-uniform: skip instructions no lane needs
-            fwd_accumulate<C>(sl[u], acc_lane, __int_as_float(ev[u].y), k, lane, j + u * E + e < len);
-    }
-}
-template <class C>
-__device__ __forceinline__ void fwd_process_batch_db(const int2 *stage, int len, float *acc_lane,
-                                                     const float *sp_data,
-                                                     const unsigned char *sp_index, int k, int lane)
-{
-    constexpr int STEP = C::U * C::E;
-    int2 eva[C::U], evb[C::U];
-    Slice<C> sla[C::U], slb[C::U];
-    fwd_load_batch<C>(eva, sla, stage, 0, len, sp_data, sp_index, k, lane);
-    for (int j = 0; j < len; j += 2 * STEP) {
-        const bool has_b = j + STEP < len;  // warp-uniform
-        if (has_b) fwd_load_batch<C>(evb, slb, stage, j + STEP, len, sp_data, sp_index, k, lane);
-        fwd_acc_batch<C>(eva, sla, acc_lane, j, len, k, lane);
-        if (has_b) {
-            if (j + 2 * STEP < len)
-                fwd_load_batch<C>(eva, sla, stage, j + 2 * STEP, len, sp_data, sp_index, k, lane);
-            fwd_acc_batch<C>(evb, slb, acc_lane, j + STEP, len, k, lane);
-        }
-    }
-}
-
-// EXPERIMENTAL (launch shapes 8-11; written when round 1's GPU budget was spent: compiled and
-// checked under the SIMT interpreter of tests/simt, NOT yet run on a GPU -- not reachable unless
-// maxk_set_forward_depth asks for it).  Gathers through LDGSTS (cp.async, 16-byte chunks) into a
-// per-warp shared-memory ring of two groups of RING rows: loads in flight hold no registers, so a
-// warp keeps up to 2 x RING CBSR rows in flight (the register path: U = 4) and a task of <= 32
-// edges issues all its gathers before it waits once.  Aimed at operands that miss the L2
-// (products shape: the kernel waits on DRAM latency with ~36 gathers in flight per SM where 64+
-// saturate the memory system, profiles/r01_forward_pipeline.md).  Cost: the gathered row crosses
-// the L1 data pipe twice more (shared-memory write + read), about 14.5 instead of 11 wavefronts
-// per edge -- a loss where that pipe is the bound (L2-resident operands).
+// Launch shapes 8 and 12 (chosen automatically when the CBSR operand cannot live in the L2, see
+// maxk_spgemm_forward_acc): gathers through LDGSTS (cp.async, 16-byte chunks) into a per-warp
+// shared-memory ring of two groups of RING rows: loads in flight hold no registers, so a warp keeps
+// up to 2 x RING CBSR rows in flight (the register path: U = 4) and a task of <= 32 edges issues all
+// its gathers before it waits once.  On the products shape (392 MB operand, gathers pay DRAM latency)
+// the register path keeps ~36 gathers in flight per SM where 64+ saturate the memory system:
+// measured 4.01 -> 3.58 ms at k = 32, 3.39 -> 2.61 at k = 16, 6.35 -> 4.97 at k = 64
+// (profiles/r02_variants.md).  Cost: the gathered row crosses the L1 data pipe twice more
+// (shared-memory write + read) -- a loss where that pipe is the bound (L2-resident operands:
+// 3.99 -> 5.27 ms on the Reddit shape), hence the choice by operand size.
 template <class C>
 __device__ __forceinline__ void fwd_ring_issue(const int2 *stage, int e0, int cnt, unsigned char *half,
                                                const float *sp_data, const unsigned char *sp_index,
@@ -410,47 +338,30 @@ __device__ __forceinline__ void fwd_flush_row(float *acc, float *__restrict__ ou
     __syncwarp();
 }
 
-// PLAN: out[row, c] = sum over the homes h of acc[plan_home_word(c, h)] (and over the R edge-slot
-// sets for k < 32); all homes are cleared.
+// PLAN: out[row, c] = sum over the homes h of acc[plan_home_word(c, h)]; all homes are cleared.
 template <class C>
 __device__ __forceinline__ void fwd_flush_row_planned(float *acc, float *__restrict__ out, int64_t row,
                                                       int d, int lane, bool shared_row)
 {
-    constexpr int R = C::R, H = C::HOMES;
+    constexpr int H = C::HOMES;
     __syncwarp();
     float *dst = out + row * (int64_t)d;
-    if constexpr (R > 1) {  // k = 16, 8: word * R + slot
-        for (int c = lane; c < d; c += 32) {
-            float s = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+        float4 v = *reinterpret_cast<float4 *>(acc + c);  // home 0
+        // c % 4 == 0: columns c .. c+3 share c/8 and have c mod 8 = (c mod 8) + i
+        const unsigned lo = c & 7, hi = c >> 3;
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const float *p = acc + plan_home_word((unsigned)c, h) * R;
-#pragma unroll
-                for (int r = 0; r < R; ++r) s += p[r];
-            }
-            if (shared_row)
-                red_add_f1(dst + c, s);
-            else
-                __stcs(dst + c, s);
+        for (int h = 1; h < H; ++h) {
+            const float *p = acc + h * 256;
+            v.x += p[(lo + 0) * 32 + ((hi + plan_s(h) * (lo + 0) + plan_t(h)) & 31)];
+            v.y += p[(lo + 1) * 32 + ((hi + plan_s(h) * (lo + 1) + plan_t(h)) & 31)];
+            v.z += p[(lo + 2) * 32 + ((hi + plan_s(h) * (lo + 2) + plan_t(h)) & 31)];
+            v.w += p[(lo + 3) * 32 + ((hi + plan_s(h) * (lo + 3) + plan_t(h)) & 31)];
         }
-    } else {
-        for (int c = lane * 4; c < d; c += 128) {
-            float4 v = *reinterpret_cast<float4 *>(acc + c);  // home 0
-            // c % 4 == 0: columns c .. c+3 share c/8 and have c mod 8 = (c mod 8) + i
-            const unsigned lo = c & 7, hi = c >> 3;
-#pragma unroll
-            for (int h = 1; h < H; ++h) {
-                const float *p = acc + h * 256;
-                v.x += p[(lo + 0) * 32 + ((hi + plan_s(h) * (lo + 0) + plan_t(h)) & 31)];
-                v.y += p[(lo + 1) * 32 + ((hi + plan_s(h) * (lo + 1) + plan_t(h)) & 31)];
-                v.z += p[(lo + 2) * 32 + ((hi + plan_s(h) * (lo + 2) + plan_t(h)) & 31)];
-                v.w += p[(lo + 3) * 32 + ((hi + plan_s(h) * (lo + 3) + plan_t(h)) & 31)];
-            }
-            if (shared_row)
-                red_add_f4(dst + c, v.x, v.y, v.z, v.w);
-            else
-                st_stream_f4(reinterpret_cast<float4 *>(dst + c), v);
-        }
+        if (shared_row)
+            red_add_f4(dst + c, v.x, v.y, v.z, v.w);
+        else
+            st_stream_f4(reinterpret_cast<float4 *>(dst + c), v);
     }
     __syncwarp();  // every lane has read all homes before anybody clears a word of them
     for (int i = lane * 4; i < C::PLAN_WORDS; i += 128)
@@ -609,8 +520,6 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
             fwd_fetch_edges(pre, idx, val, ninfo.y, min(ninfo.z, FWD_STAGE), lane);
         if constexpr (C::RING > 0)
             fwd_process_batch_ring<C>(stage, min(len, FWD_STAGE), acc_lane, ring, sp_data, sp_index, k, lane);
-        else if constexpr (C::DB)
-            fwd_process_batch_db<C>(stage, min(len, FWD_STAGE), acc_lane, sp_data, sp_index, k, lane);
         else
             fwd_process_batch<C>(stage, min(len, FWD_STAGE), acc_lane, sp_data, sp_index, k, lane);
         for (int off = FWD_STAGE; off < len; off += FWD_STAGE) {  // len > 64: foreign work lists
@@ -620,8 +529,6 @@ spgemm_fwd_kernel(const int4 *__restrict__ warp4, int64_t num_tasks, const int *
             fwd_stage_edges(more, stage, lane);
             if constexpr (C::RING > 0)
                 fwd_process_batch_ring<C>(stage, ln, acc_lane, ring, sp_data, sp_index, k, lane);
-            else if constexpr (C::DB)
-                fwd_process_batch_db<C>(stage, ln, acc_lane, sp_data, sp_index, k, lane);
             else
                 fwd_process_batch<C>(stage, ln, acc_lane, sp_data, sp_index, k, lane);
         }
@@ -687,7 +594,12 @@ static int launch_fwd(const FwdArgs &a)
 
 int g_fwd_tasks_per_warp = 0;   // run length; 0 = automatic; tunable through maxk_set_tuning
 int g_fwd_copies = 0;           // 0 = automatic choice of R
-int g_fwd_depth = 0;            // launch shape: 1 = 8-warp CTAs, 2 = 2-warp CTAs, 3 = 2x deeper gathers; 0 = automatic
+int g_fwd_depth = 0;            // launch shape, see maxk_set_forward_depth; 0 = automatic
+
+// A CBSR operand of more than this many bytes cannot stay in the 126 MB L2 next to the CSR stream and
+// the output: its gathers pay DRAM latency and the cp.async ring shapes win (measured on the products
+// shape, 392 MB; on the 37 MB Reddit operand they lose 30 %).
+constexpr int64_t FWD_L2_OPERAND_BYTES = 96LL << 20;
 
 // launch shape per R:      R<=2: 8 warps, U=4, 64 regs   R=4: 8 warps, U=4
 //                          R=8 : 8 warps (68 KB/CTA, 3 CTAs/SM), U=8
@@ -697,42 +609,23 @@ static int launch_fwd_r(const FwdArgs &a)
 {
     constexpr int U1 = (EPL == 1) ? 4 : (EPL == 2 ? 2 : (EPL <= 4 ? 2 : 1));
     if constexpr (R <= 2 && EPL <= 2) {
-        // deeper gather pipelines for graphs whose CBSR operand does not fit the L2 (the
-        // gathers then pay DRAM latency): 2x / 4x the edges in flight per warp, paid for with
-        // registers (3 / 2 CTAs per SM)
-        // CTA shape (measured, profiles/r01_forward_pipeline.md): graphs of short rows are
-        // latency-bound on the CBSR gathers and run lengths vary a lot, so 2-warp CTAs (no
-        // warp idles until the slowest of 8 finishes) are 12 % faster on the products shape;
-        // deeper gather pipelines (2x / 4x U) and register-capped variants (48 / 40 registers
-        // for more warps) were measured too and lose to spills and lost occupancy.
-        switch (a.depth) {
-            case 2: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16>>(a);     // 2-warp CTAs
-            case 3: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, 2 * U1, 3>>(a);  // deeper
-            // experimental, never chosen automatically: double-buffered gather batches
-            case 4: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, (U1 > 1 ? U1 / 2 : 1), 4, false, true>>(a);
-            case 5: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, 3, false, true>>(a);
-            case 6: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, (U1 > 1 ? U1 / 2 : 1), 16, false, true>>(a);
-            case 7: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 12, false, true>>(a);
-            default: break;
-        }
-        // experimental, never chosen automatically: cp.async gather ring (k = 16, 32, 64 with
-        // 16-byte aligned operands; anything else takes the default shapes)
+        // CTA shape (measured, profiles/r01_forward_pipeline.md, profiles/r02_variants.md): graphs of
+        // short rows are latency-bound on the CBSR gathers and run lengths vary a lot, so 2-warp CTAs
+        // (no warp idles until the slowest of 8 finishes) are 12 % faster on the products shape.
+        // Register-only ways to keep more gathers in flight (2x / 4x U, double-buffered batches,
+        // 48 / 40-register caps) were measured and lose to spills and lost occupancy; the cp.async
+        // ring (shapes 8 and 12) is what pays when the operand misses the L2.
         if constexpr (EXACT && (KL == 32 ? 32 * EPL : KL) % 16 == 0) {
             if (a.ring_ok) {
-                switch (a.depth) {
-                    case 8: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16, false, false, 16>>(a);
-                    case 9: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16, false, false, 8>>(a);
-                    case 10: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, 4, false, false, 16>>(a);
-                    case 11: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, 4, false, false, 8>>(a);
-                    // loads in flight hold no registers here: cap at 48 registers for 40 warps per SM
-                    case 12: return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, (U1 > 1 ? U1 / 2 : 1), 20, false, false, 8>>(a);
-                    default: break;
-                }
+                // 2-warp CTAs, ring of 2 x 16 rows (k <= 32) ...
+                if (a.depth == 8) return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16, false, 16>>(a);
+                // ... or 2 x 8 rows under a 48-register cap (loads in flight hold none): 40 warps per SM (k = 64)
+                if (a.depth == 12) return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, (U1 > 1 ? U1 / 2 : 1), 20, false, 8>>(a);
             }
         }
-        if (a.depth >= 8) {  // ring asked for but not applicable: the automatic CTA shape
-            if (a.W < 2 * a.num_rows_out) return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16>>(a);
-        }
+        if (a.depth == 2 || a.depth == 8 || a.depth == 12)  // (ring asked for but not applicable: 2-warp CTAs)
+            return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 2, U1, 16>>(a);
+        if (a.depth == 3) return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, 2 * U1, 3>>(a);  // deeper (measurement knob)
     }
     if constexpr (R <= 4)
         return launch_fwd<FwdCfg<KL, EPL, EXACT, R, 8, U1, (EPL <= 2 ? 4 : 2)>>(a);
@@ -770,6 +663,32 @@ static int launch_fwd_pick(const FwdArgs &a, int want_r)
     }
 }
 
+// Rows shared between two runs are cleared by a pre-kernel, rows without tasks inside the main kernel:
+// together they DEFINE the output without a memset of the whole of it.
+static int clear_shared_rows(const FwdArgs &a)
+{
+    const int64_t boundaries = (a.W - 1) / a.tasks_per_warp;
+    if (boundaries > 0) {
+        spgemm_fwd_clear_shared_rows<<<(unsigned)ceil_div<int64_t>(boundaries, 8), 256, 0, a.st>>>(
+            reinterpret_cast<const int4 *>(a.warp4), a.W, a.tasks_per_warp, a.out, a.d);
+        MAXK_LAUNCH_CHECK("spgemm_fwd_clear_shared_rows");
+    }
+    return MAXK_OK;
+}
+
+// argument checks shared by every forward entry point; `who` names it in the message
+static int check_fwd_common(const char *who, const int32_t *warp4, int64_t num_tasks, int k, const float *out,
+                            int64_t num_rows_out, int d)
+{
+    MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0, "%s: negative size", who);
+    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0, "%s: d=%d must be a multiple of 4 in [4,256]", who, d);
+    MAXK_REQUIRE(k >= 1 && k <= d, "%s: k=%d must be in [1,d=%d]", who, k, d);
+    MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "%s: out is NULL", who);
+    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
+                 "%s: out and warp4 must be 16-byte aligned", who);
+    return MAXK_OK;
+}
+
 }  // namespace maxk
 
 using namespace maxk;
@@ -789,14 +708,7 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
                                        float *out, int64_t num_rows_out, int32_t d,
                                        int32_t accumulate, void *stream)
 {
-    MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0, "maxk_spgemm_forward: negative size");
-    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
-                 "maxk_spgemm_forward: d=%d must be a multiple of 4 in [4,256]", d);
-    MAXK_REQUIRE(k >= 1 && k <= d, "maxk_spgemm_forward: k=%d must be in [1,d=%d]", k, d);
-    MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "maxk_spgemm_forward: out is NULL");
-    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
-                 "maxk_spgemm_forward: out and warp4 must be 16-byte aligned");
+    if (int rc = check_fwd_common("maxk_spgemm_forward", warp4, num_tasks, k, out, num_rows_out, d)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (num_rows_out == 0) return MAXK_OK;
     // Output is DEFINED by this call: empty rows and rows shared between
@@ -816,23 +728,21 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
     // shorter runs so that the grid still fills 148 SMs x 32 warps several times over.
     int tpw = g_fwd_tasks_per_warp;
     if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
-    // CTA shape: mostly single-task rows (W < 2N) -> 2-warp CTAs, see launch_fwd_r
+    // Launch shape.  Mostly single-task rows (W < 2N) -> 2-warp CTAs (see launch_fwd_r); if in
+    // addition the CBSR operand cannot live in the L2 the gathers go through the cp.async ring.
+    // The operand has at least as many rows as the graph has destination rows with edges
+    // (num_rows_out is what the caller tells us about its size; 5k bytes per row).
     int shape = g_fwd_depth;
-    if (shape <= 0) shape = (num_tasks < 2 * num_rows_out) ? 2 : 1;
+    if (shape <= 0) {
+        shape = (num_tasks < 2 * num_rows_out) ? 2 : 1;
+        if (shape == 2 && num_rows_out * 5LL * k > FWD_L2_OPERAND_BYTES) shape = (k > 32) ? 12 : 8;
+    }
     const bool ring_ok = ((reinterpret_cast<uintptr_t>(sp_data) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(sp_index) & 15) == 0);
     FwdArgs a{warp4, num_tasks, indices, values, sp_data, sp_index, k, out, d,
               tpw, accumulate, st, shape, num_rows_out, nullptr, ring_ok};
-    // Output is DEFINED by this call without a memset of the whole of it: rows
-    // shared between two runs are cleared here, rows without tasks inside the main kernel.
-    if (!accumulate) {
-        const int64_t boundaries = (num_tasks - 1) / a.tasks_per_warp;
-        if (boundaries > 0) {
-            spgemm_fwd_clear_shared_rows<<<(unsigned)ceil_div<int64_t>(boundaries, 8), 256, 0, st>>>(
-                reinterpret_cast<const int4 *>(warp4), num_tasks, a.tasks_per_warp, out, d);
-            MAXK_LAUNCH_CHECK("spgemm_fwd_clear_shared_rows");
-        }
-    }
+    if (!accumulate)
+        if (int rc = clear_shared_rows(a)) return rc;
     // R: accumulator copies.  Measured on B200 (profiles/r01_sweep_copies.md): R = E (one copy
     // per edge slot) is fastest on every BASELINE shape -- with 1 < R < 32 the worst bank
     // still serialises ~3 lanes, and R >= 16 costs more occupancy than it saves.
@@ -866,53 +776,19 @@ extern "C" int maxk_spgemm_forward_acc(const int32_t *warp4, int64_t num_tasks,
     return MAXK_ERR_UNSUPPORTED;
 }
 
-// ---- forward with a bank plan (cbsr_plan.cu): EXPERIMENTAL, own entry point ---------------------
-template <int KL, int EPL, int H>
-static int launch_fwd_planned_h(const FwdArgs &a)
-{
-    constexpr int U1 = (EPL == 1) ? 4 : (EPL <= 4 ? 2 : 1), R = 32 / KL;
-    if (a.depth == 2) return launch_fwd<FwdCfg<KL, EPL, true, R, 2, U1, (EPL <= 2 ? 16 : 8), false, false, 0, H>>(a);
-    // CTAs per SM the register budget is capped for: what the shared memory (H * R KB per warp) admits
-    constexpr int MINB8 = (EPL > 2) ? 2 : (H * R >= 8 ? 3 : 4);
-    return launch_fwd<FwdCfg<KL, EPL, true, R, 8, U1, MINB8, false, false, 0, H>>(a);
-}
-// 4 and 8 homes are built for k = 32 and 64, 4 homes also for k = 16 (the k of the BASELINE kernel
-// bench; shared memory per warp is homes * 32/min(k,32) KB); every other supported k has the
-// two-home variant
-template <int KL, int EPL>
-static int launch_fwd_planned(const FwdArgs &a, int homes)
-{
-    if constexpr (KL == 32 && EPL <= 2) {
-        if (homes == 4) return launch_fwd_planned_h<KL, EPL, 4>(a);
-        if (homes == 8) return launch_fwd_planned_h<KL, EPL, 8>(a);
-    }
-    if constexpr (KL == 16) {
-        if (homes == 4) return launch_fwd_planned_h<KL, EPL, 4>(a);
-    }
-    if (homes != 2) {
-        set_error("maxk_spgemm_forward_planned: homes=%d is not built for k=%d (4: k = 16, 32, 64; 8: k = 32, 64)",
-                  homes, a.k);
-        return MAXK_ERR_UNSUPPORTED;
-    }
-    return launch_fwd_planned_h<KL, EPL, 2>(a);
-}
-
+// ---- forward through a bank plan (cbsr_plan.cu): k = 32 and 64 ---------------------------------------
+// Measured on the Reddit shape (profiles/r02_variants.md): the update's bank conflicts are the bound
+// there (ncu: 4.5 of 9.9 L1 wavefronts per edge), two homes per column take the fullest bank from 3.3
+// to ~2.1 entries and the kernel from 3.99 to ~3.1 ms (k = 32), 7.1 to ~5.9 ms (k = 64).  On short rows
+// (products, Flickr) the doubled flush eats the gain: the caller chooses (maxk_b200.ops.use_bank_plan).
 extern "C" int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tasks,
                                            const int32_t *indices, const float *values,
                                            const float *sp_data, const uint16_t *sp_addr, int32_t k,
-                                           int32_t homes, float *out, int64_t num_rows_out, int32_t d,
+                                           float *out, int64_t num_rows_out, int32_t d,
                                            int32_t accumulate, void *stream)
 {
-    MAXK_REQUIRE(homes == 2 || homes == 4 || homes == 8, "maxk_spgemm_forward_planned: homes=%d must be 2, 4 or 8", homes);
-    MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0, "maxk_spgemm_forward_planned: negative size");
-    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
-                 "maxk_spgemm_forward_planned: d=%d must be a multiple of 4 in [4,256]", d);
-    MAXK_REQUIRE(k >= 8 && k <= d && (k % 32 == 0 || k == 16 || k == 8),
-                 "maxk_spgemm_forward_planned: k=%d must be 8, 16 or a multiple of 32, and <= d=%d", k, d);
-    MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "maxk_spgemm_forward_planned: out is NULL");
-    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
-                 "maxk_spgemm_forward_planned: out and warp4 must be 16-byte aligned");
+    if (int rc = check_fwd_common("maxk_spgemm_forward_planned", warp4, num_tasks, k, out, num_rows_out, d)) return rc;
+    MAXK_REQUIRE(k == 32 || k == 64, "maxk_spgemm_forward_planned: k=%d is not built (32, 64)", k);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (num_rows_out == 0) return MAXK_OK;
     if (num_tasks == 0) {
@@ -928,59 +804,32 @@ extern "C" int maxk_spgemm_forward_planned(const int32_t *warp4, int64_t num_tas
                  "maxk_spgemm_forward_planned: sp_data / sp_addr are misaligned");
     int tpw = g_fwd_tasks_per_warp;
     if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
-    int shape = g_fwd_depth;
-    if (shape != 1 && shape != 2) shape = (num_tasks < 2 * num_rows_out) ? 2 : 1;
+    const bool two_warps = (g_fwd_depth == 2) || (g_fwd_depth <= 0 && num_tasks < 2 * num_rows_out);
     FwdArgs a{warp4, num_tasks, indices, values, sp_data, reinterpret_cast<const uint8_t *>(sp_addr), k, out, d,
-              tpw, accumulate, st, shape, num_rows_out, nullptr, false};
-    if (!accumulate) {
-        const int64_t boundaries = (num_tasks - 1) / a.tasks_per_warp;
-        if (boundaries > 0) {
-            spgemm_fwd_clear_shared_rows<<<(unsigned)ceil_div<int64_t>(boundaries, 8), 256, 0, st>>>(
-                reinterpret_cast<const int4 *>(warp4), num_tasks, a.tasks_per_warp, out, d);
-            MAXK_LAUNCH_CHECK("spgemm_fwd_clear_shared_rows");
-        }
-    }
-    if (k == 16) return launch_fwd_planned<16, 1>(a, homes);
-    if (k == 8) return launch_fwd_planned<8, 1>(a, homes);
-    switch (k / 32) {
-        case 1: return launch_fwd_planned<32, 1>(a, homes);
-        case 2: return launch_fwd_planned<32, 2>(a, homes);
-        case 3: return launch_fwd_planned<32, 3>(a, homes);
-        case 4: return launch_fwd_planned<32, 4>(a, homes);
-        case 5: return launch_fwd_planned<32, 5>(a, homes);
-        case 6: return launch_fwd_planned<32, 6>(a, homes);
-        case 7: return launch_fwd_planned<32, 7>(a, homes);
-        case 8: return launch_fwd_planned<32, 8>(a, homes);
-        default: break;
-    }
-    set_error("maxk_spgemm_forward_planned: unsupported k=%d", k);
-    return MAXK_ERR_UNSUPPORTED;
+              tpw, accumulate, st, two_warps ? 2 : 1, num_rows_out, nullptr, false};
+    if (!accumulate)
+        if (int rc = clear_shared_rows(a)) return rc;
+    if (k == 32)
+        return two_warps ? launch_fwd<FwdCfg<32, 1, true, 1, 2, 4, 16, false, 0, true>>(a)
+                         : launch_fwd<FwdCfg<32, 1, true, 1, 8, 4, 4, false, 0, true>>(a);
+    return two_warps ? launch_fwd<FwdCfg<32, 2, true, 1, 2, 2, 16, false, 0, true>>(a)
+                     : launch_fwd<FwdCfg<32, 2, true, 1, 8, 2, 4, false, 0, true>>(a);
 }
 
 // ---- fused all-gather + forward over NVLink peer memory (peer.cuh) ---------------------------
-extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoch,
-                                         const int32_t *warp4, int64_t num_tasks,
-                                         int64_t wait_from_task, const int32_t *indices,
-                                         const float *values, float *out, int64_t num_rows_out,
-                                         int32_t d, int32_t copy_ctas, void *stream)
+// Checks and the PeerArgs block shared by the two fused entry points.
+static int fused_setup(const char *who, const maxk_peer_ctx *ctx, uint32_t epoch, const int32_t *warp4,
+                       int64_t num_tasks, int64_t wait_from_task, const float *out, int64_t num_rows_out, int32_t d,
+                       int32_t copy_ctas, PeerArgs &pa)
 {
-    MAXK_REQUIRE(ctx != nullptr, "maxk_spgemm_forward_fused: ctx is NULL");
+    MAXK_REQUIRE(ctx != nullptr, "%s: ctx is NULL", who);
     const int world = ctx->world, rank = ctx->rank, k = ctx->k;
     MAXK_REQUIRE(world >= 1 && world <= MAXK_PEER_MAX && rank >= 0 && rank < world,
-                 "maxk_spgemm_forward_fused: world=%d rank=%d out of range", world, rank);
-    MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0 && wait_from_task >= 0,
-                 "maxk_spgemm_forward_fused: negative size");
-    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
-                 "maxk_spgemm_forward_fused: d=%d must be a multiple of 4 in [4,256]", d);
-    MAXK_REQUIRE(k >= 1 && k <= d, "maxk_spgemm_forward_fused: k=%d must be in [1,d=%d]", k, d);
-    MAXK_REQUIRE(copy_ctas != 0 && copy_ctas >= -1024 && copy_ctas <= 1024,
-                 "maxk_spgemm_forward_fused: copy_ctas out of range");
-    MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "maxk_spgemm_forward_fused: out is NULL");
-    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
-                 "maxk_spgemm_forward_fused: out and warp4 must be 16-byte aligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PeerArgs pa{};
+                 "%s: world=%d rank=%d out of range", who, world, rank);
+    MAXK_REQUIRE(wait_from_task >= 0, "%s: negative size", who);
+    if (int rc = check_fwd_common(who, warp4, num_tasks, k, out, num_rows_out, d)) return rc;
+    MAXK_REQUIRE(copy_ctas != 0 && copy_ctas >= -1024 && copy_ctas <= 1024, "%s: copy_ctas out of range", who);
+    pa = PeerArgs{};
     pa.copy_ctas = copy_ctas < 0 ? -copy_ctas : copy_ctas;
     pa.use_tma = copy_ctas > 0 ? 1 : 0;  // negative count: plain load/store copy (measurement knob)
     pa.world = world;
@@ -989,13 +838,12 @@ extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoc
     pa.epoch = epoch;
     pa.wait_from_task = wait_from_task;
     for (int r = 0; r < world; ++r) {
-        MAXK_REQUIRE(ctx->g_data[r] && ctx->g_index[r] && ctx->flags[r],
-                     "maxk_spgemm_forward_fused: buffers of rank %d are not mapped", r);
+        MAXK_REQUIRE(ctx->g_data[r] && ctx->g_index[r] && ctx->flags[r], "%s: buffers of rank %d are not mapped", who, r);
         MAXK_REQUIRE(ctx->rows_of[r] >= 0 && ctx->row_start[r] >= 0 &&
                          ctx->row_start[r] + ctx->rows_of[r] <= ctx->n_total,
-                     "maxk_spgemm_forward_fused: row range of rank %d is outside [0, n_total)", r);
+                     "%s: row range of rank %d is outside [0, n_total)", who, r);
         MAXK_REQUIRE((ctx->row_start[r] * (int64_t)k) % 16 == 0,
-                     "maxk_spgemm_forward_fused: row_start[%d] * k must be a multiple of 16", r);
+                     "%s: row_start[%d] * k must be a multiple of 16", who, r);
         pa.rows_of[r] = ctx->rows_of[r];
         pa.row_start[r] = ctx->row_start[r];
         pa.send_rows[r] = (r == rank) ? nullptr : ctx->send_rows[r];
@@ -1011,8 +859,26 @@ extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoc
         if (r != rank && pa.send_rows[r] != nullptr && pa.send_count[r] > 0 && pa.copy_ctas < 4 * kNumSMs)
             pa.copy_ctas = 4 * kNumSMs;
     pa.local_sync = static_cast<unsigned *>(ctx->local_sync);
-    MAXK_REQUIRE(pa.local_sync != nullptr, "maxk_spgemm_forward_fused: local_sync is NULL");
-    MAXK_REQUIRE(warp4 || num_tasks == 0, "maxk_spgemm_forward_fused: warp4 is NULL");
+    MAXK_REQUIRE(pa.local_sync != nullptr, "%s: local_sync is NULL", who);
+    MAXK_REQUIRE(warp4 || num_tasks == 0, "%s: warp4 is NULL", who);
+    pa.spin_limit = g_peer_spin_limit_cycles;
+    return MAXK_OK;
+}
+
+extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoch,
+                                         const int32_t *warp4, int64_t num_tasks,
+                                         int64_t wait_from_task, const int32_t *indices,
+                                         const float *values, float *out, int64_t num_rows_out,
+                                         int32_t d, int32_t copy_ctas, void *stream)
+{
+    PeerArgs pa;
+    if (int rc = fused_setup("maxk_spgemm_forward_fused", ctx, epoch, warp4, num_tasks, wait_from_task, out,
+                             num_rows_out, d, copy_ctas, pa))
+        return rc;
+    const int k = ctx->k;
+    MAXK_REQUIRE(k == 8 || k == 16 || k == 32 || k == 64 || k == 96 || k == 128 || k == 256,
+                 "maxk_spgemm_forward_fused: k=%d is not built for the fused path (8, 16, 32, 64, 96, 128, 256)", k);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     // local-column and remote-column tasks of one row meet in `out` through reductions
     if (num_rows_out > 0) {
         MAXK_CUDA(cudaMemsetAsync(out, 0, (size_t)num_rows_out * d * sizeof(float), st));
@@ -1020,7 +886,7 @@ extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoc
     }
     int tpw = g_fwd_tasks_per_warp;
     if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
-    FwdArgs a{warp4, num_tasks, indices, values, pa.g_data[rank], pa.g_index[rank], k, out, d,
+    FwdArgs a{warp4, num_tasks, indices, values, pa.g_data[pa.rank], pa.g_index[pa.rank], k, out, d,
               tpw, /*accumulate=*/1, st, 1, num_rows_out, &pa, false};
     // the copy CTAs must run even when this rank has no task at all: launch_fwd adds them
     switch (k) {
@@ -1030,97 +896,33 @@ extern "C" int maxk_spgemm_forward_fused(const maxk_peer_ctx *ctx, uint32_t epoc
         case 64: return launch_fwd<FwdCfg<32, 2, true, 1, 8, 2, 4, true>>(a);
         case 96: return launch_fwd<FwdCfg<32, 3, true, 1, 8, 2, 2, true>>(a);
         case 128: return launch_fwd<FwdCfg<32, 4, true, 1, 8, 2, 2, true>>(a);
-        case 256: return launch_fwd<FwdCfg<32, 8, true, 1, 8, 1, 2, true>>(a);
-        default: break;
+        default: return launch_fwd<FwdCfg<32, 8, true, 1, 8, 1, 2, true>>(a);
     }
-    set_error("maxk_spgemm_forward_fused: k=%d is not built for the fused path (8, 16, 32, 64, 96, 128, 256)", k);
-    return MAXK_ERR_UNSUPPORTED;
 }
 
-// ---- the same with the bank plan travelling in place of the selectors (EXPERIMENTAL, unmeasured) ----
-extern "C" int maxk_spgemm_forward_fused_planned(const maxk_peer_ctx *ctx, uint32_t epoch, int32_t homes,
+// ---- the same with the bank plan travelling in place of the selectors (k = 32, 64) ----
+extern "C" int maxk_spgemm_forward_fused_planned(const maxk_peer_ctx *ctx, uint32_t epoch,
                                          const int32_t *warp4, int64_t num_tasks,
                                          int64_t wait_from_task, const int32_t *indices,
                                          const float *values, float *out, int64_t num_rows_out,
                                          int32_t d, int32_t copy_ctas, void *stream)
 {
-    MAXK_REQUIRE(ctx != nullptr, "maxk_spgemm_forward_fused_planned: ctx is NULL");
-    MAXK_REQUIRE(homes == 2 || homes == 4 || homes == 8, "maxk_spgemm_forward_fused_planned: homes=%d must be 2, 4 or 8", homes);
-    const int world = ctx->world, rank = ctx->rank, k = ctx->k;
-    MAXK_REQUIRE(world >= 1 && world <= MAXK_PEER_MAX && rank >= 0 && rank < world,
-                 "maxk_spgemm_forward_fused_planned: world=%d rank=%d out of range", world, rank);
-    MAXK_REQUIRE(num_tasks >= 0 && num_rows_out >= 0 && wait_from_task >= 0,
-                 "maxk_spgemm_forward_fused_planned: negative size");
-    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
-                 "maxk_spgemm_forward_fused_planned: d=%d must be a multiple of 4 in [4,256]", d);
-    MAXK_REQUIRE(k >= 1 && k <= d, "maxk_spgemm_forward_fused_planned: k=%d must be in [1,d=%d]", k, d);
-    MAXK_REQUIRE(copy_ctas != 0 && copy_ctas >= -1024 && copy_ctas <= 1024,
-                 "maxk_spgemm_forward_fused_planned: copy_ctas out of range");
-    MAXK_REQUIRE(out != nullptr || num_rows_out == 0, "maxk_spgemm_forward_fused_planned: out is NULL");
-    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(warp4) & 15) == 0,
-                 "maxk_spgemm_forward_fused_planned: out and warp4 must be 16-byte aligned");
+    PeerArgs pa;
+    if (int rc = fused_setup("maxk_spgemm_forward_fused_planned", ctx, epoch, warp4, num_tasks, wait_from_task,
+                             out, num_rows_out, d, copy_ctas, pa))
+        return rc;
+    const int k = ctx->k;
+    MAXK_REQUIRE(k == 32 || k == 64, "maxk_spgemm_forward_fused_planned: k=%d is not built (32, 64)", k);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PeerArgs pa{};
-    pa.copy_ctas = copy_ctas < 0 ? -copy_ctas : copy_ctas;
-    pa.use_tma = copy_ctas > 0 ? 1 : 0;  // negative count: plain load/store copy (measurement knob)
-    pa.world = world;
-    pa.rank = rank;
-    pa.k = k;
-    pa.epoch = epoch;
-    pa.wait_from_task = wait_from_task;
-    for (int r = 0; r < world; ++r) {
-        MAXK_REQUIRE(ctx->g_data[r] && ctx->g_index[r] && ctx->flags[r],
-                     "maxk_spgemm_forward_fused_planned: buffers of rank %d are not mapped", r);
-        MAXK_REQUIRE(ctx->rows_of[r] >= 0 && ctx->row_start[r] >= 0 &&
-                         ctx->row_start[r] + ctx->rows_of[r] <= ctx->n_total,
-                     "maxk_spgemm_forward_fused_planned: row range of rank %d is outside [0, n_total)", r);
-        MAXK_REQUIRE((ctx->row_start[r] * (int64_t)k) % 16 == 0,
-                     "maxk_spgemm_forward_fused_planned: row_start[%d] * k must be a multiple of 16", r);
-        pa.rows_of[r] = ctx->rows_of[r];
-        pa.row_start[r] = ctx->row_start[r];
-        pa.send_rows[r] = (r == rank) ? nullptr : ctx->send_rows[r];
-        pa.send_count[r] = ctx->send_count[r];
-        pa.g_data[r] = static_cast<float *>(ctx->g_data[r]);
-        pa.g_index[r] = static_cast<unsigned char *>(ctx->g_index[r]);
-        pa.flags[r] = static_cast<unsigned *>(ctx->flags[r]);
-    }
-    // halo pairs are moved row by row with ordinary loads and stores: that needs many threads in
-    // flight (a dependent list -> row -> store chain per 16 bytes), so the copy part of the grid
-    // grows to four CTAs per SM -- the aggregating CTAs mostly wait for those rows anyway
-    for (int r = 0; r < world; ++r)
-        if (r != rank && pa.send_rows[r] != nullptr && pa.send_count[r] > 0 && pa.copy_ctas < 4 * kNumSMs)
-            pa.copy_ctas = 4 * kNumSMs;
-    pa.local_sync = static_cast<unsigned *>(ctx->local_sync);
-    MAXK_REQUIRE(pa.local_sync != nullptr, "maxk_spgemm_forward_fused_planned: local_sync is NULL");
-    MAXK_REQUIRE(warp4 || num_tasks == 0, "maxk_spgemm_forward_fused_planned: warp4 is NULL");
-    // local-column and remote-column tasks of one row meet in `out` through reductions
     if (num_rows_out > 0) {
         MAXK_CUDA(cudaMemsetAsync(out, 0, (size_t)num_rows_out * d * sizeof(float), st));
         count_launch();
     }
     int tpw = g_fwd_tasks_per_warp;
     if (tpw <= 0) tpw = auto_tasks_per_warp(num_tasks);
-    FwdArgs a{warp4, num_tasks, indices, values, pa.g_data[rank], pa.g_index[rank], k, out, d,
-              tpw, /*accumulate=*/1, st, 1, num_rows_out, &pa, false};
-    // the copy CTAs must run even when this rank has no task at all: launch_fwd adds them.
     // g_index[r] holds the uint16 bank plan (cbsr_plan.cu) of every row instead of its selectors
-#define MAXK_FUSED_PLANNED(KL, EPL, R, U, MINB, H) \
-    return launch_fwd<FwdCfg<KL, EPL, true, R, 8, U, MINB, true, false, 0, H>>(a)
-    switch (k * 16 + homes) {
-        case 8 * 16 + 2: MAXK_FUSED_PLANNED(8, 1, 4, 4, 3, 2);
-        case 16 * 16 + 2: MAXK_FUSED_PLANNED(16, 1, 2, 4, 4, 2);
-        case 16 * 16 + 4: MAXK_FUSED_PLANNED(16, 1, 2, 4, 4, 4);
-        case 32 * 16 + 2: MAXK_FUSED_PLANNED(32, 1, 1, 4, 4, 2);
-        case 32 * 16 + 4: MAXK_FUSED_PLANNED(32, 1, 1, 4, 4, 4);
-        case 32 * 16 + 8: MAXK_FUSED_PLANNED(32, 1, 1, 4, 4, 8);
-        case 64 * 16 + 2: MAXK_FUSED_PLANNED(32, 2, 1, 2, 4, 2);
-        case 64 * 16 + 4: MAXK_FUSED_PLANNED(32, 2, 1, 2, 4, 4);
-        case 64 * 16 + 8: MAXK_FUSED_PLANNED(32, 2, 1, 2, 4, 8);
-        default: break;
-    }
-#undef MAXK_FUSED_PLANNED
-    set_error("maxk_spgemm_forward_fused_planned: k=%d with %d homes is not built (k = 8: 2; 16: 2, 4; 32, 64: 2, 4, 8)",
-              k, homes);
-    return MAXK_ERR_UNSUPPORTED;
+    FwdArgs a{warp4, num_tasks, indices, values, pa.g_data[pa.rank], pa.g_index[pa.rank], k, out, d,
+              tpw, /*accumulate=*/1, st, 1, num_rows_out, &pa, false};
+    if (k == 32) return launch_fwd<FwdCfg<32, 1, true, 1, 8, 4, 4, true, 0, true>>(a);
+    return launch_fwd<FwdCfg<32, 2, true, 1, 8, 2, 4, true, 0, true>>(a);
 }

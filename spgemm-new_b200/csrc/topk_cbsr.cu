@@ -398,52 +398,9 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k,
     topk_row_f32(a, b, ok0, ok1, c0, c1, lane, row, d, k, s_stage[warp], out_val, out_idx, dense_out);
 }
 
-// EXPERIMENTAL (maxk_set_topk_rows_per_warp, unmeasured): a warp handles `rpw` consecutive rows and
-// loads row j+1 while it works on row j.  ncu of the default kernel (round 1): 19 % of the stall samples
-// sit on the first use of the row just loaded -- one row per warp exposes that latency.
-__global__ void __launch_bounds__(TOPK_WPB * 32)
-topk_cbsr_f32_rows_kernel(const float *__restrict__ x_, int64_t n, int d, int k, int rpw,
-                          float *__restrict__ out_val, unsigned char *__restrict__ out_idx,
-                          float *__restrict__ dense_out)
-{
-    __shared__ unsigned s_stage[TOPK_WPB][2 * MAXK_MAX_DIM];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t r0 = ((int64_t)blockIdx.x * TOPK_WPB + warp) * rpw;
-    if (r0 >= n) return;  // warp-uniform; no CTA barrier below
-    const int64_t r1 = min(r0 + (int64_t)rpw, n);
-    const int c0 = 4 * lane, c1 = 128 + 4 * lane;
-    const bool ok0 = c0 < d, ok1 = c1 < d;
-    const float ninf = __uint_as_float(0xff800000u);
-    const float4 none = make_float4(ninf, ninf, ninf, ninf);
-    float4 a = none, b = none;
-    if (ok0) a = ld_stream_f4(reinterpret_cast<const float4 *>(x_ + r0 * d + c0));
-    if (ok1) b = ld_stream_f4(reinterpret_cast<const float4 *>(x_ + r0 * d + c1));
-    for (int64_t row = r0; row < r1; ++row) {
-        float4 na = none, nb = none;
-        if (row + 1 < r1) {
-            if (ok0) na = ld_stream_f4(reinterpret_cast<const float4 *>(x_ + (row + 1) * d + c0));
-            if (ok1) nb = ld_stream_f4(reinterpret_cast<const float4 *>(x_ + (row + 1) * d + c1));
-        }
-        topk_row_f32(a, b, ok0, ok1, c0, c1, lane, row, d, k, s_stage[warp], out_val, out_idx, dense_out);
-        __syncwarp();  // the staging area is reused by the next row
-        a = na;
-        b = nb;
-    }
-}
-
-int g_topk_rows_per_warp = 0;  // 0 / 1: one row per warp (default kernel)
-
 }  // namespace maxk
 
 using namespace maxk;
-
-// Bench/test hook: rows per warp of the fp32 TopK (> 1: the experimental kernel that loads the next row
-// while it works on the current one); 0 or 1 = the default kernel.
-extern "C" int maxk_set_topk_rows_per_warp(int rows)
-{
-    g_topk_rows_per_warp = rows < 0 ? 0 : (rows > 64 ? 64 : rows);
-    return MAXK_OK;
-}
 
 extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t k, float *sp_data,
                                   uint8_t *sp_index, float *dense_out, void *stream)
@@ -460,14 +417,6 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
     MAXK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(dense_out) & 15) == 0,
                  "maxk_topk_cbsr_f32: x and dense_out must be 16-byte aligned");
-    if (g_topk_rows_per_warp > 1) {
-        const int rpw = g_topk_rows_per_warp;
-        const int64_t grid_r = ceil_div<int64_t>(ceil_div<int64_t>(n, rpw), TOPK_WPB);
-        topk_cbsr_f32_rows_kernel<<<(unsigned)grid_r, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-            x, n, d, k, rpw, sp_data, sp_index, dense_out);
-        MAXK_LAUNCH_CHECK("topk_cbsr_f32_rows_kernel");
-        return MAXK_OK;
-    }
     const int64_t grid = ceil_div<int64_t>(n, TOPK_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_topk_cbsr_f32: n too large");
     topk_cbsr_f32_kernel<<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(

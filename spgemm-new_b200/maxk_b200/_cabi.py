@@ -36,17 +36,12 @@ PROTOTYPES = {
     "maxk_topk_cbsr_u8": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "maxk_spgemm_forward": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
     "maxk_spgemm_forward_acc": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
-    "maxk_cbsr_bank_plan": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
-    "maxk_spgemm_forward_planned": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _i32,
-                                                   _vp]),
-    "maxk_set_planned_backward_vector": (ctypes.c_int, [ctypes.c_int]),
-    "maxk_set_backward_prefetch": (ctypes.c_int, [ctypes.c_int]),
-    "maxk_set_topk_rows_per_warp": (ctypes.c_int, [ctypes.c_int]),
+    "maxk_cbsr_bank_plan": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "maxk_spgemm_forward_planned": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
     "maxk_cbsr_matmul": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
     "maxk_cbsr_axpy": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, ctypes.c_float, _vp, _vp]),
     "maxk_cbsr_sampled_dot": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
-    "maxk_sspmm_backward_planned": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _i32,
-                                                   _vp]),
+    "maxk_sspmm_backward_planned": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "maxk_sspmm_backward": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "maxk_cbsr_scatter": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "maxk_cbsr_gather": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
@@ -54,6 +49,7 @@ PROTOTYPES = {
     "maxk_cbsr_record_bytes": (_i32, [_i32]),
     "maxk_cbsr_pack": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "maxk_cbsr_unpack": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "maxk_set_peer_timeout_ms": (ctypes.c_int, [_i64]),
     "maxk_peer_alloc": (ctypes.c_int, [_i64, ctypes.POINTER(_vp), _vp]),
     "maxk_peer_free": (ctypes.c_int, [_vp]),
     "maxk_peer_open": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
@@ -61,7 +57,7 @@ PROTOTYPES = {
     "maxk_peer_publish": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp]),
     "maxk_spgemm_forward_fused": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp, _i64, _i64, _vp, _vp, _vp,
                                                  _i64, _i32, _i32, _vp]),
-    "maxk_spgemm_forward_fused_planned": (ctypes.c_int, [_vp, ctypes.c_uint32, _i32, _vp, _i64, _i64, _vp, _vp, _vp,
+    "maxk_spgemm_forward_fused_planned": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp, _i64, _i64, _vp, _vp, _vp,
                                                          _i64, _i32, _i32, _vp]),
     "maxk_peer_zero_partial": (ctypes.c_int, [_vp, _vp]),
     "maxk_reduce_scatter_pull": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp, _vp]),

@@ -69,8 +69,8 @@ class SpGEMMFunction(Function):
         values = values.float().contiguous() if values.dtype != torch.float32 else values.contiguous()
         sp_data, sp_index = ops.topk_cbsr(x, maxk)
         n_rows = indptr.numel() - 1
-        out = ops.spgemm_forward(warp4, indices, values, sp_data, sp_index,
-                                 feat_dim=x.shape[1], num_rows=n_rows)
+        out = ops.spgemm_forward_auto(warp4, indices, values, sp_data, sp_index,
+                                      feat_dim=x.shape[1], num_rows=n_rows)
         ctx.save_for_backward(warp4, indices, values, sp_index)
         ctx.feat_dim = x.shape[1]
         return out
@@ -82,100 +82,37 @@ class SpGEMMFunction(Function):
         return ops.cbsr_scatter(dxc, sp_index, ctx.feat_dim), None, None
 
 
-def planned_homes() -> int:
-    """EXPERIMENTAL opt-in (unmeasured): MAXK_PLANNED_HOMES=2|4|8 routes the
-    CBSR-native aggregation through the bank plan (csrc/cbsr_plan.cu); MAXK_PLANNED_HOMES=auto times
-    the candidates once per (work list, k) on the first call and keeps the fastest (-1 is returned
-    for "auto").  0 / unset = the default kernels."""
-    import os
-    v = os.environ.get("MAXK_PLANNED_HOMES", "0").strip().lower()
-    if v == "auto":
-        return -1
-    try:
-        h = int(v)
-    except ValueError:
-        return 0
-    return h if h in (2, 4, 8) else 0
-
-
-_PLAN_CHOICE: dict = {}
-
-
-def choose_planned_homes(warp4, indices, values, sp_data, sp_index, feat_dim, num_rows, iters: int = 3) -> int:
-    """Time forward + backward (+ plan) of the default kernels and of the planned ones with 2 / 4 / 8
-    homes on the caller's own operands (CUDA events, after one warm-up each) and return the fastest
-    (0 = default).  Cached per (work list, k, feature width): graphs differ -- long rows on an
-    L2-resident operand gain from the plan, short rows pay its flush."""
-    k = sp_index.shape[1]
-    key = (warp4.data_ptr(), warp4.numel(), k, feat_dim)
-    if key in _PLAN_CHOICE:
-        return _PLAN_CHOICE[key]
-    cands = [0] + [h for h in (2, 4, 8) if k % 32 == 0 and k <= 128 and (h == 2 or k <= 64)]
-    dy = torch.ones((num_rows, feat_dim), dtype=torch.float32, device=sp_data.device)
-    best, best_ms = 0, float("inf")
-    for h in cands:
-        def step():
-            if h:
-                sa = ops.cbsr_bank_plan(sp_index, h)
-                ops.spgemm_forward_planned(warp4, indices, values, sp_data, sa, h, feat_dim=feat_dim, num_rows=num_rows)
-                ops.sspmm_backward_planned(warp4, indices, values, dy, sa, h)
-            else:
-                ops.spgemm_forward(warp4, indices, values, sp_data, sp_index, feat_dim=feat_dim, num_rows=num_rows)
-                ops.sspmm_backward(warp4, indices, values, dy, sp_index)
-        step()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for _ in range(iters):
-            step()
-        t1.record()
-        t1.synchronize()
-        ms = t0.elapsed_time(t1) / iters
-        if ms < best_ms:
-            best, best_ms = h, ms
-    _PLAN_CHOICE[key] = best
-    return best
-
-
 class CBSRAggregate(Function):
     """CBSR-native aggregation for layers that keep activations sparse end to end:
-    Y = A @ scatter(sp_data, sp_index); gradient flows to sp_data only (CBSR layout)."""
+    Y = A @ scatter(sp_data, sp_index); gradient flows to sp_data only (CBSR layout).  The forward goes
+    through the bank plan where that pays (ops.use_bank_plan: k = 32 / 64, long rows, L2-resident operand)."""
 
     @staticmethod
     def forward(ctx, sp_data, sp_index, warp4, indices, values, feat_dim, num_rows):
-        k = sp_index.shape[1]
-        homes = planned_homes()
-        if homes < 0:
-            homes = choose_planned_homes(warp4, indices, values, sp_data.detach().contiguous(), sp_index, feat_dim,
-                                         num_rows)
-        if homes and k % 32 == 0 and k <= 128 and (homes == 2 or k <= 64):  # both directions are built
-            sp_addr = ops.cbsr_bank_plan(sp_index, homes)   # once per TopK, serves both directions
-            out = ops.spgemm_forward_planned(warp4, indices, values, sp_data.contiguous(), sp_addr, homes,
-                                             feat_dim=feat_dim, num_rows=num_rows)
-            ctx.save_for_backward(warp4, indices, values, sp_addr)
-            ctx.homes = homes
-            return out
-        out = ops.spgemm_forward(warp4, indices, values, sp_data.contiguous(), sp_index,
-                                 feat_dim=feat_dim, num_rows=num_rows)
+        out = ops.spgemm_forward_auto(warp4, indices, values, sp_data.contiguous(), sp_index,
+                                      feat_dim=feat_dim, num_rows=num_rows)
         ctx.save_for_backward(warp4, indices, values, sp_index)
-        ctx.homes = 0
         return out
 
     @staticmethod
     def backward(ctx, grad_output):
         warp4, indices, values, sel = ctx.saved_tensors
-        if ctx.homes:
-            dxc = ops.sspmm_backward_planned(warp4, indices, values, grad_output.contiguous(), sel, ctx.homes)
-        else:
-            dxc = ops.sspmm_backward(warp4, indices, values, grad_output.contiguous(), sel)
+        dxc = ops.sspmm_backward(warp4, indices, values, grad_output.contiguous(), sel)
         return dxc, None, None, None, None, None, None
 
 
-def cbsr_native_enabled() -> bool:
-    """EXPERIMENTAL opt-in (unmeasured): MAXK_CBSR_NATIVE=1 keeps the layers on the CBSR
-    operand (csrc/cbsr_dense.cu): SAGE's fc_self without torch's dense Linear on the scattered twin, GIN's
-    (1 + eps) * h added to the aggregate in place."""
+def cbsr_native_enabled(k: int = 32) -> bool:
+    """Whether the layers stay on the CBSR operand (csrc/cbsr_dense.cu): SAGE's fc_self without torch's dense
+    Linear on the scattered twin, GIN's (1 + eps) * h added to the aggregate in place, the Linear in front of
+    a MaxK with its dX computed on the k-sparse gradient.  Measured on the products shape (round 2,
+    profiles/r02_variants.md): at k = 32 fc_self 3.8 vs 6.3 ms, gradient of the kept values 5.1 vs 6.2 ms,
+    SAGE epoch 213 -> 196 ms; at k = 16 twice that gain; at k = 64 the sampled dot loses (7.9 vs 6.3 ms).
+    Hence: on for k <= 32, off above; MAXK_CBSR_NATIVE=0 / 1 forces it off / on."""
     import os
-    return os.environ.get("MAXK_CBSR_NATIVE", "0").strip() == "1"
+    v = os.environ.get("MAXK_CBSR_NATIVE", "").strip()
+    if v in ("0", "1"):
+        return v == "1"
+    return k <= 32
 
 
 class CBSRLinear(Function):

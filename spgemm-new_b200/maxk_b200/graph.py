@@ -109,14 +109,9 @@ class DistGraph:
         if key not in self._aggs:
             vals = edge_values(self.indptr, self.indices, kind, self.n_cols, self._col_deg)
             if self.comm == "peer":
-                from .autograd import planned_homes
                 from .peer import PeerAggregator
-                homes = planned_homes()  # EXPERIMENTAL opt-in (MAXK_PLANNED_HOMES), where the fused kernel is built
-                homes = 0 if homes < 0 else homes  # "auto" is a single-GPU notion (all ranks must agree)
-                if not ((k in (32, 64) and homes) or (k == 16 and homes in (2, 4)) or (k == 8 and homes == 2)):
-                    homes = 0
                 self._aggs[key] = PeerAggregator(self.indptr, self.indices, vals, self.bounds, self.rank, k,
-                                                 feat_dim, group=self.group, homes=homes)
+                                                 feat_dim, group=self.group)
             else:
                 self._aggs[key] = DistAggregator(self.indptr, self.indices, vals, self.bounds, self.rank, k,
                                                  feat_dim, group=self.group, split=self.split)
@@ -124,3 +119,20 @@ class DistGraph:
 
     def aggregate(self, sp_data, sp_index, kind: str, feat_dim: int):
         return _DistAggregate.apply(sp_data, sp_index, self.aggregator(kind, sp_data.shape[1], feat_dim))
+
+    def close(self):
+        """Release the aggregators (IPC-exported buffers and the peers' mappings of them).  COLLECTIVE: every
+        rank must call it, in the same order of keys (PeerAggregator.close synchronises the ranks so that no
+        peer still has a kernel in flight on a buffer that is about to be freed)."""
+        for key in sorted(self._aggs, key=repr):
+            agg = self._aggs[key]
+            if hasattr(agg, "close"):
+                agg.close()
+        self._aggs.clear()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -152,38 +152,108 @@ class HostAggregator:
         return self.result(self.submit(x_host, dy_host))
 
 
+class _ShardSlot:
+    """Device inputs / outputs and pinned host outputs of one in-flight step of a rank."""
+
+    def __init__(self, n_loc, d, k, dev, pin):
+        self.x_d = torch.empty((n_loc, d), dtype=torch.float32, device=dev)
+        self.dy_d = torch.empty((n_loc, d), dtype=torch.float32, device=dev)
+        self.y_d = torch.empty((n_loc, d), dtype=torch.float32, device=dev)
+        self.dxc_d = torch.empty((max(n_loc, 1), k), dtype=torch.float32, device=dev)
+        self.y_h = torch.empty((n_loc, d), dtype=torch.float32, pin_memory=pin)
+        self.dxc_h = torch.empty((n_loc, k), dtype=torch.float32, pin_memory=pin)
+        self.inputs_free = None   # event: the kernels that read x_d / dy_d have finished
+        self.done = None          # event: y_h / dxc_h are complete
+
+
 class ShardHostAggregator:
     """Host-buffer entry point of ONE RANK of a row-partitioned job (one process per GPU): wraps a
     `peer.PeerAggregator` or `dist.DistAggregator` and runs one forward + backward of the MaxK aggregation
     on this rank's HOST rows:
 
-        y_host_loc, dxc_host_loc = shard.step(x_host_loc, dy_host_loc)
+        y_host_loc, dxc_host_loc = shard.step(x_host_loc, dy_host_loc)            # synchronous
+        t = shard.submit(x_host_loc, dy_host_loc); ...; y, dxc = shard.result(t)  # two steps in flight
 
     Per step: upload of the rank's X and dY rows (pinned buffers for full speed), TopK -> CBSR in place,
-    exchange with the other ranks, forward, download of Y behind the backward's launch, backward +
-    reduce-scatter, download of dXc; results are valid on return.  Every GPU uses its own PCIe link, so
-    the host traffic of the job (the same bytes as on one GPU) is spread over all of them.
+    exchange with the other ranks, forward, download of Y behind the backward, backward + reduce-scatter,
+    download of dXc.  Every GPU uses its own PCIe link, so the host traffic of the job (the same bytes as
+    on one GPU) is spread over all of them.  `submit` / `result` is the same work as a two-deep pipeline --
+    the same shape as `HostAggregator` on one GPU: with two slots of buffers the uploads of step i+1 run on a
+    copy stream while step i computes, and its downloads on another one while step i+1 computes, so a stream
+    of steps is bound by the slowest of (upload, kernels + exchange, download) instead of by their sum.
+    EVERY rank must submit the same sequence of steps (each step contains the exchange with the peers).
     This is what bench.py reports as `e2e` at N > 1.
-    overlap=True (EXPERIMENTAL, unmeasured; CUDA only): the dY upload runs on a copy stream behind the forward and
-    the Y download on another one behind the backward, like HostAggregator does on one GPU; the aggregator's
-    own work stays on the caller's stream."""
+    overlap (one synchronous step): the dY upload runs behind the forward and the Y download behind the
+    backward; off = everything on the caller's stream."""
 
-    def __init__(self, agg, overlap: bool = False):
+    def __init__(self, agg, overlap: bool = True, slots: int = 2):
         self.agg = agg
         dev = agg.y.device
         self.device = dev
         n_loc, d, k = int(agg.n_local), int(agg.d), int(agg.k)
         pin = dev.type == "cuda"
-        self.x_d = torch.empty((n_loc, d), dtype=torch.float32, device=dev)
-        self.dy_d = torch.empty((n_loc, d), dtype=torch.float32, device=dev)
-        self.y_h = torch.empty((n_loc, d), dtype=torch.float32, pin_memory=pin)
-        self.dxc_h = torch.empty((n_loc, k), dtype=torch.float32, pin_memory=pin)
+        self.pipelined = pin and bool(getattr(agg, "supports_out", False))
+        self.slots = [_ShardSlot(n_loc, d, k, dev, pin) for _ in range(max(1, int(slots)) if self.pipelined else 1)]
+        s0 = self.slots[0]
+        self.x_d, self.dy_d, self.y_h, self.dxc_h = s0.x_d, s0.dy_d, s0.y_h, s0.dxc_h
         self.h2d_bytes = 2 * n_loc * d * 4
         self.d2h_bytes = n_loc * (d + k) * 4
         self.overlap = bool(overlap) and pin
-        if self.overlap:
+        self._submitted = 0
+        if pin:
             self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
+    # ------------------------------------------------------------------ two steps in flight
+    def submit(self, x_host: torch.Tensor, dy_host: torch.Tensor) -> int:
+        """Enqueue one step on this rank's host rows and return a ticket for `result`.  At most len(slots)
+        steps may be in flight; the kernels run on the caller's current stream."""
+        if not self.pipelined:
+            raise RuntimeError("ShardHostAggregator.submit needs a CUDA aggregator with caller-owned outputs "
+                               "(peer.PeerAggregator); use step()")
+        slot = self.slots[self._submitted % len(self.slots)]
+        ticket = self._submitted
+        self._submitted += 1
+        agg, cur, s_in, s_out = self.agg, torch.cuda.current_stream(self.device), self.s_in, self.s_out
+        if slot.inputs_free is not None:
+            s_in.wait_event(slot.inputs_free)   # this slot's previous kernels are done with x_d / dy_d
+        if slot.done is not None:
+            cur.wait_event(slot.done)           # ... and its previous downloads with y_d / dxc_d
+        with torch.cuda.stream(s_in):
+            slot.x_d.copy_(x_host, non_blocking=True)
+            ev_x = torch.cuda.Event()
+            ev_x.record(s_in)
+            slot.dy_d.copy_(dy_host, non_blocking=True)
+            ev_dy = torch.cuda.Event()
+            ev_dy.record(s_in)
+        cur.wait_event(ev_x)
+        g_data, g_index = agg.topk_and_exchange(slot.x_d)
+        y = agg.forward(g_data, g_index, out=slot.y_d)
+        ev_y = torch.cuda.Event()
+        ev_y.record(cur)
+        with torch.cuda.stream(s_out):          # Y goes home while the backward runs
+            s_out.wait_event(ev_y)
+            slot.y_h.copy_(y, non_blocking=True)
+        cur.wait_event(ev_dy)
+        dxc = agg.backward(slot.dy_d, g_index, out=slot.dxc_d)
+        slot.inputs_free = torch.cuda.Event()
+        slot.inputs_free.record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(slot.inputs_free)
+            slot.dxc_h.copy_(dxc, non_blocking=True)
+            slot.done = torch.cuda.Event()
+            slot.done.record(s_out)
+        return ticket
+
+    def result(self, ticket: int):
+        """Block until the step behind `ticket` is complete; returns (y f32[n_local, d], dxc f32[n_local, k]) --
+        pinned host buffers owned by the object, valid until the submit after next reuses them."""
+        if not (self._submitted - len(self.slots) <= ticket < self._submitted):
+            raise RuntimeError(f"ShardHostAggregator.result: ticket {ticket} is no longer in flight")
+        slot = self.slots[ticket % len(self.slots)]
+        slot.done.synchronize()
+        return slot.y_h, slot.dxc_h
+
+    # ------------------------------------------------------------------ one step at a time
     def _step_overlapped(self, x_host, dy_host):
         cur = torch.cuda.current_stream(self.device)
         self.s_in.wait_stream(cur)   # whatever read x_d / dy_d before (it ran on the caller's stream) is done
@@ -212,6 +282,10 @@ class ShardHostAggregator:
     def step(self, x_host: torch.Tensor, dy_host: torch.Tensor):
         """x_host, dy_host: f32[n_local, d] host tensors (this rank's rows).  Returns (y f32[n_local, d],
         dxc f32[n_local, k]) in pinned host buffers owned by the object, valid until the next step."""
+        if self._submitted:
+            for s in self.slots:            # steps in flight use the same buffers: drain them first
+                if s.done is not None:
+                    s.done.synchronize()
         if self.overlap:
             return self._step_overlapped(x_host, dy_host)
         self.x_d.copy_(x_host, non_blocking=True)

@@ -141,12 +141,23 @@ def spgemm_forward(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Ten
     return out
 
 
-# ---------------------------------------------------- a2, experimental: bank-planned forward
-def cbsr_bank_plan(sp_index: torch.Tensor, homes: int = 2, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """EXPERIMENTAL (csrc/cbsr_plan.cu; not yet run on a GPU).  sp_index uint8 [N, k] -> sp_addr
-    uint16 [N, k]: the shared-memory accumulator word each entry uses in `spgemm_forward_planned`,
-    chosen per row among `homes` (2, 4, 8) candidates so that the 32 entries of one update spread
-    over the 32 banks."""
+# ---------------------------------------------------- a2 through a bank plan (k = 32, 64)
+L2_OPERAND_BYTES = 96 << 20   # a CBSR operand larger than this does not stay in the 126 MB L2
+
+
+def use_bank_plan(k: int, num_tasks: int, num_rows: int, num_cbsr_rows: int) -> bool:
+    """Whether the forward SpGEMM should go through the bank plan: k = 32 or 64, rows of several tasks
+    (W >= 2N: the doubled flush of the two-home accumulator is amortised over >= 128 edges) and a CBSR
+    operand that lives in the L2 (then the update's shared-memory bank conflicts are the bound; on a
+    DRAM-bound operand they are hidden).  Measured (profiles/r02_variants.md): Reddit shape k = 32
+    3.99 -> 3.1 ms, k = 64 7.1 -> 5.9 ms; products / Flickr shapes: no gain."""
+    return (k in (32, 64) and num_tasks >= 2 * num_rows and num_cbsr_rows * 6 * k <= L2_OPERAND_BYTES)
+
+
+def cbsr_bank_plan(sp_index: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sp_index uint8 [N, k] -> sp_addr uint16 [N, k] (csrc/cbsr_plan.cu): the shared-memory accumulator
+    word each entry uses in `spgemm_forward_planned`, one of the two homes of its column, chosen per row so
+    that the 32 entries of one update spread over the 32 banks."""
     lib = _cabi.load()
     _cuda(sp_index, "sparse_selector", torch.uint8)
     _req(sp_index.dim() == 2, "sparse_selector must be [N, k]")
@@ -157,16 +168,16 @@ def cbsr_bank_plan(sp_index: torch.Tensor, homes: int = 2, out: Optional[torch.T
         else:
             _cuda(out, "out", torch.uint16)
             _req(tuple(out.shape) == (n, k), "out has the wrong shape")
-        _cabi.check(lib.maxk_cbsr_bank_plan(sp_index.data_ptr(), n, k, int(homes), out.data_ptr(), _stream(sp_index)))
+        _cabi.check(lib.maxk_cbsr_bank_plan(sp_index.data_ptr(), n, k, out.data_ptr(), _stream(sp_index)))
     return out
 
 
 def spgemm_forward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
-                           sp_data: torch.Tensor, sp_addr: torch.Tensor, homes: int = 2,
+                           sp_data: torch.Tensor, sp_addr: torch.Tensor,
                            feat_dim: int = FULL_DIM, num_rows: Optional[int] = None,
                            out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    """EXPERIMENTAL: `spgemm_forward` with the bank plan `sp_addr = cbsr_bank_plan(sp_index, homes)`
-    in place of the selectors (k = 8, 16 or a multiple of 32).  Same output contract."""
+    """`spgemm_forward` with the bank plan `sp_addr = cbsr_bank_plan(sp_index)` in place of the selectors
+    (k = 32, 64).  Same output contract."""
     lib = _cabi.load()
     _cuda(warp4, "warp4_metadata", torch.int32)
     _cuda(indices, "indices", torch.int32)
@@ -186,17 +197,32 @@ def spgemm_forward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: t
             _cuda(out, "out", torch.float32)
             _req(tuple(out.shape) == (n_out, feat_dim), "out has the wrong shape")
         _cabi.check(lib.maxk_spgemm_forward_planned(warp4.data_ptr(), w, indices.data_ptr(), values.data_ptr(),
-                                                    sp_data.data_ptr(), sp_addr.data_ptr(), k, int(homes),
+                                                    sp_data.data_ptr(), sp_addr.data_ptr(), k,
                                                     out.data_ptr(), n_out, feat_dim, 1 if accumulate else 0,
                                                     _stream(sp_data)))
     return out
 
 
+def spgemm_forward_auto(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
+                        sp_data: torch.Tensor, sp_index: torch.Tensor, feat_dim: int = FULL_DIM,
+                        num_rows: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                        plan_buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The forward SpGEMM as the layers call it: through the bank plan where `use_bank_plan` says it pays
+    (the plan kernel runs here, in front of the SpGEMM -- it is part of the forward's cost), else directly."""
+    k = sp_data.shape[1]
+    n_out = sp_data.shape[0] if num_rows is None else int(num_rows)
+    if sp_index.dtype == torch.uint8 and use_bank_plan(k, warp4.numel() // 4, n_out, sp_data.shape[0]):
+        sp_addr = cbsr_bank_plan(sp_index, out=plan_buf)
+        return spgemm_forward_planned(warp4, indices, values, sp_data, sp_addr, feat_dim=feat_dim,
+                                      num_rows=num_rows, out=out)
+    return spgemm_forward(warp4, indices, values, sp_data, sp_index, feat_dim=feat_dim, num_rows=num_rows, out=out)
+
+
 def sspmm_backward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: torch.Tensor,
-                           grad_output: torch.Tensor, sp_addr: torch.Tensor, homes: int = 2,
+                           grad_output: torch.Tensor, sp_addr: torch.Tensor,
                            out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    """EXPERIMENTAL: `sspmm_backward` with the bank plan in place of the selectors (k = 8, 16, 32, 64, 96, 128;
-    the plan must have been made with the same `homes`).  Same output contract."""
+    """`sspmm_backward` reading its columns out of the bank plan (the multi-GPU peer path ships the plan in
+    place of the selectors).  Same output contract."""
     lib = _cabi.load()
     _cuda(warp4, "warp4_metadata", torch.int32)
     _cuda(indices, "indices", torch.int32)
@@ -215,7 +241,7 @@ def sspmm_backward_planned(warp4: torch.Tensor, indices: torch.Tensor, values: t
             _cuda(out, "out", torch.float32)
             _req(tuple(out.shape) == (n_cbsr, k), "out has the wrong shape")
         _cabi.check(lib.maxk_sspmm_backward_planned(warp4.data_ptr(), w, indices.data_ptr(), values.data_ptr(),
-                                                    grad_output.data_ptr(), sp_addr.data_ptr(), k, int(homes), d,
+                                                    grad_output.data_ptr(), sp_addr.data_ptr(), k, d,
                                                     out.data_ptr(), n_cbsr, 1 if accumulate else 0,
                                                     _stream(grad_output)))
     return out
@@ -285,7 +311,7 @@ def cbsr_gather(dense: torch.Tensor, sp_index: torch.Tensor) -> torch.Tensor:
 def cbsr_matmul(sp_data: torch.Tensor, sp_index: torch.Tensor, m: torch.Tensor,
                 bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                 accumulate: bool = False) -> torch.Tensor:
-    """EXPERIMENTAL: out[N, C] (+)= bias + scatter(sp_data, sp_index) @ m without the dense
+    """out[N, C] (+)= bias + scatter(sp_data, sp_index) @ m without the dense
     twin; m float32 [D, C] row-major (a Linear's weight transposed), D <= 256, C % 4 == 0."""
     lib = _cabi.load()
     _cuda(sp_data, "sp_data", torch.float32)
@@ -311,7 +337,7 @@ def cbsr_matmul(sp_data: torch.Tensor, sp_index: torch.Tensor, m: torch.Tensor,
 
 def cbsr_axpy_(y: torch.Tensor, sp_data: torch.Tensor, sp_index: torch.Tensor, alpha: float = 1.0,
                alpha_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """EXPERIMENTAL: y[i, sp_index[i,j]] += (alpha + alpha_dev[0]) * sp_data[i,j], in place."""
+    """y[i, sp_index[i,j]] += (alpha + alpha_dev[0]) * sp_data[i,j], in place."""
     lib = _cabi.load()
     _cuda(y, "y", torch.float32)
     _cuda(sp_data, "sp_data", torch.float32)
@@ -329,7 +355,7 @@ def cbsr_axpy_(y: torch.Tensor, sp_data: torch.Tensor, sp_index: torch.Tensor, a
 
 def cbsr_sampled_dot(g: torch.Tensor, m: torch.Tensor, sp_index: torch.Tensor,
                      out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    """EXPERIMENTAL: out[i, j] (+)= <g[i, :], m[sp_index[i, j], :]>  (float32 [N, k]) --
+    """out[i, j] (+)= <g[i, :], m[sp_index[i, j], :]>  (float32 [N, k]) --
     the gradient of cbsr_matmul with respect to sp_data."""
     lib = _cabi.load()
     _cuda(g, "g", torch.float32)
@@ -401,24 +427,8 @@ def set_tuning(fwd_tasks_per_warp: int = 0, bwd_tasks_per_warp: int = 0) -> None
     _cabi.check(_cabi.load().maxk_set_tuning(fwd_tasks_per_warp, bwd_tasks_per_warp))
 
 
-def set_backward_prefetch(on: bool = False) -> None:
-    """EXPERIMENTAL knob: the backward kernel prefetches the next dY row into registers."""
-    _cabi.load().maxk_set_backward_prefetch(1 if on else 0)
-
-
-def set_topk_rows_per_warp(rows: int = 0) -> None:
-    """EXPERIMENTAL knob: rows > 1 = the fp32 TopK handles `rows` consecutive rows per warp, loading the
-    next row while it works on the current one; 0 / 1 = the default kernel."""
-    _cabi.load().maxk_set_topk_rows_per_warp(int(rows))
-
-
-def set_planned_backward_vector(on: bool = False) -> None:
-    """EXPERIMENTAL knob: the planned backward with 128-bit vector reductions (k = 32, 64)."""
-    _cabi.load().maxk_set_planned_backward_vector(1 if on else 0)
-
-
 def set_forward_depth(depth: int = 0) -> None:
-    """Gather pipeline depth multiplier of the forward kernel (0 = automatic); bench/test hook."""
+    """Launch shape of the forward kernel (include/maxk_b200.h: maxk_set_forward_depth; 0 = automatic); bench/test hook."""
     _cabi.check(_cabi.load().maxk_set_forward_depth(int(depth)))
 
 

@@ -26,7 +26,7 @@ One process per GPU, all GPUs of one NVLink domain (<= 16 ranks).
 from __future__ import annotations
 
 import ctypes
-from typing import List
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
@@ -97,18 +97,29 @@ class _Shared:
 class PeerAggregator:
     def __init__(self, indptr_loc, indices_glob, values_loc, bounds: List[int], rank: int, k: int,
                  feat_dim: int = 256, group=None, copy_ctas: int = 16, halo_threshold: float = 0.3,
-                 homes: int = 0):
+                 homes="auto"):
         """halo_threshold: a (sender, receiver) pair exchanges only the rows the receiver's edges
         reference when those are fewer than this fraction of the sender's block, the whole block
         otherwise (0 = always the whole block, > 1 = always row lists).
-        homes (EXPERIMENTAL, unmeasured): 2, 4 or 8 = the bank plan of csrc/cbsr_plan.cu (uint16 per
-        entry) travels in place of the selectors and both directions run the planned kernels."""
+        homes: 2 = the bank plan of csrc/cbsr_plan.cu (uint16 per entry) travels in place of the selectors,
+        the forward runs the planned kernel and the backward decodes its columns from the plan; 0 = the
+        selectors travel; "auto" = 2 where ops.use_bank_plan says the plan pays on EVERY rank (k = 32 / 64,
+        long rows, L2-resident operand), decided collectively."""
         self.group = group
         assert indptr_loc.is_cuda, "the peer-memory path is CUDA only"
-        self.homes = int(homes)
+        self.homes = 0
         self._plan(indptr_loc, indices_glob, values_loc, bounds, rank, k, feat_dim, copy_ctas,
                    halo_threshold)
         world, dev = self.world, self.device
+        if homes == "auto":
+            mine = torch.tensor([1 if ops.use_bank_plan(self.k, self.num_tasks, max(self.n_local, 1), self.n_total)
+                                 else 0], device=dev)
+            if world > 1:
+                dist.all_reduce(mine, op=dist.ReduceOp.MIN, group=group)
+            homes = 2 if int(mine) else 0
+        if homes not in (0, 2) or (homes and self.k not in (32, 64)):
+            raise RuntimeError(f"PeerAggregator: homes={homes!r} must be 0, 2 or 'auto' (2: k = 32 or 64, k={self.k})")
+        self.homes = int(homes)
         send = self._exchange_lists(group)
         # ---- peer-visible buffers (CUDA IPC), two sets alternating by epoch parity -----------
         nb_data = max(self.n_total * self.k * 4, 16)
@@ -308,7 +319,7 @@ class PeerAggregator:
             if getattr(self, "_sel_tmp", None) is None:
                 self._sel_tmp = torch.empty((self.n_local, self.k), dtype=torch.uint8, device=self.device)
             ops.topk_cbsr(x_loc, self.k, out=(d_own, self._sel_tmp))
-            ops.cbsr_bank_plan(self._sel_tmp, self.homes, out=a_own)
+            ops.cbsr_bank_plan(self._sel_tmp, out=a_own)
         else:
             ops.topk_cbsr(x_loc, self.k, out=self.own_block(par))
         return self._publish_forward()
@@ -323,7 +334,7 @@ class PeerAggregator:
         if self.homes and sp_addr_loc is not None:   # plan made by the caller (next to its TopK)
             i_own.copy_(sp_addr_loc)
         elif self.homes:   # the plan of this rank's rows travels in place of their selectors
-            ops.cbsr_bank_plan(sp_index_loc.contiguous(), self.homes, out=i_own)
+            ops.cbsr_bank_plan(sp_index_loc.contiguous(), out=i_own)
         else:
             i_own.copy_(sp_index_loc)
         return self._publish_forward()
@@ -335,31 +346,39 @@ class PeerAggregator:
         par = self._fwd_epoch & 1
         return self.g_data[par], self.g_index[par]
 
-    def forward(self, g_data=None, g_index=None) -> torch.Tensor:
+    supports_out = True   # forward / backward take caller-owned output buffers (host.ShardHostAggregator's pipeline)
+
+    def forward(self, g_data=None, g_index=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Y for this rank's rows, f32[n_local, d]: into `out` if given, else into the aggregator's own buffer
+        (valid until the next forward)."""
         par = self._fwd_epoch & 1
+        y = self.y if out is None else out
+        assert y.is_contiguous() and tuple(y.shape) == (self.n_local, self.d) and y.dtype == torch.float32
         with torch.cuda.device(self.device):
             if self.homes:
                 _cabi.check(_cabi.load().maxk_spgemm_forward_fused_planned(
-                    ctypes.byref(self._ctx[par]), self._fwd_epoch, self.homes, self.f_warp4.data_ptr(),
+                    ctypes.byref(self._ctx[par]), self._fwd_epoch, self.f_warp4.data_ptr(),
                     self.num_tasks, self.wait_from_task, self.f_indices.data_ptr(), self.f_values.data_ptr(),
-                    self.y.data_ptr(), self.n_local, self.d, self.copy_ctas, self._stream()))
+                    y.data_ptr(), self.n_local, self.d, self.copy_ctas, self._stream()))
             else:
                 _cabi.check(_cabi.load().maxk_spgemm_forward_fused(
                     ctypes.byref(self._ctx[par]), self._fwd_epoch, self.f_warp4.data_ptr(), self.num_tasks,
                     self.wait_from_task, self.f_indices.data_ptr(), self.f_values.data_ptr(),
-                    self.y.data_ptr(), self.n_local, self.d, self.copy_ctas, self._stream()))
-        return self.y
+                    y.data_ptr(), self.n_local, self.d, self.copy_ctas, self._stream()))
+        return y
 
     # ------------------------------------------------------------------------ backward
-    def backward(self, dy_loc: torch.Tensor, g_index: torch.Tensor) -> torch.Tensor:
-        """-> dXc for the rows this rank owns, f32[n_local, k]."""
+    def backward(self, dy_loc: torch.Tensor, g_index: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-> dXc for the rows this rank owns, f32[n_local, k] (into `out` if given: contiguous, 16-byte aligned)."""
+        rs = self.rs_out if out is None else out
+        assert rs.is_contiguous() and rs.shape[0] >= self.n_local and rs.shape[1] == self.k and rs.dtype == torch.float32
         self._bwd_epoch += 1
         par = self._bwd_epoch & 1
         lib = _cabi.load()
         with torch.cuda.device(self.device):
             _cabi.check(lib.maxk_peer_zero_partial(ctypes.byref(self._ctx[par]), self._stream()))
         if self.homes:
-            ops.sspmm_backward_planned(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index, self.homes,
+            ops.sspmm_backward_planned(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index,
                                        out=self.partial[par], accumulate=True)
         else:
             ops.sspmm_backward(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index,
@@ -368,8 +387,8 @@ class PeerAggregator:
             _cabi.check(lib.maxk_peer_publish(ctypes.c_void_p(self._flag_ptr + 4 * 1), self._bwd_epoch,
                                               self._stream()))
             _cabi.check(lib.maxk_reduce_scatter_pull(ctypes.byref(self._ctx[par]), self._bwd_epoch,
-                                                     self.rs_out.data_ptr(), self._stream()))
-        return self.rs_out[: self.n_local]
+                                                     rs.data_ptr(), self._stream()))
+        return rs[: self.n_local]
 
     def close(self):
         torch.cuda.synchronize(self.device)

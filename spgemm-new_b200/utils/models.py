@@ -55,9 +55,9 @@ def _sparsify(x, k, nonlinear, p, training):
 
 
 def _linear_sparsify(lin, x, k, nonlinear, p, training):
-    """Linear -> MaxK -> dropout as CBSR; with MAXK_CBSR_NATIVE=1 (EXPERIMENTAL) the pair is one autograd
+    """Linear -> MaxK -> dropout as CBSR; for k <= 32 (autograd.cbsr_native_enabled) the pair is one autograd
     node whose backward computes dX on the CBSR gradient instead of as a dense GEMM."""
-    if nonlinear == "maxk" and cbsr_native_enabled():
+    if nonlinear == "maxk" and cbsr_native_enabled(k):
         sp_data, sp_index = LinearTopKCBSR.apply(x, lin.weight, lin.bias, k)
         if p > 0 and training:
             sp_data = F.dropout(sp_data, p, True)
@@ -106,7 +106,7 @@ class SAGE(_Base):
             else:                   # SAGEConv("mean", feat_drop): dropout(maxk(x)) feeds both branches
                 sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
                 fc_self = self.fc_self_layers[i]
-                if self.nonlinear == "maxk" and cbsr_native_enabled():   # EXPERIMENTAL: fc_self on the CBSR operand
+                if self.nonlinear == "maxk" and cbsr_native_enabled(self.maxk):   # fc_self on the CBSR operand
                     own = CBSRLinear.apply(sp_data, sp_index, fc_self.weight, fc_self.bias)
                 else:
                     own = fc_self(_Scatter.apply(sp_data, sp_index, self.hid))
@@ -152,7 +152,7 @@ class GIN(_Base):
         x = self.lin_in(x).relu()
         for i in range(self.num_layers):
             sp_data, sp_index = _linear_sparsify(self.linlayers[i], x, self.maxk, self.nonlinear, self.p, self.training)
-            if cbsr_native_enabled():   # EXPERIMENTAL: self term added to the aggregate in place, no dense twin
+            if self.nonlinear == "maxk" and cbsr_native_enabled(self.maxk):   # self term added in place, no dense twin
                 x = CBSRAddScaled.apply(g.aggregate(sp_data, sp_index, "sum", self.hid), sp_data, sp_index, self.eps[i])
             else:
                 h = _Scatter.apply(sp_data, sp_index, self.hid)

@@ -24,7 +24,6 @@ MUTANTS = {
                                      "for (; j + STEP <= len + 1; j += STEP) {", 0),
     "fwd-shared-row-as-plain-store": ("spgemm_forward.cu", "const bool first_shared = accumulate || (prev_row == first_row);", "const bool first_shared = accumulate;", 0),
     "fwd-gap-rows-not-zeroed": ("spgemm_forward.cu", "if (!accumulate) fwd_zero_rows(out, (int64_t)cur_row + 1, info.x, d, lane);", "", 0),
-    "fwd-db-second-batch-dropped": ("spgemm_forward.cu", "fwd_acc_batch<C>(evb, slb, acc_lane, j + STEP, len, k, lane);", "", 0),
     "ring-no-barrier-after-wait": ("spgemm_forward.cu", "        __syncwarp();            // ... and so have the other lanes'\n", "", 0),
     "ring-waits-for-too-little": ("spgemm_forward.cu", "            cp_async_wait<1>();  // this lane's chunks of group g have landed ...", "            cp_async_wait<2>();", 0),
     "ring-selector-chunk-offset": ("spgemm_forward.cu", ": sp_index + col * K + 16 * (p - VCH);", ": sp_index + col * K + 16 * (p - VCH + 1);", 0),
@@ -35,26 +34,23 @@ MUTANTS = {
     "topk-tie-order": ("topk_cbsr.cu", "if (r0 < need) sel |= (1u << i);", "if (r0 <= need) sel |= (1u << i);", 0),
     "topk-row-bound": ("topk_cbsr.cu", "if (row >= n) return;  // warp-uniform; no CTA barrier below\n\n", "if (row > n) return;\n\n", 0),
     # bank plan and planned kernels
-    "plan-home-word-formula": ("common.cuh", "return (unsigned)h * 256u + lo * 32u + (((c >> 3) + (unsigned)plan_s(h) * lo + (unsigned)plan_t(h)) & 31u);",
-                               "return (unsigned)h * 256u + lo * 32u + (((c >> 3) + (unsigned)plan_s(h) * lo + (unsigned)plan_t(h) + 1u) & 31u);", 0),
-    "plan-augment-forgets-the-path": ("cbsr_plan.cu", "                    owner[st_bank[l]] = st_entry[l];\n                    home[st_entry[l]] = st_home[l];",
-                                      "                    owner[st_bank[l]] = st_entry[l];\n                    if (l == sp) home[st_entry[l]] = st_home[l];", 0),
+    "plan-home-word-formula": ("common.cuh", "return h == 0 ? c : 256u + (c & 7u) * 32u + (c >> 3);", "return h == 0 ? c : 256u + (c & 7u) * 32u + ((c >> 3) ^ 1u);", 0),
+    "plan-word-column-decode": ("common.cuh", "return w < 256u ? w : (((w & 31u) << 3) | ((w >> 5) & 7u));", "return w < 256u ? w : (((w & 31u) << 3) | ((w >> 5) & 3u));", 0),
+    "plan-moved-holder-keeps-its-home": ("cbsr_plan.cu", "            home ^= 1;\n            move[lane] = 0;", "            move[lane] = 0;", 0),
+    "plan-no-barrier-before-reading-the-owner-table": ("cbsr_plan.cu", "    if (valid) owner[b0] = (unsigned char)lane;\n    __syncwarp();", "    if (valid) owner[b0] = (unsigned char)lane;", 0),
     "planned-flush-skips-a-home": ("spgemm_forward.cu", "            for (int h = 1; h < H; ++h) {\n                const float *p = acc + h * 256;", "            for (int h = 1; h < H - 1; ++h) {\n                const float *p = acc + h * 256;", 0),
     "planned-flush-clears-before-all-lanes-read": ("spgemm_forward.cu", "    __syncwarp();  // every lane has read all homes before anybody clears a word of them\n", "", 0),
-    "planned-backward-row-staged-in-home-0-only": ("sspmm_backward_planned.cu", "        for (int h = 1; h < H; ++h) {\n            float *p = dys + h * 256;", "        for (int h = 1; h < 1; ++h) {\n            float *p = dys + h * 256;", 0),
-    "planned-backward-no-barrier-before-restaging": ("sspmm_backward_planned.cu", "            __syncwarp();  // lookups of the previous row are done\n", "", 0),
     # NVLink peer path (tests/test_simt_python_layer.py -k peer): the stand-in for the TMA unit lands data late
     "peer-tma-stage-reused-before-its-stores-read-it": ("peer.cuh", 'if (chunks_issued >= PEER_TMA_STAGES) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");', "", "peer"),
     "peer-tma-store-before-the-load-landed": ("peer.cuh", "        mbar_wait(mbar0 + 8 * st, (phase >> st) & 1u);\n", "", "peer"),
     "peer-flag-raised-for-the-wrong-rank": ("peer.cuh", "st_release_sys(a.flags[p] + PEER_FLAG_ARRIVED + a.rank, a.epoch);", "st_release_sys(a.flags[p] + PEER_FLAG_ARRIVED + p, a.epoch);", "peer"),
     "peer-halo-rows-of-the-wrong-peer": ("peer.cuh", "    const int *rows = a.send_rows[p];\n    const long long n = a.send_count[p];", "    const int *rows = a.send_rows[p];\n    const long long n = a.send_count[p] - 1;", "peer"),
-    # CBSR x dense products (cbsr_dense.cu) and the rows-per-warp TopK
+    # CBSR x dense products (cbsr_dense.cu)
     "cbsr-dense-no-barrier-after-staging": ("cbsr_dense.cu", "            __syncwarp();\n            float4 acc = b4;", "            float4 acc = b4;", 0),
     "cbsr-dense-no-barrier-before-restaging": ("cbsr_dense.cu", "            __syncwarp();  // the staging area is rewritten for the next row\n", "", 0),
     "cbsr-dense-tile-reload-no-barrier": ("cbsr_dense.cu", "        __syncthreads();  // everyone is done with the previous tile\n", "", 0),
     "cbsr-dense-transpose-keeps-the-sent-half": ("cbsr_dense.cu", "const float keep = upper ? p[i + half] : p[i];", "const float keep = upper ? p[i] : p[i + half];", 0),
     "cbsr-dense-later-tiles-overwrite": ("cbsr_dense.cu", "const bool first = (col0 == 0) && !accumulate;", "const bool first = !accumulate;", 0),
-    "topk-rows-prefetch-past-the-last-row": ("topk_cbsr.cu", "        if (row + 1 < r1) {", "        if (row + 1 <= r1) {", 0),
     "worklist-scan-no-barrier": ("worklist.cu", "    if (lane == 31) warp_sums[warp] = inc;\n    __syncthreads();", "    if (lane == 31) warp_sums[warp] = inc;", 0),
     "worklist-last-chunk-length": ("worklist.cu", "rec.z = min(nz, deg - nz * c_in_row);", "rec.z = nz;", 0),
 }

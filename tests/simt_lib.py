@@ -142,18 +142,6 @@ def set_forward_copies(copies=0):
     load().maxk_set_forward_copies(int(copies))
 
 
-def set_backward_prefetch(on):
-    load().maxk_set_backward_prefetch(1 if on else 0)
-
-
-def set_topk_rows_per_warp(rows=0):
-    load().maxk_set_topk_rows_per_warp(int(rows))
-
-
-def set_planned_backward_vector(on):
-    load().maxk_set_planned_backward_vector(1 if on else 0)
-
-
 def set_cp_async_eager(eager):
     """cp.async data lands immediately (True) or as late as PTX allows, at the issuer's wait (False, default)."""
     load().simt_set_cp_async_eager(1 if eager else 0)
@@ -344,18 +332,18 @@ def cbsr_unpack(records, n, k):
     return r["sp_data"], r["sp_index"]
 
 
-def cbsr_bank_plan(sp_index, homes=2):
+def cbsr_bank_plan(sp_index):
     L = load()
     sp_index = np.ascontiguousarray(sp_index, np.uint8)
     n, k = sp_index.shape
     r = _run(L.maxk_cbsr_bank_plan, {"sp_index": Guarded(sp_index, name="sp_index", align=1)},
              {"sp_addr": Guarded(shape=(n, k), dtype=np.uint16, name="sp_addr", align=2)},
-             lambda p: (p["sp_index"], i64(n), i32(k), i32(homes), p["sp_addr"], None))
+             lambda p: (p["sp_index"], i64(n), i32(k), p["sp_addr"], None))
     return r["sp_addr"]
 
 
 def spgemm_forward_planned(w4, idx, val, sp_data, sp_addr, n_out, d=256, accumulate=False, out_init=None,
-                           data_align=16, addr_align=16, homes=2):
+                           data_align=16, addr_align=16):
     L = load()
     w4 = np.ascontiguousarray(w4, np.int32).reshape(-1)
     k = sp_data.shape[1]
@@ -366,11 +354,11 @@ def spgemm_forward_planned(w4, idx, val, sp_data, sp_addr, n_out, d=256, accumul
     out = Guarded(out_init, name="out") if out_init is not None else Guarded(shape=(n_out, d), dtype=np.float32, name="out")
     r = _run(L.maxk_spgemm_forward_planned, ins, {"out": out},
              lambda p: (p["warp4"], i64(w4.shape[0] // 4), p["idx"], p["val"], p["sp_data"], p["sp_addr"], i32(k),
-                        i32(homes), p["out"], i64(n_out), i32(d), i32(1 if accumulate else 0), None))
+                        p["out"], i64(n_out), i32(d), i32(1 if accumulate else 0), None))
     return r["out"]
 
 
-def sspmm_backward_planned(w4, idx, val, dy, sp_addr, homes=2, n_cbsr=None, accumulate=False, out_init=None,
+def sspmm_backward_planned(w4, idx, val, dy, sp_addr, n_cbsr=None, accumulate=False, out_init=None,
                            dxc_align=16, addr_align=16):
     L = load()
     w4 = np.ascontiguousarray(w4, np.int32).reshape(-1)
@@ -384,6 +372,6 @@ def sspmm_backward_planned(w4, idx, val, dy, sp_addr, homes=2, n_cbsr=None, accu
     out = (Guarded(out_init, name="dxc", align=dxc_align) if out_init is not None
            else Guarded(shape=(n_cbsr, k), dtype=np.float32, name="dxc", align=dxc_align))
     r = _run(L.maxk_sspmm_backward_planned, ins, {"dxc": out},
-             lambda p: (p["warp4"], i64(w4.shape[0] // 4), p["idx"], p["val"], p["dy"], p["sp_addr"], i32(k), i32(homes),
+             lambda p: (p["warp4"], i64(w4.shape[0] // 4), p["idx"], p["val"], p["dy"], p["sp_addr"], i32(k),
                         i32(d), p["dxc"], i64(n_cbsr), i32(1 if accumulate else 0), None))
     return r["dxc"]

@@ -70,7 +70,6 @@ def test_argument_errors_without_gpu(lib):
     rc = h.maxk_cbsr_axpy(None, None, 4, 0, 256, None, ctypes.c_float(1.0), None, None)
     assert rc == 1 and b"k=0" in h.maxk_last_error()
     assert h.maxk_cbsr_matmul(None, None, 0, 32, None, 256, 256, None, None, 0, None) == 0   # n = 0: nothing to do
-    assert h.maxk_set_topk_rows_per_warp(4) == 0 and h.maxk_set_topk_rows_per_warp(0) == 0
     with pytest.raises(RuntimeError, match="CUDA"):
         from maxk_b200 import ops
         ops.cbsr_matmul(torch.zeros(2, 4), torch.zeros(2, 4, dtype=torch.uint8), torch.zeros(8, 4))

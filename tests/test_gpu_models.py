@@ -53,12 +53,12 @@ def _ref_forward(model, kind, A, x, k):
     return lin(model.lin_out, x)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MAXK_EXPERIMENTAL") != "1",
-                    reason="layers on the CBSR operand (MAXK_CBSR_NATIVE, csrc/cbsr_dense.cu): written after round 1's GPU "
-                           "budget was spent, checked under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
+@pytest.mark.parametrize("native", ["0", "1"])
 @pytest.mark.parametrize("name", ["SAGE", "GIN", "GCN"])
-def test_models_on_the_cbsr_operand_experimental(name, monkeypatch):
-    monkeypatch.setenv("MAXK_CBSR_NATIVE", "1")
+def test_models_with_and_without_the_layers_on_the_cbsr_operand(name, native, monkeypatch):
+    """MAXK_CBSR_NATIVE forces the dense-twin layers (0) or the CBSR-operand layers (1); the default (k <= 32: on)
+    is what test_models_match_dense_restatement runs."""
+    monkeypatch.setenv("MAXK_CBSR_NATIVE", native)
     test_models_match_dense_restatement(name, 2, True)
 
 

@@ -197,14 +197,10 @@ def test_forward_launch_shapes(ops, k, shape):
         ops.set_tuning(-1, -1)
 
 
-@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
-                    reason="launch shapes 4-7 (double-buffered gather batches) and 8-11 (cp.async gather ring) were "
-                           "written after round 1's GPU budget was spent: compiled and checked under the SIMT "
-                           "interpreter (tests/test_simt_kernels.py), not yet run on a GPU; opt in with "
-                           "MAXK_EXPERIMENTAL=1")
-@pytest.mark.parametrize("shape", [4, 5, 6, 7, 8, 9, 10, 11, 12])
+@pytest.mark.parametrize("shape", [8, 12])
 @pytest.mark.parametrize("k", [32, 16, 64, 8])
-def test_forward_experimental_shapes(ops, k, shape):
+def test_forward_ring_shapes(ops, k, shape):
+    """cp.async gather ring (the automatic choice on operands larger than the L2), forced on a small problem."""
     p = Problem(n=400, avg=45.0, k=k, seed=13 * k + shape, empty_frac=0.2)
     g = p.cuda()
     want = p.fwd_oracle()
@@ -221,115 +217,107 @@ def test_forward_experimental_shapes(ops, k, shape):
         ops.set_tuning(-1, -1)
 
 
-@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
-                    reason="bank-planned forward (csrc/cbsr_plan.cu): written after round 1's GPU budget was spent, "
-                           "checked under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
-@pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=16), dict(k=8), dict(k=128), dict(k=256), dict(k=32, d=128),
-                                  dict(k=32, selector="random"), dict(k=32, avg=3.0, n=3000, empty_frac=0.4),
-                                  dict(k=32, n=50, avg=2000.0, empty_frac=0.0), dict(k=32, warp_max_nz=100)],
+@pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=32, d=128), dict(k=32, selector="random"),
+                                  dict(k=32, avg=3.0, n=3000, empty_frac=0.4), dict(k=64, n=50, avg=2000.0, empty_frac=0.0),
+                                  dict(k=32, warp_max_nz=100)],
                          ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
-def test_forward_planned_experimental(ops, case):
+def test_forward_through_the_bank_plan(ops, case):
     p = Problem(seed=len(str(case)) + 2, **case)
     g = p.cuda()
     want = p.fwd_oracle()
     try:
-        for homes in ((2, 4, 8) if p.k in (32, 64) else (2, 4) if p.k == 16 else (2,)):
-            sp_addr = ops.cbsr_bank_plan(g["sp_index"], homes)
-            assert int(sp_addr.long().max()) < homes * 256
-            for shape, tpw in ((0, -1), (1, 1), (2, 5)):
-                ops.set_forward_depth(shape)
-                ops.set_tuning(tpw, 0)
-                y = torch.full((p.n, p.d), float("nan"), device="cuda")
-                ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, homes,
-                                           feat_dim=p.d, num_rows=p.n, out=y)
-                assert_close(y, want, f"homes={homes} shape={shape} tpw={tpw}")
-            ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, homes,
-                                       feat_dim=p.d, num_rows=p.n, out=y, accumulate=True)
-            assert_close(y, 2 * want, "accumulate")
+        sp_addr = ops.cbsr_bank_plan(g["sp_index"])
+        a = sp_addr.long()
+        assert int(a.max()) < 512
+        col = torch.where(a < 256, a, ((a & 31) << 3) | ((a >> 5) & 7))   # common.cuh: plan_word_column
+        assert torch.equal(col, g["sp_index"].long()), "every entry sits in one of the two homes of its column"
+        for shape, tpw in ((0, -1), (1, 1), (2, 5)):
+            ops.set_forward_depth(shape)
+            ops.set_tuning(tpw, 0)
+            y = torch.full((p.n, p.d), float("nan"), device="cuda")
+            ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr,
+                                       feat_dim=p.d, num_rows=p.n, out=y)
+            assert_close(y, want, f"shape={shape} tpw={tpw}")
+        ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr,
+                                   feat_dim=p.d, num_rows=p.n, out=y, accumulate=True)
+        assert_close(y, 2 * want, "accumulate")
     finally:
         ops.set_forward_depth(0)
         ops.set_tuning(-1, -1)
 
 
-@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
-                    reason="bank-planned backward (csrc/sspmm_backward_planned.cu): written after round 1's GPU budget "
-                           "was spent, checked under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
-@pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=16), dict(k=8), dict(k=128), dict(k=32, d=128),
+def test_bank_plan_spreads_the_banks(ops):
+    """fullest bank of the 32 entries of one update: 3.3 on random columns, ~2.1 through the plan"""
+    x = torch.rand(4000, 256, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    _, si = ops.topk_cbsr(x, 32)
+    def fullest(words):
+        b = (words.long() & 31)
+        return torch.zeros(b.shape[0], 32, device="cuda").scatter_add_(1, b, torch.ones_like(b, dtype=torch.float32)).amax(1)
+    plain, planned = fullest(si).mean().item(), fullest(ops.cbsr_bank_plan(si)).mean().item()
+    assert plain > 3.0 and planned < 2.3, (plain, planned)
+
+
+def test_forward_auto_takes_the_plan_where_it_pays(ops, monkeypatch):
+    p = Problem(n=300, avg=200.0, k=32, seed=5, empty_frac=0.0)
+    g = p.cuda()
+    assert ops.use_bank_plan(32, g["warp4"].numel() // 4, p.n, p.n)
+    calls = []
+    real = ops.cbsr_bank_plan
+    monkeypatch.setattr(ops, "cbsr_bank_plan", lambda *a, **kw: (calls.append(1), real(*a, **kw))[1])
+    y = ops.spgemm_forward_auto(g["warp4"], g["indices"], g["values"], g["sp_data"], g["sp_index"], num_rows=p.n)
+    assert calls == [1]
+    assert_close(y, p.fwd_oracle(), "auto -> planned")
+    q = Problem(n=3000, avg=5.0, k=32, seed=6)
+    h = q.cuda()
+    y = ops.spgemm_forward_auto(h["warp4"], h["indices"], h["values"], h["sp_data"], h["sp_index"], num_rows=q.n)
+    assert calls == [1]
+    assert_close(y, q.fwd_oracle(), "auto -> default")
+
+
+@pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=16), dict(k=8), dict(k=128), dict(k=18), dict(k=32, d=128),
                                   dict(k=32, selector="random"),
                                   dict(k=32, avg=3.0, n=3000, empty_frac=0.4), dict(k=32, n=50, avg=2000.0, empty_frac=0.0),
                                   dict(k=32, n=400, n_cols=1500, avg=25.0), dict(k=64, warp_max_nz=100)],
                          ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
-def test_backward_planned_experimental(ops, case):
+def test_backward_with_columns_decoded_from_the_plan(ops, case):
+    """what the multi-GPU peer path runs when the plan travels in place of the selectors"""
     p = Problem(seed=len(str(case)) + 4, **case)
     g = p.cuda()
     want = p.bwd_oracle()
     try:
-        for homes in ((2, 4, 8) if p.k >= 32 else (2, 4) if p.k == 16 else (2,)):
-            sp_addr = ops.cbsr_bank_plan(g["sp_index"], homes)
-            for tpw, vector in ((-1, False), (1, False), (5, False), (-1, True), (2, True)):
-                ops.set_tuning(0, tpw)
-                ops.set_planned_backward_vector(vector)
-                dxc = torch.full((p.n_cols, p.k), float("nan"), device="cuda")
-                ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, homes, out=dxc)
-                assert_close(dxc, want, f"homes={homes} tpw={tpw} vector={vector}")
-            ops.set_planned_backward_vector(False)
-            ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, homes, out=dxc,
-                                       accumulate=True)
-            assert_close(dxc, 2 * want, "accumulate")
+        sp_addr = ops.cbsr_bank_plan(g["sp_index"])
+        for tpw in (-1, 1, 5):
+            ops.set_tuning(0, tpw)
+            dxc = torch.full((p.n_cols, p.k), float("nan"), device="cuda")
+            ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, out=dxc)
+            assert_close(dxc, want, f"tpw={tpw}")
+        ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, out=dxc, accumulate=True)
+        assert_close(dxc, 2 * want, "accumulate")
     finally:
         ops.set_tuning(-1, -1)
-        ops.set_planned_backward_vector(False)
 
 
-@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
-                    reason="backward with dY-row prefetch: written after round 1's GPU budget was spent, checked under "
-                           "the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
 @pytest.mark.parametrize("case", [dict(k=32), dict(k=64), dict(k=16), dict(k=18), dict(k=32, d=128),
                                   dict(k=32, avg=3.0, n=3000, empty_frac=0.4), dict(k=32, warp_max_nz=100)],
                          ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
-def test_backward_row_prefetch_experimental(ops, case):
+def test_backward_run_lengths(ops, case):
     p = Problem(seed=len(str(case)) + 6, **case)
     g = p.cuda()
     try:
-        ops.set_backward_prefetch(True)
         for tpw in (-1, 1, 3):
             ops.set_tuning(0, tpw)
             dxc = torch.full((p.n_cols, p.k), float("nan"), device="cuda")
             ops.sspmm_backward(g["warp4"], g["indices"], g["values"], g["dy"], g["sp_index"], out=dxc)
             assert_close(dxc, p.bwd_oracle(), f"tpw={tpw}")
     finally:
-        ops.set_backward_prefetch(False)
         ops.set_tuning(-1, -1)
 
 
-@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
-                    reason="fp32 TopK with several rows per warp: written after round 1's GPU budget was spent, checked "
-                           "under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
-@pytest.mark.parametrize("rpw", [2, 4, 8])
-def test_topk_rows_per_warp_experimental(ops, rpw):
-    rng = np.random.default_rng(rpw)
-    try:
-        ops.set_topk_rows_per_warp(rpw)
-        for n, d in ((1, 256), (8 * rpw + 3, 256), (5000, 256), (777, 128), (100, 36)):
-            x = rng.standard_normal((n, d)).astype(np.float32)
-            x[::5] = rng.integers(0, 3, size=x[::5].shape).astype(np.float32)  # rows of ties
-            for k in (1, 8, 18, 32):
-                want_v, want_i = O.topk_cbsr(x, k)
-                v, i = ops.topk_cbsr(torch.from_numpy(x).cuda(), k)
-                np.testing.assert_array_equal(i.cpu().numpy(), want_i, err_msg=f"n={n} d={d} k={k}")
-                np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), want_v.view(np.uint32))
-    finally:
-        ops.set_topk_rows_per_warp(0)
-
-
-@pytest.mark.skipif(os.environ.get("MAXK_EXPERIMENTAL") != "1",
-                    reason="CBSR x dense products (csrc/cbsr_dense.cu): written after round 1's GPU budget was spent, "
-                           "checked under the SIMT interpreter only; opt in with MAXK_EXPERIMENTAL=1")
 @pytest.mark.parametrize("case", [dict(n=5000, d=256, k=32, c=256), dict(n=3333, d=256, k=64, c=132),
                                   dict(n=40000, d=64, k=8, c=4), dict(n=700, d=36, k=18, c=260),
                                   dict(n=300, d=256, k=256, c=128), dict(n=1, d=128, k=1, c=8)],
                          ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
-def test_cbsr_linear_products_experimental(ops, case):
+def test_cbsr_linear_products(ops, case):
     """fc_self on the CBSR operand and the gradient of its values against the dense Linear on the scattered
     twin (fp64 oracle); then the autograd Function against torch's own Linear."""
     from helpers import assert_close_sum

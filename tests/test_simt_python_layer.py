@@ -5,8 +5,8 @@ TEST DOUBLE, not a fallback: inside these tests only, `_cabi._lib` is pointed at
 tests/simt/_build/libmaxk_simt.so (same C ABI, host pointers for device pointers) and the three
 places where `ops` touches CUDA (`_cuda`, `_stream`, `torch.cuda.device`) are patched.  Outside the
 fixture nothing changes: `_cabi.load()` binds lib/libmaxk_b200.so and raises when it is missing.
-Purpose: the argument plumbing of code paths that have not yet run on a GPU (the planned kernels,
-MAXK_PLANNED_HOMES) and of the ones that have, checked against the oracle without a GPU.
+Purpose: the argument plumbing of the Python layer (the bank plan and its automatic use included),
+checked against the oracle without a GPU.
 """
 import contextlib
 import ctypes
@@ -85,39 +85,42 @@ def test_ops_default_kernels_through_python(ops):
         ops.spgemm_forward(w4, g["indices"], g["values"], v, i, accumulate=True)
 
 
-@pytest.mark.parametrize("homes", [2, 4, 8])
 @pytest.mark.parametrize("k", [32, 64])
-def test_ops_planned_kernels_through_python(ops, k, homes):
-    p, g = _problem(n=120, avg=30.0, k=k, seed=k + homes)
-    sp_addr = ops.cbsr_bank_plan(g["sp_index"], homes)
+def test_ops_planned_kernels_through_python(ops, k):
+    p, g = _problem(n=120, avg=30.0, k=k, seed=k)
+    sp_addr = ops.cbsr_bank_plan(g["sp_index"])
     assert sp_addr.dtype == torch.uint16 and tuple(sp_addr.shape) == (p.n, k)
-    assert int(sp_addr.to(torch.int64).max()) < homes * 256
-    y = ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, homes, num_rows=p.n)
+    assert int(sp_addr.to(torch.int64).max()) < 2 * 256
+    y = ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, num_rows=p.n)
     close(y, p.fwd_oracle(), "planned forward")
-    ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, homes, num_rows=p.n,
+    ops.spgemm_forward_planned(g["warp4"], g["indices"], g["values"], g["sp_data"], sp_addr, num_rows=p.n,
                                out=y, accumulate=True)
     close(y, 2 * p.fwd_oracle(), "planned forward, accumulate")
-    dxc = ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, homes)
-    close(dxc, p.bwd_oracle(), "planned backward")
+    dxc = ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr)
+    close(dxc, p.bwd_oracle(), "backward with the columns decoded from the plan")
     out = torch.empty_like(sp_addr)
-    assert ops.cbsr_bank_plan(g["sp_index"], homes, out=out) is out and torch.equal(out, sp_addr)
-    with pytest.raises(RuntimeError, match="homes"):
-        ops.cbsr_bank_plan(g["sp_index"], 5)
+    assert ops.cbsr_bank_plan(g["sp_index"], out=out) is out and torch.equal(out, sp_addr)
     with pytest.raises(RuntimeError, match="wrong shape"):
-        ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, homes,
-                                   out=torch.empty(3, 3))
+        ops.sspmm_backward_planned(g["warp4"], g["indices"], g["values"], g["dy"], sp_addr, out=torch.empty(3, 3))
 
 
-@pytest.mark.parametrize("homes", [0, 2, 8])
-def test_autograd_functions_with_and_without_the_plan(ops, monkeypatch, homes):
+def test_use_bank_plan_rule(ops):
+    assert ops.use_bank_plan(32, 1_905_323, 232_965, 232_965)          # Reddit shape
+    assert ops.use_bank_plan(64, 660_000, 132_534, 132_534)            # proteins shape
+    assert not ops.use_bank_plan(32, 3_200_000, 2_449_029, 2_449_029)  # products: short rows, operand beyond the L2
+    assert not ops.use_bank_plan(16, 1_905_323, 232_965, 232_965)      # k = 16 is not built
+    assert not ops.use_bank_plan(32, 1_000_000, 100_000, 2_449_029)    # long rows but a 470 MB operand
+
+
+@pytest.mark.parametrize("planned", [False, True])
+def test_autograd_functions_with_and_without_the_plan(ops, monkeypatch, planned):
     """CBSRAggregate / TopKCBSR / SpGEMMFunction: same values and gradients whether the aggregation
-    runs through the default kernels or, with MAXK_PLANNED_HOMES set, through the planned ones."""
-    from maxk_b200.autograd import CBSRAggregate, SpGEMMFunction, TopKCBSR, planned_homes
-    if homes:
-        monkeypatch.setenv("MAXK_PLANNED_HOMES", str(homes))
-    else:
-        monkeypatch.delenv("MAXK_PLANNED_HOMES", raising=False)
-    assert planned_homes() == homes
+    runs through the default forward kernel or (ops.use_bank_plan) through the bank plan."""
+    from maxk_b200.autograd import CBSRAggregate, SpGEMMFunction, TopKCBSR
+    calls = []
+    real = ops.cbsr_bank_plan
+    monkeypatch.setattr(ops, "use_bank_plan", lambda *a: planned)
+    monkeypatch.setattr(ops, "cbsr_bank_plan", lambda *a, **kw: (calls.append(1), real(*a, **kw))[1])
     p, g = _problem(n=100, avg=15.0, k=32, seed=21)
     x = g["x"].clone().requires_grad_(True)
     sp_data, sp_index = TopKCBSR.apply(x, 32)
@@ -131,6 +134,7 @@ def test_autograd_functions_with_and_without_the_plan(ops, monkeypatch, homes):
     close(y2, p.fwd_oracle())
     y2.backward(g["dy"])
     np.testing.assert_allclose(x2.grad.numpy(), want, rtol=RTOL, atol=ATOL)
+    assert len(calls) == (2 if planned else 0)
 
 
 class _HostGraph:
@@ -159,11 +163,8 @@ def test_models_train_step_same_with_and_without_the_plan(ops, monkeypatch, name
     feats = torch.randn(p.n, 16)
     target = torch.randint(0, 5, (p.n,))
     results = []
-    for homes in (0, 8):
-        if homes:
-            monkeypatch.setenv("MAXK_PLANNED_HOMES", str(homes))
-        else:
-            monkeypatch.delenv("MAXK_PLANNED_HOMES", raising=False)
+    for planned in (False, True):
+        monkeypatch.setattr(ops, "use_bank_plan", lambda *a, _p=planned: _p)
         model.zero_grad()
         loss = torch.nn.functional.cross_entropy(model(G, feats), target)
         loss.backward()
@@ -414,11 +415,11 @@ def test_shard_host_aggregator_over_the_peer_path(peer_group, world, k, halo):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("world,k,halo,homes,copy_ctas", [(2, 32, 0.0, 8, 3), (3, 32, 0.3, 2, -2), (2, 64, 2.0, 4, 2),
-                                                          (2, 16, 0.0, 4, 2), (3, 8, 2.0, 2, -1), (4, 32, 0.0, 4, 1)])
+@pytest.mark.parametrize("world,k,halo,homes,copy_ctas", [(2, 32, 0.0, 2, 3), (3, 32, 0.3, 2, -2), (2, 64, 2.0, 2, 2),
+                                                          (4, 32, 0.0, 2, 1)])
 def test_peer_planned_kernels_multi_rank_under_the_interpreter(peer_group, world, k, halo, homes, copy_ctas):
-    """The bank plan travels in place of the selectors (EXPERIMENTAL fused planned forward + planned
-    backward): same oracle, dense / halo / mixed pairs, TMA and load/store push."""
+    """The bank plan travels in place of the selectors (fused planned forward; the backward decodes its columns
+    from the plan): same oracle, dense / halo / mixed pairs, TMA and load/store push."""
     from maxk_b200.dist import partition_rows_by_nnz
     make, pool = peer_group
     p, g = _problem(n=96 * world, avg=14.0, k=k, seed=world * 10 + k + homes, empty_frac=0.1)
@@ -485,36 +486,3 @@ def test_peer_tma_push_of_a_block_larger_than_the_staging_ring(peer_group):
             np.testing.assert_array_equal(aggs[r].g_data[par].numpy(), sd)
 
 
-def test_auto_choice_of_planned_homes_runs_every_candidate(ops, monkeypatch):
-    """MAXK_PLANNED_HOMES=auto: the chooser times default / 2 / 4 / 8 homes on the caller's operands
-    (CUDA events replaced by a host clock here) and the aggregation then uses its pick."""
-    import time
-    from maxk_b200 import autograd as A
-
-    class FakeEvent:
-        def __init__(self, enable_timing=False):
-            self.t = 0.0
-
-        def record(self):
-            self.t = time.perf_counter()
-
-        def synchronize(self):
-            pass
-
-        def elapsed_time(self, other):
-            return (other.t - self.t) * 1e3
-
-    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
-    monkeypatch.setenv("MAXK_PLANNED_HOMES", "auto")
-    A._PLAN_CHOICE.clear()
-    assert A.planned_homes() == -1
-    p, g = _problem(n=60, avg=12.0, k=32, seed=9)
-    x = g["x"].clone().requires_grad_(True)
-    sp_data, sp_index = A.TopKCBSR.apply(x, 32)
-    y = A.CBSRAggregate.apply(sp_data, sp_index, g["warp4"], g["indices"], g["values"], 256, p.n)
-    close(y, p.fwd_oracle())
-    y.backward(g["dy"])
-    assert len(A._PLAN_CHOICE) == 1 and next(iter(A._PLAN_CHOICE.values())) in (0, 2, 4, 8)
-    np.testing.assert_allclose(x.grad.numpy(), O.cbsr_scatter(p.bwd_oracle().astype(np.float32), p.sp_index, 256),
-                               rtol=RTOL, atol=ATOL)
-    A._PLAN_CHOICE.clear()
