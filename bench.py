@@ -281,10 +281,12 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--sweep", action="store_true", help="also time k=8/16/64, TopK and the work list")
-    ap.add_argument("--planned", type=int, default=0, choices=(0, 2, 4, 8),
-                    help="EXPERIMENTAL: forward and backward through the bank plan with this many homes per column "
-                         "(csrc/cbsr_plan.cu).  N=1: the plan is made next to the TopK, outside the step, and timed "
-                         "separately; N>1 (peer transport): the plan travels in place of the selectors")
+    ap.add_argument("--no-plan", action="store_true",
+                    help="measurement knob: the forward without the bank plan (csrc/cbsr_plan.cu) even where "
+                         "ops.use_bank_plan says it pays")
+    ap.add_argument("--epochs", type=int, default=5,
+                    help="epochs of the training leg (products-shaped graph, SAGE MaxK k=32; 0 = skip the leg)")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the parity check of one extra step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--comm", choices=("peer", "nccl"), default="peer",
@@ -292,7 +294,9 @@ def main():
     ap.add_argument("--ref-kernels", action="store_true",
                     help="also time the reference CUDA kernels (oracle/_ref) on the same inputs")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    if args.impl == "own" and args.warmup < 3:
+        log(f"[bench] --warmup {args.warmup} raised to 3 (timing rules: at least 3 warm-up steps); the line reports 3")
+        args.warmup = 3
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -304,6 +308,14 @@ def main():
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         g, scale = make_reddit(dev)
         value, ms, info = run_cpu_reference(g, args.k, max(1, args.steps), max(0, args.warmup))
+        ref_gpu = time_reference_kernels(g, args.k, dev)
+        if ref_gpu is not None:
+            from maxk_b200 import graphs as _graphs
+            deg_all = (g["indptr"][1:] - g["indptr"][:-1]).long()
+            w_all = int(((deg_all + 63) // 64).sum())
+            b_all = _graphs.algorithmic_bytes(g["v_num"], g["e_num"], w_all, args.k, FEAT_DIM)
+            ref_gpu["GBps"] = (b_all["fwd"] + b_all["bwd"]) / (ref_gpu["ms_per_step"] * 1e-3) / 1e9
+            log(f"[ref kernels on this GPU] fwd {ref_gpu['fwd_ms']:.3f} ms  bwd {ref_gpu['bwd_ms']:.3f} ms  {ref_gpu['GBps']:.0f} GB/s")
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -316,6 +328,10 @@ def main():
                 "cpu_baseline": info,
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
+        line["config"]["note"] = ("the CPU step times forward + backward only (its TopK runs before the timed region); "
+                                  "the own arm's e2e additionally has TopK and the host<->device copies inside")
+        if ref_gpu is not None:
+            line["reference_kernels_on_this_gpu"] = ref_gpu
         print(json.dumps(line), flush=True)
         return 0
 
@@ -347,7 +363,8 @@ def main():
             from maxk_b200.peer import PeerAggregator
             try:
                 agg = PeerAggregator.from_global_csr(g["indptr"], g["indices"], g["values"], bounds,
-                                                     rank, k, FEAT_DIM, copy_ctas=16, homes=args.planned)
+                                                     rank, k, FEAT_DIM, copy_ctas=16,
+                                                     homes=0 if args.no_plan else "auto")
                 ok = 1
             except Exception as exc:  # noqa: BLE001
                 log(f"[rank {rank}] peer-memory path unavailable: {exc}")
@@ -359,8 +376,6 @@ def main():
         if agg is None:
             agg = DistAggregator.from_global_csr(g["indptr"], g["indices"], g["values"], bounds, rank, k,
                                                  FEAT_DIM)
-        del g["indices"], g["values"]
-        torch.cuda.empty_cache()
         n_loc = agg.n_local
         gen = torch.Generator(dev).manual_seed(123 + rank)
         x_loc = torch.rand(n_loc, FEAT_DIM, device=dev, generator=gen)
@@ -370,14 +385,10 @@ def main():
         w = int(w_total)
 
         sd_loc, si_loc = ops.topk_cbsr(x_loc, k)   # like N=1: TopK is outside the step
-        planned_peer = bool(args.planned) and comm == "peer"
-        sa_loc = ops.cbsr_bank_plan(si_loc, args.planned) if planned_peer else None  # ... and so is the plan
+        planned_peer = comm == "peer" and bool(getattr(agg, "homes", 0))
 
         def step():
-            if planned_peer:
-                gd, gi = agg.exchange(sd_loc, si_loc, sa_loc)
-            else:
-                gd, gi = agg.exchange(sd_loc, si_loc)   # CBSR all-gather (NCCL, async)
+            gd, gi = agg.exchange(sd_loc, si_loc)    # own block into the peer-visible buffer (+ its bank plan)
             agg.forward(gd, gi)                      # local columns overlap the all-gather
             agg.backward(dy_loc, gi)                 # + reduce-scatter of the partial gradients
         fwd_ms = bwd_ms = None
@@ -388,7 +399,8 @@ def main():
         x = torch.rand(n, FEAT_DIM, device=dev, generator=gen)
         dy = torch.rand(n, FEAT_DIM, device=dev, generator=gen)
         sp_data, sp_index = ops.topk_cbsr(x, k)
-        sp_addr = ops.cbsr_bank_plan(sp_index, args.planned) if args.planned else None
+        use_plan = (not args.no_plan) and ops.use_bank_plan(k, w, n, n)
+        sp_addr = torch.empty((n, k), dtype=torch.uint16, device=dev) if use_plan else None
         y = torch.empty(n, FEAT_DIM, device=dev)
         dxc = torch.empty(n, k, device=dev)
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -398,17 +410,14 @@ def main():
             i = step_no[0]
             if i >= 0:
                 ev[i][0].record()
-            if sp_addr is not None:
-                ops.spgemm_forward_planned(warp4, g["indices"], g["values"], sp_data, sp_addr, args.planned,
-                                           out=y, num_rows=n)
+            if use_plan:   # the plan is made from sp_index INSIDE the step: it is part of the forward's cost
+                ops.cbsr_bank_plan(sp_index, out=sp_addr)
+                ops.spgemm_forward_planned(warp4, g["indices"], g["values"], sp_data, sp_addr, out=y, num_rows=n)
             else:
                 ops.spgemm_forward(warp4, g["indices"], g["values"], sp_data, sp_index, out=y, num_rows=n)
             if i >= 0:
                 ev[i][1].record()
-            if sp_addr is not None and k % 32 == 0 and k <= 128:
-                ops.sspmm_backward_planned(warp4, g["indices"], g["values"], dy, sp_addr, args.planned, out=dxc)
-            else:
-                ops.sspmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dxc)
+            ops.sspmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dxc)
             if i >= 0:
                 ev[i][2].record()
 
@@ -466,8 +475,42 @@ def main():
             "sspmm_bwd": {"ms": bwd_ms, "GBps": bytes_["bwd"] / bwd_ms / 1e6,
                           "frac_of_hbm_peak": bytes_["bwd"] / bwd_ms / 1e6 / peak,
                           "edges_per_s": e / (bwd_ms * 1e-3)}}
+        roofline["includes"] = ("CUDA events around the forward of every timed step: "
+                                + ("bank-plan kernel (cbsr_plan.cu) + " if use_plan else "")
+                                + "row-clearing pre-kernel + spgemm_fwd_kernel") if dom == "spgemm_fwd" else \
+                               "CUDA events around the backward of every timed step: memset of dXc + sspmm_bwd_kernel"
+        # the same kernels with the L2 flushed in front of every launch (a 512 MB buffer is
+        # overwritten, outside the event pair) -- the CBSR operand then comes from HBM once per launch
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+        cold_f = cold_b = cold_p = 0.0
+        reps = 5
+        ce = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        for _ in range(reps):
+            flush.zero_()
+            ce[0].record()
+            if use_plan:
+                ops.cbsr_bank_plan(sp_index, out=sp_addr)
+                ce[1].record()
+                ops.spgemm_forward_planned(warp4, g["indices"], g["values"], sp_data, sp_addr, out=y, num_rows=n)
+            else:
+                ce[1].record()
+                ops.spgemm_forward(warp4, g["indices"], g["values"], sp_data, sp_index, out=y, num_rows=n)
+            ce[2].record()
+            flush.zero_()
+            ce[3].record()
+            ops.sspmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dxc)
+            ce[4].record()
+            torch.cuda.synchronize()
+            cold_p += ce[0].elapsed_time(ce[1]) / reps
+            cold_f += ce[0].elapsed_time(ce[2]) / reps
+            cold_b += ce[3].elapsed_time(ce[4]) / reps
+        del flush
+        extra["kernels"]["spgemm_fwd"].update({"ms_cold_l2": cold_f, "frac_of_hbm_peak_cold_l2": bytes_["fwd"] / cold_f / 1e6 / peak,
+                                               "bank_plan": bool(use_plan), "bank_plan_ms_cold_l2": cold_p if use_plan else None})
+        extra["kernels"]["sspmm_bwd"].update({"ms_cold_l2": cold_b, "frac_of_hbm_peak_cold_l2": bytes_["bwd"] / cold_b / 1e6 / peak})
         log(f"[own] fwd {fwd_ms:.3f} ms  bwd {bwd_ms:.3f} ms  step {ms_per_step:.3f} ms  "
-            f"{value:.0f} GB/s  roofline {dom} {roofline['frac']:.3f} of {peak_src} peak")
+            f"{value:.0f} GB/s  roofline {dom} {roofline['frac']:.3f} of {peak_src} peak;  L2 flushed before every "
+            f"launch: fwd {cold_f:.3f} ms (plan {cold_p:.3f})  bwd {cold_b:.3f} ms")
     elif not args.no_e2e:
         # N > 1: forward and backward of a few extra steps timed apart (CUDA events on every rank, max over
         # ranks); the roofline is PER GPU -- each rank's share of the algorithmic bytes against one GPU's peak
@@ -476,7 +519,7 @@ def main():
             reps, f_ms, b_ms = 5, 0.0, 0.0
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             for _ in range(reps):
-                gd, gi = agg.exchange(sd_loc, si_loc, sa_loc) if planned_peer else agg.exchange(sd_loc, si_loc)
+                gd, gi = agg.exchange(sd_loc, si_loc)
                 evs[0].record()
                 agg.forward(gd, gi)
                 evs[1].record()
@@ -522,7 +565,7 @@ def main():
             sd, si = ops.topk_cbsr(x, kk)
             dx2 = torch.empty(n, kk, device=dev)
             bb = graphs.algorithmic_bytes(n, e, w, kk, FEAT_DIM)
-            tf = timeit(lambda: ops.spgemm_forward(warp4, g["indices"], g["values"], sd, si, out=y, num_rows=n))
+            tf = timeit(lambda: ops.spgemm_forward_auto(warp4, g["indices"], g["values"], sd, si, out=y, num_rows=n))
             tb = timeit(lambda: ops.sspmm_backward(warp4, g["indices"], g["values"], dy, si, out=dx2))
             tt = timeit(lambda: ops.topk_cbsr(x, kk))
             sweep[f"k{kk}"] = {"fwd_ms": tf, "bwd_ms": tb, "topk_ms": tt,
@@ -534,17 +577,31 @@ def main():
         sweep["worklist_ms"] = tm
         sweep["worklist_frac"] = bytes_["meta"] / tm / 1e6 / peak
         extra["sweep"] = sweep
-    if world == 1 and args.ref_kernels:
-        from oracle import ref_kernels as R
-        if R.available():
-            yr = torch.zeros(n, FEAT_DIM, device=dev)
-            dr = torch.zeros(n, k, device=dev)
-            tf = timeit(lambda: R.spmm_forward(warp4, g["indices"], g["values"], sp_data, sp_index, FEAT_DIM, out=yr), 4, 4)
-            tb = timeit(lambda: R.spmm_backward(warp4, g["indices"], g["values"], dy, sp_index, out=dr), 4, 4)
-            extra["reference_kernels_on_this_gpu"] = {
-                "fwd_ms": tf, "bwd_ms": tb, "note": "kernels/*.cu compiled unmodified for sm_100a, reference "
-                "launch shape, outputs not re-zeroed (reference protocol, spmm_base.h:56-74)"}
-            log(f"[ref kernels] fwd {tf:.3f} ms  bwd {tb:.3f} ms")
+    if world == 1 and args.ref_kernels:   # (the driver gets this from `--impl reference`; here for one-call comparisons)
+        rk = time_reference_kernels(g, k, dev)
+        if rk is not None:
+            extra["reference_kernels_on_this_gpu"] = rk
+            log(f"[ref kernels] fwd {rk['fwd_ms']:.3f} ms  bwd {rk['bwd_ms']:.3f} ms")
+
+    # ------------------------------------------------- N > 1: did the timed step compute the right thing?
+    parity = None
+    if world > 1 and not args.no_parity:
+        ok = 1
+        try:
+            parity = multi_gpu_parity(agg, g, bounds, rank, world, k, dev, sd_loc, si_loc, dy_loc, dist, ops)
+        except Exception as exc:  # noqa: BLE001
+            log(f"[rank {rank}] parity leg failed: {type(exc).__name__}: {exc}")
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0:
+            parity = {"parity_ok": False, "error": "the parity leg raised on at least one rank (see stderr)"}
+        if rank == 0:
+            log(f"[parity] N={world}: {parity}")
+    if world > 1:
+        g.pop("indices", None)
+        g.pop("values", None)
+        torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------------------ e2e
     e2e = None
@@ -589,7 +646,7 @@ def main():
         ok = 1
         try:
             from maxk_b200.host import ShardHostAggregator
-            shard = ShardHostAggregator(agg, overlap=os.environ.get("MAXK_SHARD_OVERLAP", "0") == "1")
+            shard = ShardHostAggregator(agg)
             xh = x_loc.cpu().pin_memory()
             dyh = dy_loc.cpu().pin_memory()
         except Exception as exc:  # noqa: BLE001
@@ -606,23 +663,43 @@ def main():
                 dist.barrier()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                for _ in range(e_steps):
+                for _ in range(e_steps):   # one step at a time: upload, kernels + exchange, download, return
                     shard.step(xh, dyh)
                 torch.cuda.synchronize()
-                e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
-                tmax = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+                sync_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+                pipelined = shard.pipelined
+                e_ms = sync_ms
+                if pipelined:
+                    # a stream of steps through the same public API, two in flight: submit(i+1) before result(i).
+                    # Every step still uploads its own X and dY rows and downloads its own Y and dXc rows.
+                    dist.barrier()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    prev = None
+                    for _ in range(e_steps):
+                        t = shard.submit(xh, dyh)
+                        if prev is not None:
+                            shard.result(prev)
+                        prev = t
+                    shard.result(prev)
+                    torch.cuda.synchronize()
+                    e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+                tmax = torch.tensor([e_ms, sync_ms], device=dev, dtype=torch.float64)
                 dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
                 nbytes = torch.tensor([shard.h2d_bytes, shard.d2h_bytes], device=dev, dtype=torch.int64)
                 dist.all_reduce(nbytes)
-                e_ms = float(tmax)
+                e_ms, sync_ms = float(tmax[0]), float(tmax[1])
                 e2e = {"value": step_bytes / (e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_ms,
                        "h2d_bytes_per_step": int(nbytes[0]), "d2h_bytes_per_step": int(nbytes[1]), "steps": e_steps,
+                       "ms_per_step_synchronous": sync_ms,
                        "includes": f"per step and rank (max over {world} ranks, wall clock between synchronisations): H2D of "
                                    "the rank's X and dY rows (pinned), TopK->CBSR in place, exchange, forward, backward + "
-                                   "reduce-scatter, D2H of its Y and dXc rows; ShardHostAggregator.step, one step at a time"
-                                   + (" (EXPERIMENTAL overlap of the dY upload / Y download with the kernels)" if shard.overlap else "")
+                                   "reduce-scatter, D2H of its Y and dXc rows; "
+                                   + ("ShardHostAggregator.submit/result with two steps in flight "
+                                      "(ms_per_step_synchronous = ShardHostAggregator.step, one at a time)" if pipelined
+                                      else "ShardHostAggregator.step, one step at a time")
                                    + "; bytes are summed over the ranks"}
-                log(f"[e2e] {e_ms:.2f} ms/step  {e2e['value']:.0f} GB/s over {world} ranks")
+                log(f"[e2e] {e_ms:.2f} ms/step  {e2e['value']:.0f} GB/s over {world} ranks (synchronous {sync_ms:.2f} ms/step)")
                 del shard, xh, dyh
             except Exception as exc:  # noqa: BLE001
                 log(f"[rank {rank}] N > 1 e2e leg skipped: {type(exc).__name__}: {exc}")
@@ -653,27 +730,60 @@ def main():
                                  "(37 MB) is L2-resident by design",
                            "step_algorithmic_bytes": step_bytes},
                 "clocks": clocks, "gpu_launches": launches}
-        if world > 1 and args.planned and comm == "peer":
-            line["config"]["forward"] = (f"EXPERIMENTAL bank-planned kernels, {args.planned} homes per column; the plan is "
-                                         "made next to the TopK, outside the step, and travels over NVLink in place "
-                                         "of the selectors")
-        if world == 1 and args.planned:
-            line["config"]["forward"] = (f"EXPERIMENTAL bank-planned forward and backward, {args.planned} homes per "
-                                         "column; the plan kernel runs next to the TopK, outside the step (plan_ms)")
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-            for _ in range(10):
-                ops.cbsr_bank_plan(sp_index, args.planned, out=sp_addr)
-            t1.record()
-            torch.cuda.synchronize()
-            line["plan_ms"] = t0.elapsed_time(t1) / 10
+        line["config"]["timed_region"] = ("value: forward SpGEMM (incl. its bank-plan kernel where used) + backward SSpMM of "
+                                          "every step; TopK->CBSR and the work list are made once, before the timed region "
+                                          "(their times: --sweep / profiles/r02_sweep.json); e2e has TopK inside")
+        if world == 1:
+            line["config"]["forward"] = ("through the two-home bank plan (cbsr_plan.cu), plan kernel inside the step"
+                                         if use_plan else "default kernel (no bank plan)")
+        elif comm == "peer":
+            line["config"]["forward"] = ("bank plan made inside the step, travels over NVLink in place of the selectors; the "
+                                         "backward decodes its columns from it" if planned_peer else "selectors travel (no bank plan)")
         if roofline:
             line["roofline"] = roofline
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         if e2e:
             line["e2e"] = e2e
+        if parity:
+            line.update({"parity_ok": parity.get("parity_ok"), "parity": parity})
         line.update(extra)
+    else:
+        line = None
+
+    # ------------------------------------------------------------------ epoch leg (second half of the metric)
+    # Full-graph training epochs/s on the products-shaped graph at the N of this run, through the same package
+    # (maxk_b200.train).  Extra key `epoch`, after the timed region.  A watchdog prints the line without it if the
+    # leg does not finish (it contains collectives): the bench line must not be lost to its extra leg.
+    if args.epochs > 0:
+        def give_up():
+            if rank == 0:
+                line["epoch"] = {"error": "the epoch leg did not finish within 300 s"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        dog = threading.Timer(300.0, give_up)
+        dog.daemon = True
+        dog.start()
+        try:
+            if world > 1:
+                getattr(agg, "close", lambda: None)()   # collective: the Reddit job's peer buffers are released on every rank
+                del agg
+            else:
+                del warp4, x, dy, sp_data, sp_index, y, dxc
+            g.clear()
+            torch.cuda.empty_cache()
+            from maxk_b200 import train
+            rec = train.run_epochs("products", epochs=args.epochs, warmup=2, device=dev, rank=rank, world=world,
+                                   comm=comm if world > 1 else "peer")
+            if rank == 0:
+                line["epoch"] = rec
+                log(f"[epoch] products-shaped SAGE k=32: {rec['ms_per_epoch']:.2f} ms/epoch = {rec['value']:.3f} epochs/s at N={world}")
+        except Exception as exc:  # noqa: BLE001
+            log(f"[rank {rank}] epoch leg failed: {type(exc).__name__}: {exc}")
+            if rank == 0:
+                line["epoch"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        dog.cancel()
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -79,3 +79,32 @@ def topk_u8(x, k):
     ind = torch.zeros((n, k), dtype=torch.uint8, device=x.device)
     _check(lib.ref_topk_u8(x.data_ptr(), val.data_ptr(), ind.data_ptr(), k, n, d), "topk")
     return val, ind
+
+
+# ---- zero-edit route: the reference's OWN binding file, unmodified, on our library ----
+ZEROEDIT_PATH = os.path.join(_HERE, "_ref", "zeroedit", "maxk_cuda_kernels.so")
+
+
+def build_zeroedit(reference_root: str = "/root/reference") -> bool:
+    """Compile /root/reference/cuda_kernel_bindings.cpp + kernels/spmm_cusparse.cu where they lie and link them
+    against spgemm-new_b200/lib/libmaxk_b200.so (oracle/Makefile `zeroedit`); False when the tree is absent."""
+    if not os.path.isfile(os.path.join(reference_root, "cuda_kernel_bindings.cpp")):
+        return os.path.exists(ZEROEDIT_PATH)
+    import sys
+    subprocess.check_call(["make", "-C", _HERE, "-s", "zeroedit", f"REF={reference_root}", f"PYTHON={sys.executable}"])
+    return True
+
+
+def zeroedit_available() -> bool:
+    return os.path.exists(ZEROEDIT_PATH)
+
+
+def load_zeroedit():
+    """The reference's pybind module `maxk_cuda_kernels` (cuda_kernel_bindings.cpp:429-490) built on our kernels.
+    Loaded under a private name so that it does not shadow the package's Python mirror of the same name."""
+    import importlib.util
+    import torch  # noqa: F401  (libtorch must be loaded first)
+    spec = importlib.util.spec_from_file_location("maxk_cuda_kernels", ZEROEDIT_PATH)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

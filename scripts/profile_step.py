@@ -17,8 +17,6 @@ ap.add_argument("--shape", default="reddit")
 ap.add_argument("--k", type=int, default=32)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--scale", type=float, default=1.0)
-ap.add_argument("--planned", type=int, default=0, choices=(0, 2, 4, 8),
-                help="EXPERIMENTAL: also run the bank plan and the planned forward / backward with this many homes")
 ap.add_argument("--depth", type=int, default=0, help="forward launch shape (maxk_set_forward_depth)")
 a = ap.parse_args()
 g = graphs.make_graph(a.shape, seed=0, device="cuda", values="uniform", scale=a.scale)
@@ -32,11 +30,7 @@ ops.set_forward_depth(a.depth)
 for _ in range(a.iters):
     w4 = ops.build_worklist(g["indptr"])
     sd, si = ops.topk_cbsr(x, a.k)
-    ops.spgemm_forward(w4, g["indices"], g["values"], sd, si, out=y, num_rows=n)
+    ops.spgemm_forward_auto(w4, g["indices"], g["values"], sd, si, out=y, num_rows=n)   # bank plan where it pays
     ops.sspmm_backward(w4, g["indices"], g["values"], dy, si, out=dxc)
-    if a.planned:
-        sa = ops.cbsr_bank_plan(si, a.planned)
-        ops.spgemm_forward_planned(w4, g["indices"], g["values"], sd, sa, a.planned, out=y, num_rows=n)
-        ops.sspmm_backward_planned(w4, g["indices"], g["values"], dy, sa, a.planned, out=dxc)
 torch.cuda.synchronize()
 print("ok", n, g["e_num"], w4.numel() // 4, float(y.sum()), float(dxc.sum()))

@@ -18,7 +18,7 @@ ap.add_argument("--copies", default="0,1,2,4,8,16")
 ap.add_argument("--tpw", default="16")
 ap.add_argument("--depth", default="0")
 ap.add_argument("--bwd-tpw", default="")
-ap.add_argument("--planned", action="store_true", help="also time the experimental bank-planned forward (k % 32 == 0)")
+ap.add_argument("--planned", action="store_true", help="also time the bank plan and the planned forward (k = 32, 64)")
 ap.add_argument("--iters", type=int, default=10)
 a = ap.parse_args()
 
@@ -61,51 +61,21 @@ for k in [int(v) for v in a.ks.split(",")]:
                 print(json.dumps(r), flush=True)
     ops.set_forward_copies(0)
     ops.set_forward_depth(0)
-    if a.planned and (k % 32 == 0 or k in (8, 16)):
+    if a.planned and k in (32, 64):
         # the plan is made once per TopK, the planned forward runs once per layer: both are timed
         ref = ops.spgemm_forward(w4, g["indices"], g["values"], sd, si, num_rows=n)
-        for homes in ((2, 4, 8) if k in (32, 64) else (2, 4) if k == 16 else (2,)):
-            sa = ops.cbsr_bank_plan(si, homes)
-            t_plan = timeit(lambda: ops.cbsr_bank_plan(si, homes, out=sa), a.iters)
-            for tpw in [int(v) for v in a.tpw.split(",")]:
-                for dep in (1, 2):
-                    ops.set_forward_depth(dep)
-                    ops.set_tuning(tpw, 0)
-                    t = timeit(lambda: ops.spgemm_forward_planned(w4, g["indices"], g["values"], sd, sa, homes, out=y,
-                                                                  num_rows=n), a.iters)
-                    err = float((y - ref).abs().max() / ref.abs().max())
-                    r = {"kernel": "fwd_planned", "shape": a.shape, "k": k, "homes": homes, "tpw": tpw, "depth": dep,
-                         "ms": round(t, 4), "plan_ms": round(t_plan, 4), "frac": round(b["fwd"] / t / 1e6 / peak, 3),
-                         "frac_with_plan": round(b["fwd"] / (t + t_plan) / 1e6 / peak, 3), "rel_err_vs_default": err}
-                    res.append(r)
-                    print(json.dumps(r), flush=True)
-        ops.set_forward_depth(0)
-        if k <= 128:  # the backward through the same plan
-            dxc = torch.empty(n, k, device="cuda")
-            ref_b = ops.sspmm_backward(w4, g["indices"], g["values"], dy, si)
-            t_def = timeit(lambda: ops.sspmm_backward(w4, g["indices"], g["values"], dy, si, out=dxc), a.iters)
-            for homes in ((2, 4, 8) if k >= 32 else (2, 4) if k == 16 else (2,)):
-                sa = ops.cbsr_bank_plan(si, homes)
-                for vector in ((False, True) if k in (32, 64) else (False,)):
-                    ops.set_planned_backward_vector(vector)
-                    t = timeit(lambda: ops.sspmm_backward_planned(w4, g["indices"], g["values"], dy, sa, homes, out=dxc), a.iters)
-                    err = float((dxc - ref_b).abs().max() / ref_b.abs().max())
-                    r = {"kernel": "bwd_planned", "shape": a.shape, "k": k, "homes": homes,
-                         "reductions": "v4" if vector else "scalar", "ms": round(t, 4), "default_ms": round(t_def, 4),
-                         "frac": round(b["bwd"] / t / 1e6 / peak, 3), "rel_err_vs_default": err}
-                    res.append(r)
-                    print(json.dumps(r), flush=True)
-                ops.set_planned_backward_vector(False)
-    if a.planned:  # the default backward with and without the dY-row prefetch (experimental knob)
-        dxc = torch.empty(n, k, device="cuda")
-        for pf in (False, True):
-            ops.set_backward_prefetch(pf)
-            t = timeit(lambda: ops.sspmm_backward(w4, g["indices"], g["values"], dy, si, out=dxc), a.iters)
-            r = {"kernel": "bwd", "shape": a.shape, "k": k, "row_prefetch": pf, "ms": round(t, 4),
-                 "frac": round(b["bwd"] / t / 1e6 / peak, 3)}
+        sa = ops.cbsr_bank_plan(si)
+        t_plan = timeit(lambda: ops.cbsr_bank_plan(si, out=sa), a.iters)
+        for dep in (1, 2):
+            ops.set_forward_depth(dep)
+            t = timeit(lambda: ops.spgemm_forward_planned(w4, g["indices"], g["values"], sd, sa, out=y, num_rows=n), a.iters)
+            err = float((y - ref).abs().max() / ref.abs().max())
+            r = {"kernel": "fwd_planned", "shape": a.shape, "k": k, "depth": dep,
+                 "ms": round(t, 4), "plan_ms": round(t_plan, 4), "frac": round(b["fwd"] / t / 1e6 / peak, 3),
+                 "frac_with_plan": round(b["fwd"] / (t + t_plan) / 1e6 / peak, 3), "rel_err_vs_default": err}
             res.append(r)
             print(json.dumps(r), flush=True)
-        ops.set_backward_prefetch(False)
+        ops.set_forward_depth(0)
     if a.bwd_tpw:
         dxc = torch.empty(n, k, device="cuda")
         for tpw in [int(v) for v in a.bwd_tpw.split(",")]:

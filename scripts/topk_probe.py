@@ -21,14 +21,9 @@ dists = (("uniform", torch.rand(n, 256, device="cuda", generator=g)),
          ("quantised", (torch.rand(n, 256, device="cuda", generator=g) * 8).floor()))
 for name, x in dists:
     for k in (8, 32, 64):
-        if quick:   # for ncu: one launch per (distribution, k); TOPK_RPW=4 selects the rows-per-warp kernel
-            ops.set_topk_rows_per_warp(int(os.environ.get("TOPK_RPW", "0")))
+        if quick:   # for ncu: one launch per (distribution, k)
             ops.topk_cbsr(x, k); continue
         b = 4 * n * 256 + 5 * n * k
-        for rpw in (0, 2, 4, 8):  # 0 = default kernel; > 1 = experimental rows-per-warp kernel
-            ops.set_topk_rows_per_warp(rpw)
-            t = timeit(lambda: ops.topk_cbsr(x, k))
-            print(f"topk {name:12s} k={k:3d} rows/warp={max(rpw, 1)}: {t*1e3:7.1f} us  {b/t/1e6:7.0f} GB/s  "
-                  f"frac {b/t/1e6/6543.7:.3f}", flush=True)
-        ops.set_topk_rows_per_warp(0)
+        t = timeit(lambda: ops.topk_cbsr(x, k))
+        print(f"topk {name:12s} k={k:3d}: {t*1e3:7.1f} us  {b/t/1e6:7.0f} GB/s  frac {b/t/1e6/6543.7:.3f}", flush=True)
 torch.cuda.synchronize()

@@ -12,8 +12,11 @@ many random (larger cases) ways, buffers carry (writer, epoch) tags, and the che
 Operations per rank and step e (same order as PeerAggregator.exchange/forward/backward):
 
   F1  TopK writes the own block of the own gathered buffer g[e & 1]
-  F2  push: write the own block into every peer's g[e & 1], then raise arrive[peer][rank] = e
+  F2  push: wait until arrive[rank][p] >= e - 1 for all p (every peer has entered step e - 1 and is done with the
+      buffers of step e - 2), write the own block into every peer's g[e & 1], then raise arrive[peer][rank] = e
   F3  wait until arrive[rank][p] >= e for all p; READ every block of the own g[e & 1]   (begin .. end)
+      -- a rank WITHOUT tasks on remote columns (directed / asymmetric partitions) never waits here and reads its own
+      block only: the wait in F2 is what keeps such a rank from running two steps ahead (`no_wait` ranks below)
   B1  zero + scatter into the own partial buffer part[b & 1]                             (all blocks)
   B2  publish bwd[rank] = b
   B3  wait until bwd[p] >= b for all p; READ block `rank` of every peer's part[b & 1]    (begin .. end)
@@ -32,9 +35,11 @@ class Violation(Exception):
 
 
 class Model:
-    def __init__(self, world, programs, buffers=2):
+    def __init__(self, world, programs, buffers=2, no_wait=(), gate_push=True):
         self.w = world
         self.nbuf = buffers
+        self.no_wait = set(no_wait)     # ranks whose forward has no task on a remote column
+        self.gate_push = gate_push      # F2 waits for the peers' arrivals of the step before
         # g[r][parity][block] = epoch of the data that block holds; part[r][parity] = epoch
         self.g = [[[0] * world for _ in range(buffers)] for _ in range(world)]
         self.part = [[0] * buffers for _ in range(world)]
@@ -49,8 +54,10 @@ class Model:
         if self.pc[r] >= len(self.prog[r]):
             return False
         op, e = self.prog[r][self.pc[r]]
+        if op == "F2" and self.gate_push:
+            return all(self.arrive[r][p] >= e - 1 for p in range(self.w) if p != r)
         if op == "F3b":
-            return all(self.arrive[r][p] >= e for p in range(self.w) if p != r)
+            return r in self.no_wait or all(self.arrive[r][p] >= e for p in range(self.w) if p != r)
         if op == "B3b":
             return all(self.bwd[p] >= e for p in range(self.w) if p != r)
         return True
@@ -69,17 +76,17 @@ class Model:
             for p in range(self.w):
                 if p == r:
                     continue
-                if self.reading_g[p] == par:
+                if self.reading_g[p] == par and p not in self.no_wait:   # (a no-wait rank reads its own block only)
                     raise Violation(f"rank {r} pushes epoch {e} into g[{par}] of rank {p} which is being read")
                 self.g[p][par][r] = e
                 self.arrive[p][r] = e
         elif op == "F3b":
-            for blk in range(self.w):
+            for blk in ([r] if r in self.no_wait else range(self.w)):
                 if self.g[r][par][blk] != e:
                     raise Violation(f"rank {r} step {e}: block {blk} holds epoch {self.g[r][par][blk]}")
             self.reading_g[r] = par
         elif op == "F3e":
-            for blk in range(self.w):   # still intact at the end of the kernel
+            for blk in ([r] if r in self.no_wait else range(self.w)):   # still intact at the end of the kernel
                 if self.g[r][par][blk] != e:
                     raise Violation(f"rank {r} step {e}: block {blk} changed under the kernel")
             self.reading_g[r] = None
@@ -116,9 +123,9 @@ def program(pattern):
     return ops
 
 
-def run_random(world, pattern, seed, buffers=2):
+def run_random(world, pattern, seed, buffers=2, no_wait=(), gate_push=True):
     rng = random.Random(seed)
-    m = Model(world, [program(pattern) for _ in range(world)], buffers)
+    m = Model(world, [program(pattern) for _ in range(world)], buffers, no_wait, gate_push)
     # an adversarial flavour: one rank is favoured so that it runs as far ahead as it can
     fav = rng.randrange(world)
     while not m.done():
@@ -131,11 +138,11 @@ def run_random(world, pattern, seed, buffers=2):
         m.step(r)
 
 
-def explore_all(world, pattern, buffers=2):
+def explore_all(world, pattern, buffers=2, no_wait=(), gate_push=True):
     """Depth-first search over every interleaving (with state memoisation)."""
     progs = [program(pattern) for _ in range(world)]
     seen = set()
-    stack = [Model(world, progs, buffers)]
+    stack = [Model(world, progs, buffers, no_wait, gate_push)]
     count = 0
     import copy
     while stack:
@@ -193,3 +200,18 @@ def test_strict_alternation_would_not_even_need_the_second_buffer():
     set is what makes F F F B B B (several layers per step) and forward-only streams safe."""
     assert explore_all(2, "FBFBFB", buffers=1) > 10
     assert explore_all(3, "FBFB", buffers=1) > 100
+
+
+def test_a_rank_without_remote_tasks_cannot_run_ahead():
+    """A rank whose own tasks never read a remote column does not wait in its aggregating warps.  With the push
+    gated on the peers' arrivals of the step before (peer.cuh: peer_push_block) forward-only streams stay safe in
+    every interleaving; WITHOUT that gate -- round 1's protocol -- such a rank runs two steps ahead and overwrites a
+    block a slower peer is still reading (the checker must catch it)."""
+    for no_wait in ((0,), (1,), (0, 1)):
+        assert explore_all(2, "FFFFF", no_wait=no_wait) > 10
+    assert explore_all(3, "FFFF", no_wait=(2,)) > 100
+    assert explore_all(2, "FFFBBB", no_wait=(0,)) > 10
+    for seed in range(200):
+        run_random(8, "FFFFFFFF", seed, no_wait=(seed % 8, (seed + 3) % 8))
+    with pytest.raises(Violation):
+        explore_all(2, "FFFF", no_wait=(0,), gate_push=False)
