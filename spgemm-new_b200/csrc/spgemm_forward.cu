@@ -209,20 +209,30 @@ __device__ __forceinline__ void fwd_process_batch(const int2 *stage, int len, fl
 // (profiles/r02_variants.md).  Cost: the gathered row crosses the L1 data pipe twice more
 // (shared-memory write + read) -- a loss where that pipe is the bound (L2-resident operands:
 // 3.99 -> 5.27 ms on the Reddit shape), hence the choice by operand size.
+// Lanes map to (row, 16-byte chunk) by shifts: K/4 lanes copy the values of one row (so one instruction
+// covers 32 / (K/4) rows), K/16 lanes its selectors.  (Round 2, ncu of the products shape: the first form
+// of this function -- one flat chunk index per lane, divided by the chunks per row -- and of the accumulate
+// below made the kernel ISSUE-bound at 53 instructions per edge, 31 of them in the accumulate.)
 template <class C>
 __device__ __forceinline__ void fwd_ring_issue(const int2 *stage, int e0, int cnt, unsigned char *half,
                                                const float *sp_data, const unsigned char *sp_index,
                                                int lane)
 {
-    constexpr int K = C::K, CH = 5 * K / 16, VCH = K / 4;  // 16-byte chunks per row: values, selectors
-    const int n = cnt * CH;
-    for (int c = lane; c < n; c += 32) {
-        const int e = c / CH, p = c - e * CH;
-        const int64_t col = stage[e0 + e].x;
-        const unsigned char *src =
-            (p < VCH) ? reinterpret_cast<const unsigned char *>(sp_data) + col * (4 * K) + 16 * p
-                      : sp_index + col * K + 16 * (p - VCH);
-        cp_async16(half + e * C::ROW_BYTES + 16 * p, src);
+    constexpr int K = C::K, LV = K / 4, LS = K / 16;  // lanes per row: values, selectors
+    static_assert(LV <= 32 && (32 % LV) == 0 && LS >= 1 && (32 % LS) == 0, "ring: k = 16, 32, 64, 128");
+    const int2 *st = stage + e0;
+    {
+        const int cv = lane % LV;
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(sp_data) + 16 * cv;
+        unsigned char *dst = half + 16 * cv;
+        for (int e = lane / LV; e < cnt; e += 32 / LV)
+            cp_async16(dst + e * C::ROW_BYTES, src + (int64_t)st[e].x * (4 * K));
+    }
+    {
+        const int cs = lane % LS;
+        unsigned char *dst = half + 4 * K + 16 * cs;
+        for (int e = lane / LS; e < cnt; e += 32 / LS)
+            cp_async16(dst + e * C::ROW_BYTES, sp_index + (int64_t)st[e].x * K + 16 * cs);
     }
     cp_async_commit();  // every lane, also those without a chunk: group counts stay warp-uniform
 }
@@ -231,36 +241,53 @@ __device__ __forceinline__ void fwd_ring_accumulate(const int2 *stage, int e0, i
                                                     const unsigned char *half, float *acc_lane, int k,
                                                     int lane)
 {
-    constexpr int U = C::U, E = C::E, K = C::K;
+    constexpr int U = C::U, E = C::E, K = C::K, RB = C::ROW_BYTES;
     const int es = lane & (E - 1);
-    for (int j = 0; j < cnt; j += U * E) {
+    const int entry = (C::KL < 32) ? lane / E : lane;
+    // this lane's view of the rows: value word `entry` (+ 32 i), selector byte 4K + entry (+ 32 i) of row es, es + E, ...
+    const unsigned char *pv = half + es * RB + 4 * entry;
+    const unsigned char *ps = half + es * RB + 4 * K + entry;
+    const int2 *st = stage + e0 + es;
+    int j = 0;
+    for (; j + U * E <= cnt; j += U * E) {  // every lane has an edge in each of the U instructions: no predicates
         Slice<C> sl[U];
         float w[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int e = j + u * E + es;
-            w[u] = 0.f;
-            if (e < cnt) {
-                w[u] = __int_as_float(stage[e0 + e].y);
-                const unsigned char *row = half + e * C::ROW_BYTES;
-                if constexpr (C::KL < 32) {
-                    const int entry = lane / E;
-                    sl[u].v[0] = reinterpret_cast<const float *>(row)[entry];
-                    sl[u].s[0] = row[4 * K + entry];
-                } else {
+            w[u] = __int_as_float(st[u * E].y);
 #pragma unroll
-                    for (int i = 0; i < C::EPL; ++i) {  // conflict-free: consecutive words / bytes
-                        sl[u].v[i] = reinterpret_cast<const float *>(row)[lane + 32 * i];
-                        sl[u].s[i] = row[4 * K + lane + 32 * i];
-                    }
-                }
+            for (int i = 0; i < C::EPL; ++i) {  // conflict-free: consecutive words / bytes
+                sl[u].v[i] = *reinterpret_cast<const float *>(pv + u * E * RB + 128 * i);
+                sl[u].s[i] = ps[u * E * RB + 32 * i];
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (j + u * E < cnt)  // warp-uniform
-                fwd_accumulate<C>(sl[u], acc_lane, w[u], k, lane, j + u * E + es < cnt);
+        for (int u = 0; u < U; ++u) fwd_accumulate<C>(sl[u], acc_lane, w[u], k, lane, true);
+        pv += U * E * RB;
+        ps += U * E * RB;
+        st += U * E;
+    }
+    for (; j < cnt; j += E) {  // tail: one instruction at a time, lanes without an edge idle
+        const bool on = j + es < cnt;
+        Slice<C> sl;
+        float w = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::EPL; ++i) {
+            sl.v[i] = 0.f;
+            sl.s[i] = 0;
         }
+        if (on) {
+            w = __int_as_float(st[0].y);
+#pragma unroll
+            for (int i = 0; i < C::EPL; ++i) {
+                sl.v[i] = *reinterpret_cast<const float *>(pv + 128 * i);
+                sl.s[i] = ps[32 * i];
+            }
+        }
+        fwd_accumulate<C>(sl, acc_lane, w, k, lane, on);
+        pv += E * RB;
+        ps += E * RB;
+        st += E;
     }
 }
 template <class C>

@@ -26,12 +26,15 @@ MUTANTS = {
     "fwd-gap-rows-not-zeroed": ("spgemm_forward.cu", "if (!accumulate) fwd_zero_rows(out, (int64_t)cur_row + 1, info.x, d, lane);", "", 0),
     "ring-no-barrier-after-wait": ("spgemm_forward.cu", "        __syncwarp();            // ... and so have the other lanes'\n", "", 0),
     "ring-waits-for-too-little": ("spgemm_forward.cu", "            cp_async_wait<1>();  // this lane's chunks of group g have landed ...", "            cp_async_wait<2>();", 0),
-    "ring-selector-chunk-offset": ("spgemm_forward.cu", ": sp_index + col * K + 16 * (p - VCH);", ": sp_index + col * K + 16 * (p - VCH + 1);", 0),
+    "ring-selector-chunk-offset": ("spgemm_forward.cu", "sp_index + (int64_t)st[e].x * K + 16 * cs);", "sp_index + (int64_t)st[e].x * K + 16 * cs + 16);", 0),
     "bwd-stage-no-barrier": ("sspmm_backward.cu", "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));\n    __syncwarp();", "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));", 0),
     "bwd-dy-restage-no-barrier": ("sspmm_backward.cu", "            cur_row = info.x;\n            __syncwarp();", "            cur_row = info.x;", 0),
     "bwd-selector-of-wrong-node": ("sspmm_backward.cu", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + q[u]);", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + (q[u] ^ 1));", 0),
     "topk-emit-no-barrier": ("topk_cbsr.cu", "    __syncwarp();\n    unsigned char *oi = out_idx + row * k + lane;", "    unsigned char *oi = out_idx + row * k + lane;", 0),
     "topk-tie-order": ("topk_cbsr.cu", "if (r0 < need) sel |= (1u << i);", "if (r0 <= need) sel |= (1u << i);", 0),
+    "topk-pair-counts-of-the-other-half": ("topk_cbsr.cu", "            const int g = (int)((tot >> sh) & 0xffffu) - k;", "            const int g = (int)(tot & 0xffffu) - k;", 0),
+    "topk-pair-failed-row-not-redone": ("topk_cbsr.cu", "        if (!((failed >> (16 * h)) & 1u)) continue;", "        if (!((failed >> (16 * h)) & 1u) || h == 1) continue;", 0),
+    "topk-pair-scan-crosses-the-halves": ("topk_cbsr.cu", "            const unsigned t = __shfl_up_sync(full, inc, o, 16);\n            if (hl >= o) inc += t;", "            const unsigned t = __shfl_up_sync(full, inc, o, 16);\n            if (lane >= o) inc += t;", 0),
     "topk-row-bound": ("topk_cbsr.cu", "if (row >= n) return;  // warp-uniform; no CTA barrier below\n\n", "if (row > n) return;\n\n", 0),
     # bank plan and planned kernels
     "plan-home-word-formula": ("common.cuh", "return h == 0 ? c : 256u + (c & 7u) * 32u + (c >> 3);", "return h == 0 ? c : 256u + (c & 7u) * 32u + ((c >> 3) ^ 1u);", 0),

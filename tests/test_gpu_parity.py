@@ -317,6 +317,31 @@ def test_backward_run_lengths(ops, case):
                                   dict(n=40000, d=64, k=8, c=4), dict(n=700, d=36, k=18, c=260),
                                   dict(n=300, d=256, k=256, c=128), dict(n=1, d=128, k=1, c=8)],
                          ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
+@pytest.mark.parametrize("pair", [True, False])
+def test_topk_two_rows_per_warp_and_one(ops, pair):
+    """d = 256: the two-rows-per-warp kernel (default) and the one-row kernel, bit-exact against the oracle, with
+    tie / NaN / infinity rows (robust path) next to ordinary rows in the same warp, odd row counts, dense output."""
+    rng = np.random.default_rng(17)
+    try:
+        ops.set_topk_pair(pair)
+        for n in (1, 2, 17, 4099):
+            x = rng.standard_normal((n, 256)).astype(np.float32)
+            x[::5] = rng.integers(0, 3, size=x[::5].shape).astype(np.float32)
+            if n > 4:
+                x[4, 17] = np.nan
+                x[1, :] = -np.inf
+                x[2, 5] = np.inf
+            xt = torch.from_numpy(x).cuda()
+            for k in (1, 8, 18, 32, 64, 256):
+                want_v, want_i = O.topk_cbsr(x, k)
+                v, i, dense = ops.topk_cbsr(xt, k, want_dense=True)
+                np.testing.assert_array_equal(i.cpu().numpy(), want_i, err_msg=f"n={n} k={k}")
+                np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), want_v.view(np.uint32))
+                np.testing.assert_array_equal(dense.cpu().numpy().view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
+    finally:
+        ops.set_topk_pair(True)
+
+
 def test_cbsr_linear_products(ops, case):
     """fc_self on the CBSR operand and the gradient of its values against the dense Linear on the scattered
     twin (fp64 oracle); then the autograd Function against torch's own Linear."""

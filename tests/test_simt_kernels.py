@@ -28,6 +28,7 @@ def _reset_knobs():
     S.set_forward_depth(0)
     S.set_forward_copies(0)
     S.set_cp_async_eager(False)
+    S.set_topk_pair(True)
 
 
 # ------------------------------------------------------------------------------ a4
@@ -81,6 +82,30 @@ def test_simt_topk_ties_and_specials():
         v, i = S.topk_f32(x, k)
         np.testing.assert_array_equal(i, want_i, err_msg=f"k={k}")
         np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
+
+
+@pytest.mark.parametrize("pair", [True, False])
+def test_simt_topk_two_rows_per_warp_and_one(pair):
+    """d = 256: the two-rows-per-warp kernel (default) and the one-row kernel give the oracle's bits for every n around
+    the pair / CTA boundaries, with rows the fast path finishes next to rows it must hand to the robust path (ties,
+    NaN, infinities) in the SAME warp, the dense MaxK output included."""
+    S.set_topk_pair(pair)
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 15, 16, 17, 33):
+        x = rng.standard_normal((n, 256)).astype(np.float32)
+        x[::3] = rng.integers(0, 3, size=x[::3].shape).astype(np.float32)   # every third row: ties everywhere
+        if n > 4:
+            x[4, 17] = np.nan
+            x[1, :] = -np.inf
+            x[2, 5] = np.inf
+        for k in (1, 8, 18, 32, 64, 255, 256):
+            want_v, want_i = O.topk_cbsr(x, k)
+            v, i, dense = S.topk_f32(x, k, want_dense=True)
+            np.testing.assert_array_equal(i, want_i, err_msg=f"n={n} k={k}")
+            np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
+            np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
+        (dense,) = S.topk_f32(x, 32, want_dense=True, want_cbsr=False)
+        np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, 32).view(np.uint32))
 
 
 def test_simt_topk_goldens_from_torch(golden_dir):
