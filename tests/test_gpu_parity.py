@@ -313,10 +313,6 @@ def test_backward_run_lengths(ops, case):
         ops.set_tuning(-1, -1)
 
 
-@pytest.mark.parametrize("case", [dict(n=5000, d=256, k=32, c=256), dict(n=3333, d=256, k=64, c=132),
-                                  dict(n=40000, d=64, k=8, c=4), dict(n=700, d=36, k=18, c=260),
-                                  dict(n=300, d=256, k=256, c=128), dict(n=1, d=128, k=1, c=8)],
-                         ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
 @pytest.mark.parametrize("pair", [True, False])
 def test_topk_two_rows_per_warp_and_one(ops, pair):
     """d = 256: the two-rows-per-warp kernel (default) and the one-row kernel, bit-exact against the oracle, with
@@ -342,6 +338,10 @@ def test_topk_two_rows_per_warp_and_one(ops, pair):
         ops.set_topk_pair(True)
 
 
+@pytest.mark.parametrize("case", [dict(n=5000, d=256, k=32, c=256), dict(n=3333, d=256, k=64, c=132),
+                                  dict(n=40000, d=64, k=8, c=4), dict(n=700, d=36, k=18, c=260),
+                                  dict(n=300, d=256, k=256, c=128), dict(n=1, d=128, k=1, c=8)],
+                         ids=lambda c: "-".join(f"{a}{b}" for a, b in c.items()))
 def test_cbsr_linear_products(ops, case):
     """fc_self on the CBSR operand and the gradient of its values against the dense Linear on the scattered
     twin (fp64 oracle); then the autograd Function against torch's own Linear."""
