@@ -89,8 +89,6 @@ MAXK_API int maxk_worklist_fill(const int32_t *indptr, int64_t num_rows, int32_t
  * values are bit copies.  NaN ranks largest, -0 == +0.  d % 4 == 0, 1 <= k <= d <= 256.
  * dense_out (optional, may be NULL): x * mask, float32[n,d] (MaxK.forward,
  * utils/models.py:48-52).  sp_data / sp_index may be NULL when only dense_out is wanted. */
-/* Bench/test hook: rows of full width (d == 256) go two to a warp (1, default) or one to a warp (0). */
-MAXK_API int maxk_set_topk_pair(int on);
 MAXK_API int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t k, float *sp_data,
                        uint8_t *sp_index, float *dense_out, void *stream);
 /* uint8 flavour of the reference kernel's own data type (cuda_topk_maxk,

@@ -24,10 +24,6 @@ for name, x in dists:
         if quick:   # for ncu: one launch per (distribution, k)
             ops.topk_cbsr(x, k); continue
         b = 4 * n * 256 + 5 * n * k
-        for pair in (True, False):
-            ops.set_topk_pair(pair)
-            t = timeit(lambda: ops.topk_cbsr(x, k))
-            print(f"topk {name:12s} k={k:3d} {'two rows / warp' if pair else 'one row / warp '}: {t*1e3:7.1f} us  "
-                  f"{b/t/1e6:7.0f} GB/s  frac {b/t/1e6/6543.7:.3f}", flush=True)
-        ops.set_topk_pair(True)
+        t = timeit(lambda: ops.topk_cbsr(x, k))
+        print(f"topk {name:12s} k={k:3d}: {t*1e3:7.1f} us  {b/t/1e6:7.0f} GB/s  frac {b/t/1e6/6543.7:.3f}", flush=True)
 torch.cuda.synchronize()

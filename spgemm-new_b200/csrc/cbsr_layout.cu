@@ -52,7 +52,8 @@ cbsr_gather_kernel(const float *__restrict__ dense, const unsigned char *__restr
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = i / k;
-        sp_data[i] = __ldg(dense + row * d + sp_index[i]);
+        const int c = sp_index[i];  // selectors >= d (possible when d < 256) read nothing, like the other layout kernels
+        sp_data[i] = c < d ? __ldg(dense + row * d + c) : 0.f;
     }
 }
 

@@ -20,7 +20,14 @@
 //     stores are coalesced; optional dense x*mask output (MaxK.forward,
 //     utils/models.py:48-52) from the same registers.
 // Pure streaming kernel: 4*d bytes read + 5*k bytes written per row -> HBM-bound by design;
-// the instruction count per row decides how close it gets (profiles/r01_topk_*.md).
+// the instruction count per row decides how close it gets: ncu (rounds 1 and 2) shows it ISSUE-bound
+// (smsp__issue_active 78 %, DRAM 27 %) at ~360 warp instructions per row -- bracket set-up ~70, ~3.7
+// probes x 53 (21 of them the eight compares, the rest the root finder and the REDUX), emission ~100.
+// Measured and dropped in round 2 (profiles/r02_variants.md, r02_topk.md): several rows per warp with
+// the next row prefetched (8-17 % slower: the loop costs more than the latency it hides) and two rows
+// per warp in half-warps (the warp-uniform overhead is shared, but 16 elements per lane compile to a
+// longer compare / staging sequence: 128 vs 100 us).  What round 2 kept: the full-width (d = 256)
+// specialisation, two-instruction bracket keys and a loop-free emission for k <= 32 (108 -> 99.5 us).
 #include "common.cuh"
 
 namespace maxk {
@@ -435,188 +442,10 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k,
     }
 }
 
-// ---- fp32 rows of full width (d == 256), TWO ROWS PER WARP --------------------------------------------
-// The one-row kernel above is issue-bound, not HBM-bound (ncu, round 1 and 2: 390 warp instructions per
-// row, smsp__issue_active 78 %, DRAM 27 %), and half of those instructions are warp-UNIFORM overhead that
-// does not depend on how many elements a lane holds: the bracket set-up, the root finder's bookkeeping (33
-// of a probe's 53 instructions), the REDUX, the prefix scan of the emission, address arithmetic.  Here a
-// half-warp owns a row (16 lanes x 16 elements), so one warp instruction serves two rows: the per-element
-// work (compares, staging stores) costs the same per row, the uniform overhead half.  Same algorithm and the
-// same proof of exactness as topk_row_f32's fast path -- a probe that separates exactly k elements with the
-// plain float compare !(x < t) -- with per-half thresholds (SIMT: each lane carries its own row's bracket),
-// both rows' counts in one REDUX (packed 16 + 16 bits).  A row the fast path cannot finish (ties at the
-// k-th value, infinite end points, a collapsed bracket, too many probes) is handed, whole, to topk_row_f32
-// on the full warp afterwards -- the robust path is unchanged.
-constexpr int TOPK_PAIR_WPB = 8;
-
-__device__ __forceinline__ unsigned lane_mask16_nlt(const float (&x)[16], float t)
-{
-    // two independent 8-bit sums: FSETP + SEL per element, one IADD3 per two elements (see lane_mask_nlt)
-    unsigned lo = 0u, hi = 0u;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        lo += !(x[i] < t) ? (1u << i) : 0u;
-        hi += !(x[8 + i] < t) ? (1u << i) : 0u;
-    }
-    return lo | (hi << 8);
-}
-
-__global__ void __launch_bounds__(TOPK_PAIR_WPB * 32)
-topk_cbsr_f32_pair_kernel(const float *__restrict__ x_, int64_t n, int k, float *__restrict__ out_val,
-                          unsigned char *__restrict__ out_idx, float *__restrict__ dense_out)
-{
-    constexpr int D = MAXK_MAX_DIM;
-    __shared__ unsigned s_val[TOPK_PAIR_WPB][2 * D];  // [half][D] here; topk_row_f32's 2 * D staging words in the fallback
-    __shared__ unsigned char s_idx[TOPK_PAIR_WPB][2][D];
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int half = lane >> 4, hl = lane & 15, sh = 16 * half;
-    const int64_t r0 = 2 * ((int64_t)blockIdx.x * TOPK_PAIR_WPB + warp);
-    if (r0 >= n) return;  // warp-uniform; no CTA barrier below
-    const int64_t row = r0 + half;
-    const bool have = row < n;  // odd n: the upper half of the last warp re-reads row r0 and stays silent
-
-    // element 4q + i of a lane sits at column 64 q + 4 hl + i: quarter q of every lane precedes quarter q + 1
-    const float4 *xr = reinterpret_cast<const float4 *>(x_ + (have ? row : r0) * D) + hl;
-    float x[16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 v = ld_stream_f4(xr + 16 * q);
-        x[4 * q] = v.x, x[4 * q + 1] = v.y, x[4 * q + 2] = v.z, x[4 * q + 3] = v.w;
-    }
-    float lmax = x[0], lmin = x[0];
-#pragma unroll
-    for (int i = 1; i < 16; ++i) {
-        lmax = fmaxf(lmax, x[i]);
-        lmin = fminf(lmin, x[i]);
-    }
-    // per-half extremes: two full-warp REDUX each, the other half contributing the neutral element
-    const unsigned kmax = f32_rough_key(lmax), kmin = f32_rough_key(lmin);
-    const unsigned mx0 = __reduce_max_sync(full, half ? 0u : kmax), mx1 = __reduce_max_sync(full, half ? kmax : 0u);
-    const unsigned mn0 = __reduce_min_sync(full, half ? 0xffffffffu : kmin), mn1 = __reduce_min_sync(full, half ? kmin : 0xffffffffu);
-    float fh = rough_key_to_f32(half ? mx1 : mx0);
-    float fl = rough_key_to_f32(half ? mn1 : mn0);
-
-    unsigned sel = 0u;
-    int state = have ? 0 : 1;  // uniform within a half: 0 searching, 1 finished (sel is the selection), 2 the robust path
-    if (k == D) {
-        sel = 0xffffu;
-        state = 1;
-    }
-    float gl = (float)(D - k), gh = fminf((float)(1 - k), -0.5f);
-    int run = 0;
-#pragma unroll 1
-    for (int it = 0; it < TOPK_FAST_MAX_PROBES; ++it) {
-        if (!__any_sync(full, state == 0)) break;
-        float fm = fmaf(fh - fl, gl * rcp_approx(gl - gh), fl);
-        if (!(fm > fl && fm < fh)) fm = 0.5f * fl + 0.5f * fh;
-        // adjacent floats, infinite or NaN end points: the robust path (the count below is then ignored)
-        if (state == 0 && !(fm > fl && fm < fh)) state = 2;
-        const unsigned m = lane_mask16_nlt(x, fm);
-        const unsigned tot = __reduce_add_sync(full, state == 0 ? ((unsigned)__popc(m) << sh) : 0u);
-        if (state == 0) {
-            const int g = (int)((tot >> sh) & 0xffffu) - k;
-            if (g == 0) {
-                sel = m;
-                state = 1;
-            } else if (g > 0) {
-                fl = fm;
-                gl = (float)g;
-                if (run > 0) gh *= 0.5f;
-                run = run > 0 ? run + 1 : 1;
-            } else {
-                fh = fm;
-                gh = (float)g;
-                if (run < 0) gl *= 0.5f;
-                run = run < 0 ? run - 1 : -1;
-            }
-            if (run >= TOPK_FAST_MAX_RUN || run <= -TOPK_FAST_MAX_RUN) state = 2;  // ties likely
-        }
-    }
-    const bool fail = have && state != 1;  // 2, or out of probes
-    const bool emit = have && !fail;
-
-    // ---- emission: ascending column order through a per-half staging row ------------------------------
-    if (out_idx != nullptr) {
-        const unsigned s = emit ? sel : 0u;
-        const unsigned n0 = __popc(s & 0xfu), n1 = __popc(s & 0xf0u), n2 = __popc(s & 0xf00u), n3 = __popc(s >> 12);
-        const unsigned mine = n0 | (n1 << 8) | (n2 << 16) | (n3 << 24);  // <= 64 per quarter and half: 8 bits each
-        unsigned inc = mine;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const unsigned t = __shfl_up_sync(full, inc, o, 16);
-            if (hl >= o) inc += t;
-        }
-        const unsigned tot = __shfl_sync(full, inc, 15, 16);
-        const unsigned exc = inc - mine;
-        unsigned pos[4];
-        pos[0] = exc & 0xffu;
-        pos[1] = (tot & 0xffu) + ((exc >> 8) & 0xffu);
-        pos[2] = (tot & 0xffu) + ((tot >> 8) & 0xffu) + ((exc >> 16) & 0xffu);
-        pos[3] = (tot & 0xffu) + ((tot >> 8) & 0xffu) + ((tot >> 16) & 0xffu) + (exc >> 24);
-        unsigned *sv = s_val[warp] + half * D;
-        unsigned char *si = s_idx[warp][half];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            unsigned p = pos[q];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (s & (1u << (4 * q + i))) {
-                    sv[p] = __float_as_uint(x[4 * q + i]);
-                    si[p] = (unsigned char)(64 * q + 4 * hl + i);
-                    ++p;
-                }
-            }
-        }
-        __syncwarp();
-        if (emit) {
-            unsigned *ov = reinterpret_cast<unsigned *>(out_val) + row * k;
-            unsigned char *oi = out_idx + row * k;
-            for (int j = hl; j < k; j += 16) {
-                ov[j] = sv[j];
-                oi[j] = si[j];
-            }
-        }
-    }
-    if (dense_out != nullptr && emit) {
-        float4 *o = reinterpret_cast<float4 *>(dense_out + row * D) + hl;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 v;
-            v.x = (sel & (1u << (4 * q))) ? x[4 * q] : 0.f;
-            v.y = (sel & (2u << (4 * q))) ? x[4 * q + 1] : 0.f;
-            v.z = (sel & (4u << (4 * q))) ? x[4 * q + 2] : 0.f;
-            v.w = (sel & (8u << (4 * q))) ? x[4 * q + 3] : 0.f;
-            st_stream_f4(o + 16 * q, v);
-        }
-    }
-
-    // ---- rows the fast path left: the one-row code on the full warp ------------------------------------
-    const unsigned failed = __ballot_sync(full, fail);
-    if (failed == 0u) return;
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        if (!((failed >> (16 * h)) & 1u)) continue;
-        __syncwarp();  // the staging words are reused
-        const int64_t r = r0 + h;
-        const float4 *xo = reinterpret_cast<const float4 *>(x_ + r * D);
-        const float4 a = ld_stream_f4(xo + lane), b = ld_stream_f4(xo + 32 + lane);
-        topk_row_f32<true>(a, b, true, true, 4 * lane, 128 + 4 * lane, lane, r, D, k, s_val[warp], out_val, out_idx,
-                           dense_out);
-    }
-}
-
-int g_topk_pair = 1;  // d == 256: two rows per warp (0: one row per warp; measurement knob maxk_set_topk_pair)
-
 }  // namespace maxk
 
 using namespace maxk;
 
-extern "C" int maxk_set_topk_pair(int on)
-{
-    g_topk_pair = on ? 1 : 0;
-    return MAXK_OK;
-}
 
 extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t k, float *sp_data,
                                   uint8_t *sp_index, float *dense_out, void *stream)
@@ -635,13 +464,6 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
                  "maxk_topk_cbsr_f32: x and dense_out must be 16-byte aligned");
     const int64_t grid = ceil_div<int64_t>(n, TOPK_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_topk_cbsr_f32: n too large");
-    if (d == MAXK_MAX_DIM && g_topk_pair) {
-        const int64_t pgrid = ceil_div<int64_t>(ceil_div<int64_t>(n, 2), TOPK_PAIR_WPB);
-        topk_cbsr_f32_pair_kernel<<<(unsigned)pgrid, TOPK_PAIR_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-            x, n, k, sp_data, sp_index, dense_out);
-        MAXK_LAUNCH_CHECK("topk_cbsr_f32_pair_kernel");
-        return MAXK_OK;
-    }
     if (d == MAXK_MAX_DIM)
         topk_cbsr_f32_kernel<true><<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
             x, n, d, k, sp_data, sp_index, dense_out);

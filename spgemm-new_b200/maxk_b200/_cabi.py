@@ -32,7 +32,6 @@ PROTOTYPES = {
     "maxk_worklist_workspace_bytes": (_i64, [_i64]),
     "maxk_worklist_count": (ctypes.c_int, [_vp, _i64, _i32, _vp, ctypes.POINTER(_i64), _vp]),
     "maxk_worklist_fill": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp]),
-    "maxk_set_topk_pair": (ctypes.c_int, [ctypes.c_int]),
     "maxk_topk_cbsr_f32": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "maxk_topk_cbsr_u8": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "maxk_spgemm_forward": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),

@@ -427,11 +427,6 @@ def set_tuning(fwd_tasks_per_warp: int = 0, bwd_tasks_per_warp: int = 0) -> None
     _cabi.check(_cabi.load().maxk_set_tuning(fwd_tasks_per_warp, bwd_tasks_per_warp))
 
 
-def set_topk_pair(on: bool = True) -> None:
-    """TopK of full-width rows (d = 256): two rows per warp (default) or one; bench/test hook."""
-    _cabi.check(_cabi.load().maxk_set_topk_pair(1 if on else 0))
-
-
 def set_forward_depth(depth: int = 0) -> None:
     """Launch shape of the forward kernel (include/maxk_b200.h: maxk_set_forward_depth; 0 = automatic); bench/test hook."""
     _cabi.check(_cabi.load().maxk_set_forward_depth(int(depth)))

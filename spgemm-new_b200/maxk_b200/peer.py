@@ -164,6 +164,9 @@ class PeerAggregator:
         assert self.world <= PEER_MAX, f"at most {PEER_MAX} ranks"
         self.bounds = list(bounds)
         self.k, self.d = int(k), int(feat_dim)
+        if self.k not in (8, 16, 32, 64, 96, 128, 256):   # on every rank, before anything is launched
+            raise ValueError(f"the fused peer-memory forward is built for k = 8, 16, 32, 64, 96, 128, 256 (k = {self.k}): "
+                             "use comm='nccl' for other widths")
         if any((b * self.k) % 16 for b in bounds[:-1]):
             raise ValueError("row block starts must satisfy start * k % 16 == 0: use "
                              "partition_rows_by_nnz(indptr, world, align=16)")

@@ -32,9 +32,6 @@ MUTANTS = {
     "bwd-selector-of-wrong-node": ("sspmm_backward.cu", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + q[u]);", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + (q[u] ^ 1));", 0),
     "topk-emit-no-barrier": ("topk_cbsr.cu", "    __syncwarp();\n    unsigned char *oi = out_idx + row * k + lane;", "    unsigned char *oi = out_idx + row * k + lane;", 0),
     "topk-tie-order": ("topk_cbsr.cu", "if (r0 < need) sel |= (1u << i);", "if (r0 <= need) sel |= (1u << i);", 0),
-    "topk-pair-counts-of-the-other-half": ("topk_cbsr.cu", "            const int g = (int)((tot >> sh) & 0xffffu) - k;", "            const int g = (int)(tot & 0xffffu) - k;", 0),
-    "topk-pair-failed-row-not-redone": ("topk_cbsr.cu", "        if (!((failed >> (16 * h)) & 1u)) continue;", "        if (!((failed >> (16 * h)) & 1u) || h == 1) continue;", 0),
-    "topk-pair-scan-crosses-the-halves": ("topk_cbsr.cu", "            const unsigned t = __shfl_up_sync(full, inc, o, 16);\n            if (hl >= o) inc += t;", "            const unsigned t = __shfl_up_sync(full, inc, o, 16);\n            if (lane >= o) inc += t;", 0),
     "topk-row-bound": ("topk_cbsr.cu", "if (row >= n) return;  // warp-uniform; no CTA barrier below\n\n", "if (row > n) return;\n\n", 0),
     # bank plan and planned kernels
     "plan-home-word-formula": ("common.cuh", "return h == 0 ? c : 256u + (c & 7u) * 32u + (c >> 3);", "return h == 0 ? c : 256u + (c & 7u) * 32u + ((c >> 3) ^ 1u);", 0),

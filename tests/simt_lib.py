@@ -138,10 +138,6 @@ def set_forward_depth(depth=0):
     load().maxk_set_forward_depth(int(depth))
 
 
-def set_topk_pair(on=True):
-    load().maxk_set_topk_pair(1 if on else 0)
-
-
 def set_forward_copies(copies=0):
     load().maxk_set_forward_copies(int(copies))
 

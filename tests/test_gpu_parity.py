@@ -313,13 +313,11 @@ def test_backward_run_lengths(ops, case):
         ops.set_tuning(-1, -1)
 
 
-@pytest.mark.parametrize("pair", [True, False])
-def test_topk_two_rows_per_warp_and_one(ops, pair):
-    """d = 256: the two-rows-per-warp kernel (default) and the one-row kernel, bit-exact against the oracle, with
-    tie / NaN / infinity rows (robust path) next to ordinary rows in the same warp, odd row counts, dense output."""
+def test_topk_full_width_rows(ops):
+    """d = 256 (its own specialisation): bit-exact against the oracle, with tie / NaN / infinity rows (robust path)
+    next to ordinary rows, odd row counts, dense output."""
     rng = np.random.default_rng(17)
     try:
-        ops.set_topk_pair(pair)
         for n in (1, 2, 17, 4099):
             x = rng.standard_normal((n, 256)).astype(np.float32)
             x[::5] = rng.integers(0, 3, size=x[::5].shape).astype(np.float32)
@@ -335,7 +333,7 @@ def test_topk_two_rows_per_warp_and_one(ops, pair):
                 np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), want_v.view(np.uint32))
                 np.testing.assert_array_equal(dense.cpu().numpy().view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
     finally:
-        ops.set_topk_pair(True)
+        pass
 
 
 @pytest.mark.parametrize("case", [dict(n=5000, d=256, k=32, c=256), dict(n=3333, d=256, k=64, c=132),

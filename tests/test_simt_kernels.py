@@ -28,7 +28,6 @@ def _reset_knobs():
     S.set_forward_depth(0)
     S.set_forward_copies(0)
     S.set_cp_async_eager(False)
-    S.set_topk_pair(True)
 
 
 # ------------------------------------------------------------------------------ a4
@@ -84,12 +83,9 @@ def test_simt_topk_ties_and_specials():
         np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
 
 
-@pytest.mark.parametrize("pair", [True, False])
-def test_simt_topk_two_rows_per_warp_and_one(pair):
-    """d = 256: the two-rows-per-warp kernel (default) and the one-row kernel give the oracle's bits for every n around
-    the pair / CTA boundaries, with rows the fast path finishes next to rows it must hand to the robust path (ties,
-    NaN, infinities) in the SAME warp, the dense MaxK output included."""
-    S.set_topk_pair(pair)
+def test_simt_topk_full_width_rows():
+    """d = 256 (its own specialisation): the oracle's bits for every n around the CTA boundaries, rows the fast path
+    finishes next to rows that need the robust path (ties, NaN, infinities), the dense MaxK output included."""
     rng = np.random.default_rng(5)
     for n in (1, 2, 3, 15, 16, 17, 33):
         x = rng.standard_normal((n, 256)).astype(np.float32)
