@@ -1,0 +1,19 @@
+#!/bin/bash
+# Round 2, multi-GPU call:  gpurun --gpus N -- 'bash scripts/gpu_runs/r2_multi.sh N [quick]'
+# Parity of the peer-memory path on real GPUs (peer_check: plan travelling, pipelined host entry point), then the
+# bench line at N exactly as the driver launches it (parity_ok, per-GPU roofline, pipelined e2e, epoch leg).
+N=${1:-2}
+O=gpurun_out; mkdir -p $O
+run() { local t=$1 port=$2; shift 2; timeout "$t" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
+        --master-addr 127.0.0.1 --master-port "$port" "$@"; }
+if [ "$2" != "benchonly" ]; then
+run 500 29701 scripts/peer_check.py --quick > $O/r4_peer_check_n$N.log 2> $O/r4_peer_check_n$N.err
+echo "peer_check rc=$? true=$(grep -c 'all-ranks True' $O/r4_peer_check_n$N.log) false=$(grep -c 'all-ranks False' $O/r4_peer_check_n$N.log)"
+fi
+run 600 29702 bench.py --gpus $N --steps 40 --warmup 5 > $O/r4_scale_n$N.json 2> $O/r4_bench_n$N.err
+echo "bench rc=$? $(cut -c1-150 $O/r4_scale_n$N.json)"
+tail -5 $O/r4_bench_n$N.err | cut -c1-300
+if [ "$2" == "phases" ]; then
+run 300 29703 scripts/dist_phases.py > $O/r4_phases_n$N.json 2> $O/r4_phases_n$N.err
+echo "phases rc=$? $(cut -c1-600 $O/r4_phases_n$N.json)"
+fi

@@ -22,22 +22,23 @@ dist.init_process_group("nccl", device_id=dev)
 quick = "--quick" in sys.argv
 time_only = "--time-only" in sys.argv
 ok = True
-# (shape, scale, k, halo_threshold): 0.5 = automatic choice per pair, 0 = whole blocks always,
-# 2 = row lists always
-cases = (("flickr", 1.0, 32, 0.5), ("reddit", 0.05, 16, 0.5), ("products", 0.05, 64, 2.0),
-         ("reddit", 0.02, 8, 2.0), ("products", 0.05, 32, 0.0), ("flickr", 1.0, 16, 2.0))
+# (shape, scale, k, halo_threshold, homes): halo 0.5 = automatic choice per pair, 0 = whole blocks always,
+# 2 = row lists always; homes 2 = the bank plan travels in place of the selectors, "auto" = ops.use_bank_plan
+cases = (("flickr", 1.0, 32, 0.5, 0), ("reddit", 0.05, 16, 0.5, "auto"), ("products", 0.05, 64, 2.0, 0),
+         ("reddit", 0.05, 32, 0.5, 2), ("reddit", 0.05, 64, 0.0, "auto"), ("products", 0.05, 32, 2.0, 2),
+         ("reddit", 0.02, 8, 2.0, 0), ("products", 0.05, 32, 0.0, "auto"), ("flickr", 1.0, 16, 2.0, 0))
 if time_only:
     cases = cases[:1]
-for shape, scale, k, halo in cases:
+for shape, scale, k, halo, homes in cases:
     g = graphs.make_graph(shape, seed=1, device=dev, values="uniform", scale=scale)
     n = g["v_num"]
     w4 = ops.build_worklist(g["indptr"])
     bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
     lo, hi = bounds[rank], bounds[rank + 1]
     agg = PeerAggregator.from_global_csr(g["indptr"], g["indices"], g["values"], bounds, rank, k, 256,
-                                         copy_ctas=(3 if k != 16 else -5), halo_threshold=halo)
+                                         copy_ctas=(3 if k != 16 else -5), halo_threshold=halo, homes=homes)
     if rank == 0:
-        print(f"peer {shape} k={k} halo_threshold={halo}: dense send pairs {sum(agg.send_dense)}, "
+        print(f"peer {shape} k={k} halo_threshold={halo} homes={homes}->{agg.homes}: dense send pairs {sum(agg.send_dense)}, "
               f"rows pushed per step {agg.exchange_rows} of {agg.n_local} x {world - 1}", flush=True)
     for step in range(5):  # different inputs every step: a stale buffer would show
         x = torch.rand(n, 256, device=dev, generator=torch.Generator(dev).manual_seed(3 + step))
@@ -80,6 +81,28 @@ for shape, scale, k, halo in cases:
                       f"all-ranks {bool(flag.item())}", flush=True)
             ok = ok and bool(flag.item())
         del shard
+    # ... and two steps in flight (submit / result), every result checked
+    shard = ShardHostAggregator(agg)
+    refs, prev = {}, None
+    for step in range(5):
+        x = torch.rand(n, 256, device=dev, generator=torch.Generator(dev).manual_seed(170 + step))
+        dy = torch.rand(n, 256, device=dev, generator=torch.Generator(dev).manual_seed(180 + step))
+        sd, si = ops.topk_cbsr(x, k)
+        refs[step] = (ops.spgemm_forward(w4, g["indices"], g["values"], sd, si, num_rows=n)[lo:hi].cpu(),
+                      ops.sspmm_backward(w4, g["indices"], g["values"], dy, si)[lo:hi].cpu())
+        t = shard.submit(x[lo:hi].cpu().pin_memory(), dy[lo:hi].cpu().pin_memory())
+        for done in ([prev] if prev is not None else []) + ([t] if step == 4 else []):
+            y_h, dxc_h = shard.result(done)
+            e1 = torch.allclose(y_h, refs[done][0], rtol=1e-5, atol=1e-6)
+            e2 = torch.allclose(dxc_h, refs[done][1], rtol=1e-5, atol=1e-6)
+            flag = torch.tensor([int(e1 and e2)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(f"shard-host pipelined {shape} k={k} world={world} step {done}: fwd {e1} bwd {e2} "
+                      f"all-ranks {bool(flag.item())}", flush=True)
+            ok = ok and bool(flag.item())
+        prev = t
+    del shard
     agg.close()
     del agg
 
