@@ -345,7 +345,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from maxk_b200 import _cabi, graphs, ops
-    from maxk_b200.host import HostAggregator
+    from maxk_b200.host import HostAggregator, bind_to_device_numa_node
+    numa_node = bind_to_device_numa_node(dev)   # pinned host buffers of the e2e leg land next to this rank's GPU
 
     g, scale = make_reddit(dev)          # same seed on every rank -> identical graph
     n, e, k = g["v_num"], g["e_num"], args.k
@@ -633,7 +634,7 @@ def main():
         e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
         e2e = {"value": step_bytes / (e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_ms,
                "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
-               "steps": e_steps, "ms_per_step_synchronous": sync_ms,
+               "steps": e_steps, "ms_per_step_synchronous": sync_ms, "numa_node_of_rank0": numa_node,
                "includes": "per step: H2D X+dY (pinned), TopK->CBSR, SpGEMM, SSpMM, D2H Y+dXc; "
                            "HostAggregator.submit/result with two steps in flight "
                            "(ms_per_step_synchronous = HostAggregator.step, one at a time)"}
@@ -691,7 +692,7 @@ def main():
                 e_ms, sync_ms = float(tmax[0]), float(tmax[1])
                 e2e = {"value": step_bytes / (e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_ms,
                        "h2d_bytes_per_step": int(nbytes[0]), "d2h_bytes_per_step": int(nbytes[1]), "steps": e_steps,
-                       "ms_per_step_synchronous": sync_ms,
+                       "ms_per_step_synchronous": sync_ms, "numa_node_of_rank0": numa_node,
                        "includes": f"per step and rank (max over {world} ranks, wall clock between synchronisations): H2D of "
                                    "the rank's X and dY rows (pinned), TopK->CBSR in place, exchange, forward, backward + "
                                    "reduce-scatter, D2H of its Y and dXc rows; "

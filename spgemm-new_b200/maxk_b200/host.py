@@ -27,6 +27,32 @@ from . import ops
 from .autograd import worklist_for
 
 
+def bind_to_device_numa_node(device=None):
+    """Restrict the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that pinned host
+    buffers allocated AFTERWARDS are placed in that node's memory and the copy engines do not cross the socket
+    interconnect.  One process per GPU: call it once, before the host buffers are created.  Returns the node, or
+    None when the topology cannot be read (then nothing is changed)."""
+    import os
+    try:
+        dev = torch.device(device if device is not None else torch.cuda.current_device())
+        pr = torch.cuda.get_device_properties(dev)
+        pci = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001  (no sysfs, no permission, old torch: leave the process where it is)
+        return None
+
+
 class _Slot:
     """Device inputs/outputs and pinned host outputs of one in-flight step."""
 

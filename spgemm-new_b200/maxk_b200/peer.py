@@ -380,15 +380,18 @@ class PeerAggregator:
         lib = _cabi.load()
         with torch.cuda.device(self.device):
             _cabi.check(lib.maxk_peer_zero_partial(ctypes.byref(self._ctx[par]), self._stream()))
-        if self.homes:
-            ops.sspmm_backward_planned(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index,
-                                       out=self.partial[par], accumulate=True)
-        else:
-            ops.sspmm_backward(self.b_warp4, self.b_indices, self.b_values, dy_loc, g_index,
-                               out=self.partial[par], accumulate=True)
+        # Tasks on OTHER ranks' columns first: their partial gradients are what the peers wait for, so they are
+        # published before the tasks on this rank's own columns run (those only touch the own block, which nobody
+        # else reads) -- the peers' pulls and this rank's wait for their flags overlap with that second kernel.
+        bwd = ops.sspmm_backward_planned if self.homes else ops.sspmm_backward
+        w4 = self.f_warp4.view(-1, 4)
+        split = int(self.wait_from_task)
+        bwd(w4[split:].reshape(-1), self.f_indices, self.f_values, dy_loc, g_index, out=self.partial[par], accumulate=True)
         with torch.cuda.device(self.device):
             _cabi.check(lib.maxk_peer_publish(ctypes.c_void_p(self._flag_ptr + 4 * 1), self._bwd_epoch,
                                               self._stream()))
+        bwd(w4[:split].reshape(-1), self.f_indices, self.f_values, dy_loc, g_index, out=self.partial[par], accumulate=True)
+        with torch.cuda.device(self.device):
             _cabi.check(lib.maxk_reduce_scatter_pull(ctypes.byref(self._ctx[par]), self._bwd_epoch,
                                                      rs.data_ptr(), self._stream()))
         return rs[: self.n_local]
