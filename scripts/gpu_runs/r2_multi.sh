@@ -17,3 +17,7 @@ if [ "$2" == "phases" ]; then
 run 300 29703 scripts/dist_phases.py > $O/r4_phases_n$N.json 2> $O/r4_phases_n$N.err
 echo "phases rc=$? $(cut -c1-600 $O/r4_phases_n$N.json)"
 fi
+if [ "$2" == "rmat" ] || [ "$3" == "rmat" ]; then
+run 900 29704 scripts/rmat_sweep.py --cases 20:20,20:100,20:500,24:5,24:20,25:5,26:5 > $O/r4_rmat_n$N.jsonl 2> $O/r4_rmat_n$N.err
+echo "rmat rc=$? lines=$(grep -c '^{' $O/r4_rmat_n$N.jsonl)"
+fi
