@@ -442,9 +442,339 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k,
     }
 }
 
+
+// ---- fp32 rows, several rows per warp (round 2, second form) -------------------------------------
+// The one-row-per-warp kernel above is issue-bound (ncu: ~365 warp instructions per row, issue slots 80 %
+// busy, DRAM 27 %) and most of what it issues is warp-UNIFORM: the bracket update, the reductions over 32
+// lanes and the 32-lane scans cost the same whether a lane holds 8 elements or 64.  Here L = 4 or 8 lanes
+// own a row (E = D / L elements per lane IN CONTIGUOUS COLUMNS, so that one short scan over L lanes places
+// a lane's output), a warp works on R = 32 / L rows at once, and every warp-wide instruction serves R rows:
+//   * the rows arrive through cp.async (coalesced 16-byte chunks, no registers held while in flight) in a
+//     padded shared-memory layout -- every lane segment shifted by 4 words -- from which each lane reads its
+//     E contiguous values with conflict-free LDS.128 (a quarter-warp's eight segments start in eight
+//     different bank quads);
+//   * minimum / maximum: E FMNMX each + log2(L) shuffles (no keys, no REDUX);
+//   * the same value-space regula falsi as above, every row group with its own bracket; a probe costs two
+//     instructions per element (compare + predicated add) and log2(L) shuffle steps, the bracket update is
+//     paid once per R rows; groups that are finished keep their threshold and idle along until the slowest
+//     group of the warp is done (measured probe counts: 3.7 on average per row, ~5 for the slowest of 8);
+//   * emission: exclusive scan of the lanes' counts within the group, then per element compare +
+//     predicated 64-bit store of (value bits, column) into a staging area that has the layout of the
+//     OUTPUT (the R rows of a warp are contiguous in sp_data and in sp_index), copied out coalesced;
+//   * rows the fast path cannot finish (ties at the k-th value, infinite end points, NaN-only groups) are
+//     re-read in the one-row layout and go through the robust key search above, one at a time.
+// Used for D in {64, 128, 256} and k <= D / 2 (the staging area of the output overlays the input rows).
+template <int L>
+__device__ __forceinline__ int group_sum(int v)
+{
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// staging of one robustly selected row (one-row layout of `sel`): values at sv[], columns at si[]
+__device__ __forceinline__ void topk_stage_row(unsigned sel, const unsigned (&raw)[8], unsigned *sv, unsigned *si,
+                                               int lane, int c0, int c1)
+{
+    const unsigned n0 = __popc(sel & 0xfu), n1 = __popc(sel >> 4);
+    const unsigned inc = warp_incl_scan(n0 | (n1 << 16), lane);
+    const unsigned tot0 = __shfl_sync(0xffffffffu, inc, 31) & 0xffffu;
+    unsigned p0 = (inc & 0xffffu) - n0, p1 = tot0 + (inc >> 16) - n1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (sel & (1u << i)) {
+            sv[p0] = raw[i];
+            si[p0] = (unsigned)(c0 + i);
+            ++p0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (sel & (16u << i)) {
+            sv[p1] = raw[4 + i];
+            si[p1] = (unsigned)(c1 + i);
+            ++p1;
+        }
+    }
+}
+
+// c += !(x < t) as one compare and one predicated add (the C form compiles to three instructions per
+// element in a single dependency chain)
+__device__ __forceinline__ void count_nlt(int &c, float x, float t)
+{
+    asm("{.reg .pred p; setp.geu.f32 p, %1, %2; @p add.s32 %0, %0, 1;}" : "+r"(c) : "f"(x), "f"(t));
+}
+// if (!(x < t)) { value -> [w], column -> [w + IDX_OFF], w += 4 }   (w: 32-bit shared-memory address)
+template <int IDX_OFF>
+__device__ __forceinline__ void stage_if_nlt(unsigned &w, float x, float t, unsigned col)
+{
+    asm volatile(
+        "{.reg .pred p; setp.geu.f32 p, %1, %2; @p st.shared.f32 [%0], %1; @p st.shared.u32 [%0+%4], %3; "
+        "@p add.u32 %0, %0, 4;}"
+        : "+r"(w)
+        : "f"(x), "f"(t), "r"(col), "n"(IDX_OFF)
+        : "memory");
+}
+
+constexpr int TOPK_GROUP_WPB = 8;
+template <int D, int L>
+constexpr int topk_group_smem_words_per_warp() { return (32 / L) * (D + 4 * L); }
+
+template <int D, int L>
+__global__ void __launch_bounds__(TOPK_GROUP_WPB * 32)
+topk_cbsr_f32_group_kernel(const float *__restrict__ x_, int64_t n, int k, float *__restrict__ out_val,
+                           unsigned char *__restrict__ out_idx, float *__restrict__ dense_out, int vec_out)
+{
+    constexpr int E = D / L;        // elements per lane
+    constexpr int R = 32 / L;       // rows per warp
+    constexpr int J = E / 4;        // float4 per lane
+    constexpr int C4 = D / 4;       // float4 per row
+    constexpr int SEG = E + 4;      // words per lane segment in shared memory (4 words of padding)
+    constexpr int RS = L * SEG;     // words per row in shared memory
+    constexpr int IDXW = R * D / 2; // staging area of the output: R * k <= IDXW values, then as many columns
+    static_assert(E % 4 == 0 && (R * C4) % 32 == 0, "row groups must tile the warp");
+    extern __shared__ __align__(16) unsigned s_topk_group[];
+
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = ((int64_t)blockIdx.x * TOPK_GROUP_WPB + warp) * R;
+    if (row0 >= n) return;  // warp-uniform; no CTA barrier below
+    unsigned *sm = s_topk_group + warp * (R * RS);
+    const int g = lane / L, l = lane % L;
+
+    // ---- the warp's R rows -> shared memory (rows past the end: the last row again, never written out)
+    const int rows_here = (n - row0 < R) ? (int)(n - row0) : R;
+    {   // rows past the end are not loaded: their groups work on stale shared memory and are never written out
+        const float *xw = x_ + row0 * D;
+#pragma unroll
+        for (int it = 0; it < R * C4 / 32; ++it) {
+            const int q = it * 32 + lane;
+            const int gg = q / C4, c4 = q % C4;
+            if (gg < rows_here) cp_async16(sm + gg * RS + (c4 / J) * SEG + (c4 % J) * 4, xw + gg * D + 4 * c4);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    float x[E];
+    {
+        const float4 *seg = reinterpret_cast<const float4 *>(sm + g * RS + l * SEG);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const float4 v = seg[j];
+            x[4 * j] = v.x;
+            x[4 * j + 1] = v.y;
+            x[4 * j + 2] = v.z;
+            x[4 * j + 3] = v.w;
+        }
+    }
+    __syncwarp();  // the input rows are in registers: the area becomes the staging area of the output
+
+    // ---- bracket: the group's minimum and maximum (fminf / fmaxf skip NaN; NaN-only groups fail below)
+    float fl = x[0], fh = x[0];
+#pragma unroll
+    for (int i = 1; i < E; ++i) {
+        fl = fminf(fl, x[i]);
+        fh = fmaxf(fh, x[i]);
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) {
+        fl = fminf(fl, __shfl_xor_sync(full, fl, o));
+        fh = fmaxf(fh, __shfl_xor_sync(full, fh, o));
+    }
+
+    // ---- regula falsi (Illinois weights) on g(t) = count(!(x < t)) - k, one bracket per row group.
+    // state (uniform within a group): 0 searching, 1 t separates exactly k elements, 2 robust search needed
+    int state = 0, c = 0, c_lo = 0, run = 0;  // c / c_lo: the lane's count at t (all / first half of its columns)
+    float t = fl;
+    float gl = (float)(D - k), gh = fminf((float)(1 - k), -0.5f);
+    if (k == D) {  // everything is kept: nothing is below -inf, NaN included
+        t = __uint_as_float(0xff800000u);
+        state = 1;
+        c = E;
+        c_lo = E / 2;
+    }
+#pragma unroll 1
+    for (int it = 0; it < TOPK_FAST_MAX_PROBES; ++it) {
+        if (__all_sync(full, state != 0)) break;
+        if (state == 0) {
+            float fm = fmaf(fh - fl, gl * rcp_approx(gl - gh), fl);
+            if (!(fm > fl && fm < fh)) fm = 0.5f * fl + 0.5f * fh;
+            if (!(fm > fl && fm < fh)) state = 2;  // adjacent floats, infinite or NaN end points
+            t = fm;
+        }
+        // four independent chains of predicated adds; ca + cb counts the first half of the lane's columns
+        int ca = 0, cb = 0, cc = 0, cd = 0;
+#pragma unroll
+        for (int i = 0; i < E / 2; i += 2) {
+            count_nlt(ca, x[i], t);
+            count_nlt(cb, x[i + 1], t);
+            count_nlt(cc, x[E / 2 + i], t);
+            count_nlt(cd, x[E / 2 + i + 1], t);
+        }
+        c_lo = ca + cb;
+        c = c_lo + cc + cd;
+        const int gcount = group_sum<L>(c) - k;
+        if (state == 0) {
+            if (gcount == 0) {
+                state = 1;
+            } else if (gcount > 0) {
+                fl = t;
+                gl = (float)gcount;
+                if (run > 0) gh *= 0.5f;
+                run = run > 0 ? run + 1 : 1;
+            } else {
+                fh = t;
+                gh = (float)gcount;
+                if (run < 0) gl *= 0.5f;
+                run = run < 0 ? run - 1 : -1;
+            }
+            if (run >= TOPK_FAST_MAX_RUN || run <= -TOPK_FAST_MAX_RUN) state = 2;
+        }
+    }
+    if (state == 0) state = 2;
+    const unsigned okmask = __ballot_sync(full, state == 1);  // bit g * L: row group g finished on the fast path
+
+    // ---- emission of the finished groups into the staging area (pairs in output order)
+    if (out_idx != nullptr) {
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < L; o <<= 1) {
+            const int v = __shfl_up_sync(full, inc, o, L);
+            if (l >= o) inc += v;
+        }
+        if (state == 1) {
+            // two independent store chains: the lane's first and second half of columns
+            unsigned w = (unsigned)__cvta_generic_to_shared(sm + (g * k + inc - c));
+            unsigned w2 = w + 4u * (unsigned)c_lo;
+            const unsigned col0 = (unsigned)(l * E);
+#pragma unroll
+            for (int i = 0; i < E / 2; ++i) {
+                stage_if_nlt<4 * IDXW>(w, x[i], t, col0 + i);
+                stage_if_nlt<4 * IDXW>(w2, x[E / 2 + i], t, col0 + E / 2 + i);
+            }
+        }
+    }
+
+    // ---- the rows left to the robust search, one at a time in the one-row layout
+    unsigned todo = ~okmask;
+#pragma unroll 1
+    for (int gg = 0; gg < R; ++gg) {
+        if (!((todo >> (gg * L)) & 1u) || row0 + gg >= n) continue;  // warp-uniform
+        const int64_t row = row0 + gg;
+        const int c0 = 4 * lane, c1 = 128 + 4 * lane;
+        const bool ok0 = c0 < D, ok1 = c1 < D;
+        const float *xr = x_ + row * D;
+        const float ninf = __uint_as_float(0xff800000u);
+        float4 a = make_float4(ninf, ninf, ninf, ninf), b = a;
+        if (ok0) a = ld_stream_f4(reinterpret_cast<const float4 *>(xr + c0));
+        if (ok1) b = ld_stream_f4(reinterpret_cast<const float4 *>(xr + c1));
+        const unsigned raw[8] = {__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w),
+                                 __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)};
+        const unsigned sel = topk_select_slow_f32(raw[0], raw[1], raw[2], raw[3], raw[4], raw[5], raw[6], raw[7],
+                                                  ok0, ok1, D, k, lane);
+        if (out_idx != nullptr) topk_stage_row(sel, raw, sm + gg * k, sm + IDXW + gg * k, lane, c0, c1);
+        if (dense_out != nullptr) {
+            float *o = dense_out + row * D;
+            float4 va, vb;
+            va.x = (sel & 1u) ? a.x : 0.f;
+            va.y = (sel & 2u) ? a.y : 0.f;
+            va.z = (sel & 4u) ? a.z : 0.f;
+            va.w = (sel & 8u) ? a.w : 0.f;
+            vb.x = (sel & 16u) ? b.x : 0.f;
+            vb.y = (sel & 32u) ? b.y : 0.f;
+            vb.z = (sel & 64u) ? b.z : 0.f;
+            vb.w = (sel & 128u) ? b.w : 0.f;
+            if (ok0) st_stream_f4(reinterpret_cast<float4 *>(o + c0), va);
+            if (ok1) st_stream_f4(reinterpret_cast<float4 *>(o + c1), vb);
+        }
+    }
+
+    // ---- staging area -> sp_data / sp_index (the warp's rows are contiguous in both)
+    if (out_idx != nullptr) {
+        __syncwarp();
+        const int total = rows_here * k;
+        unsigned *ov = reinterpret_cast<unsigned *>(out_val) + row0 * k;
+        unsigned char *oi = out_idx + row0 * k;
+        if (vec_out) {  // 16-byte aligned sp_data, 4-byte aligned sp_index, k % 4 == 0
+            const uint4 *sv4 = reinterpret_cast<const uint4 *>(sm), *si4 = reinterpret_cast<const uint4 *>(sm + IDXW);
+#pragma unroll 1
+            for (int e = lane; 4 * e < total; e += 32) {
+                const uint4 v = sv4[e], ci = si4[e];
+                reinterpret_cast<uint4 *>(ov)[e] = v;
+                reinterpret_cast<unsigned *>(oi)[e] = ci.x | (ci.y << 8) | (ci.z << 16) | (ci.w << 24);
+            }
+        } else {
+#pragma unroll 1
+            for (int e = lane; e < total; e += 32) {
+                ov[e] = sm[e];
+                oi[e] = (unsigned char)sm[IDXW + e];
+            }
+        }
+    }
+
+    // ---- dense x * mask of the finished groups (MaxK.forward): back through the padded rows
+    if (dense_out != nullptr) {
+        __syncwarp();
+        if (state == 1) {
+            float4 *seg = reinterpret_cast<float4 *>(sm + g * RS + l * SEG);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                float4 v;
+                v.x = !(x[4 * j] < t) ? x[4 * j] : 0.f;
+                v.y = !(x[4 * j + 1] < t) ? x[4 * j + 1] : 0.f;
+                v.z = !(x[4 * j + 2] < t) ? x[4 * j + 2] : 0.f;
+                v.w = !(x[4 * j + 3] < t) ? x[4 * j + 3] : 0.f;
+                seg[j] = v;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < R * C4 / 32; ++it) {
+            const int q = it * 32 + lane;
+            const int gg = q / C4, c4 = q % C4;
+            if (gg < rows_here && ((okmask >> (gg * L)) & 1u))
+                st_stream_f4(reinterpret_cast<float4 *>(dense_out + (row0 + gg) * D + 4 * c4),
+                             *reinterpret_cast<const float4 *>(sm + gg * RS + (c4 / J) * SEG + (c4 % J) * 4));
+        }
+    }
+}
+
+template <int D, int L>
+int launch_topk_group(const float *x, int64_t n, int k, float *sp_data, uint8_t *sp_index, float *dense_out,
+                      cudaStream_t stream)
+{
+    constexpr int R = 32 / L;
+    constexpr size_t smem = (size_t)TOPK_GROUP_WPB * topk_group_smem_words_per_warp<D, L>() * sizeof(unsigned);
+    const int64_t grid = ceil_div<int64_t>(n, (int64_t)TOPK_GROUP_WPB * R);
+    MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_topk_cbsr_f32: n too large");
+    if (smem > 48 * 1024) {
+        const int rc = opt_in_dynamic_smem(reinterpret_cast<const void *>(&topk_cbsr_f32_group_kernel<D, L>),
+                                           "topk_cbsr_f32_group_kernel");
+        if (rc != MAXK_OK) return rc;
+    }
+    const int vec_out = (k % 4 == 0) && (reinterpret_cast<uintptr_t>(sp_data) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(sp_index) & 3) == 0;
+    topk_cbsr_f32_group_kernel<D, L><<<(unsigned)grid, TOPK_GROUP_WPB * 32, smem, stream>>>(
+        x, n, k, sp_data, sp_index, dense_out, vec_out);
+    MAXK_LAUNCH_CHECK("topk_cbsr_f32_group_kernel");
+    return MAXK_OK;
+}
+
+// lanes per row of the grouped kernel: 0 = one row per warp (the kernel above), 4 or 8; -1 = automatic
+int g_topk_group_lanes = -1;
+
 }  // namespace maxk
 
 using namespace maxk;
+
+extern "C" int maxk_set_topk_group(int lanes)
+{
+    MAXK_REQUIRE(lanes == -1 || lanes == 0 || lanes == 2 || lanes == 4 || lanes == 8,
+                 "maxk_set_topk_group: lanes per row must be -1 (automatic), 0 (one row per warp), 2, 4 or 8");
+    g_topk_group_lanes = lanes;
+    return MAXK_OK;
+}
 
 
 extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t k, float *sp_data,
@@ -464,6 +794,23 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
                  "maxk_topk_cbsr_f32: x and dense_out must be 16-byte aligned");
     const int64_t grid = ceil_div<int64_t>(n, TOPK_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_topk_cbsr_f32: n too large");
+    {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (2 * k <= d) {   // -1: what round 2 measured as fastest per width (profiles/r02_topk_grouped.md)
+            const int want = g_topk_group_lanes;
+#define MAXK_TOPK_GROUP(DD, LL, AUTO)                                                   \
+    if (d == DD && (want == LL || (want < 0 && (AUTO))))                               \
+        return launch_topk_group<DD, LL>(x, n, k, sp_data, sp_index, dense_out, st);
+            MAXK_TOPK_GROUP(256, 8, false)
+            MAXK_TOPK_GROUP(256, 4, false)
+            MAXK_TOPK_GROUP(128, 8, false)
+            MAXK_TOPK_GROUP(128, 4, true)
+            MAXK_TOPK_GROUP(64, 8, false)
+            MAXK_TOPK_GROUP(64, 4, false)
+            MAXK_TOPK_GROUP(64, 2, true)
+#undef MAXK_TOPK_GROUP
+        }
+    }
     if (d == MAXK_MAX_DIM)
         topk_cbsr_f32_kernel<true><<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
             x, n, d, k, sp_data, sp_index, dense_out);

@@ -432,6 +432,11 @@ def set_forward_depth(depth: int = 0) -> None:
     _cabi.check(_cabi.load().maxk_set_forward_depth(int(depth)))
 
 
+def set_topk_group(lanes: int = -1) -> None:
+    """Lanes per row of the fp32 TopK kernel (8 / 4 = grouped kernel, 0 = one row per warp, -1 = automatic); bench/test hook."""
+    _cabi.check(_cabi.load().maxk_set_topk_group(int(lanes)))
+
+
 def set_forward_copies(copies: int = 0) -> None:
     """Accumulator copies of the forward kernel (0 = automatic); bench/test hook."""
     _cabi.check(_cabi.load().maxk_set_forward_copies(int(copies)))

@@ -81,6 +81,10 @@ PTX = [
      "{{ float *p_ = (float *)({0}); p_[0] += ({1}); p_[1] += ({2}); p_[2] += ({3}); p_[3] += ({4}); }}"),
     (r"^red\.relaxed\.gpu\.global\.add\.f32 ", "{{ *(float *)({0}) += ({1}); }}"),
     (r"^rcp\.approx\.ftz\.f32 ", "{{ ({0}) = 1.0f / ({1}); }}"),
+    (r"setp\.geu\.f32 p, %1, %2; @p add\.s32 %0, %0, 1;", "{{ if (!(({1}) < ({2}))) ({0}) += 1; }}"),
+    (r"setp\.geu\.f32 p, %1, %2; @p st\.shared\.f32 \[%0\], %1; @p st\.shared\.u32 \[%0\+%4\], %3;",
+     "{{ if (!(({1}) < ({2}))) {{ *(float *)::simt::smem_resolve({0}) = ({1}); "
+     "*(unsigned *)::simt::smem_resolve(({0}) + ({4})) = ({3}); ({0}) += 4; }} }}"),
     (r"^ld\.acquire\.(sys|gpu)\.global\.u32 ", "{{ ({0}) = *(const volatile unsigned *)({1}); }}"),
     (r"^st\.release\.(sys|gpu)\.global\.u32 ", "{{ *(volatile unsigned *)({0}) = ({1}); }}"),
     (r"^ld\.global\.L1::no_allocate\.v4\.u32 ",

@@ -138,6 +138,11 @@ def set_forward_depth(depth=0):
     load().maxk_set_forward_depth(int(depth))
 
 
+def set_topk_group(lanes=-1):
+    rc = load().maxk_set_topk_group(int(lanes))
+    assert rc == 0, rc
+
+
 def set_forward_copies(copies=0):
     load().maxk_set_forward_copies(int(copies))
 
@@ -173,15 +178,15 @@ def worklist(indptr, warp_max_nz=64):
         ws.close()
 
 
-def topk_f32(x, k, want_dense=False, want_cbsr=True):
+def topk_f32(x, k, want_dense=False, want_cbsr=True, out_align=(4, 1)):
     L = load()
     x = np.ascontiguousarray(x, np.float32)
     n, d = x.shape
     ins = {"x": Guarded(x, name="x")}
     outs = {}
     if want_cbsr:
-        outs["sp_data"] = Guarded(shape=(n, k), dtype=np.float32, name="sp_data", align=4)
-        outs["sp_index"] = Guarded(shape=(n, k), dtype=np.uint8, name="sp_index", align=1)
+        outs["sp_data"] = Guarded(shape=(n, k), dtype=np.float32, name="sp_data", align=out_align[0])
+        outs["sp_index"] = Guarded(shape=(n, k), dtype=np.uint8, name="sp_index", align=out_align[1])
     if want_dense:
         outs["dense"] = Guarded(shape=(n, d), dtype=np.float32, name="dense")
     r = _run(L.maxk_topk_cbsr_f32, ins, outs,

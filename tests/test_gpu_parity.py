@@ -98,6 +98,53 @@ def test_topk_goldens_from_torch(ops, golden_dir):
         assert torch.equal(v, tv.gather(1, order))
 
 
+@pytest.mark.parametrize("lanes", [0, 2, 4, 8])
+def test_topk_rows_per_warp(ops, lanes):
+    """One row per warp and the grouped kernel (4 / 8 lanes per row) on the same rows: oracle bits for ragged n, ties /
+    NaN / infinities inside a warp of otherwise fast rows, unaligned output views; torch.topk on 100 k tie-free rows."""
+    ops.set_topk_group(lanes)
+    try:
+        rng = np.random.default_rng(60 + lanes)
+        for n in (1, 5, 8, 9, 33, 257, 1001):
+            x = rng.standard_normal((n, 256)).astype(np.float32)
+            if n > 8:
+                x[::5] = rng.integers(0, 3, size=x[::5].shape).astype(np.float32)
+                x[6, 17] = np.nan
+                x[7, :] = -np.inf
+                x[2, 5] = np.inf
+                x[3, :] = np.nan
+            for k in (1, 8, 18, 32, 64, 128, 129):
+                want_v, want_i = O.topk_cbsr(x, k)
+                v, i, dense = ops.topk_cbsr(_cu(x), k, want_dense=True)
+                np.testing.assert_array_equal(i.cpu().numpy(), want_i, err_msg=f"n={n} k={k} lanes={lanes}")
+                np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), want_v.view(np.uint32))
+                np.testing.assert_array_equal(dense.cpu().numpy().view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
+                # caller-provided outputs that are not 16-byte aligned (the scalar copy-out)
+                buf_v = torch.empty(n * k + 1, dtype=torch.float32, device="cuda")
+                buf_i = torch.empty(n * k + 1, dtype=torch.uint8, device="cuda")
+                ov, oi = buf_v[1:].view(n, k), buf_i[1:].view(n, k)
+                ops.topk_cbsr(_cu(x), k, out=(ov, oi))
+                np.testing.assert_array_equal(oi.cpu().numpy(), want_i)
+                np.testing.assert_array_equal(ov.cpu().numpy().view(np.uint32), want_v.view(np.uint32))
+        for gen in (torch.rand, torch.randn):
+            x = gen(100_003, 256, device="cuda")
+            for k in (8, 32, 64):
+                v, i = ops.topk_cbsr(x, k)
+                tv, ti = torch.topk(x, k, dim=1)
+                order = ti.argsort(dim=1)
+                assert torch.equal(i.long(), ti.gather(1, order))
+                assert torch.equal(v, tv.gather(1, order))
+        for d, k in ((128, 16), (128, 64), (64, 8), (64, 32)):
+            x = torch.randn(50_001, d, device="cuda")
+            v, i = ops.topk_cbsr(x, k)
+            tv, ti = torch.topk(x, k, dim=1)
+            order = ti.argsort(dim=1)
+            assert torch.equal(i.long(), ti.gather(1, order))
+            assert torch.equal(v, tv.gather(1, order))
+    finally:
+        ops.set_topk_group(-1)
+
+
 def test_topk_u8(ops):
     rng = np.random.default_rng(3)
     for d in (256, 64):

@@ -27,6 +27,7 @@ def _reset_knobs():
     S.set_tuning(-1, -1)
     S.set_forward_depth(0)
     S.set_forward_copies(0)
+    S.set_topk_group(-1)
     S.set_cp_async_eager(False)
 
 
@@ -102,6 +103,39 @@ def test_simt_topk_full_width_rows():
             np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
         (dense,) = S.topk_f32(x, 32, want_dense=True, want_cbsr=False)
         np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, 32).view(np.uint32))
+
+
+@pytest.mark.parametrize("lanes", [0, 2, 4, 8])
+def test_simt_topk_rows_per_warp(lanes):
+    """The grouped kernel (4 / 8 lanes per row, 8 / 4 rows per warp) and the one-row kernel on the same rows: every
+    n around the warp and CTA boundaries, rows the fast path finishes next to rows that need the robust search
+    (ties, NaN, infinities) inside one warp, both output copies (128-bit when sp_data / sp_index are aligned)."""
+    S.set_topk_group(lanes)
+    rng = np.random.default_rng(50 + lanes)
+    for eager in (False, True):
+        S.set_cp_async_eager(eager)
+        for n in (1, 3, 4, 5, 8, 9, 31, 32, 33, 65):
+            x = rng.standard_normal((n, 256)).astype(np.float32)
+            if n > 8:
+                x[::5] = rng.integers(0, 3, size=x[::5].shape).astype(np.float32)   # ties everywhere
+                x[6, 17] = np.nan
+                x[7, :] = -np.inf
+                x[2, 5] = np.inf
+                x[3, :] = np.nan
+            for k in (1, 8, 18, 32, 64, 128, 129):
+                want_v, want_i = O.topk_cbsr(x, k)
+                for al in ((4, 1), (16, 4)):
+                    v, i, dense = S.topk_f32(x, k, want_dense=True, out_align=al)
+                    np.testing.assert_array_equal(i, want_i, err_msg=f"n={n} k={k} lanes={lanes}")
+                    np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
+                    np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
+    for d, k in ((128, 16), (128, 64), (64, 8), (64, 32)):
+        x = rng.uniform(-1, 1, size=(37, d)).astype(np.float32)
+        x[5, :] = 0.25
+        want_v, want_i = O.topk_cbsr(x, k)
+        v, i = S.topk_f32(x, k)
+        np.testing.assert_array_equal(i, want_i, err_msg=f"d={d} k={k} lanes={lanes}")
+        np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
 
 
 def test_simt_topk_goldens_from_torch(golden_dir):
