@@ -162,6 +162,20 @@ MAXK_API int maxk_cbsr_gather(const float *dense, const uint8_t *sp_index, int64
 MAXK_API int maxk_cbsr_mask(const float *in, const uint8_t *sp_index, int64_t n, int32_t k, int32_t d,
                    float *out, void *stream);
 
+/* ---- f3 (i): the Linear in front of a MaxK with the selection in its epilogue ------------
+ * (sp_data, sp_index) = TopK_k(x @ weight^T + bias): replaces `self.linlayers[i](x)` followed by `MaxK.apply`
+ * (utils/models.py:336-341, 365-369) without the dense [n, d] activation in HBM.  One tcgen05 kernel: TMA-fed
+ * TF32 tensor-core products with a two-term operand split (fp32 accuracy), fp32 accumulators in TMEM, TopK in the
+ * epilogue.  x [n, in_dim] and weight [d, in_dim] row-major fp32, bias [d] or NULL; d must be 256, in_dim a
+ * multiple of 4; x, workspace, linear_out 16-byte aligned.  workspace: maxk_linear_topk_workspace_bytes(d, in_dim)
+ * bytes of device memory (the split weight), overwritten by every call.  linear_out (optional, [n, d]): the
+ * Linear's own output, for callers that want it; sp_data / sp_index may then be NULL.  Selection semantics are
+ * maxk_topk_cbsr_f32's applied to the kernel's own fp32 result (ties -> lowest column). */
+MAXK_API int64_t maxk_linear_topk_workspace_bytes(int32_t d, int32_t in_dim);
+MAXK_API int maxk_linear_topk_cbsr(const float *x, int64_t n, int32_t in_dim, const float *weight, const float *bias,
+                                   int32_t d, int32_t k, float *sp_data, uint8_t *sp_index, float *linear_out,
+                                   void *workspace, void *stream);
+
 /* ---- the dense layer next to the aggregation on the CBSR operand itself,
  * without the dense [n, d] twin (measured on the products shape, k = 32: 3.8 vs 6.3 ms for fc_self,
  * 5.1 vs 6.2 ms for the gradient of the kept values, profiles/r02_variants.md).  m is a dense float32 [d, c] matrix,

@@ -115,6 +115,13 @@ def cbsr_native_enabled(k: int = 32) -> bool:
     return k <= 32
 
 
+def linear_topk_fused_enabled() -> bool:
+    """Whether LinearTopKCBSR's forward is the fused tcgen05 kernel (csrc/linear_topk.cu) where its shapes allow
+    (output width 256, fp32).  MAXK_LINEAR_TOPK_FUSED=0 selects the library GEMM followed by the TopK kernel."""
+    import os
+    return os.environ.get("MAXK_LINEAR_TOPK_FUSED", "1").strip() != "0"
+
+
 class CBSRLinear(Function):
     """y = scatter(sp_data, sp_index) @ weight^T + bias computed from the CBSR pair (N*k*C multiply-adds, no
     dense [N, D] twin in the forward or in the gradient of the values).  Same result as
@@ -167,14 +174,20 @@ class CBSRAddScaled(Function):
 class LinearTopKCBSR(Function):
     """(sp_data, sp_index) = TopK_k(x @ weight^T + bias): the Linear in front of the MaxK of the GCN / GIN layers
     (utils/models.py:318-322, 365-369) together with the selection.  The forward is the dense library GEMM
-    followed by the TopK kernel; what changes is the backward: the gradient that reaches the Linear's output is
+    followed by the TopK kernel -- or, at output width 256, ONE tcgen05 kernel with the selection in the GEMM's
+    epilogue (csrc/linear_topk.cu); the backward: the gradient that reaches the Linear's output is
     k-sparse per row, so dX = scatter(g) @ weight is computed on the CBSR pair (N*k*in multiply-adds,
     csrc/cbsr_dense.cu) instead of as a dense [N, D] x [D, in] GEMM.  dW and db use the scattered twin."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, k):
-        y = torch.nn.functional.linear(x, weight, bias)
-        sp_data, sp_index = ops.topk_cbsr(y.contiguous(), k)
+        if linear_topk_fused_enabled() and ops.linear_topk_supported(x, weight):
+            # one tcgen05 kernel, selection in the GEMM's epilogue: no dense [N, 256] activation in HBM
+            sp_data, sp_index = ops.linear_topk_cbsr(x.contiguous(), weight.detach().contiguous(),
+                                                     None if bias is None else bias.detach().contiguous(), k)
+        else:
+            y = torch.nn.functional.linear(x, weight, bias)
+            sp_data, sp_index = ops.topk_cbsr(y.contiguous(), k)
         ctx.save_for_backward(x, weight, sp_index)
         ctx.has_bias = bias is not None
         ctx.mark_non_differentiable(sp_index)

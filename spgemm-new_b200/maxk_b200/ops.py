@@ -91,6 +91,48 @@ def topk_cbsr(x: torch.Tensor, k: int, want_dense: bool = False, want_cbsr: bool
     return sp_data, sp_index
 
 
+_LT_WORKSPACE = {}
+
+
+def linear_topk_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Shapes the fused tcgen05 kernel takes (csrc/linear_topk.cu): fp32, output width 256, in_dim % 4 == 0."""
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2
+            and weight.dim() == 2 and weight.shape[0] == FULL_DIM and weight.shape[1] == x.shape[1]
+            and x.shape[1] % 4 == 0 and x.shape[1] >= 4)
+
+
+def linear_topk_cbsr(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], k: int,
+                     want_linear: bool = False, want_cbsr: bool = True):
+    """(sp_data, sp_index[, linear_out]) = TopK_k(x @ weight^T + bias) in one tcgen05 kernel: the dense [N, 256]
+    activation never reaches HBM (include/maxk_b200.h: maxk_linear_topk_cbsr; ref utils/models.py:336-341)."""
+    lib = _cabi.load()
+    _cuda(x, "x", torch.float32)
+    _cuda(weight, "weight", torch.float32)
+    _req(x.dim() == 2 and weight.dim() == 2 and weight.shape[1] == x.shape[1], "x [N, in] and weight [D, in] expected")
+    n, in_dim = x.shape
+    d = weight.shape[0]
+    _req(0 < k <= d, "Invalid k value")
+    if bias is not None:
+        _cuda(bias, "bias", torch.float32)
+        _req(bias.numel() == d, "bias must have D elements")
+    sp_data = sp_index = lin = None
+    with torch.cuda.device(x.device):
+        if want_cbsr:
+            sp_data = torch.empty((n, k), dtype=torch.float32, device=x.device)
+            sp_index = torch.empty((n, k), dtype=torch.uint8, device=x.device)
+        if want_linear:
+            lin = torch.empty((n, d), dtype=torch.float32, device=x.device)
+        key = (x.device.index, d, in_dim, torch.cuda.current_stream(x.device).cuda_stream)
+        ws = _LT_WORKSPACE.get(key)
+        if ws is None:   # one workspace per (device, shape, stream): the split weight is rewritten by every call
+            ws = torch.empty(int(lib.maxk_linear_topk_workspace_bytes(d, in_dim)), dtype=torch.uint8, device=x.device)
+            _LT_WORKSPACE[key] = ws
+        _cabi.check(lib.maxk_linear_topk_cbsr(x.data_ptr(), n, in_dim, weight.data_ptr(), _ptr(bias), d, k,
+                                              _ptr(sp_data), _ptr(sp_index), _ptr(lin), ws.data_ptr(), _stream(x)))
+    out = tuple(t for t in (sp_data, sp_index, lin) if t is not None)
+    return out if len(out) > 1 else out[0]
+
+
 def topk_cbsr_u8(x: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _cabi.load()
     _cuda(x, "Input", None)

@@ -30,7 +30,7 @@ CXXFLAGS = ["-std=c++17", "-O1", "-g", "-fPIC", "-fvisibility=hidden", "-fno-omi
 
 def _deps():
     d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    d += [os.path.join(HERE, f) for f in ("translate.py", "build.py", "simt_runtime.cpp")]
+    d += [os.path.join(HERE, f) for f in ("translate.py", "build.py", "simt_runtime.cpp", "tensor_core_stubs.cpp")]
     d += [os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(ROOT, "include", "maxk_b200.h")]
     return d
 
@@ -47,7 +47,7 @@ def build(force=False):
         return LIB
     os.makedirs(GEN, exist_ok=True)
     gen = translate.translate_tree(CSRC, GEN)
-    srcs = [p for p in gen if p.endswith(".cpp")] + [os.path.join(HERE, "simt_runtime.cpp")]
+    srcs = [p for p in gen if p.endswith(".cpp")] + [os.path.join(HERE, f) for f in ("simt_runtime.cpp", "tensor_core_stubs.cpp")]
     cxx = os.environ.get("SIMT_CXX", "g++")
 
     def compile_one(src):
