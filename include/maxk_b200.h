@@ -69,9 +69,9 @@ MAXK_API int maxk_set_forward_copies(int copies);
  * operands, otherwise shape 2)); 0 = automatic: 1 for long rows, 2 for short rows, 8 (k <= 32) or
  * 12 (k = 64) for short rows on an operand too large for the L2. */
 MAXK_API int maxk_set_forward_depth(int depth);
-/* Bench/test hook: rows per warp of the fp32 TopK kernel, given as LANES PER ROW: 8 or 4 (four / eight rows per
- * warp, the grouped kernel: d in {64, 128, 256} and k <= d / 2), 0 = one row per warp, -1 = automatic. */
-MAXK_API int maxk_set_topk_group(int lanes);
+/* Bench/test hook: the grouped fp32 TopK kernel (several rows per warp; d = 128 / 64 with k <= d / 2):
+ * -1 = automatic (on where it is faster), 0 = one row per warp everywhere, 1 = on. */
+MAXK_API int maxk_set_topk_group(int on);
 
 /* ---- a4: work list (replaces kernels/generate_meta.py:8-48 and the disk round trip of
  * load_warp4_metadata, cuda_kernel_bindings.cpp:287-317) ------------------------------

@@ -19,8 +19,8 @@ dists = (("uniform", torch.rand(n, 256, device="cuda", generator=g)),
          ("normal", torch.randn(n, 256, device="cuda", generator=g)),
          ("relu_normal", torch.randn(n, 256, device="cuda", generator=g).relu()),
          ("quantised", (torch.rand(n, 256, device="cuda", generator=g) * 8).floor()))
-lanes_list = (0, 8, 4) if hasattr(ops, "set_topk_group") else (0,)
-for name, x in dists:
+lanes_list = (0,)
+for name, x in dists[:2] if os.environ.get('TOPK_PROBE_SHORT') else dists:
     for k in (8, 32, 64):
         for lanes in lanes_list:
             ops.set_topk_group(lanes)
@@ -28,16 +28,14 @@ for name, x in dists:
                 ops.topk_cbsr(x, k); continue
             b = 4 * n * 256 + 5 * n * k
             t = timeit(lambda: ops.topk_cbsr(x, k))
-            print(f"topk {name:12s} k={k:3d} lanes/row={lanes or 32:2d}: {t*1e3:7.1f} us  {b/t/1e6:7.0f} GB/s  frac {b/t/1e6/6543.7:.3f}", flush=True)
+            print(f"topk {name:12s} k={k:3d} {'grouped' if lanes else 'one row / warp':14s}: {t*1e3:7.1f} us  {b/t/1e6:7.0f} GB/s  frac {b/t/1e6/6543.7:.3f}", flush=True)
 ops.set_topk_group(-1)
 for d, k in ((128, 16), (128, 32), (64, 16)):
     x = torch.randn(n * 256 // d, d, device="cuda", generator=g)
-    for lanes in (0, 2, 4, 8):
-        if lanes == 2 and d != 64:
-            continue
+    for lanes in (0, -1):
         ops.set_topk_group(lanes)
         b = x.numel() * 4 + 5 * x.shape[0] * k
         t = timeit(lambda: ops.topk_cbsr(x, k))
-        print(f"topk normal d={d} k={k:3d} lanes/row={lanes or 32:2d}: {t*1e3:7.1f} us  {b/t/1e6:7.0f} GB/s  frac {b/t/1e6/6543.7:.3f}", flush=True)
+        print(f"topk normal d={d} k={k:3d} {'grouped' if lanes else 'one row / warp':14s}: {t*1e3:7.1f} us  {b/t/1e6:7.0f} GB/s  frac {b/t/1e6/6543.7:.3f}", flush=True)
 ops.set_topk_group(-1)
 torch.cuda.synchronize()

@@ -39,8 +39,12 @@ namespace maxk {
 
 constexpr int LT_D = 256;          // output width = MMA N
 constexpr int LT_TILE_M = 128;     // rows per tile = MMA M = TMEM lanes
-constexpr int LT_BK = 32;          // K chunk: 32 fp32 = one 128-byte swizzle row
-constexpr int LT_STAGES = 2;
+#ifndef MAXK_LT_BK
+#define MAXK_LT_BK 16
+#endif
+constexpr int LT_BK = MAXK_LT_BK;  // K chunk: 16 fp32 = one 64-byte swizzle row (32: 128-byte rows, two stages)
+constexpr int LT_STAGES = 64 / LT_BK;  // 192 KB of operand ring either way
+static_assert(LT_BK == 16 || LT_BK == 32, "the ring is laid out for 64- or 128-byte swizzle rows");
 constexpr int LT_A_BYTES = LT_TILE_M * LT_BK * 4;   // 16 KB
 constexpr int LT_B_BYTES = LT_D * LT_BK * 4;        // 32 KB
 constexpr int LT_STAGE_BYTES = 2 * LT_A_BYTES + 2 * LT_B_BYTES;  // A_hi, A_lo, B_hi, B_lo = 96 KB
@@ -88,6 +92,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded wait (about 4 s): a protocol error must end as a trap the host sees, not as a hung GPU.
+template <bool RELAXED = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     const long long t0 = clock64();
@@ -101,6 +106,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
+        if constexpr (RELAXED) __nanosleep(64);  // a waiter whose latency does not matter leaves the issue slots
         if (clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol error ends as a trap, not as a hung GPU
             printf("linear_topk: barrier at %u (parity %u) never completed, block %d thread %d\n", bar, parity,
                    (int)blockIdx.x, (int)threadIdx.x);
@@ -130,12 +136,14 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(LT_IDESC), "r"(accumulate)
         : "memory");
 }
-// shared-memory matrix descriptor, K-major, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp: SmemDescriptor):
-// start address >> 4 at [0,14), leading byte offset (unused with a swizzle) = 1 at [16,30), stride byte offset =
-// 1024 B (eight 128-byte rows) >> 4 at [32,46), version 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64)
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
+// shared-memory matrix descriptor, K-major, rows of LT_BK fp32 = one swizzle span (cute/arch/mma_sm100_desc.hpp:
+// SmemDescriptor): start address >> 4 at [0,14), leading byte offset (unused with a swizzle) = 1 at [16,30), stride
+// byte offset = eight rows (1024 B or 512 B) >> 4 at [32,46), version 1 at [46,48), layout type at [61,64):
+// SWIZZLE_128B = 2, SWIZZLE_64B = 4
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr)
 {
-    return ((uint64_t)0x40004040u << 32) | (1u << 16) | ((addr >> 4) & 0x3fffu);
+    constexpr uint32_t hi = (LT_BK == 32 ? (2u << 29) : (4u << 29)) | (1u << 14) | (uint32_t)(8 * LT_BK * 4 / 16);
+    return ((uint64_t)hi << 32) | (1u << 16) | ((addr >> 4) & 0x3fffu);
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads)
 {
@@ -196,7 +204,7 @@ __global__ void lt_split_weight_kernel(const float *__restrict__ w, int64_t coun
 __global__ void __launch_bounds__(LT_THREADS, 1)
 linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                    const float *__restrict__ bias, int64_t n, int in_dim, int k, float *__restrict__ out_val,
-                   unsigned char *__restrict__ out_idx, float *__restrict__ linear_out)
+                   unsigned char *__restrict__ out_idx, float *__restrict__ linear_out, int vec_out)
 {
     extern __shared__ unsigned char lt_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -255,7 +263,7 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             uint32_t ph = 0;
             for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kc = 0; kc < num_kc; ++kc) {
-                    mbar_wait(bar_empty(s), ph ^ 1u);
+                    mbar_wait<true>(bar_empty(s), ph ^ 1u);
                     const uint32_t st = sbase + (uint32_t)(s * LT_STAGE_BYTES);
                     mbar_expect_tx(bar_full(s), LT_TX_BYTES);
                     tma_load_2d(st, &map_x, kc * LT_BK, (int)(tile * LT_TILE_M), bar_full(s));
@@ -284,9 +292,9 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     mbar_wait(bar_conv(s), ph);
                     tc_fence_after();
                     const uint32_t st = sbase + (uint32_t)(s * LT_STAGE_BYTES);
-                    const uint64_t a_hi = smem_desc_sw128(st), a_lo = smem_desc_sw128(st + LT_A_BYTES);
-                    const uint64_t b_hi = smem_desc_sw128(st + 2 * LT_A_BYTES);
-                    const uint64_t b_lo = smem_desc_sw128(st + 2 * LT_A_BYTES + LT_B_BYTES);
+                    const uint64_t a_hi = smem_desc_kmajor(st), a_lo = smem_desc_kmajor(st + LT_A_BYTES);
+                    const uint64_t b_hi = smem_desc_kmajor(st + 2 * LT_A_BYTES);
+                    const uint64_t b_lo = smem_desc_kmajor(st + 2 * LT_A_BYTES + LT_B_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < LT_BK / 8; ++kk) {  // 8 tf32 = 32 bytes per K step: + 2 in 16-byte units
                         const uint64_t adv = (uint64_t)(2 * kk);
@@ -399,8 +407,13 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             fl = fminf(xf[(r * 2) * 2], xf[(r * 2 + 1) * 2]);
             fh = fmaxf(xf[(r * 2) * 2 + 1], xf[(r * 2 + 1) * 2 + 1]);
 
-            // ---- regula falsi (Illinois weights) on g(t) = count(!(x < t)) - k; both halves of a row run the
-            // same state machine on the same totals.  state: 0 searching, 1 exactly k separated, 2 robust search
+            // ---- regula falsi (Illinois weights) on g(t) = count(!(x < t)) - k; both halves of a row run the same
+            // state machine on the same totals (identical control flow in the two warps that meet at the named
+            // barrier).  state: 0 searching, 1 t separates exactly k elements, 2 robust search needed.
+            // The 32 rows of a warp probe in lock step: 11.8 probes per warp against 3.9 per row (ncu, round 2).  An
+            // exact finish -- bracket down to <= 16 candidates per half, write them to shared memory, select the
+            // j-th largest, prove it with one counting pass -- was built and measured: SLOWER (3.3 vs 2.0 ms on the
+            // products shape), its own extraction / selection passes cost more than the probes they replace.
             int state = 0, c = 0, c_other = 0, run = 0, par = 0;
             float t = fl;
             float gl = (float)(LT_D - k), gh = fminf((float)(1 - k), -0.5f);
@@ -416,7 +429,7 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 if (state == 0) {
                     float fm = fmaf(fh - fl, gl * rcp_approx(gl - gh), fl);
                     if (!(fm > fl && fm < fh)) fm = 0.5f * fl + 0.5f * fh;
-                    if (!(fm > fl && fm < fh)) state = 2;
+                    if (!(fm > fl && fm < fh)) state = 2;  // adjacent floats, infinite or NaN end points
                     t = fm;
                 }
                 int ca = 0, cb = 0, cc = 0, cd = 0;
@@ -466,6 +479,17 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     for (int i = 0; i < LT_HALF; ++i) stage2_if_nlt(w, wi, x[i], t, col0 + i);
                 }
                 named_bar_sync(bar_id, 64);
+                if (rpp == 32 && okmask == full && vec_out) {
+                    // the common case: all 32 rows staged, contiguous in sp_data / sp_index -> 128-bit copies
+                    const int64_t o = (tile * LT_TILE_M + 32 * q) * k;
+                    const int tid = half * 32 + lane;
+                    float4 *gv = reinterpret_cast<float4 *>(out_val + o);
+                    uint4 *gi = reinterpret_cast<uint4 *>(out_idx + o);
+                    const float4 *s4 = reinterpret_cast<const float4 *>(sv);
+                    const uint4 *i4 = reinterpret_cast<const uint4 *>(si);
+                    for (int e = tid; e < 8 * k; e += 64) gv[e] = s4[e];
+                    for (int e = tid; e < 2 * k; e += 64) gi[e] = i4[e];
+                } else
 #pragma unroll 1
                 for (int rr = first + half; rr < last; rr += 2) {  // the two warps take alternate rows
                     if (!((okmask >> rr) & 1u)) continue;
@@ -548,7 +572,8 @@ static int make_map_f32(CUtensorMap *map, const float *base, int64_t rows, int c
     const cuuint32_t box[2] = {(cuuint32_t)LT_BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, LT_BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("maxk_linear_topk_cbsr: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
@@ -612,8 +637,10 @@ extern "C" int maxk_linear_topk_cbsr(const float *x, int64_t n, int32_t in_dim, 
     MAXK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = ceil_div<int64_t>(n, LT_TILE_M);
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    const int vec_out = (k % 4 == 0) && (reinterpret_cast<uintptr_t>(sp_data) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(sp_index) & 15) == 0;
     linear_topk_kernel<<<grid, LT_THREADS, LtShared::total + 1024, st>>>(map_x, map_w, bias, n, in_dim, k, sp_data,
-                                                                         sp_index, linear_out);
+                                                                         sp_index, linear_out, vec_out);
     MAXK_LAUNCH_CHECK("linear_topk_kernel");
     return MAXK_OK;
 }

@@ -198,7 +198,9 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k,
 //     OUTPUT (the R rows of a warp are contiguous in sp_data and in sp_index), copied out coalesced;
 //   * rows the fast path cannot finish (ties at the k-th value, infinite end points, NaN-only groups) are
 //     re-read in the one-row layout and go through the robust key search above, one at a time.
-// Used for D in {64, 128, 256} and k <= D / 2 (the staging area of the output overlays the input rows).
+// Used for D = 128 (L = 4) and D = 64 (L = 2) with k <= D / 2 (the staging area of the output overlays the input
+// rows).  Measured in round 2 with L = 1, 2, 4, 8 at every width (profiles/r02_topk_grouped.md): at D = 256 the rows
+// of a warp probing in lock step cost more than the shared overhead saves, and the one-row kernel stays.
 template <int L>
 __device__ __forceinline__ int group_sum(int v)
 {
@@ -490,21 +492,19 @@ int launch_topk_group(const float *x, int64_t n, int k, float *sp_data, uint8_t 
     return MAXK_OK;
 }
 
-// lanes per row of the grouped kernel: 0 = one row per warp (the kernel above), 4 or 8; -1 = automatic
-int g_topk_group_lanes = -1;
+// grouped kernel where it is the faster one (d = 128, 64): -1 / 1 = yes, 0 = one row per warp everywhere
+int g_topk_group = -1;
 
 }  // namespace maxk
 
 using namespace maxk;
 
-extern "C" int maxk_set_topk_group(int lanes)
+extern "C" int maxk_set_topk_group(int on)
 {
-    MAXK_REQUIRE(lanes == -1 || lanes == 0 || lanes == 2 || lanes == 4 || lanes == 8,
-                 "maxk_set_topk_group: lanes per row must be -1 (automatic), 0 (one row per warp), 2, 4 or 8");
-    g_topk_group_lanes = lanes;
+    MAXK_REQUIRE(on == -1 || on == 0 || on == 1, "maxk_set_topk_group: -1 (automatic), 0 (one row per warp) or 1");
+    g_topk_group = on;
     return MAXK_OK;
 }
-
 
 extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t k, float *sp_data,
                                   uint8_t *sp_index, float *dense_out, void *stream)
@@ -525,19 +525,12 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_topk_cbsr_f32: n too large");
     {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        if (2 * k <= d) {   // -1: what round 2 measured as fastest per width (profiles/r02_topk_grouped.md)
-            const int want = g_topk_group_lanes;
-#define MAXK_TOPK_GROUP(DD, LL, AUTO)                                                   \
-    if (d == DD && (want == LL || (want < 0 && (AUTO))))                               \
-        return launch_topk_group<DD, LL>(x, n, k, sp_data, sp_index, dense_out, st);
-            MAXK_TOPK_GROUP(256, 8, false)
-            MAXK_TOPK_GROUP(256, 4, false)
-            MAXK_TOPK_GROUP(128, 8, false)
-            MAXK_TOPK_GROUP(128, 4, true)
-            MAXK_TOPK_GROUP(64, 8, false)
-            MAXK_TOPK_GROUP(64, 4, false)
-            MAXK_TOPK_GROUP(64, 2, true)
-#undef MAXK_TOPK_GROUP
+        // round 2 measured 1, 2, 4 and 8 lanes per row (profiles/r02_topk_grouped.md): at d = 128 four lanes
+        // (134 vs 246 us one row per warp), at d = 64 two lanes (172 vs 432 us) win; at d = 256 the one-row kernel
+        // stays ahead (101 vs 108 us: the rows of a warp probe in lock step and the slowest of 8 sets the pace)
+        if (2 * k <= d && g_topk_group != 0) {
+            if (d == 128) return launch_topk_group<128, 4>(x, n, k, sp_data, sp_index, dense_out, st);
+            if (d == 64) return launch_topk_group<64, 2>(x, n, k, sp_data, sp_index, dense_out, st);
         }
     }
     if (d == MAXK_MAX_DIM)

@@ -474,9 +474,9 @@ def set_forward_depth(depth: int = 0) -> None:
     _cabi.check(_cabi.load().maxk_set_forward_depth(int(depth)))
 
 
-def set_topk_group(lanes: int = -1) -> None:
-    """Lanes per row of the fp32 TopK kernel (8 / 4 = grouped kernel, 0 = one row per warp, -1 = automatic); bench/test hook."""
-    _cabi.check(_cabi.load().maxk_set_topk_group(int(lanes)))
+def set_topk_group(on: int = -1) -> None:
+    """Grouped fp32 TopK kernel (several rows per warp, d = 128 / 64): -1 automatic, 0 off, 1 on; bench/test hook."""
+    _cabi.check(_cabi.load().maxk_set_topk_group(int(on)))
 
 
 def set_forward_copies(copies: int = 0) -> None:

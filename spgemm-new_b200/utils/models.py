@@ -96,7 +96,13 @@ class SAGE(_Base):
             init.xavier_uniform_(self.fc_neigh_layers[i].weight)
 
     def forward(self, g, x):
-        x = self.lin_in(x)
+        # upstream variant: layer 0 only ever sees MaxK(lin_in(x)) -- the input Linear and the first selection are one
+        # node (the fused tcgen05 kernel at width 256: the dense [N, hidden] activation of lin_in never exists)
+        first = None
+        if not self.fork_variant and self.num_layers > 0 and self.nonlinear == "maxk":
+            first = _linear_sparsify(self.lin_in, x, self.maxk, self.nonlinear, self.p, self.training)
+        else:
+            x = self.lin_in(x)
         for i in range(self.num_layers):
             if self.fork_variant:   # models.py:230-253: sum aggregation, self branch on raw x, dropout after
                 sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, 0.0, False)
@@ -104,7 +110,10 @@ class SAGE(_Base):
                     g.aggregate(sp_data, sp_index, "sum", self.hid))
                 x = F.dropout(x, self.p, self.training)
             else:                   # SAGEConv("mean", feat_drop): dropout(maxk(x)) feeds both branches
-                sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
+                if i == 0 and first is not None:
+                    sp_data, sp_index = first
+                else:
+                    sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
                 fc_self = self.fc_self_layers[i]
                 if self.nonlinear == "maxk" and cbsr_native_enabled(self.maxk):   # fc_self on the CBSR operand
                     own = CBSRLinear.apply(sp_data, sp_index, fc_self.weight, fc_self.bias)

@@ -98,9 +98,9 @@ def test_topk_goldens_from_torch(ops, golden_dir):
         assert torch.equal(v, tv.gather(1, order))
 
 
-@pytest.mark.parametrize("lanes", [0, 2, 4, 8])
+@pytest.mark.parametrize("lanes", [0, -1])
 def test_topk_rows_per_warp(ops, lanes):
-    """One row per warp and the grouped kernel (4 / 8 lanes per row) on the same rows: oracle bits for ragged n, ties /
+    """One row per warp and the grouped kernel (d = 128 / 64) on the same rows: oracle bits for ragged n, ties /
     NaN / infinities inside a warp of otherwise fast rows, unaligned output views; torch.topk on 100 k tie-free rows."""
     ops.set_topk_group(lanes)
     try:
