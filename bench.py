@@ -783,6 +783,34 @@ def main():
             log(f"[rank {rank}] epoch leg failed: {type(exc).__name__}: {exc}")
             if rank == 0:
                 line["epoch"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        # -------------------------------------------------------------- fused Linear + TopK leg
+        # The Linear -> MaxK pair of the GCN / GIN layers on the products-sized activation: the own tcgen05 kernel
+        # (TopK in the GEMM's epilogue, no dense [N, 256] tensor in HBM) against torch's fp32 Linear + the TopK kernel.
+        if world == 1:
+            try:
+                torch.cuda.empty_cache()
+                gen = torch.Generator(device=dev).manual_seed(7)
+                n_lt = 2_449_029
+                xl = torch.randn(n_lt, 256, device=dev, generator=gen)
+                wl = torch.randn(256, 256, device=dev, generator=gen) / 16
+                bl = torch.randn(256, device=dev, generator=gen) * 0.1
+                launches0 = _cabi.launch_count()
+                t_f = timeit_events(lambda: ops.linear_topk_cbsr(xl, wl, bl, 32), iters=5, warm=3)
+                fused_launches = (_cabi.launch_count() - launches0) // 8
+                t_l = timeit_events(lambda: torch.nn.functional.linear(xl, wl, bl), iters=5, warm=3)
+                yl = torch.nn.functional.linear(xl, wl, bl)
+                t_t = timeit_events(lambda: ops.topk_cbsr(yl, 32), iters=5, warm=3)
+                line["linear_topk"] = {
+                    "what": "TopK_32(X W^T + b), X [2449029, 256] fp32 (products-sized), W [256, 256]: own tcgen05 kernel "
+                            "(3 x TF32 operand split, TMEM accumulators, TopK in the epilogue) vs torch fp32 Linear + TopK kernel",
+                    "fused_ms": t_f, "torch_linear_fp32_ms": t_l, "topk_kernel_ms": t_t,
+                    "speedup": (t_l + t_t) / t_f, "fp32_equiv_TFLOPs": 2.0 * n_lt * 256 * 256 / t_f / 1e9,
+                    "hbm_bytes_avoided": 8 * n_lt * 256, "launches_per_call": fused_launches}
+                log(f"[linear_topk] fused {t_f:.3f} ms vs Linear {t_l:.3f} + TopK {t_t:.3f} ms")
+                del xl, yl
+            except Exception as exc:  # noqa: BLE001
+                log(f"linear_topk leg failed: {type(exc).__name__}: {exc}")
+                line["linear_topk"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         dog.cancel()
     if rank == 0:
         print(json.dumps(line), flush=True)
