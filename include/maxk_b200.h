@@ -176,6 +176,29 @@ MAXK_API int maxk_linear_topk_cbsr(const float *x, int64_t n, int32_t in_dim, co
                                    int32_t d, int32_t k, float *sp_data, uint8_t *sp_index, float *linear_out,
                                    void *workspace, void *stream);
 
+/* The dense Linear next to the path on the same tensor-core machinery (fp32 accuracy from split TF32 products;
+ * replaces the library SGEMMs torch.nn.Linear runs in fp32 for utils/models.py:151-392 -- the forward and the two
+ * backward products of a 256-wide layer):
+ *   maxk_linear_f32:   out[n, d] = x[n, in_dim] @ weight[d, in_dim]^T + bias      (d = 256; also dX = dY @ W with
+ *                      weight := W^T when in_dim of the layer is 256)
+ *   maxk_linear_wgrad: dw[d, in_dim] (+)= grad_out[n, d]^T @ x[n, in_dim]         (d = 256, in_dim <= 256)
+ * All pointers 16-byte aligned, in_dim a multiple of 4; workspace as for maxk_linear_topk_cbsr. */
+MAXK_API int maxk_linear_f32(const float *x, int64_t n, int32_t in_dim, const float *weight, const float *bias,
+                             int32_t d, float *out, void *workspace, void *stream);
+MAXK_API int maxk_linear_wgrad(const float *grad_out, const float *x, int64_t n, int32_t d, int32_t in_dim, float *dw,
+                               int32_t accumulate, void *stream);
+
+/* ---- LayerNorm of the layers (`self.normlayers[i]`, utils/models.py:207-213; nn.LayerNorm(hidden, affine)) -------
+ * forward:  y = (x - mean) * rstd * gamma + beta per row of d <= 256 (multiple of 4) floats; mean / rstd [n] are kept
+ *           for the backward; gamma / beta may be NULL (1 / 0).
+ * backward: dx = rstd * (g*gamma - mean_d(g*gamma) - xhat * mean_d(g*gamma*xhat)); dgamma [d] = sum_rows g*xhat and
+ *           dbeta [d] = sum_rows g are overwritten (either may be NULL).  One warp per row, HBM-bound. */
+MAXK_API int maxk_layernorm_forward(const float *x, int64_t n, int32_t d, const float *gamma, const float *beta,
+                                    float eps, float *y, float *mean, float *rstd, void *stream);
+MAXK_API int maxk_layernorm_backward(const float *grad_out, const float *x, const float *mean, const float *rstd,
+                                     const float *gamma, int64_t n, int32_t d, float *dx, float *dgamma, float *dbeta,
+                                     void *stream);
+
 /* ---- the dense layer next to the aggregation on the CBSR operand itself,
  * without the dense [n, d] twin (measured on the products shape, k = 32: 3.8 vs 6.3 ms for fc_self,
  * 5.1 vs 6.2 ms for the gradient of the kept values, profiles/r02_variants.md).  m is a dense float32 [d, c] matrix,

@@ -272,3 +272,27 @@ def synth_graph(n: int, avg_deg: float, seed: int = 0, kind: str = "powerlaw",
     order = np.lexsort((idx, rows))
     idx = idx[order]
     return indptr.astype(np.int32), idx.astype(np.int32)
+
+
+def layernorm(x, gamma=None, beta=None, eps: float = 1e-5):
+    """nn.LayerNorm over the last dimension (utils/models.py:207-213), fp64: (y, mean, rstd)."""
+    x = np.asarray(x, np.float64)
+    mean = x.mean(axis=1, keepdims=True)
+    var = ((x - mean) ** 2).mean(axis=1, keepdims=True)
+    rstd = 1.0 / np.sqrt(var + eps)
+    y = (x - mean) * rstd
+    if gamma is not None:
+        y = y * np.asarray(gamma, np.float64)
+    if beta is not None:
+        y = y + np.asarray(beta, np.float64)
+    return y, mean[:, 0], rstd[:, 0]
+
+
+def layernorm_grad(g, x, gamma=None, eps: float = 1e-5):
+    """Gradients of `layernorm`, fp64: (dx, dgamma, dbeta)."""
+    g, x = np.asarray(g, np.float64), np.asarray(x, np.float64)
+    _, mean, rstd = layernorm(x, None, None, eps)
+    xhat = (x - mean[:, None]) * rstd[:, None]
+    w = g if gamma is None else g * np.asarray(gamma, np.float64)
+    dx = rstd[:, None] * (w - w.mean(axis=1, keepdims=True) - xhat * (w * xhat).mean(axis=1, keepdims=True))
+    return dx, (g * xhat).sum(axis=0), g.sum(axis=0)

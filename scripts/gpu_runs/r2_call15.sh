@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round 2, call 15 (1 GPU): LayerNorm kernels (parity, timing), tensor-core Linears: epochs of the three models, kernel profile.
+O=gpurun_out; mkdir -p $O
+step() { local t=$1 name=$2; shift 2; timeout "$t" "$@" > "$O/$name" 2> "$O/$name.err"; echo "[$name] rc=$? $(tail -c 400 "$O/$name" | tail -2 | cut -c1-300)"; }
+step 600 r15_pytest.log python -m pytest tests -m gpu -q
+step 300 r15_lt_probe.jsonl python scripts/linear_topk_probe.py
+for m in sage gcn gin; do
+  step 400 r15_epoch_${m}.json python scripts/train_epoch.py --shape products --model $m --k 32 --epochs 5 --warmup 2
+done
+step 300 r15_profile_sage.log python scripts/epoch_profile.py --model sage
+step 300 r15_profile_gcn.log python scripts/epoch_profile.py --model gcn

@@ -32,10 +32,26 @@ for name, n in (("reddit", 232965), ("products", 2449029)):
             torch.backends.cuda.matmul.allow_tf32 = True
             t_lin_tf32 = timeit(lambda: torch.nn.functional.linear(x, w, b))
             torch.backends.cuda.matmul.allow_tf32 = False
+            gy = torch.randn(n, 256, device="cuda", generator=g)
+            t_wg = timeit(lambda: ops.linear_wgrad(gy, x))
+            t_wg_lib = timeit(lambda: gy.t() @ x)
+            del gy
+            norm = torch.nn.LayerNorm(256).cuda()
+            yy = torch.randn(n, 256, device="cuda", generator=g)
+            t_ln_lib = timeit(lambda: norm(yy))
+            t_ln = timeit(lambda: ops.layernorm_forward(yy, norm.weight, norm.bias))
+            o_, mean_, rstd_ = ops.layernorm_forward(yy, norm.weight, norm.bias)
+            t_lnb = timeit(lambda: ops.layernorm_backward(o_, yy, mean_, rstd_, norm.weight))
+            yr = yy.clone().requires_grad_(True)
+            def lib_bwd():
+                norm.zero_grad(); yr.grad = None
+                norm(yr).backward(o_)
+            t_ln_lib_fb = timeit(lib_bwd)
+            del yy, yr, o_
             flops = 2.0 * n * in_dim * 256
             print(json.dumps({"shape": name, "n": n, "in_dim": in_dim, "k": k, "fused_ms": round(t_fused, 4),
                               "fused_linear_only_ms_incl_dense_write": round(t_gemm_only, 4), "torch_linear_fp32_ms": round(t_lin, 4), "topk_ms": round(t_topk, 4),
-                              "torch_linear_tf32_ms": round(t_lin_tf32, 4),
+                              "torch_linear_tf32_ms": round(t_lin_tf32, 4), "wgrad_ms": round(t_wg, 4), "layernorm_fwd_ms": round(t_ln, 4), "torch_layernorm_fwd_ms": round(t_ln_lib, 4), "layernorm_bwd_ms": round(t_lnb, 4), "torch_layernorm_fwd_plus_bwd_ms": round(t_ln_lib_fb, 4), "torch_wgrad_fp32_ms": round(t_wg_lib, 4),
                               "speedup_vs_fp32_linear_plus_topk": round((t_lin + t_topk) / t_fused, 2),
                               "fused_TFLOPs_fp32_equiv": round(flops / t_fused / 1e9, 1),
                               "hbm_bytes_saved": 8 * n * 256}), flush=True)

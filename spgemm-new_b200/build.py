@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmaxk_b200.so")
 SOURCES = ["api.cu", "worklist.cu", "topk_cbsr.cu", "spgemm_forward.cu", "sspmm_backward.cu",
-           "cbsr_layout.cu", "cbsr_plan.cu", "cbsr_dense.cu", "peer.cu", "linear_topk.cu"]
+           "cbsr_layout.cu", "cbsr_plan.cu", "cbsr_dense.cu", "peer.cu", "linear_topk.cu", "linear_wgrad.cu", "layernorm.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -27,12 +27,11 @@
 //
 // Bound: tensor pipe (3 x 8 K steps x 128 cycles = 12.3 k cycles per tile) against ~640 KB of L2 -> SM traffic per
 // tile (W is re-streamed for every tile); DESIGN.md 4.7 has the numbers.  d = 256 only (one MMA spans the row).
-#include <cuda.h>
-
 #include <mutex>
 #include <set>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "topk_select.cuh"
 
 namespace maxk {
@@ -76,66 +75,6 @@ struct LtShared {
     static constexpr int total = tmem_ptr + 16;
 };
 
-// ---- PTX wrappers -----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait (about 4 s): a protocol error must end as a trap the host sees, not as a hung GPU.
-template <bool RELAXED = false>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    const long long t0 = clock64();
-    while (true) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        if constexpr (RELAXED) __nanosleep(64);  // a waiter whose latency does not matter leaves the issue slots
-        if (clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol error ends as a trap, not as a hung GPU
-            printf("linear_topk: barrier at %u (parity %u) never completed, block %d thread %d\n", bar, parity,
-                   (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(LT_IDESC), "r"(accumulate)
-        : "memory");
-}
 // shared-memory matrix descriptor, K-major, rows of LT_BK fp32 = one swizzle span (cute/arch/mma_sm100_desc.hpp:
 // SmemDescriptor): start address >> 4 at [0,14), leading byte offset (unused with a swizzle) = 1 at [16,30), stride
 // byte offset = eight rows (1024 B or 512 B) >> 4 at [32,46), version 1 at [46,48), layout type at [61,64):
@@ -145,29 +84,6 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr)
     constexpr uint32_t hi = (LT_BK == 32 ? (2u << 29) : (4u << 29)) | (1u << 14) | (uint32_t)(8 * LT_BK * 4 / 16);
     return ((uint64_t)hi << 32) | (1u << 16) | ((addr >> 4) & 0x3fffu);
 }
-__device__ __forceinline__ void named_bar_sync(int id, int threads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-// 32 consecutive TMEM columns of this thread's lane -> registers
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
-{
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // if (!(x < t)) { value -> [w], column byte -> [wi], advance both }   (w, wi: 32-bit shared-memory addresses)
 __device__ __forceinline__ void stage2_if_nlt(unsigned &w, unsigned &wi, float x, float t, unsigned col)
 {
@@ -183,12 +99,6 @@ __device__ __forceinline__ void stage2_if_nlt(unsigned &w, unsigned &wi, float x
         : "memory");
 }
 
-// x - hi, where hi = x with the 13 low mantissa bits cleared (exact in fp32); 0 for infinities (inf - inf is NaN)
-__device__ __forceinline__ float lt_lo_part(float v, float hi)
-{
-    return fabsf(v) == __uint_as_float(0x7f800000u) ? 0.f : v - hi;
-}
-
 // ---- W -> (TF32 part, remainder), rows [0, 256) and [256, 512) of the workspace ------------------------------------
 __global__ void lt_split_weight_kernel(const float *__restrict__ w, int64_t count, float *__restrict__ ws)
 {
@@ -197,7 +107,7 @@ __global__ void lt_split_weight_kernel(const float *__restrict__ w, int64_t coun
     const float v = w[i];
     const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     ws[i] = hi;
-    ws[count + i] = lt_lo_part(v, hi);
+    ws[count + i] = tf32_lo_part(v, hi);
 }
 
 // ---- the fused kernel ----------------------------------------------------------------------------------------------
@@ -298,9 +208,9 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
                     for (int kk = 0; kk < LT_BK / 8; ++kk) {  // 8 tf32 = 32 bytes per K step: + 2 in 16-byte units
                         const uint64_t adv = (uint64_t)(2 * kk);
-                        tc_mma_tf32(tmem_d, a_hi + adv, b_lo + adv, (kc | kk) != 0 ? 1u : 0u);
-                        tc_mma_tf32(tmem_d, a_lo + adv, b_hi + adv, 1u);
-                        tc_mma_tf32(tmem_d, a_hi + adv, b_hi + adv, 1u);
+                        tc_mma_tf32(tmem_d, a_hi + adv, b_lo + adv, LT_IDESC, (kc | kk) != 0 ? 1u : 0u);
+                        tc_mma_tf32(tmem_d, a_lo + adv, b_hi + adv, LT_IDESC, 1u);
+                        tc_mma_tf32(tmem_d, a_hi + adv, b_hi + adv, LT_IDESC, 1u);
                     }
                     tc_commit(bar_empty(s));  // the ring slot is free once these MMAs have read it
                     if (kc == num_kc - 1) tc_commit(bar_tfull(b));
@@ -329,10 +239,10 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
                     h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
                     h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                    l.x = lt_lo_part(v.x, h.x);
-                    l.y = lt_lo_part(v.y, h.y);
-                    l.z = lt_lo_part(v.z, h.z);
-                    l.w = lt_lo_part(v.w, h.w);
+                    l.x = tf32_lo_part(v.x, h.x);
+                    l.y = tf32_lo_part(v.y, h.y);
+                    l.z = tf32_lo_part(v.z, h.z);
+                    l.w = tf32_lo_part(v.w, h.w);
                     a_hi[i] = h;
                     a_lo[i] = l;
                 }
@@ -369,6 +279,42 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             float x[LT_HALF];
             mbar_wait(bar_tfull(b), ((uint32_t)it >> 1) & 1u);
             tc_fence_after();
+            if (out_idx == nullptr) {
+                // ---- the Linear alone (uniform): 16 columns at a time through shared memory, so that a store
+                // instruction writes eight full 64-byte row segments instead of 32 half sectors 1 KB apart
+                float *stg = reinterpret_cast<float *>(lt_smem + LtShared::rowbuf + q * LtShared::quarter_bytes) +
+                             half * (32 * 20);  // 32 rows x 16 values, row stride 20 words: conflict-free STS.128
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * LT_D + half * LT_HALF);
+                const int64_t row0 = tile * LT_TILE_M + 32 * q;
+#pragma unroll 1
+                for (int c = 0; c < LT_HALF / 16; ++c) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)(16 * c), v);
+                    tmem_ld_wait();
+                    if (c == LT_HALF / 16 - 1) {
+                        tc_fence_before();
+                        mbar_arrive(bar_tempty(b));
+                    }
+                    float4 *w4 = reinterpret_cast<float4 *>(stg + lane * 20);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(sb + 16 * c + i);
+                        w4[i >> 2] = make_float4(v[i] + bv.x, v[i + 1] + bv.y, v[i + 2] + bv.z, v[i + 3] + bv.w);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const int rr = i4 * 8 + (lane >> 2);
+                        const float4 val = *reinterpret_cast<const float4 *>(stg + rr * 20 + (lane & 3) * 4);
+                        if (row0 + rr < n)
+                            st_stream_f4(reinterpret_cast<float4 *>(linear_out + (row0 + rr) * LT_D + half * LT_HALF +
+                                                                    16 * c + (lane & 3) * 4),
+                                         val);
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
             {
                 const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b * LT_D + half * LT_HALF);
 #pragma unroll
@@ -390,7 +336,6 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
                 for (int i = 0; i < LT_HALF; i += 4) o[i >> 2] = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
             }
-            if (out_idx == nullptr) continue;  // uniform: the Linear alone
 
             // ---- bracket: the row's minimum and maximum (this half, then the partner's through shared memory)
             float fl = x[0], fh = x[0];
@@ -541,47 +486,6 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
 }
 
-// ---- host side ----------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (fn != nullptr) return fn;
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-        return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-    return fn;
-}
-
-// fp32 matrix [rows, cols] row-major, box [box_rows x 32 columns], 128-byte swizzle, out-of-range -> zeros
-static int make_map_f32(CUtensorMap *map, const float *base, int64_t rows, int cols, int box_rows, const char *what)
-{
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (fn == nullptr) {
-        set_error("maxk_linear_topk_cbsr: cuTensorMapEncodeTiled is not available from this driver");
-        return MAXK_ERR_CUDA;
-    }
-    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)LT_BK, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, LT_BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("maxk_linear_topk_cbsr: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
-        return MAXK_ERR_CUDA;
-    }
-    return MAXK_OK;
-}
-
 }  // namespace maxk
 
 using namespace maxk;
@@ -619,8 +523,8 @@ extern "C" int maxk_linear_topk_cbsr(const float *x, int64_t n, int32_t in_dim, 
     MAXK_LAUNCH_CHECK("lt_split_weight_kernel");
 
     CUtensorMap map_x, map_w;
-    if (int rc = make_map_f32(&map_x, x, n, in_dim, LT_TILE_M, "x")) return rc;
-    if (int rc = make_map_f32(&map_w, ws, 2 * (int64_t)d, in_dim, LT_D, "weight")) return rc;
+    if (int rc = make_map_f32(&map_x, x, n, in_dim, LT_TILE_M, LT_BK, "x")) return rc;
+    if (int rc = make_map_f32(&map_w, ws, 2 * (int64_t)d, in_dim, LT_D, LT_BK, "weight")) return rc;
 
     static std::mutex mu;
     static std::set<int> opted;
@@ -643,4 +547,11 @@ extern "C" int maxk_linear_topk_cbsr(const float *x, int64_t n, int32_t in_dim, 
                                                                          sp_index, linear_out, vec_out);
     MAXK_LAUNCH_CHECK("linear_topk_kernel");
     return MAXK_OK;
+}
+
+extern "C" int maxk_linear_f32(const float *x, int64_t n, int32_t in_dim, const float *weight, const float *bias,
+                               int32_t d, float *out, void *workspace, void *stream)
+{
+    MAXK_REQUIRE(out != nullptr || n == 0, "maxk_linear_f32: out is NULL");
+    return maxk_linear_topk_cbsr(x, n, in_dim, weight, bias, d, 1, nullptr, nullptr, out, workspace, stream);
 }

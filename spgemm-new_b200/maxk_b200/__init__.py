@@ -6,9 +6,10 @@ include/maxk_b200.h.  Importing this package does not load the CUDA library; the
 first operator call does, and fails loudly if it is missing.
 """
 from . import _cabi, ops  # noqa: F401
-from .autograd import CBSRAddScaled, CBSRAggregate, CBSRLinear, LinearTopKCBSR, MaxK, SpGEMMFunction, TopKCBSR, worklist_for  # noqa: F401
+from .autograd import (CBSRAddScaled, CBSRAggregate, CBSRLinear, LinearTopKCBSR, MaxK, SpGEMMFunction,  # noqa: F401
+                       TensorCoreLinear, TopKCBSR, worklist_for)
 
 from .host import HostAggregator, ShardHostAggregator  # noqa: F401,E402
 
-__all__ = ["ops", "MaxK", "SpGEMMFunction", "CBSRAggregate", "CBSRLinear", "CBSRAddScaled", "LinearTopKCBSR", "TopKCBSR", "worklist_for",
+__all__ = ["ops", "MaxK", "SpGEMMFunction", "CBSRAggregate", "CBSRLinear", "CBSRAddScaled", "LinearTopKCBSR", "TensorCoreLinear", "TopKCBSR", "worklist_for",
            "HostAggregator", "ShardHostAggregator"]

@@ -122,6 +122,87 @@ def linear_topk_fused_enabled() -> bool:
     return os.environ.get("MAXK_LINEAR_TOPK_FUSED", "1").strip() != "0"
 
 
+def tc_linear_enabled() -> bool:
+    """Whether the 256-wide dense Linears next to the path run on the own tensor-core kernels (csrc/linear_topk.cu
+    without the selection, csrc/linear_wgrad.cu: split-TF32 products at fp32 accuracy) instead of the library's fp32
+    SGEMM.  MAXK_TC_LINEAR=0 restores torch.nn.functional.linear everywhere."""
+    import os
+    return os.environ.get("MAXK_TC_LINEAR", "1").strip() != "0"
+
+
+def weight_grad(grad_out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """grad_out^T @ x, the weight gradient of a Linear: the tcgen05 kernel where its shapes fit, else the library."""
+    if tc_linear_enabled() and ops.linear_wgrad_supported(grad_out, x):
+        return ops.linear_wgrad(grad_out, x)
+    return grad_out.t() @ x
+
+
+class TensorCoreLinear(Function):
+    """y = x @ weight^T + bias for a 256-wide Linear (fc_neigh of SAGE, utils/models.py:238-244) with all three
+    products on the tensor cores at fp32 accuracy: forward and dX through csrc/linear_topk.cu (the GEMM without the
+    selection), dW through csrc/linear_wgrad.cu."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        y = ops.linear_f32(x, weight.detach(), None if bias is None else bias.detach())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        d_x = d_w = d_b = None
+        if ctx.needs_input_grad[0]:
+            wt = weight.detach().t().contiguous()        # dX = g @ W = g @ (W^T)^T: "weight" [in, 256]
+            d_x = ops.linear_f32(g, wt) if ops.linear_topk_supported(g, wt) else g @ weight
+        if ctx.needs_input_grad[1]:
+            d_w = weight_grad(g, x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            d_b = g.sum(0)
+        return d_x, d_w, d_b
+
+
+def linear(lin: torch.nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """`lin(x)` through TensorCoreLinear where the shapes allow (output width 256), else torch's own."""
+    if tc_linear_enabled() and ops.linear_topk_supported(x, lin.weight):
+        return TensorCoreLinear.apply(x, lin.weight, lin.bias)
+    return lin(x)
+
+
+class LayerNormFn(Function):
+    """nn.LayerNorm(d, elementwise_affine) forward / backward on csrc/layernorm.cu (one read and one write of the
+    activation each way; the library's kernels take 4.1 + 9.6 ms per layer on the products shape)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = x.contiguous()
+        y, mean, rstd = ops.layernorm_forward(x, None if gamma is None else gamma.detach(),
+                                              None if beta is None else beta.detach(), eps)
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        ctx.has_beta = beta is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        affine = (gamma is not None and ctx.needs_input_grad[1]) or (ctx.has_beta and ctx.needs_input_grad[2])
+        dx, dgamma, dbeta = ops.layernorm_backward(g, x, mean, rstd, None if gamma is None else gamma.detach(), affine)
+        return (dx, dgamma if gamma is not None else None, dbeta if ctx.has_beta else None, None)
+
+
+def layer_norm(norm, x: torch.Tensor) -> torch.Tensor:
+    """`norm(x)` for an nn.LayerNorm over the last dimension through LayerNormFn where the shapes allow (fp32, CUDA,
+    width <= 256); anything else (nn.Identity, other widths) is called as it is.  MAXK_LAYERNORM=0 disables."""
+    import os
+    if (isinstance(norm, torch.nn.LayerNorm) and len(norm.normalized_shape) == 1 and ops.layernorm_supported(x)
+            and norm.normalized_shape[0] == x.shape[1] and os.environ.get("MAXK_LAYERNORM", "1").strip() != "0"):
+        return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
+    return norm(x)
+
+
 class CBSRLinear(Function):
     """y = scatter(sp_data, sp_index) @ weight^T + bias computed from the CBSR pair (N*k*C multiply-adds, no
     dense [N, D] twin in the forward or in the gradient of the values).  Same result as
@@ -144,7 +225,7 @@ class CBSRLinear(Function):
         d_sp = ops.cbsr_sampled_dot(g, m, sp_index) if ctx.needs_input_grad[0] else None
         d_w = None
         if ctx.needs_input_grad[2]:
-            d_w = g.t() @ ops.cbsr_scatter(sp_data, sp_index, m.shape[0])   # [C, D]
+            d_w = weight_grad(g, ops.cbsr_scatter(sp_data, sp_index, m.shape[0]))   # [C, D]
         d_b = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[3] else None
         return d_sp, None, d_w, d_b
 
@@ -206,7 +287,7 @@ class LinearTopKCBSR(Function):
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dense = ops.cbsr_scatter(g_data, sp_index, weight.shape[0])
             if ctx.needs_input_grad[1]:
-                d_w = dense.t() @ x
+                d_w = weight_grad(dense, x)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 d_b = dense.sum(0)
         return d_x, d_w, d_b, None

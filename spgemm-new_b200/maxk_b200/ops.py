@@ -122,15 +122,100 @@ def linear_topk_cbsr(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch
             sp_index = torch.empty((n, k), dtype=torch.uint8, device=x.device)
         if want_linear:
             lin = torch.empty((n, d), dtype=torch.float32, device=x.device)
-        key = (x.device.index, d, in_dim, torch.cuda.current_stream(x.device).cuda_stream)
-        ws = _LT_WORKSPACE.get(key)
-        if ws is None:   # one workspace per (device, shape, stream): the split weight is rewritten by every call
-            ws = torch.empty(int(lib.maxk_linear_topk_workspace_bytes(d, in_dim)), dtype=torch.uint8, device=x.device)
-            _LT_WORKSPACE[key] = ws
+        ws = _lt_workspace(lib, x, d, in_dim)
         _cabi.check(lib.maxk_linear_topk_cbsr(x.data_ptr(), n, in_dim, weight.data_ptr(), _ptr(bias), d, k,
                                               _ptr(sp_data), _ptr(sp_index), _ptr(lin), ws.data_ptr(), _stream(x)))
     out = tuple(t for t in (sp_data, sp_index, lin) if t is not None)
     return out if len(out) > 1 else out[0]
+
+
+def _lt_workspace(lib, x, d, in_dim):
+    key = (x.device.index, d, in_dim, torch.cuda.current_stream(x.device).cuda_stream)
+    ws = _LT_WORKSPACE.get(key)
+    if ws is None:   # one workspace per (device, shape, stream): the split weight is rewritten by every call
+        ws = torch.empty(int(lib.maxk_linear_topk_workspace_bytes(d, in_dim)), dtype=torch.uint8, device=x.device)
+        _LT_WORKSPACE[key] = ws
+    return ws
+
+
+def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x @ weight^T + bias on the tensor cores at fp32 accuracy (split TF32 products; csrc/linear_topk.cu without the
+    selection).  weight [256, in]."""
+    lib = _cabi.load()
+    _req(linear_topk_supported(x, weight), "linear_f32: fp32 CUDA tensors, x [N, in], weight [256, in], in % 4 == 0")
+    x, weight = x.contiguous(), weight.contiguous()
+    n, in_dim = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((n, FULL_DIM), dtype=torch.float32, device=x.device)
+        if bias is not None:
+            bias = bias.contiguous()
+        _cabi.check(lib.maxk_linear_f32(x.data_ptr(), n, in_dim, weight.data_ptr(), _ptr(bias), FULL_DIM,
+                                        out.data_ptr(), _lt_workspace(lib, x, FULL_DIM, in_dim).data_ptr(), _stream(x)))
+    return out
+
+
+def linear_wgrad_supported(grad_out: torch.Tensor, x: torch.Tensor) -> bool:
+    return (grad_out.is_cuda and grad_out.dtype == torch.float32 and x.dtype == torch.float32 and grad_out.dim() == 2
+            and x.dim() == 2 and grad_out.shape[1] == FULL_DIM and x.shape[0] == grad_out.shape[0]
+            and 4 <= x.shape[1] <= FULL_DIM and x.shape[1] % 4 == 0)
+
+
+def linear_wgrad(grad_out: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+                 accumulate: bool = False) -> torch.Tensor:
+    """grad_out^T @ x -> [256, in]: the weight gradient of a Linear, reduction over the rows on the tensor cores
+    (csrc/linear_wgrad.cu)."""
+    lib = _cabi.load()
+    _req(linear_wgrad_supported(grad_out, x), "linear_wgrad: fp32 CUDA tensors, grad_out [N, 256], x [N, in <= 256], in % 4 == 0")
+    grad_out, x = grad_out.contiguous(), x.contiguous()
+    n, in_dim = x.shape
+    with torch.cuda.device(x.device):
+        if out is None:
+            _req(not accumulate, "accumulate=True needs an `out` tensor")
+            out = torch.empty((FULL_DIM, in_dim), dtype=torch.float32, device=x.device)
+        _cuda(out, "out", torch.float32)
+        _req(tuple(out.shape) == (FULL_DIM, in_dim), "out must be [256, in]")
+        _cabi.check(lib.maxk_linear_wgrad(grad_out.data_ptr(), x.data_ptr(), n, FULL_DIM, in_dim, out.data_ptr(),
+                                          1 if accumulate else 0, _stream(x)))
+    return out
+
+
+def layernorm_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and 4 <= x.shape[1] <= FULL_DIM and x.shape[1] % 4 == 0
+
+
+def layernorm_forward(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float = 1e-5):
+    """-> (y, mean, rstd): nn.LayerNorm over the last dimension of x [N, d <= 256] (csrc/layernorm.cu)."""
+    lib = _cabi.load()
+    _req(layernorm_supported(x), "layernorm_forward: fp32 CUDA tensor [N, d], d a multiple of 4 in [4, 256]")
+    x = x.contiguous()
+    n, d = x.shape
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        mean = torch.empty(n, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+        gamma = None if gamma is None else gamma.contiguous()
+        beta = None if beta is None else beta.contiguous()
+        _cabi.check(lib.maxk_layernorm_forward(x.data_ptr(), n, d, _ptr(gamma), _ptr(beta), float(eps), y.data_ptr(),
+                                               mean.data_ptr(), rstd.data_ptr(), _stream(x)))
+    return y, mean, rstd
+
+
+def layernorm_backward(g: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
+                       gamma: Optional[torch.Tensor], want_affine_grads: bool = True):
+    """-> (dx, dgamma, dbeta) of layernorm_forward."""
+    lib = _cabi.load()
+    g, x = g.contiguous(), x.contiguous()
+    n, d = x.shape
+    with torch.cuda.device(x.device):
+        dx = torch.empty_like(x)
+        dgamma = dbeta = None
+        if want_affine_grads:
+            dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
+            dbeta = torch.empty(d, dtype=torch.float32, device=x.device)
+        gamma = None if gamma is None else gamma.contiguous()
+        _cabi.check(lib.maxk_layernorm_backward(g.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                _ptr(gamma), n, d, dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), _stream(x)))
+    return dx, dgamma, dbeta
 
 
 def topk_cbsr_u8(x: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:

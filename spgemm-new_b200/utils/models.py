@@ -22,7 +22,7 @@ import torch.nn.init as init
 from torch.nn import Linear
 
 from maxk_b200.autograd import (CBSRAddScaled, CBSRLinear, LinearTopKCBSR, MaxK, SpGEMMFunction, TopKCBSR,  # noqa: F401  (re-exported like the reference)
-                                cbsr_native_enabled)
+                                cbsr_native_enabled, layer_norm as _layer_norm, linear as _linear)
 from maxk_b200 import ops
 from torch.autograd import Function
 
@@ -106,8 +106,8 @@ class SAGE(_Base):
         for i in range(self.num_layers):
             if self.fork_variant:   # models.py:230-253: sum aggregation, self branch on raw x, dropout after
                 sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, 0.0, False)
-                x = self.fc_self_layers[i](x) + self.fc_neigh_layers[i](
-                    g.aggregate(sp_data, sp_index, "sum", self.hid))
+                x = _linear(self.fc_self_layers[i], x) + _linear(self.fc_neigh_layers[i],
+                                                                 g.aggregate(sp_data, sp_index, "sum", self.hid))
                 x = F.dropout(x, self.p, self.training)
             else:                   # SAGEConv("mean", feat_drop): dropout(maxk(x)) feeds both branches
                 if i == 0 and first is not None:
@@ -118,9 +118,9 @@ class SAGE(_Base):
                 if self.nonlinear == "maxk" and cbsr_native_enabled(self.maxk):   # fc_self on the CBSR operand
                     own = CBSRLinear.apply(sp_data, sp_index, fc_self.weight, fc_self.bias)
                 else:
-                    own = fc_self(_Scatter.apply(sp_data, sp_index, self.hid))
-                x = own + self.fc_neigh_layers[i](g.aggregate(sp_data, sp_index, "mean", self.hid))
-            x = self.normlayers[i](x)
+                    own = _linear(fc_self, _Scatter.apply(sp_data, sp_index, self.hid))
+                x = own + _linear(self.fc_neigh_layers[i], g.aggregate(sp_data, sp_index, "mean", self.hid))
+            x = _layer_norm(self.normlayers[i], x)
         return self.lin_out(x)
 
 
@@ -137,11 +137,11 @@ class GCN(_Base):
         self.conv_bias = nn.ParameterList([nn.Parameter(torch.zeros(hid_size)) for _ in range(num_hid_layers)])
 
     def forward(self, g, x):
-        x = self.lin_in(x).relu()
+        x = _linear(self.lin_in, x).relu()
         for i in range(self.num_layers):
             sp_data, sp_index = _linear_sparsify(self.linlayers[i], x, self.maxk, self.nonlinear, self.p, self.training)
             x = g.aggregate(sp_data, sp_index, "gcn", self.hid) + self.conv_bias[i]
-            x = self.normlayers[i](x)
+            x = _layer_norm(self.normlayers[i], x)
         return self.lin_out(x)
 
 
@@ -158,7 +158,7 @@ class GIN(_Base):
         self.eps = nn.ParameterList([nn.Parameter(torch.zeros(1)) for _ in range(num_hid_layers)])
 
     def forward(self, g, x):
-        x = self.lin_in(x).relu()
+        x = _linear(self.lin_in, x).relu()
         for i in range(self.num_layers):
             sp_data, sp_index = _linear_sparsify(self.linlayers[i], x, self.maxk, self.nonlinear, self.p, self.training)
             if self.nonlinear == "maxk" and cbsr_native_enabled(self.maxk):   # self term added in place, no dense twin
@@ -166,5 +166,5 @@ class GIN(_Base):
             else:
                 h = _Scatter.apply(sp_data, sp_index, self.hid)
                 x = (1.0 + self.eps[i]) * h + g.aggregate(sp_data, sp_index, "sum", self.hid)
-            x = self.normlayers[i](x)
+            x = _layer_norm(self.normlayers[i], x)
         return self.lin_out(x)

@@ -237,6 +237,7 @@ inline float __int_as_float(int v) { return ::simt::from_bits<float>((uint32_t)v
 inline unsigned __float_as_uint(float v) { return (unsigned)::simt::to_bits(v); }
 inline int __float_as_int(float v) { return (int)(uint32_t)::simt::to_bits(v); }
 inline float __frcp_rn(float v) { return 1.0f / v; }
+inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
 inline float __fdividef(float a, float b) { return a / b; }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline size_t __cvta_generic_to_shared(const void *p) { return ::simt::smem_token(p); }

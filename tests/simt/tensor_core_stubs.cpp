@@ -20,3 +20,16 @@ extern "C" MAXK_API int maxk_linear_topk_cbsr(const float *, int64_t, int32_t, c
     maxk::set_error("maxk_linear_topk_cbsr: tensor-core kernel, not available under the SIMT interpreter");
     return MAXK_ERR_UNSUPPORTED;
 }
+
+extern "C" MAXK_API int maxk_linear_f32(const float *, int64_t, int32_t, const float *, const float *, int32_t, float *,
+                                        void *, void *)
+{
+    maxk::set_error("maxk_linear_f32: tensor-core kernel, not available under the SIMT interpreter");
+    return MAXK_ERR_UNSUPPORTED;
+}
+
+extern "C" MAXK_API int maxk_linear_wgrad(const float *, const float *, int64_t, int32_t, int32_t, float *, int32_t, void *)
+{
+    maxk::set_error("maxk_linear_wgrad: tensor-core kernel, not available under the SIMT interpreter");
+    return MAXK_ERR_UNSUPPORTED;
+}

@@ -182,7 +182,7 @@ def translate(text):
 
 # tcgen05 / TMA tensor maps / TMEM have no stand-in here: these files run on a B200 only (their C entry points are
 # stubbed by tensor_core_stubs.cpp so that the library still exports the whole header)
-TENSOR_CORE_ONLY = {"linear_topk.cu"}
+TENSOR_CORE_ONLY = {"linear_topk.cu", "linear_wgrad.cu", "tc_common.cuh"}
 
 
 def translate_tree(src_dir, dst_dir):

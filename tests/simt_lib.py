@@ -380,3 +380,40 @@ def sspmm_backward_planned(w4, idx, val, dy, sp_addr, n_cbsr=None, accumulate=Fa
              lambda p: (p["warp4"], i64(w4.shape[0] // 4), p["idx"], p["val"], p["dy"], p["sp_addr"], i32(k),
                         i32(d), p["dxc"], i64(n_cbsr), i32(1 if accumulate else 0), None))
     return r["dxc"]
+
+
+def layernorm_forward(x, gamma=None, beta=None, eps=1e-5):
+    L = load()
+    x = np.ascontiguousarray(x, np.float32)
+    n, d = x.shape
+    ins = {"x": Guarded(x, name="x")}
+    if gamma is not None:
+        ins["gamma"] = Guarded(np.asarray(gamma, np.float32), name="gamma")
+    if beta is not None:
+        ins["beta"] = Guarded(np.asarray(beta, np.float32), name="beta")
+    r = _run(L.maxk_layernorm_forward, ins,
+             {"y": Guarded(shape=(n, d), dtype=np.float32, name="y"),
+              "mean": Guarded(shape=(n,), dtype=np.float32, name="mean", align=4),
+              "rstd": Guarded(shape=(n,), dtype=np.float32, name="rstd", align=4)},
+             lambda p: (p["x"], i64(n), i32(d), p.get("gamma"), p.get("beta"), ctypes.c_float(eps), p["y"], p["mean"],
+                        p["rstd"], None))
+    return r["y"], r["mean"], r["rstd"]
+
+
+def layernorm_backward(g, x, mean, rstd, gamma=None, want_affine=True):
+    L = load()
+    x = np.ascontiguousarray(x, np.float32)
+    n, d = x.shape
+    ins = {"g": Guarded(np.asarray(g, np.float32), name="g"), "x": Guarded(x, name="x"),
+           "mean": Guarded(np.asarray(mean, np.float32), name="mean", align=4),
+           "rstd": Guarded(np.asarray(rstd, np.float32), name="rstd", align=4)}
+    if gamma is not None:
+        ins["gamma"] = Guarded(np.asarray(gamma, np.float32), name="gamma")
+    outs = {"dx": Guarded(shape=(n, d), dtype=np.float32, name="dx")}
+    if want_affine:
+        outs["dgamma"] = Guarded(shape=(d,), dtype=np.float32, name="dgamma", align=4)
+        outs["dbeta"] = Guarded(shape=(d,), dtype=np.float32, name="dbeta", align=4)
+    r = _run(L.maxk_layernorm_backward, ins, outs,
+             lambda p: (p["g"], p["x"], p["mean"], p["rstd"], p.get("gamma"), i64(n), i32(d), p["dx"], p.get("dgamma"),
+                        p.get("dbeta"), None))
+    return r["dx"], r.get("dgamma"), r.get("dbeta")

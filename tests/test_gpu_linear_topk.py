@@ -117,3 +117,43 @@ def test_autograd_node_uses_the_fused_forward(ops):
     assert torch.allclose(x.grad, dense @ lin.weight.detach(), rtol=1e-4, atol=1e-4)
     assert torch.allclose(lin.bias.grad, dense.sum(0), rtol=1e-5, atol=1e-5)
     assert torch.allclose(lin.weight.grad, dense.t() @ x.detach(), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,in_dim", [(1, 256), (130, 64), (1000, 100), (40001, 256), (300000, 256), (5000, 36)])
+def test_linear_alone_and_weight_gradient(ops, n, in_dim):
+    """maxk_linear_f32 (coalesced dense epilogue) and maxk_linear_wgrad against fp64 products of the same operands."""
+    g = torch.Generator("cuda").manual_seed(7 * n + in_dim)
+    x = torch.randn(n, in_dim, device="cuda", generator=g)
+    w = torch.randn(256, in_dim, device="cuda", generator=g) / in_dim ** 0.5
+    b = torch.randn(256, device="cuda", generator=g)
+    y = ops.linear_f32(x, w, b)
+    want = x.double() @ w.double().t() + b.double()
+    scale = x.double().abs() @ w.double().abs().t() + 1.0
+    assert ((y.double() - want).abs() / scale).max().item() < 4e-6
+    gy = torch.randn(n, 256, device="cuda", generator=g)
+    dw = ops.linear_wgrad(gy, x)
+    want = gy.double().t() @ x.double()
+    scale = gy.double().abs().t() @ x.double().abs() + 1.0
+    err = ((dw.double() - want).abs() / scale).max().item()
+    ref = (((gy.t() @ x).double() - want).abs() / scale).max().item()
+    assert err < 4e-6, (n, in_dim, err, ref)
+    acc = dw.clone()
+    ops.linear_wgrad(gy, x, out=acc, accumulate=True)                      # += semantics
+    assert ((acc.double() - 2 * dw.double()).abs() / scale).max().item() < 1e-6   # the CTAs' partials add in any order
+
+
+def test_tensor_core_linear_autograd(ops):
+    from maxk_b200.autograd import TensorCoreLinear
+    g = torch.Generator("cuda").manual_seed(11)
+    x = torch.randn(3000, 256, device="cuda", generator=g, requires_grad=True)
+    lin = torch.nn.Linear(256, 256).cuda()
+    gy = torch.randn(3000, 256, device="cuda", generator=g)
+    y = TensorCoreLinear.apply(x, lin.weight, lin.bias)
+    y.backward(gy)
+    got = (y.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    x.grad = None
+    lin.zero_grad()
+    y2 = lin(x)
+    y2.backward(gy)
+    for a, b_, tol in zip(got, (y2.detach(), x.grad, lin.weight.grad, lin.bias.grad), (1e-4, 1e-4, 2e-3, 1e-3)):
+        assert torch.allclose(a, b_, rtol=1e-4, atol=tol), float((a - b_).abs().max())

@@ -555,3 +555,28 @@ def test_simt_library_is_not_the_product():
     src = open(_cabi.__file__).read()
     assert "simt" not in src.lower()
     assert os.path.basename(_cabi.LIB_PATH) == "libmaxk_b200.so"
+
+
+# ------------------------------------------------------------------------------ LayerNorm of the layers
+@pytest.mark.parametrize("d", [256, 128, 64, 36, 4])
+def test_simt_layernorm_forward_backward(d):
+    rng = np.random.default_rng(900 + d)
+    for n in (1, 7, 8, 9, 300, 2500):        # 2500 rows: the persistent grid wraps around
+        x = (rng.standard_normal((n, d)) * 3 + 1.5).astype(np.float32)
+        gamma = rng.standard_normal(d).astype(np.float32)
+        beta = rng.standard_normal(d).astype(np.float32)
+        for ga, be in ((gamma, beta), (None, None)):
+            y, mean, rstd = S.layernorm_forward(x, ga, be)
+            wy, wm, wr = O.layernorm(x, ga, be)
+            np.testing.assert_allclose(y, wy, rtol=2e-5, atol=2e-5)
+            np.testing.assert_allclose(mean, wm, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(rstd, wr, rtol=1e-5, atol=1e-6)
+            g = rng.standard_normal((n, d)).astype(np.float32)
+            dx, dga, dbe = S.layernorm_backward(g, x, mean, rstd, ga)
+            wdx, wdg, wdb = O.layernorm_grad(g, x, ga)
+            np.testing.assert_allclose(dx, wdx, rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(dga, wdg, rtol=1e-4, atol=1e-4 * max(1, n ** 0.5))
+            np.testing.assert_allclose(dbe, wdb, rtol=1e-4, atol=1e-4 * max(1, n ** 0.5))
+            (dx2, none_g, none_b) = S.layernorm_backward(g, x, mean, rstd, ga, want_affine=False)
+            np.testing.assert_array_equal(dx2, dx)
+            assert none_g is None and none_b is None
