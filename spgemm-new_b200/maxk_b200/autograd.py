@@ -279,13 +279,22 @@ class LinearTopKCBSR(Function):
         x, weight, sp_index = ctx.saved_tensors
         g_data = g_data.contiguous()
         d_x = d_w = d_b = None
+        dense = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dense = ops.cbsr_scatter(g_data, sp_index, weight.shape[0])
         if ctx.needs_input_grad[0]:
-            if weight.shape[1] % 4 == 0:
+            wt = weight.detach().t().contiguous()                      # dX = scatter(g) @ W = scatter(g) @ (W^T)^T
+            if tc_linear_enabled() and g_data.is_cuda and tuple(weight.shape) == (ops.FULL_DIM, ops.FULL_DIM):
+                # a 256 x 256 layer: with the tensor-core GEMM at 1.6 ms the dense product beats the k-sparse one
+                # (cbsr_matmul: 3.8 ms at k = 32 on the products shape); the scattered twin exists for dW anyway
+                if dense is None:
+                    dense = ops.cbsr_scatter(g_data, sp_index, weight.shape[0])
+                d_x = ops.linear_f32(dense, wt)
+            elif weight.shape[1] % 4 == 0:
                 d_x = ops.cbsr_matmul(g_data, sp_index, weight.detach().contiguous())   # rows of W picked by sel
             else:
                 d_x = ops.cbsr_scatter(g_data, sp_index, weight.shape[0]) @ weight
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dense = ops.cbsr_scatter(g_data, sp_index, weight.shape[0])
+        if dense is not None:
             if ctx.needs_input_grad[1]:
                 d_w = weight_grad(dense, x)
             if ctx.has_bias and ctx.needs_input_grad[2]:
