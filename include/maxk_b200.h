@@ -179,12 +179,12 @@ MAXK_API int maxk_linear_topk_cbsr(const float *x, int64_t n, int32_t in_dim, co
 /* The dense Linear next to the path on the same tensor-core machinery (fp32 accuracy from split TF32 products;
  * replaces the library SGEMMs torch.nn.Linear runs in fp32 for utils/models.py:151-392 -- the forward and the two
  * backward products of a 256-wide layer):
- *   maxk_linear_f32:   out[n, d] = x[n, in_dim] @ weight[d, in_dim]^T + bias      (d = 256; also dX = dY @ W with
- *                      weight := W^T when in_dim of the layer is 256)
+ *   maxk_linear_f32:   out[n, d] = x[n, in_dim] @ weight[d, in_dim]^T + bias + residual[n, d]   (d = 256; bias and
+ *                      residual may be NULL, residual may be `out`; also dX = dY @ W with weight := W^T)
  *   maxk_linear_wgrad: dw[d, in_dim] (+)= grad_out[n, d]^T @ x[n, in_dim]         (d = 256, in_dim <= 256)
  * All pointers 16-byte aligned, in_dim a multiple of 4; workspace as for maxk_linear_topk_cbsr. */
 MAXK_API int maxk_linear_f32(const float *x, int64_t n, int32_t in_dim, const float *weight, const float *bias,
-                             int32_t d, float *out, void *workspace, void *stream);
+                             const float *residual, int32_t d, float *out, void *workspace, void *stream);
 MAXK_API int maxk_linear_wgrad(const float *grad_out, const float *x, int64_t n, int32_t d, int32_t in_dim, float *dw,
                                int32_t accumulate, void *stream);
 
@@ -198,6 +198,17 @@ MAXK_API int maxk_layernorm_forward(const float *x, int64_t n, int32_t d, const 
 MAXK_API int maxk_layernorm_backward(const float *grad_out, const float *x, const float *mean, const float *rstd,
                                      const float *gamma, int64_t n, int32_t d, float *dx, float *dgamma, float *dbeta,
                                      void *stream);
+
+/* LayerNorm + TopK in one pass (SAGE: the LayerNorm that closes layer i feeds only the MaxK that opens layer i + 1,
+ * utils/models.py:252 / 230): (sp_data, sp_index) = TopK_k(LayerNorm(x)); the normalised activation is written only
+ * if y_out is given.  Backward: the k-sparse gradient of the kept values goes straight into the LayerNorm backward
+ * (maxk_layernorm_backward_cbsr: grad_data [n, k] at the columns sp_index) -- no scattered dense twin. */
+MAXK_API int maxk_layernorm_topk_cbsr(const float *x, int64_t n, int32_t d, const float *gamma, const float *beta,
+                                      float eps, int32_t k, float *sp_data, uint8_t *sp_index, float *mean,
+                                      float *rstd, float *y_out, void *stream);
+MAXK_API int maxk_layernorm_backward_cbsr(const float *grad_data, const uint8_t *sp_index, int32_t k, const float *x,
+                                          const float *mean, const float *rstd, const float *gamma, int64_t n,
+                                          int32_t d, float *dx, float *dgamma, float *dbeta, void *stream);
 
 /* ---- the dense layer next to the aggregation on the CBSR operand itself,
  * without the dense [n, d] twin (measured on the products shape, k = 32: 3.8 vs 6.3 ms for fc_self,

@@ -114,7 +114,8 @@ __global__ void lt_split_weight_kernel(const float *__restrict__ w, int64_t coun
 __global__ void __launch_bounds__(LT_THREADS, 1)
 linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                    const float *__restrict__ bias, int64_t n, int in_dim, int k, float *__restrict__ out_val,
-                   unsigned char *__restrict__ out_idx, float *__restrict__ linear_out, int vec_out)
+                   unsigned char *__restrict__ out_idx, float *__restrict__ linear_out, int vec_out,
+                   const float *residual)
 {
     extern __shared__ unsigned char lt_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -305,11 +306,18 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
                     for (int i4 = 0; i4 < 4; ++i4) {
                         const int rr = i4 * 8 + (lane >> 2);
-                        const float4 val = *reinterpret_cast<const float4 *>(stg + rr * 20 + (lane & 3) * 4);
-                        if (row0 + rr < n)
-                            st_stream_f4(reinterpret_cast<float4 *>(linear_out + (row0 + rr) * LT_D + half * LT_HALF +
-                                                                    16 * c + (lane & 3) * 4),
-                                         val);
+                        float4 val = *reinterpret_cast<const float4 *>(stg + rr * 20 + (lane & 3) * 4);
+                        if (row0 + rr < n) {
+                            const int64_t o = (row0 + rr) * LT_D + half * LT_HALF + 16 * c + (lane & 3) * 4;
+                            if (residual != nullptr) {  // out = x W^T + b + residual (may be `out` itself)
+                                const float4 rv = *reinterpret_cast<const float4 *>(residual + o);
+                                val.x += rv.x;
+                                val.y += rv.y;
+                                val.z += rv.z;
+                                val.w += rv.w;
+                            }
+                            st_stream_f4(reinterpret_cast<float4 *>(linear_out + o), val);
+                        }
                     }
                     __syncwarp();
                 }
@@ -496,25 +504,25 @@ extern "C" int64_t maxk_linear_topk_workspace_bytes(int32_t d, int32_t in_dim)
     return (int64_t)2 * d * in_dim * (int64_t)sizeof(float);
 }
 
-extern "C" int maxk_linear_topk_cbsr(const float *x, int64_t n, int32_t in_dim, const float *weight, const float *bias,
-                                     int32_t d, int32_t k, float *sp_data, uint8_t *sp_index, float *linear_out,
-                                     void *workspace, void *stream)
+static int linear_topk_launch(const float *x, int64_t n, int32_t in_dim, const float *weight, const float *bias,
+                              int32_t d, int32_t k, float *sp_data, uint8_t *sp_index, float *linear_out,
+                              const float *residual, void *workspace, void *stream)
 {
-    MAXK_REQUIRE(n >= 0, "maxk_linear_topk_cbsr: negative n");
-    MAXK_REQUIRE(d == LT_D, "maxk_linear_topk_cbsr: output width d=%d must be 256 (one MMA spans the row)", d);
-    MAXK_REQUIRE(in_dim >= 4 && in_dim % 4 == 0, "maxk_linear_topk_cbsr: in_dim=%d must be a positive multiple of 4",
+    MAXK_REQUIRE(n >= 0, "maxk_linear_topk_cbsr / maxk_linear_f32: negative n");
+    MAXK_REQUIRE(d == LT_D, "maxk_linear_topk_cbsr / maxk_linear_f32: output width d=%d must be 256 (one MMA spans the row)", d);
+    MAXK_REQUIRE(in_dim >= 4 && in_dim % 4 == 0, "maxk_linear_topk_cbsr / maxk_linear_f32: in_dim=%d must be a positive multiple of 4",
                  in_dim);
-    MAXK_REQUIRE(k >= 1 && k <= d, "maxk_linear_topk_cbsr: Invalid k value (k=%d, d=%d)", k, d);
+    MAXK_REQUIRE(k >= 1 && k <= d, "maxk_linear_topk_cbsr / maxk_linear_f32: Invalid k value (k=%d, d=%d)", k, d);
     if (n == 0) return MAXK_OK;
     MAXK_REQUIRE((sp_data == nullptr) == (sp_index == nullptr),
-                 "maxk_linear_topk_cbsr: sp_data and sp_index must both be given or both NULL");
-    MAXK_REQUIRE(sp_index != nullptr || linear_out != nullptr, "maxk_linear_topk_cbsr: no output");
+                 "maxk_linear_topk_cbsr / maxk_linear_f32: sp_data and sp_index must both be given or both NULL");
+    MAXK_REQUIRE(sp_index != nullptr || linear_out != nullptr, "maxk_linear_topk_cbsr / maxk_linear_f32: no output");
     MAXK_REQUIRE(x != nullptr && weight != nullptr && workspace != nullptr,
-                 "maxk_linear_topk_cbsr: x, weight and workspace must not be NULL");
+                 "maxk_linear_topk_cbsr / maxk_linear_f32: x, weight and workspace must not be NULL");
     MAXK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(linear_out) & 15) == 0,
-                 "maxk_linear_topk_cbsr: x, workspace and linear_out must be 16-byte aligned");
-    MAXK_REQUIRE(n < (int64_t)1 << 31, "maxk_linear_topk_cbsr: n too large for one tensor map");
+                 "maxk_linear_topk_cbsr / maxk_linear_f32: x, workspace and linear_out must be 16-byte aligned");
+    MAXK_REQUIRE(n < (int64_t)1 << 31, "maxk_linear_topk_cbsr / maxk_linear_f32: n too large for one tensor map");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     float *ws = static_cast<float *>(workspace);
@@ -544,14 +552,22 @@ extern "C" int maxk_linear_topk_cbsr(const float *x, int64_t n, int32_t in_dim, 
     const int vec_out = (k % 4 == 0) && (reinterpret_cast<uintptr_t>(sp_data) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(sp_index) & 15) == 0;
     linear_topk_kernel<<<grid, LT_THREADS, LtShared::total + 1024, st>>>(map_x, map_w, bias, n, in_dim, k, sp_data,
-                                                                         sp_index, linear_out, vec_out);
+                                                                         sp_index, linear_out, vec_out, residual);
     MAXK_LAUNCH_CHECK("linear_topk_kernel");
     return MAXK_OK;
 }
 
+extern "C" int maxk_linear_topk_cbsr(const float *x, int64_t n, int32_t in_dim, const float *weight, const float *bias,
+                                     int32_t d, int32_t k, float *sp_data, uint8_t *sp_index, float *linear_out,
+                                     void *workspace, void *stream)
+{
+    return linear_topk_launch(x, n, in_dim, weight, bias, d, k, sp_data, sp_index, linear_out, nullptr, workspace, stream);
+}
+
 extern "C" int maxk_linear_f32(const float *x, int64_t n, int32_t in_dim, const float *weight, const float *bias,
-                               int32_t d, float *out, void *workspace, void *stream)
+                               const float *residual, int32_t d, float *out, void *workspace, void *stream)
 {
     MAXK_REQUIRE(out != nullptr || n == 0, "maxk_linear_f32: out is NULL");
-    return maxk_linear_topk_cbsr(x, n, in_dim, weight, bias, d, 1, nullptr, nullptr, out, workspace, stream);
+    MAXK_REQUIRE((reinterpret_cast<uintptr_t>(residual) & 15) == 0, "maxk_linear_f32: residual must be 16-byte aligned");
+    return linear_topk_launch(x, n, in_dim, weight, bias, d, 1, nullptr, nullptr, out, residual, workspace, stream);
 }

@@ -178,6 +178,64 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k,
 }
 
 
+// ---- LayerNorm + TopK: the normalisation that closes layer i and the selection that opens layer i + 1 -----------
+// (SAGE: `h = self.norm(h)` then `MaxK(h)` of the next layer, utils/models.py:252 / 230; the normalised activation
+// feeds nothing else, so it need not reach HBM.)  One warp per row: mean / variance / affine in registers exactly as
+// layernorm.cu does, then the row goes into the search above; mean and rstd are kept for the backward
+// (layernorm.cu: layernorm_bwd_cbsr_kernel takes the k-sparse gradient as it comes back from the aggregation).
+__global__ void __launch_bounds__(TOPK_WPB * 32)
+layernorm_topk_kernel(const float *__restrict__ x_, int64_t n, int d, const float *__restrict__ gamma,
+                      const float *__restrict__ beta, float eps, int k, float *__restrict__ out_val,
+                      unsigned char *__restrict__ out_idx, float *__restrict__ mean_out, float *__restrict__ rstd_out,
+                      float *__restrict__ y_out)
+{
+    __shared__ unsigned s_stage[TOPK_WPB][2 * MAXK_MAX_DIM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * TOPK_WPB + warp;
+    if (row >= n) return;  // warp-uniform; no CTA barrier below
+    const int c0 = 4 * lane, c1 = 128 + 4 * lane;
+    const bool ok0 = c0 < d, ok1 = c1 < d;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(1.f, 1.f, 1.f, 1.f);
+    const float *xr = x_ + row * d;
+    const float4 a = ok0 ? ld_stream_f4(reinterpret_cast<const float4 *>(xr + c0)) : zero;
+    const float4 b = ok1 ? ld_stream_f4(reinterpret_cast<const float4 *>(xr + c1)) : zero;
+    const float4 ga = ok0 ? (gamma ? __ldg(reinterpret_cast<const float4 *>(gamma + c0)) : one) : zero;
+    const float4 gb = ok1 ? (gamma ? __ldg(reinterpret_cast<const float4 *>(gamma + c1)) : one) : zero;
+    const float4 ba = ok0 && beta ? __ldg(reinterpret_cast<const float4 *>(beta + c0)) : zero;
+    const float4 bb = ok1 && beta ? __ldg(reinterpret_cast<const float4 *>(beta + c1)) : zero;
+    const float inv_d = 1.f / (float)d;
+    float sum = (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_d;
+    float4 da = make_float4(a.x - mean, a.y - mean, a.z - mean, a.w - mean);
+    float4 db = make_float4(b.x - mean, b.y - mean, b.z - mean, b.w - mean);
+    if (!ok0) da = zero;
+    if (!ok1) db = zero;
+    float sq = (da.x * da.x + da.y * da.y) + (da.z * da.z + da.w * da.w) + (db.x * db.x + db.y * db.y) +
+               (db.z * db.z + db.w * db.w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_d + eps);
+    if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+    const float ninf = __uint_as_float(0xff800000u);
+    float4 ya = make_float4(ninf, ninf, ninf, ninf), yb = ya;  // columns >= d never qualify
+    if (ok0)
+        ya = make_float4(fmaf(da.x * rstd, ga.x, ba.x), fmaf(da.y * rstd, ga.y, ba.y), fmaf(da.z * rstd, ga.z, ba.z),
+                         fmaf(da.w * rstd, ga.w, ba.w));
+    if (ok1)
+        yb = make_float4(fmaf(db.x * rstd, gb.x, bb.x), fmaf(db.y * rstd, gb.y, bb.y), fmaf(db.z * rstd, gb.z, bb.z),
+                         fmaf(db.w * rstd, gb.w, bb.w));
+    if (y_out != nullptr) {
+        if (ok0) st_stream_f4(reinterpret_cast<float4 *>(y_out + row * d + c0), ya);
+        if (ok1) st_stream_f4(reinterpret_cast<float4 *>(y_out + row * d + c1), yb);
+    }
+    topk_row_f32<false>(ya, yb, ok0, ok1, c0, c1, lane, row, d, k, s_stage[warp], out_val, out_idx, nullptr);
+}
+
 // ---- fp32 rows, several rows per warp (round 2, second form) -------------------------------------
 // The one-row-per-warp kernel above is issue-bound (ncu: ~365 warp instructions per row, issue slots 80 %
 // busy, DRAM 27 %) and most of what it issues is warp-UNIFORM: the bracket update, the reductions over 32
@@ -559,5 +617,27 @@ extern "C" int maxk_topk_cbsr_u8(const uint8_t *x, int64_t n, int32_t d, int32_t
     topk_cbsr_u8_kernel<<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         x, n, d, k, value, index);
     MAXK_LAUNCH_CHECK("topk_cbsr_u8_kernel");
+    return MAXK_OK;
+}
+
+extern "C" int maxk_layernorm_topk_cbsr(const float *x, int64_t n, int32_t d, const float *gamma, const float *beta,
+                                        float eps, int32_t k, float *sp_data, uint8_t *sp_index, float *mean,
+                                        float *rstd, float *y_out, void *stream)
+{
+    MAXK_REQUIRE(n >= 0, "maxk_layernorm_topk_cbsr: negative n");
+    MAXK_REQUIRE(d > 0 && d <= MAXK_MAX_DIM && d % 4 == 0,
+                 "maxk_layernorm_topk_cbsr: d=%d must be a multiple of 4 in [4,256]", d);
+    MAXK_REQUIRE(k >= 1 && k <= d, "maxk_layernorm_topk_cbsr: Invalid k value (k=%d, d=%d)", k, d);
+    if (n == 0) return MAXK_OK;
+    MAXK_REQUIRE(x != nullptr && sp_data != nullptr && sp_index != nullptr && mean != nullptr && rstd != nullptr,
+                 "maxk_layernorm_topk_cbsr: NULL pointer");
+    MAXK_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y_out) |
+                   reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+                 "maxk_layernorm_topk_cbsr: x, y_out, gamma and beta must be 16-byte aligned");
+    const int64_t grid = ceil_div<int64_t>(n, TOPK_WPB);
+    MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_layernorm_topk_cbsr: n too large");
+    layernorm_topk_kernel<<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, n, d, gamma, beta, eps, k, sp_data, sp_index, mean, rstd, y_out);
+    MAXK_LAUNCH_CHECK("layernorm_topk_kernel");
     return MAXK_OK;
 }

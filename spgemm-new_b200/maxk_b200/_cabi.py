@@ -32,10 +32,12 @@ PROTOTYPES = {
     "maxk_set_topk_group": (ctypes.c_int, [ctypes.c_int]),
     "maxk_linear_topk_workspace_bytes": (_i64, [_i32, _i32]),
     "maxk_linear_topk_cbsr": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "maxk_linear_f32": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "maxk_linear_f32": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "maxk_linear_wgrad": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp]),
     "maxk_layernorm_forward": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp]),
     "maxk_layernorm_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "maxk_layernorm_topk_cbsr": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, ctypes.c_float, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "maxk_layernorm_backward_cbsr": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "maxk_worklist_workspace_bytes": (_i64, [_i64]),
     "maxk_worklist_count": (ctypes.c_int, [_vp, _i64, _i32, _vp, ctypes.POINTER(_i64), _vp]),
     "maxk_worklist_fill": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp]),

@@ -13,6 +13,7 @@ Same signatures and return shapes.  Differences, all deliberate:
 from __future__ import annotations
 
 from collections import OrderedDict
+from typing import Optional
 
 import torch
 from torch.autograd import Function
@@ -143,11 +144,13 @@ class TensorCoreLinear(Function):
     selection), dW through csrc/linear_wgrad.cu."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, residual=None):
         x = x.contiguous()
-        y = ops.linear_f32(x, weight.detach(), None if bias is None else bias.detach())
+        y = ops.linear_f32(x, weight.detach(), None if bias is None else bias.detach(),
+                           None if residual is None else residual.detach())   # + residual in the GEMM's epilogue
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.has_residual = residual is not None
         return y
 
     @staticmethod
@@ -162,14 +165,15 @@ class TensorCoreLinear(Function):
             d_w = weight_grad(g, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             d_b = g.sum(0)
-        return d_x, d_w, d_b
+        return d_x, d_w, d_b, (g if ctx.has_residual and ctx.needs_input_grad[3] else None)
 
 
-def linear(lin: torch.nn.Linear, x: torch.Tensor) -> torch.Tensor:
-    """`lin(x)` through TensorCoreLinear where the shapes allow (output width 256), else torch's own."""
+def linear(lin: torch.nn.Linear, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`lin(x)` (+ residual) through TensorCoreLinear where the shapes allow (output width 256), else torch's own."""
     if tc_linear_enabled() and ops.linear_topk_supported(x, lin.weight):
-        return TensorCoreLinear.apply(x, lin.weight, lin.bias)
-    return lin(x)
+        return TensorCoreLinear.apply(x, lin.weight, lin.bias, residual)
+    y = lin(x)
+    return y if residual is None else residual + y
 
 
 class LayerNormFn(Function):
@@ -191,6 +195,37 @@ class LayerNormFn(Function):
         affine = (gamma is not None and ctx.needs_input_grad[1]) or (ctx.has_beta and ctx.needs_input_grad[2])
         dx, dgamma, dbeta = ops.layernorm_backward(g, x, mean, rstd, None if gamma is None else gamma.detach(), affine)
         return (dx, dgamma if gamma is not None else None, dbeta if ctx.has_beta else None, None)
+
+
+class LayerNormTopKCBSR(Function):
+    """(sp_data, sp_index) = TopK_k(LayerNorm(x)): the LayerNorm that closes a SAGE layer together with the MaxK that
+    opens the next one (utils/models.py:252 / 230).  The normalised activation is never written; the backward takes
+    the k-sparse gradient of the kept values as it comes from the aggregation (csrc/layernorm.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, k):
+        x = x.contiguous()
+        sp_data, sp_index, mean, rstd = ops.layernorm_topk_cbsr(x, None if gamma is None else gamma.detach(),
+                                                                None if beta is None else beta.detach(), eps, k)
+        ctx.save_for_backward(x, mean, rstd, gamma, sp_index)
+        ctx.has_beta = beta is not None
+        ctx.mark_non_differentiable(sp_index)
+        return sp_data, sp_index
+
+    @staticmethod
+    def backward(ctx, g_data, _g_index):
+        x, mean, rstd, gamma, sp_index = ctx.saved_tensors
+        affine = (gamma is not None and ctx.needs_input_grad[1]) or (ctx.has_beta and ctx.needs_input_grad[2])
+        dx, dgamma, dbeta = ops.layernorm_backward_cbsr(g_data, sp_index, x, mean, rstd,
+                                                        None if gamma is None else gamma.detach(), affine)
+        return dx, (dgamma if gamma is not None else None), (dbeta if ctx.has_beta else None), None, None
+
+
+def layer_norm_topk_supported(norm, x: torch.Tensor) -> bool:
+    import os
+    return (isinstance(norm, torch.nn.LayerNorm) and len(norm.normalized_shape) == 1 and ops.layernorm_supported(x)
+            and norm.normalized_shape[0] == x.shape[1] and os.environ.get("MAXK_LAYERNORM", "1").strip() != "0"
+            and os.environ.get("MAXK_LAYERNORM_TOPK", "1").strip() != "0")
 
 
 def layer_norm(norm, x: torch.Tensor) -> torch.Tensor:

@@ -138,9 +138,10 @@ def _lt_workspace(lib, x, d, in_dim):
     return ws
 
 
-def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x @ weight^T + bias on the tensor cores at fp32 accuracy (split TF32 products; csrc/linear_topk.cu without the
-    selection).  weight [256, in]."""
+def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+               residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x @ weight^T + bias (+ residual [N, 256], added in the GEMM's epilogue) on the tensor cores at fp32 accuracy
+    (split TF32 products; csrc/linear_topk.cu without the selection).  weight [256, in]."""
     lib = _cabi.load()
     _req(linear_topk_supported(x, weight), "linear_f32: fp32 CUDA tensors, x [N, in], weight [256, in], in % 4 == 0")
     x, weight = x.contiguous(), weight.contiguous()
@@ -149,7 +150,11 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
         out = torch.empty((n, FULL_DIM), dtype=torch.float32, device=x.device)
         if bias is not None:
             bias = bias.contiguous()
-        _cabi.check(lib.maxk_linear_f32(x.data_ptr(), n, in_dim, weight.data_ptr(), _ptr(bias), FULL_DIM,
+        if residual is not None:
+            _cuda(residual, "residual", torch.float32)
+            _req(tuple(residual.shape) == (n, FULL_DIM), "residual must be [N, 256]")
+            residual = residual.contiguous()
+        _cabi.check(lib.maxk_linear_f32(x.data_ptr(), n, in_dim, weight.data_ptr(), _ptr(bias), _ptr(residual), FULL_DIM,
                                         out.data_ptr(), _lt_workspace(lib, x, FULL_DIM, in_dim).data_ptr(), _stream(x)))
     return out
 
@@ -215,6 +220,48 @@ def layernorm_backward(g: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rst
         gamma = None if gamma is None else gamma.contiguous()
         _cabi.check(lib.maxk_layernorm_backward(g.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                                 _ptr(gamma), n, d, dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), _stream(x)))
+    return dx, dgamma, dbeta
+
+
+def layernorm_topk_cbsr(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float, k: int,
+                        want_dense: bool = False):
+    """-> (sp_data, sp_index, mean, rstd[, y]) = TopK_k(LayerNorm(x)) in one pass (csrc/topk_cbsr.cu)."""
+    lib = _cabi.load()
+    _req(layernorm_supported(x), "layernorm_topk_cbsr: fp32 CUDA tensor [N, d], d a multiple of 4 in [4, 256]")
+    x = x.contiguous()
+    n, d = x.shape
+    _req(0 < k <= d, "Invalid k value")
+    with torch.cuda.device(x.device):
+        sp_data = torch.empty((n, k), dtype=torch.float32, device=x.device)
+        sp_index = torch.empty((n, k), dtype=torch.uint8, device=x.device)
+        mean = torch.empty(n, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x) if want_dense else None
+        gamma = None if gamma is None else gamma.contiguous()
+        beta = None if beta is None else beta.contiguous()
+        _cabi.check(lib.maxk_layernorm_topk_cbsr(x.data_ptr(), n, d, _ptr(gamma), _ptr(beta), float(eps), k,
+                                                 sp_data.data_ptr(), sp_index.data_ptr(), mean.data_ptr(),
+                                                 rstd.data_ptr(), _ptr(y), _stream(x)))
+    return (sp_data, sp_index, mean, rstd, y) if want_dense else (sp_data, sp_index, mean, rstd)
+
+
+def layernorm_backward_cbsr(g_data: torch.Tensor, sp_index: torch.Tensor, x: torch.Tensor, mean: torch.Tensor,
+                            rstd: torch.Tensor, gamma: Optional[torch.Tensor], want_affine_grads: bool = True):
+    """-> (dx, dgamma, dbeta): LayerNorm backward for an upstream gradient that is k-sparse per row (CBSR layout)."""
+    lib = _cabi.load()
+    g_data, x = g_data.contiguous(), x.contiguous()
+    n, d = x.shape
+    k = sp_index.shape[1]
+    with torch.cuda.device(x.device):
+        dx = torch.empty_like(x)
+        dgamma = dbeta = None
+        if want_affine_grads:
+            dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
+            dbeta = torch.empty(d, dtype=torch.float32, device=x.device)
+        gamma = None if gamma is None else gamma.contiguous()
+        _cabi.check(lib.maxk_layernorm_backward_cbsr(g_data.data_ptr(), sp_index.data_ptr(), k, x.data_ptr(),
+                                                     mean.data_ptr(), rstd.data_ptr(), _ptr(gamma), n, d, dx.data_ptr(),
+                                                     _ptr(dgamma), _ptr(dbeta), _stream(x)))
     return dx, dgamma, dbeta
 
 

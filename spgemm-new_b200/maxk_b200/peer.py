@@ -26,6 +26,7 @@ One process per GPU, all GPUs of one NVLink domain (<= 16 ranks).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional
 
 import torch
@@ -171,6 +172,11 @@ class PeerAggregator:
             raise ValueError("row block starts must satisfy start * k % 16 == 0: use "
                              "partition_rows_by_nnz(indptr, world, align=16)")
         self.copy_ctas = int(copy_ctas)
+        # measurement knob: copy CTAs of the fused forward's push (one SM's TMA unit moves ~15 GB/s over NVLink,
+        # so a large block wants more of them than the default)
+        env = os.environ.get("MAXK_PEER_COPY_CTAS", "").strip()
+        if env:
+            self.copy_ctas = int(env)
         self.halo_threshold = float(halo_threshold)
         self.n_local = bounds[rank + 1] - bounds[rank]
         self.n_total = int(bounds[-1])

@@ -22,7 +22,8 @@ import torch.nn.init as init
 from torch.nn import Linear
 
 from maxk_b200.autograd import (CBSRAddScaled, CBSRLinear, LinearTopKCBSR, MaxK, SpGEMMFunction, TopKCBSR,  # noqa: F401  (re-exported like the reference)
-                                cbsr_native_enabled, layer_norm as _layer_norm, linear as _linear)
+                                LayerNormTopKCBSR, cbsr_native_enabled, layer_norm as _layer_norm,
+                                layer_norm_topk_supported as _ln_topk_ok, linear as _linear)
 from maxk_b200 import ops
 from torch.autograd import Function
 
@@ -105,7 +106,7 @@ class SAGE(_Base):
     def forward(self, g, x):
         # upstream variant: layer 0 only ever sees MaxK(lin_in(x)) -- the input Linear and the first selection are one
         # node (the fused tcgen05 kernel at width 256: the dense [N, hidden] activation of lin_in never exists)
-        first = None
+        first = pending = None
         if not self.fork_variant and self.num_layers > 0 and self.nonlinear == "maxk":
             first = _linear_sparsify(self.lin_in, x, self.maxk, self.nonlinear, self.p, self.training)
         else:
@@ -119,6 +120,11 @@ class SAGE(_Base):
             else:                   # SAGEConv("mean", feat_drop): dropout(maxk(x)) feeds both branches
                 if i == 0 and first is not None:
                     sp_data, sp_index = first
+                elif pending is not None:   # LayerNorm of layer i - 1 and this layer's MaxK in one pass
+                    sp_data, sp_index = LayerNormTopKCBSR.apply(x, pending.weight, pending.bias, pending.eps, self.maxk)
+                    if self.p > 0 and self.training:
+                        sp_data = F.dropout(sp_data, self.p, True)
+                    pending = None
                 else:
                     sp_data, sp_index = _sparsify(x, self.maxk, self.nonlinear, self.p, self.training)
                 fc_self = self.fc_self_layers[i]
@@ -130,8 +136,12 @@ class SAGE(_Base):
                     own = CBSRLinear.apply(sp_data, sp_index, fc_self.weight, fc_self.bias)
                 else:
                     own = _linear(fc_self, _Scatter.apply(sp_data, sp_index, self.hid))
-                x = own + _linear(self.fc_neigh_layers[i], g.aggregate(sp_data, sp_index, "mean", self.hid))
-            x = _layer_norm(self.normlayers[i], x)
+                x = _linear(self.fc_neigh_layers[i], g.aggregate(sp_data, sp_index, "mean", self.hid), residual=own)
+            if (not self.fork_variant and self.nonlinear == "maxk" and i + 1 < self.num_layers
+                    and _ln_topk_ok(self.normlayers[i], x)):
+                pending = self.normlayers[i]   # its output feeds only the next layer's MaxK: fused there
+            else:
+                x = _layer_norm(self.normlayers[i], x)
         return self.lin_out(x)
 
 

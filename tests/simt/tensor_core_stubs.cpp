@@ -21,8 +21,8 @@ extern "C" MAXK_API int maxk_linear_topk_cbsr(const float *, int64_t, int32_t, c
     return MAXK_ERR_UNSUPPORTED;
 }
 
-extern "C" MAXK_API int maxk_linear_f32(const float *, int64_t, int32_t, const float *, const float *, int32_t, float *,
-                                        void *, void *)
+extern "C" MAXK_API int maxk_linear_f32(const float *, int64_t, int32_t, const float *, const float *, const float *,
+                                        int32_t, float *, void *, void *)
 {
     maxk::set_error("maxk_linear_f32: tensor-core kernel, not available under the SIMT interpreter");
     return MAXK_ERR_UNSUPPORTED;

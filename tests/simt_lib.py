@@ -417,3 +417,44 @@ def layernorm_backward(g, x, mean, rstd, gamma=None, want_affine=True):
              lambda p: (p["g"], p["x"], p["mean"], p["rstd"], p.get("gamma"), i64(n), i32(d), p["dx"], p.get("dgamma"),
                         p.get("dbeta"), None))
     return r["dx"], r.get("dgamma"), r.get("dbeta")
+
+
+def layernorm_topk(x, gamma, beta, k, eps=1e-5, want_dense=False):
+    L = load()
+    x = np.ascontiguousarray(x, np.float32)
+    n, d = x.shape
+    ins = {"x": Guarded(x, name="x")}
+    if gamma is not None:
+        ins["gamma"] = Guarded(np.asarray(gamma, np.float32), name="gamma")
+    if beta is not None:
+        ins["beta"] = Guarded(np.asarray(beta, np.float32), name="beta")
+    outs = {"sp_data": Guarded(shape=(n, k), dtype=np.float32, name="sp_data", align=4),
+            "sp_index": Guarded(shape=(n, k), dtype=np.uint8, name="sp_index", align=1),
+            "mean": Guarded(shape=(n,), dtype=np.float32, name="mean", align=4),
+            "rstd": Guarded(shape=(n,), dtype=np.float32, name="rstd", align=4)}
+    if want_dense:
+        outs["y"] = Guarded(shape=(n, d), dtype=np.float32, name="y")
+    r = _run(L.maxk_layernorm_topk_cbsr, ins, outs,
+             lambda p: (p["x"], i64(n), i32(d), p.get("gamma"), p.get("beta"), ctypes.c_float(eps), i32(k), p["sp_data"],
+                        p["sp_index"], p["mean"], p["rstd"], p.get("y"), None))
+    return r
+
+
+def layernorm_backward_cbsr(g_data, sp_index, x, mean, rstd, gamma=None):
+    L = load()
+    x = np.ascontiguousarray(x, np.float32)
+    n, d = x.shape
+    k = sp_index.shape[1]
+    ins = {"g": Guarded(np.asarray(g_data, np.float32), name="g_data", align=4),
+           "si": Guarded(np.asarray(sp_index, np.uint8), name="sp_index", align=1), "x": Guarded(x, name="x"),
+           "mean": Guarded(np.asarray(mean, np.float32), name="mean", align=4),
+           "rstd": Guarded(np.asarray(rstd, np.float32), name="rstd", align=4)}
+    if gamma is not None:
+        ins["gamma"] = Guarded(np.asarray(gamma, np.float32), name="gamma")
+    outs = {"dx": Guarded(shape=(n, d), dtype=np.float32, name="dx"),
+            "dgamma": Guarded(shape=(d,), dtype=np.float32, name="dgamma", align=4),
+            "dbeta": Guarded(shape=(d,), dtype=np.float32, name="dbeta", align=4)}
+    r = _run(L.maxk_layernorm_backward_cbsr, ins, outs,
+             lambda p: (p["g"], p["si"], i32(k), p["x"], p["mean"], p["rstd"], p.get("gamma"), i64(n), i32(d), p["dx"],
+                        p["dgamma"], p["dbeta"], None))
+    return r["dx"], r["dgamma"], r["dbeta"]

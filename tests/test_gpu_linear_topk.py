@@ -130,6 +130,10 @@ def test_linear_alone_and_weight_gradient(ops, n, in_dim):
     want = x.double() @ w.double().t() + b.double()
     scale = x.double().abs() @ w.double().abs().t() + 1.0
     assert ((y.double() - want).abs() / scale).max().item() < 4e-6
+    res = torch.randn(n, 256, device="cuda", generator=g)
+    y2 = ops.linear_f32(x, w, None, residual=res)                          # + residual in the epilogue
+    want2 = x.double() @ w.double().t() + res.double()
+    assert ((y2.double() - want2).abs() / scale).max().item() < 4e-6
     gy = torch.randn(n, 256, device="cuda", generator=g)
     dw = ops.linear_wgrad(gy, x)
     want = gy.double().t() @ x.double()

@@ -580,3 +580,31 @@ def test_simt_layernorm_forward_backward(d):
             (dx2, none_g, none_b) = S.layernorm_backward(g, x, mean, rstd, ga, want_affine=False)
             np.testing.assert_array_equal(dx2, dx)
             assert none_g is None and none_b is None
+
+
+@pytest.mark.parametrize("d", [256, 128, 36])
+def test_simt_layernorm_topk_and_its_sparse_backward(d):
+    """LayerNorm + TopK in one pass: the selection is the oracle's TopK of the kernel's OWN normalised row (bit-exact),
+    the normalised row is the LayerNorm oracle's; the backward on the k-sparse gradient equals the dense LayerNorm
+    backward on its scattered twin."""
+    rng = np.random.default_rng(40 + d)
+    for n in (1, 9, 70):
+        x = (rng.standard_normal((n, d)) * 2 - 0.5).astype(np.float32)
+        gamma = rng.standard_normal(d).astype(np.float32)
+        beta = rng.standard_normal(d).astype(np.float32)
+        for k in sorted({1, 8, 32, d // 2, d} & set(range(1, d + 1))):
+            r = S.layernorm_topk(x, gamma, beta, k, want_dense=True)
+            wy, wm, wr = O.layernorm(x, gamma, beta)
+            np.testing.assert_allclose(r["y"], wy, rtol=2e-5, atol=2e-5)
+            want_v, want_i = O.topk_cbsr(r["y"], k)
+            np.testing.assert_array_equal(r["sp_index"], want_i, err_msg=f"n={n} d={d} k={k}")
+            np.testing.assert_array_equal(r["sp_data"].view(np.uint32), want_v.view(np.uint32))
+            r2 = S.layernorm_topk(x, gamma, beta, k)          # without the dense output
+            np.testing.assert_array_equal(r2["sp_index"], want_i)
+            g_data = rng.standard_normal((n, k)).astype(np.float32)
+            dx, dga, dbe = S.layernorm_backward_cbsr(g_data, r["sp_index"], x, r["mean"], r["rstd"], gamma)
+            dense_g = O.cbsr_scatter(g_data, r["sp_index"], d)
+            wdx, wdg, wdb = O.layernorm_grad(dense_g, x, gamma)
+            np.testing.assert_allclose(dx, wdx, rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(dga, wdg, rtol=1e-4, atol=1e-4 * max(1, n ** 0.5))
+            np.testing.assert_allclose(dbe, wdb, rtol=1e-4, atol=1e-4 * max(1, n ** 0.5))
