@@ -6,9 +6,9 @@
 // MaxK.apply) without the dense [n, 256] activation ever reaching HBM: the reference writes it (4nD bytes) and its
 // TopK reads it back (4nD bytes).  One persistent warp-specialised kernel per SM:
 //
-//   warp 0      TMA producer: per 128-row tile and 32-column K chunk one X box [128 x 32] and two W boxes
-//               [256 x 32] (high and low parts of W, split once per call by a prep kernel) into a two-stage
-//               shared-memory ring (128-byte swizzle), completion on an mbarrier;
+//   warp 0      TMA producer: per 128-row tile and 16-column K chunk one X box [128 x 16] and two W boxes
+//               [256 x 16] (high and low parts of W, split once per call by a prep kernel) into a four-stage
+//               shared-memory ring (64-byte swizzle, 48 KB per stage), completion on an mbarrier;
 //   warps 2-3   split the X box in place into its TF32 part and the remainder  x = hi + lo  (fp32 accuracy
 //               from TF32 tensor-core products: hi*hi + hi*lo + lo*hi, the dropped lo*lo term is < 2^-21
 //               relative), generic-proxy writes fenced for the tensor core;
@@ -20,13 +20,17 @@
 //               one tcgen05.ld pass (TMEM reads are 64 B / clock / SM: the search must not re-read it), the
 //               accumulator is released at once; bias added; then the same value-space regula falsi as
 //               topk_cbsr.cu with the two halves of a row exchanging their counts through shared memory
-//               (named barrier per row quarter), emission by predicated stores straight to sp_data /
-//               sp_index (a thread's columns are contiguous: the lower half starts at 0, the upper half at the
-//               lower half's count -- no scan); rows the fast path cannot finish (ties at the k-th value) are
-//               passed through shared memory to the robust key-space search of topk_select.cuh.
+//               (named barrier per row quarter), emission by predicated stores into a shared-memory staging area
+//               that has the layout of sp_data / sp_index (a thread's columns are contiguous: the lower half
+//               starts at 0, the upper half at the lower half's count -- no scan), 128-bit copy-out; rows the fast
+//               path cannot finish (ties at the k-th value) are passed through shared memory to the robust
+//               key-space search of topk_select.cuh.
 //
-// Bound: tensor pipe (3 x 8 K steps x 128 cycles = 12.3 k cycles per tile) against ~640 KB of L2 -> SM traffic per
-// tile (W is re-streamed for every tile); DESIGN.md 4.7 has the numbers.  d = 256 only (one MMA spans the row).
+// Bound: tensor pipe (3 products x 32 K steps x 128 cycles = 12.3 k cycles per tile) against ~640 KB of L2 -> SM
+// traffic per tile (W is re-streamed for every tile); measured 1.83 ms on 2 449 029 x 256 (tensor pipe 44 % busy, the
+// epilogue's instruction issue is the limit: DESIGN.md 4.7).  d = 256 only (one MMA spans the row).
+// The same kernel without the selection (sp_index == NULL) is the dense Linear of DESIGN.md 4.8: its epilogue drains
+// the accumulator 16 columns at a time through shared memory into full 64-byte row segments (+ optional residual).
 #include <mutex>
 #include <set>
 
