@@ -168,6 +168,46 @@ class TensorCoreLinear(Function):
         return d_x, d_w, d_b, (g if ctx.has_residual and ctx.needs_input_grad[3] else None)
 
 
+class NarrowOutputLinear(Function):
+    """y = x @ weight^T + bias for the classifier at the end of the models (`lin_out`: 256 -> classes, utils/models.py:
+    216-218), whose BACKWARD runs on the tensor-core kernels with the roles of the operands exchanged: with the
+    gradient padded to a multiple of 4 columns, dX = g_pad @ W_pad is `linear_f32` with in_dim = classes, and
+    dW^T = x^T @ g_pad is `linear_wgrad` with x as the 256-wide operand (both far from the MMA floor: the narrow
+    dimension is the MMA's N / K, so they run at the speed of reading x).  The forward stays the library's (its
+    output is not 256 wide)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        c = weight.shape[0]
+        cp = (c + 3) // 4 * 4
+        g_pad = torch.nn.functional.pad(g, (0, cp - c)) if cp != c else g.contiguous()
+        d_x = d_w = d_b = None
+        if ctx.needs_input_grad[0]:
+            w_pad = torch.nn.functional.pad(weight.detach(), (0, 0, 0, cp - c)) if cp != c else weight.detach()
+            d_x = ops.linear_f32(g_pad, w_pad.t().contiguous())          # "weight" [256, cp]: out = g_pad @ W_pad
+        if ctx.needs_input_grad[1]:
+            d_w = ops.linear_wgrad(x, g_pad).t()[:c].contiguous()         # [256, cp]^T -> [c, 256]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            d_b = g.sum(0)
+        return d_x, d_w, d_b
+
+
+def output_linear(lin: torch.nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """`lin(x)` for a 256 -> classes layer with its backward on the tensor-core kernels (NarrowOutputLinear)."""
+    if (tc_linear_enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+            and x.shape[1] == ops.FULL_DIM and lin.weight.shape[1] == ops.FULL_DIM and 4 <= lin.weight.shape[0] < ops.FULL_DIM):
+        return NarrowOutputLinear.apply(x, lin.weight, lin.bias)
+    return linear(lin, x)
+
+
 def linear(lin: torch.nn.Linear, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`lin(x)` (+ residual) through TensorCoreLinear where the shapes allow (output width 256), else torch's own."""
     if tc_linear_enabled() and ops.linear_topk_supported(x, lin.weight):

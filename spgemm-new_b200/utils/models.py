@@ -23,7 +23,8 @@ from torch.nn import Linear
 
 from maxk_b200.autograd import (CBSRAddScaled, CBSRLinear, LinearTopKCBSR, MaxK, SpGEMMFunction, TopKCBSR,  # noqa: F401  (re-exported like the reference)
                                 LayerNormTopKCBSR, cbsr_native_enabled, layer_norm as _layer_norm,
-                                layer_norm_topk_supported as _ln_topk_ok, linear as _linear)
+                                layer_norm_topk_supported as _ln_topk_ok, linear as _linear,
+                                output_linear as _output_linear)
 from maxk_b200 import ops
 from torch.autograd import Function
 
@@ -142,7 +143,7 @@ class SAGE(_Base):
                 pending = self.normlayers[i]   # its output feeds only the next layer's MaxK: fused there
             else:
                 x = _layer_norm(self.normlayers[i], x)
-        return self.lin_out(x)
+        return _output_linear(self.lin_out, x)
 
 
 class GCN(_Base):
@@ -163,7 +164,7 @@ class GCN(_Base):
             sp_data, sp_index = _linear_sparsify(self.linlayers[i], x, self.maxk, self.nonlinear, self.p, self.training)
             x = g.aggregate(sp_data, sp_index, "gcn", self.hid) + self.conv_bias[i]
             x = _layer_norm(self.normlayers[i], x)
-        return self.lin_out(x)
+        return _output_linear(self.lin_out, x)
 
 
 class GIN(_Base):
@@ -188,4 +189,4 @@ class GIN(_Base):
                 h = _Scatter.apply(sp_data, sp_index, self.hid)
                 x = (1.0 + self.eps[i]) * h + g.aggregate(sp_data, sp_index, "sum", self.hid)
             x = _layer_norm(self.normlayers[i], x)
-        return self.lin_out(x)
+        return _output_linear(self.lin_out, x)

@@ -161,3 +161,22 @@ def test_tensor_core_linear_autograd(ops):
     y2.backward(gy)
     for a, b_, tol in zip(got, (y2.detach(), x.grad, lin.weight.grad, lin.bias.grad), (1e-4, 1e-4, 2e-3, 1e-3)):
         assert torch.allclose(a, b_, rtol=1e-4, atol=tol), float((a - b_).abs().max())
+
+
+def test_narrow_output_linear_backward(ops):
+    """The classifier's backward on the tensor-core kernels (roles of the operands exchanged) against torch's."""
+    from maxk_b200.autograd import output_linear
+    g = torch.Generator("cuda").manual_seed(21)
+    for classes in (47, 41, 112, 7):
+        lin = torch.nn.Linear(256, classes).cuda()
+        x = torch.randn(20_001, 256, device="cuda", generator=g, requires_grad=True)
+        gy = torch.randn(20_001, classes, device="cuda", generator=g)
+        y = output_linear(lin, x)
+        y.backward(gy)
+        got = (y.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+        x.grad = None
+        lin.zero_grad()
+        y2 = lin(x)
+        y2.backward(gy)
+        for a, b_, tol in zip(got, (y2.detach(), x.grad, lin.weight.grad, lin.bias.grad), (1e-5, 1e-4, 5e-3, 1e-3)):
+            assert a.shape == b_.shape and torch.allclose(a, b_, rtol=1e-4, atol=tol), float((a - b_).abs().max())
