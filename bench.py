@@ -289,7 +289,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the parity check of one extra step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--comm", choices=("peer", "nccl"), default="peer",
+    ap.add_argument("--comm", choices=("peer", "nccl"), default=None,
                     help="N>1: our fused kernels over NVLink peer memory (default) or NCCL collectives")
     ap.add_argument("--ref-kernels", action="store_true",
                     help="also time the reference CUDA kernels (oracle/_ref) on the same inputs")
@@ -355,7 +355,7 @@ def main():
     if world > 1:
         from maxk_b200.dist import DistAggregator, partition_rows_by_nnz
         bounds = partition_rows_by_nnz(g["indptr"], world, align=16)
-        comm = args.comm
+        comm = args.comm or "peer"
         agg = None
         if comm == "peer":
             # fused push all-gather + SpGEMM kernel and pull reduce-scatter over NVLink peer
@@ -774,8 +774,9 @@ def main():
             g.clear()
             torch.cuda.empty_cache()
             from maxk_b200 import train
+            # transport of the epoch: the one asked for with --comm, else by block size (train.Trainer: "auto")
             rec = train.run_epochs("products", epochs=args.epochs, warmup=2, device=dev, rank=rank, world=world,
-                                   comm=comm if world > 1 else "peer")
+                                   comm=(args.comm or "auto") if world > 1 else "peer")
             if rank == 0:
                 line["epoch"] = rec
                 log(f"[epoch] products-shaped SAGE k=32: {rec['ms_per_epoch']:.2f} ms/epoch = {rec['value']:.3f} epochs/s at N={world}")

@@ -27,7 +27,7 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--tf32", action="store_true", help="TF32 tensor cores for the dense Linear layers")
 ap.add_argument("--no-split", action="store_true")
-ap.add_argument("--comm", choices=("nccl", "peer"), default="peer")
+ap.add_argument("--comm", choices=("nccl", "peer", "auto"), default="auto")
 ap.add_argument("--row-cost", type=float, default=train.DEFAULT_ROW_COST)
 a = ap.parse_args()
 
