@@ -111,3 +111,48 @@ def test_training_reduces_loss_and_dropout_is_on_cbsr_values():
     # eval has no dropout; rows split over several warps' runs are combined with reductions
     # whose order is free (as with the reference's atomics), so equality is up to fp32 rounding
     assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["SAGE", "GCN", "GIN"])
+def test_models_hidden256_on_the_own_dense_kernels(name, monkeypatch):
+    """Width 256, k = 32: the layers as the epochs run them -- Linear + TopK in one tcgen05 kernel, tensor-core Linears
+    and weight gradients, own LayerNorm (+ TopK), the classifier's backward on the tensor-core kernels -- against the
+    fp64 dense restatement, and against the same model with every one of those switched back to the library.  A
+    selection may differ on a row whose 32nd and 33rd values are closer than the two GEMMs' rounding, so the check
+    is on the fraction of entries inside the tolerance."""
+    from utils import models as M
+    torch.manual_seed(2)
+    G, A, n = _graph(n=700, avg=14.0, seed=9)
+    k, hid = 32, 256
+    model = getattr(M, name)(20, hid, 2, 7, maxk=k, feat_drop=0.5, norm=True).cuda().eval()
+    feats = torch.randn(n, 20, device="cuda")
+    target = torch.randn(n, 7, device="cuda")
+
+    def run():
+        for p in model.parameters():
+            p.grad = None
+        out = model(G, feats)
+        (out * target).sum().backward()
+        return out.detach().clone(), {pn: p.grad.clone() for pn, p in model.named_parameters()}
+
+    out_own, grads_own = run()
+    for var in ("MAXK_TC_LINEAR", "MAXK_LAYERNORM", "MAXK_LINEAR_TOPK_FUSED"):
+        monkeypatch.setenv(var, "0")
+    out_lib, grads_lib = run()
+    for var in ("MAXK_TC_LINEAR", "MAXK_LAYERNORM", "MAXK_LINEAR_TOPK_FUSED"):
+        monkeypatch.delenv(var)
+    for p in model.parameters():
+        p.grad = None
+    ref = _ref_forward(model, name, A, feats, k)
+    (ref * target.double()).sum().backward()
+
+    def close_frac(a, b, tol):
+        a, b = a.double(), b.double()
+        return float(((a - b).abs() <= tol * (1.0 + b.abs())).double().mean())
+
+    assert close_frac(out_own, ref.detach(), 5e-4) > 0.995
+    assert close_frac(out_own, out_lib, 5e-4) > 0.995
+    for pn, p in model.named_parameters():
+        scale = float(p.grad.abs().max()) + 1e-6
+        assert close_frac(grads_own[pn] / scale, p.grad / scale, 5e-3) > 0.99, pn
+        assert close_frac(grads_own[pn] / scale, grads_lib[pn] / scale, 5e-3) > 0.99, pn
