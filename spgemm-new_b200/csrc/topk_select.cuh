@@ -9,6 +9,34 @@ namespace maxk {
 constexpr int TOPK_WPB = 8;
 constexpr int TOPK_FAST_MAX_PROBES = 14;  // then the key-space search takes over
 constexpr int TOPK_FAST_MAX_RUN = 5;      // same end point moved this often in a row -> ties likely
+constexpr int TOPK_EXTRACT_MAX = 8;       // a probe within this many elements of k is finished by extraction
+
+// Where the fp32 search of a one-row-per-warp kernel starts; made once per launch on the host (k and d are launch
+// constants, the kernel is issue-bound and every instruction of its set-up is paid per row).
+//   mode 0: between the row minimum and maximum, gl = d - k (exact), w = gl / (gl - gh);
+//   mode 1 / 2 (d == 256, k <= 32): from order statistics of the lane maxima -- between the minimum over lane PAIRS
+//   (expected rank 41.5 of 256) and over lane QUADS (rank 17) for k >= 17, between the quad minimum and the row
+//   maximum below that; the lower end of the bracket is the minimum over the lane maxima (rank ~91, at least 32
+//   elements not below it), gl = 91 - k an estimate that only steers.  The ranks hold for any continuous distribution.
+struct TopkSeed {
+    float w, gl;
+    int mode;
+};
+inline TopkSeed topk_seed(int d, int k)
+{
+    TopkSeed s;
+    if (d == MAXK_MAX_DIM && k <= 32) {
+        s.mode = k >= 17 ? 1 : 2;
+        s.w = k >= 17 ? (41.5f - (float)k) / 24.5f : (17.f - (float)k) / 16.f;
+        s.gl = (float)(91 - k);
+    } else {
+        const float gl = (float)(d - k), gh = (float)(1 - k) < -0.5f ? (float)(1 - k) : -0.5f;
+        s.mode = 0;
+        s.w = gl / (gl - gh);
+        s.gl = gl;
+    }
+    return s;
+}
 
 // order-preserving key of an fp32 bit pattern, branch-free:
 // NaN ranks largest (torch rule), -0 == +0, otherwise unsigned order == float order
@@ -73,6 +101,72 @@ __device__ __forceinline__ float rcp_approx(float v)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
+}
+
+// warp-wide minimum / maximum of fp32 values in ONE instruction (sm_100a: CREDUX.MIN/MAX.F32, result in a uniform
+// register): NaN operands are skipped, an all-NaN warp yields NaN.  No order-preserving keys, no conversions.
+__device__ __forceinline__ float warp_max_f32(float v)
+{
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float warp_min_f32(float v)
+{
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// one step of an inclusive warp scan: the shuffle's own "source lane in range" predicate guards the add
+// (SHFL.UP + predicated IADD; the C form costs SHFL + ISETP + SEL + IADD)
+__device__ __forceinline__ void scan_step_up(unsigned &v, int o)
+{
+    asm volatile("{.reg .pred p; .reg .b32 r; shfl.sync.up.b32 r|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, r;}"
+                 : "+r"(v)
+                 : "r"(o));
+}
+
+// The float just above v in the order of `<` (v finite; -0 counts as +0).
+__device__ __forceinline__ float f32_next_up(float v)
+{
+    const int b = __float_as_int(v);
+    return __int_as_float(v > 0.f ? b + 1 : (v < 0.f ? b - 1 : 1));
+}
+
+// ---- finishing a search by extraction ----------------------------------------------------------------------------
+// A probe at t selected the elements with !(x[i] < t) and left g = count - k, g != 0 and |g| small.  Instead of probing
+// on, name the threshold that WOULD separate exactly k elements if the |g| elements to move sat in different lanes:
+//   g < 0 (too few):  the |g|-th largest of the lanes' largest values below t  (every lane offers its best unselected)
+//   g > 0 (too many): just above the g-th smallest of the lanes' smallest selected values
+// |g| rounds of one CREDUX each; the caller probes the result like any other threshold, so a lane that held two of
+// the wanted elements, or a tie, only costs another step -- never a wrong answer.
+__device__ __forceinline__ float topk_extract_threshold(const float (&x)[8], float t, int g)
+{
+    const float pinf = __uint_as_float(0x7f800000u), ninf = __uint_as_float(0xff800000u);
+    float m;
+    if (g < 0) {
+        float u = ninf;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u = fmaxf(u, (x[i] < t) ? x[i] : ninf);
+#pragma unroll 1
+        while (true) {
+            m = warp_max_f32(u);
+            if (++g == 0) break;
+            u = (u == m) ? ninf : u;
+        }
+        return m;
+    }
+    float u = pinf;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u = fminf(u, (x[i] < t) ? pinf : x[i]);
+#pragma unroll 1
+    while (true) {
+        m = warp_min_f32(u);
+        if (--g == 0) break;
+        u = (u == m) ? pinf : u;
+    }
+    return f32_next_up(m);
 }
 
 // Element i of a lane sits at column  (i < 4 ? 4*lane + i : 128 + 4*lane + (i-4)):
@@ -223,7 +317,9 @@ __device__ __forceinline__ void topk_emit(unsigned sel, const unsigned (&raw)[8]
                                           unsigned char *__restrict__ out_idx)
 {
     const unsigned n0 = __popc(sel & 0xfu), n1 = __popc(sel >> 4);
-    const unsigned inc = warp_incl_scan(n0 | (n1 << 16), lane);
+    unsigned inc = n0 | (n1 << 16);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) scan_step_up(inc, o);
     const unsigned tot0 = __shfl_sync(0xffffffffu, inc, 31) & 0xffffu;
     unsigned *w0 = stage + ((inc & 0xffffu) - n0);
     unsigned *w1 = stage + (tot0 + (inc >> 16) - n1);

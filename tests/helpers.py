@@ -57,3 +57,32 @@ def assert_close_sum(got, want, abs_terms, n_terms, what=""):
     allowed = np.maximum(ATOL + RTOL * np.abs(want), (n_terms + 2) * 2.0 ** -24 * np.asarray(abs_terms, np.float64))
     bad = np.abs(got - want) > allowed
     assert not bad.any(), (what, int(bad.sum()), float(np.abs(got - want).max()))
+
+
+def topk_distribution_cases(n, seed):
+    """Rows that exercise every way the fp32 TopK search can end (tests/test_gpu_parity.py and the SIMT mirror):
+    smooth distributions (first probe from order statistics, finish by extraction), heavy tails, values on a coarse
+    grid (ties inside the extraction window -> robust path), half-zero rows, denormals, signed zeros, NaN and
+    infinities mixed in, values next to the fp32 maximum."""
+    rng = np.random.default_rng(seed)
+    shape = (n, 256)
+    cases = {
+        "normal": rng.standard_normal(shape),
+        "uniform": rng.random(shape),
+        "lognormal": np.exp(3 * rng.standard_normal(shape)),
+        "grid16": np.round(rng.standard_normal(shape) * 16) / 16,
+        "grid4": np.round(rng.standard_normal(shape) * 4) / 4,
+        "relu": np.maximum(rng.standard_normal(shape), 0),
+        "denormal": rng.standard_normal(shape) * 1e-41,
+        "huge": np.clip(rng.standard_normal(shape) * 1e38, -3.3e38, 3.3e38),
+    }
+    z = rng.standard_normal(shape)
+    z[rng.random(shape) < 0.3] = 0.0
+    z[rng.random(shape) < 0.1] = -0.0
+    cases["zeros"] = z
+    s = rng.standard_normal(shape)
+    s[rng.random(shape) < 0.05] = np.nan
+    s[rng.random(shape) < 0.02] = np.inf
+    s[rng.random(shape) < 0.02] = -np.inf
+    cases["nan_inf"] = s
+    return {name: np.ascontiguousarray(x, dtype=np.float32) for name, x in cases.items()}

@@ -222,6 +222,23 @@ inline unsigned __reduce_max_sync(unsigned m, unsigned v) { return (unsigned)::s
 inline unsigned __reduce_and_sync(unsigned m, unsigned v) { return (unsigned)::simt::collective(m, ::simt::OP_AND, v, 0, 32); }
 inline unsigned __reduce_or_sync(unsigned m, unsigned v) { return (unsigned)::simt::collective(m, ::simt::OP_OR, v, 0, 32); }
 
+// redux.sync.{min,max}.f32 (sm_100a): NaN operands are skipped, an all-NaN warp yields NaN.  Done on order-preserving
+// keys through the integer collective (key 0 / 0xffffffff = "no value").
+inline float simt_redux_f32(float v, bool want_max)
+{
+    uint32_t b;
+    __builtin_memcpy(&b, &v, 4);
+    const bool nan = (b & 0x7fffffffu) > 0x7f800000u;
+    uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    if (nan) key = want_max ? 0u : 0xffffffffu;
+    const uint32_t r = (uint32_t)::simt::collective(0xffffffffu, want_max ? ::simt::OP_UMAX : ::simt::OP_UMIN, key, 0, 32);
+    if (r == (want_max ? 0u : 0xffffffffu)) return __builtin_nanf("");
+    const uint32_t rb = (r & 0x80000000u) ? (r & 0x7fffffffu) : ~r;
+    float out;
+    __builtin_memcpy(&out, &rb, 4);
+    return out;
+}
+
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }

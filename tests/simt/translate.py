@@ -81,6 +81,11 @@ PTX = [
      "{{ float *p_ = (float *)({0}); p_[0] += ({1}); p_[1] += ({2}); p_[2] += ({3}); p_[3] += ({4}); }}"),
     (r"^red\.relaxed\.gpu\.global\.add\.f32 ", "{{ *(float *)({0}) += ({1}); }}"),
     (r"^rcp\.approx\.ftz\.f32 ", "{{ ({0}) = 1.0f / ({1}); }}"),
+    (r"^redux\.sync\.max\.f32 %0, %1, 0xffffffff;", "{{ ({0}) = ::simt_redux_f32(({1}), true); }}"),
+    (r"^redux\.sync\.min\.f32 %0, %1, 0xffffffff;", "{{ ({0}) = ::simt_redux_f32(({1}), false); }}"),
+    (r"shfl\.sync\.up\.b32 r\|p, %0, %1, 0, 0xffffffff; @p add\.u32 %0, %0, r;",
+     "{{ unsigned n_ = __shfl_up_sync(0xffffffffu, ({0}), (unsigned)({1})); "
+     "if ((int)(threadIdx.x & 31u) >= (int)({1})) ({0}) += n_; }}"),
     (r"setp\.geu\.f32 p, %1, %2; @p add\.s32 %0, %0, 1;", "{{ if (!(({1}) < ({2}))) ({0}) += 1; }}"),
     (r"setp\.geu\.f32 p, %1, %2; @p st\.shared\.f32 \[%0\], %1; @p st\.shared\.u32 \[%0\+%4\], %3;",
      "{{ if (!(({1}) < ({2}))) {{ *(float *)::simt::smem_resolve({0}) = ({1}); "

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ATOL, RTOL, Problem, assert_close
+from helpers import ATOL, RTOL, Problem, assert_close, topk_distribution_cases
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -358,6 +358,18 @@ def test_backward_run_lengths(ops, case):
             assert_close(dxc, p.bwd_oracle(), f"tpw={tpw}")
     finally:
         ops.set_tuning(-1, -1)
+
+
+def test_topk_distributions_bit_exact(ops):
+    """Full-width rows of ten value distributions x every k around the seeds' switch points (16 / 17, 32 / 33):
+    indices and value bits equal to the oracle's, whichever way the search ended."""
+    for name, x in topk_distribution_cases(3000, seed=23).items():
+        xt = torch.from_numpy(x).cuda()
+        for k in (1, 2, 3, 8, 16, 17, 24, 31, 32, 33, 64):
+            want_v, want_i = O.topk_cbsr(x, k)
+            v, i = ops.topk_cbsr(xt, k)
+            np.testing.assert_array_equal(i.cpu().numpy(), want_i, err_msg=f"{name} k={k}")
+            np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), want_v.view(np.uint32), err_msg=f"{name} k={k}")
 
 
 def test_topk_full_width_rows(ops):

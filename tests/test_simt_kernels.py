@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 import simt_lib as S
-from helpers import ATOL, RTOL, Problem
+from helpers import ATOL, RTOL, Problem, topk_distribution_cases
 from oracle import oracle as O
 
 
@@ -82,6 +82,17 @@ def test_simt_topk_ties_and_specials():
         v, i = S.topk_f32(x, k)
         np.testing.assert_array_equal(i, want_i, err_msg=f"k={k}")
         np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
+
+
+def test_simt_topk_distributions_bit_exact():
+    """Mirror of test_gpu_parity.test_topk_distributions_bit_exact (fewer rows): order-statistics seed, extraction
+    finish and the hand-over to the robust search on ten value distributions."""
+    for name, x in topk_distribution_cases(40, seed=23).items():
+        for k in (1, 3, 16, 17, 32, 33, 64):
+            want_v, want_i = O.topk_cbsr(x, k)
+            v, i = S.topk_f32(x, k)
+            np.testing.assert_array_equal(i, want_i, err_msg=f"{name} k={k}")
+            np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32), err_msg=f"{name} k={k}")
 
 
 def test_simt_topk_full_width_rows():
