@@ -78,28 +78,29 @@ __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool 
 
     // ---- bracket and first threshold ------------------------------------------------------------------------------
     // fmaxf / CREDUX skip NaN (NaN elements rank largest and pass every `!(x < t)` on their own).
-    const float lmax = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
-    float fh = warp_max_f32(lmax), fl, gl, gh = fminf((float)(1 - k), -0.5f), t;
+    const float hi0 = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), hi1 = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));
+    const float lmax = fmaxf(hi0, hi1);
+    float fh = warp_max_f32(lmax), fl, gl = seed.gl, gh = seed.gh, t;
     if (seed.mode != 0) {
-        // Order statistics instead of the row minimum (full-width rows, k <= 32; `seed` is made on the host,
-        // topk_seed()): every lane's maximum is one of the row's elements, so A = min over lanes of the lane maxima
-        // has at least 32 >= k elements not below it -- a valid lower end whose rank is ~91 of 256 for ANY continuous
-        // distribution; B = min over lane pairs (~rank 41), C = min over lane quads (~rank 17) cost a shuffle + FMNMX +
-        // CREDUX each and put the first probe at the right RANK whatever the shape of the distribution (the linear
-        // interpolation between minimum and maximum it replaces needed 6.4 probes per row on normal data against 4.0
-        // on uniform data).
-        fl = warp_min_f32(lmax);
+        // Order statistics of the lane maxima instead of the row minimum (full-width rows, k <= 64; topk_seed() has
+        // the ranks): a shuffle + FMNMX + CREDUX each, and the first probe lands at the right RANK whatever the shape
+        // of the distribution (the linear interpolation between minimum and maximum it replaces needed 6.4 probes per
+        // row on normal data against 4.0 on uniform data).
+        const float A = warp_min_f32(lmax);
         const float pm = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, 1));
-        const float qm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 2));
-        const float B = warp_min_f32(pm), C = warp_min_f32(qm);
-        const float lo = seed.mode == 1 ? B : C, hi = seed.mode == 1 ? C : fh;
-        gl = seed.gl;
+        const float B = warp_min_f32(pm);
+        float lo = A, hi = B;
+        if (seed.mode != 3) {
+            const float C = warp_min_f32(fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 2)));
+            lo = seed.mode == 1 ? B : C;
+            hi = seed.mode == 1 ? C : fh;
+        }
+        fl = seed.low == 1 ? A : warp_min_f32(fminf(hi0, hi1));
         t = fmaf(hi - lo, seed.w, lo);
     } else {
         const float lo0 = fminf(fminf(a.x, a.y), fminf(a.z, a.w)), lo1 = fminf(fminf(b.x, b.y), fminf(b.z, b.w));
         fl = warp_min_f32(FULL ? fminf(lo0, lo1) : fminf(ok0 ? lo0 : pinf, ok1 ? lo1 : pinf));
-        gl = seed.gl;  // d - k, exact: every element, NaN included, is not below the minimum
-        t = fmaf(fh - fl, seed.w, fl);
+        t = fmaf(fh - fl, seed.w, fl);  // gl = d - k is exact: every element, NaN included, is not below the minimum
     }
 
     // ---- fast path: regula falsi (Illinois weights) on g(t) = count(!(x < t)) - k, finished by extraction -------
@@ -170,8 +171,11 @@ __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool 
     }
 }
 
+// Six CTAs per SM (40 registers): the out-of-line robust search would otherwise set the kernel's register count (45:
+// five CTAs, measured 6 % slower); eight CTAs (32 registers, two spills) measure the same as six
+// (profiles/r02_topk_occupancy.jsonl) -- the kernel is bound by issue slots, not by latency.
 template <bool FULL>
-__global__ void __launch_bounds__(TOPK_WPB * 32)
+__global__ void __launch_bounds__(TOPK_WPB * 32, 6)
 topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, TopkSeed seed,
                      float *__restrict__ out_val, unsigned char *__restrict__ out_idx,
                      float *__restrict__ dense_out)
@@ -204,7 +208,7 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, Topk
 // feeds nothing else, so it need not reach HBM.)  One warp per row: mean / variance / affine in registers exactly as
 // layernorm.cu does, then the row goes into the search above; mean and rstd are kept for the backward
 // (layernorm.cu: layernorm_bwd_cbsr_kernel takes the k-sparse gradient as it comes back from the aggregation).
-__global__ void __launch_bounds__(TOPK_WPB * 32)
+__global__ void __launch_bounds__(TOPK_WPB * 32, 6)
 layernorm_topk_kernel(const float *__restrict__ x_, int64_t n, int d, const float *__restrict__ gamma,
                       const float *__restrict__ beta, float eps, int k, TopkSeed seed, float *__restrict__ out_val,
                       unsigned char *__restrict__ out_idx, float *__restrict__ mean_out, float *__restrict__ rstd_out,

@@ -14,26 +14,42 @@ constexpr int TOPK_EXTRACT_MAX = 8;       // a probe within this many elements o
 // Where the fp32 search of a one-row-per-warp kernel starts; made once per launch on the host (k and d are launch
 // constants, the kernel is issue-bound and every instruction of its set-up is paid per row).
 //   mode 0: between the row minimum and maximum, gl = d - k (exact), w = gl / (gl - gh);
-//   mode 1 / 2 (d == 256, k <= 32): from order statistics of the lane maxima -- between the minimum over lane PAIRS
-//   (expected rank 41.5 of 256) and over lane QUADS (rank 17) for k >= 17, between the quad minimum and the row
-//   maximum below that; the lower end of the bracket is the minimum over the lane maxima (rank ~91, at least 32
-//   elements not below it), gl = 91 - k an estimate that only steers.  The ranks hold for any continuous distribution.
+//   mode 1..3 (d == 256, k <= 64): from ORDER STATISTICS of the lanes' maxima.  With 8 elements per lane, the minimum
+//   over the 32 lane maxima (A), over the 16 maxima of lane pairs (B) and over the 8 maxima of lane quads (C) have
+//   expected ranks 100.6, 48.3 and 20.7 of 256 for ANY continuous distribution (measured on 20 000 rows; standard
+//   deviations 22 / 14 / 8), the row maximum has rank 1: the first threshold is interpolated BY RANK between the two
+//   statistics that enclose k -- (C, max) for k <= 20, (B, C) for k <= 48, (A, B) above.  The lower end of the
+//   bracket must have at least k elements not below it: A has >= 32 (one per lane), and for 32 < k <= 64 the minimum G
+//   over the 64 maxima of the lanes' four-element groups has >= 64 (expected rank 175).  gl = rank - k is an estimate
+//   that only steers the interpolation; gh = min(1 - k, -0.5) as before.
 struct TopkSeed {
-    float w, gl;
-    int mode;
+    float w, gl, gh;
+    int mode;  // 0: minimum / maximum; 1: (B, C); 2: (C, max); 3: (A, B)
+    int low;   // lower end of the bracket: 0 = row minimum, 1 = A, 2 = G
 };
 inline TopkSeed topk_seed(int d, int k)
 {
     TopkSeed s;
-    if (d == MAXK_MAX_DIM && k <= 32) {
-        s.mode = k >= 17 ? 1 : 2;
-        s.w = k >= 17 ? (41.5f - (float)k) / 24.5f : (17.f - (float)k) / 16.f;
-        s.gl = (float)(91 - k);
+    s.gh = (float)(1 - k) < -0.5f ? (float)(1 - k) : -0.5f;
+    if (d == MAXK_MAX_DIM && k <= 64) {
+        const float ra = 100.6f, rb = 48.3f, rc = 20.7f, rg = 175.f;
+        if (k <= 20) {
+            s.mode = 2;
+            s.w = (rc - (float)k) / (rc - 1.f);
+        } else if (k <= 48) {
+            s.mode = 1;
+            s.w = (rb - (float)k) / (rb - rc);
+        } else {
+            s.mode = 3;
+            s.w = (ra - (float)k) / (ra - rb);
+        }
+        s.low = k <= 32 ? 1 : 2;
+        s.gl = (k <= 32 ? ra : rg) - (float)k;
     } else {
-        const float gl = (float)(d - k), gh = (float)(1 - k) < -0.5f ? (float)(1 - k) : -0.5f;
         s.mode = 0;
-        s.w = gl / (gl - gh);
-        s.gl = gl;
+        s.low = 0;
+        s.gl = (float)(d - k);
+        s.w = s.gl / (s.gl - s.gh);
     }
     return s;
 }
@@ -146,9 +162,9 @@ __device__ __forceinline__ float topk_extract_threshold(const float (&x)[8], flo
     const float pinf = __uint_as_float(0x7f800000u), ninf = __uint_as_float(0xff800000u);
     float m;
     if (g < 0) {
-        float u = ninf;
+        float u = (x[0] < t) ? x[0] : ninf;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) u = fmaxf(u, (x[i] < t) ? x[i] : ninf);
+        for (int i = 1; i < 8; ++i) u = fmaxf(u, (x[i] < t) ? x[i] : ninf);
 #pragma unroll 1
         while (true) {
             m = warp_max_f32(u);
@@ -157,9 +173,9 @@ __device__ __forceinline__ float topk_extract_threshold(const float (&x)[8], flo
         }
         return m;
     }
-    float u = pinf;
+    float u = (x[0] < t) ? pinf : x[0];  // (a NaN here is skipped by the CREDUX like by fminf)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) u = fminf(u, (x[i] < t) ? pinf : x[i]);
+    for (int i = 1; i < 8; ++i) u = fminf(u, (x[i] < t) ? pinf : x[i]);
 #pragma unroll 1
     while (true) {
         m = warp_min_f32(u);
@@ -243,13 +259,46 @@ __device__ __forceinline__ unsigned topk_select_by_keys(const unsigned (&key)[8]
                     exact = true;
                     break;
                 }
+                // Snap the probe to an ELEMENT before it becomes an end point: the bracket then shrinks by whole value
+                // levels, and a probe that fell into the gap next to the k-th largest value ends the search at once.
+                // Without this, ties at the k-th value (values on a grid, zeros after a ReLU) cost one bisection
+                // step per key bit between two levels -- ~23 probes per row (round 2: 8-level rows 520-715 us per
+                // 233 k rows against 85 us for tie-free rows).
                 if (c > k) {
-                    L = M;
-                    cL = c;
+                    unsigned lm = 0xffffffffu;  // smallest element not below M: same count
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) lm = min(lm, key[i] >= M ? key[i] : 0xffffffffu);
+                    const unsigned m = __reduce_min_sync(0xffffffffu, lm);
+                    if (m == 0xffffffffu) {  // more than k NaNs
+                        thr = m;
+                        break;
+                    }
+                    const int c1 = warp_count_ge(key, m + 1u);
+                    if (c1 < k) {  // m is the k-th largest value, tied
+                        thr = m;
+                        break;
+                    }
+                    if (c1 == k) {
+                        thr = m + 1u;
+                        exact = true;
+                        break;
+                    }
+                    L = m + 1u;
+                    cL = c1;
                     stuck = stuck > 0 ? stuck + 1 : 1;
                 } else {
-                    H = M;
-                    cH = c;
+                    unsigned lm = 0u;  // largest element below M (there is one: cL >= k > c)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) lm = max(lm, key[i] < M ? key[i] : 0u);
+                    const unsigned m = __reduce_max_sync(0xffffffffu, lm);
+                    const int cm = warp_count_ge(key, m);
+                    if (cm >= k) {  // the elements above m are the c < k not below M: m is the k-th largest value
+                        thr = m;
+                        exact = (cm == k);
+                        break;
+                    }
+                    H = m;
+                    cH = cm;
                     stuck = stuck < 0 ? stuck - 1 : -1;
                 }
             }
