@@ -8,26 +8,29 @@
 // any k and N (Q7) and with an exact tie rule (Q8):
 //   * one warp per row, 8 elements per lane in registers (two 128-bit loads per lane);
 //   * fp32 fast path: the threshold is searched in VALUE space with plain float compares
-//     (`!(x < t)`, so NaN ranks largest and -0 == +0 for free) -- an Illinois-weighted
-//     regula falsi on count(x >= t) - k between the row minimum and maximum, one
-//     REDUX-counted probe (8 FSETP + 8 SEL + 4 IADD3 + POPC + REDUX) per step, ending on the first probe
-//     that separates exactly k elements.  No keys, no key<->float conversions in the loop
-//     (v3 spent 77 instructions per probe on them; v1 walked the key bit by bit);
+//     (`!(x < t)`, so NaN ranks largest and -0 == +0 for free); one REDUX-counted probe (8 FSETP + 8 SEL +
+//     4 IADD3 + POPC + REDUX) per step, ending on the first probe that separates exactly k elements.
+//     The first probe comes from ORDER STATISTICS of the lane maxima (CREDUX.MIN/MAX.F32: no keys, no
+//     conversions; topk_select.cuh: TopkSeed) and lands at the right rank whatever the distribution; once a
+//     probe is within 8 elements of k the next threshold is NAMED by extraction from the lanes' nearest values
+//     (topk_extract_threshold) instead of interpolated: 2.4 probes + 1.1 extractions per row on uniform data,
+//     2.7 + 1.1 on normal data (round 1 / early round 2: Illinois regula falsi between the row minimum and
+//     maximum, 4.0 / 6.4 probes);
 //   * rows the fast path cannot finish (ties at the k-th value, +-inf end points, a bracket
-//     that collapsed to adjacent floats) fall to the robust key-space search, which
-//     resolves ties by column order exactly;
+//     that collapsed to adjacent floats) fall to the robust key-space search, which snaps its probes to
+//     elements (whole value levels per step) and resolves ties by column order exactly;
 //   * emission positions from one packed warp scan, staged in shared memory so the global
 //     stores are coalesced; optional dense x*mask output (MaxK.forward,
 //     utils/models.py:48-52) from the same registers.
 // Pure streaming kernel: 4*d bytes read + 5*k bytes written per row -> HBM-bound by design;
 // the instruction count per row decides how close it gets: ncu (rounds 1 and 2) shows it ISSUE-bound
-// (smsp__issue_active 78 %, DRAM 27 %) at ~360 warp instructions per row -- bracket set-up ~70, ~3.7
-// probes x 53 (21 of them the eight compares, the rest the root finder and the REDUX), emission ~100.
+// (smsp__issue_active 78 %, DRAM 27 %).  ~350 warp instructions per row now (set-up ~66, 2.45 probes x 55,
+// 1.1 extractions x 45, emission ~97); 368 before the order-statistics seed and the extraction (510 on
+// normal data).  232 965 x 256, k = 32: 86 us uniform / 89 us normal (99.4 / 131.2 before).
 // Measured and dropped in round 2 (profiles/r02_variants.md, r02_topk.md): several rows per warp with
 // the next row prefetched (8-17 % slower: the loop costs more than the latency it hides) and two rows
 // per warp in half-warps (the warp-uniform overhead is shared, but 16 elements per lane compile to a
-// longer compare / staging sequence: 128 vs 100 us).  What round 2 kept: the full-width (d = 256)
-// specialisation, two-instruction bracket keys and a loop-free emission for k <= 32 (108 -> 99.5 us).
+// longer compare / staging sequence: 128 vs 100 us).
 #include "common.cuh"
 #include "topk_select.cuh"
 
