@@ -16,7 +16,7 @@ def timeit(fn, iters=20, warm=3):
     return s.elapsed_time(e) / iters
 
 g = torch.Generator("cuda").manual_seed(1)
-out = {"topk_minb": os.environ.get("MAXK_TOPK_MINB"), "lntopk_minb": os.environ.get("MAXK_LNTOPK_MINB")}
+out = {"variant": os.environ.get("MAXK_TOPK_VARIANT")}
 for n, tag in ((232965, "reddit"), (2449029, "products")):
     for name, x in (("uniform", torch.rand(n, 256, device="cuda", generator=g)),
                     ("normal", torch.randn(n, 256, device="cuda", generator=g))):

@@ -174,18 +174,22 @@ __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool 
     }
 }
 
-// Six CTAs per SM (40 registers): the out-of-line robust search would otherwise set the kernel's register count (45:
-// five CTAs, measured 6 % slower); eight CTAs (32 registers, two spills) measure the same as six
-// (profiles/r02_topk_occupancy.jsonl) -- the kernel is bound by issue slots, not by latency.
+// 48 warps per SM by launch bounds (40 registers): the out-of-line robust search would otherwise set the kernel's
+// register count (45: 40 warps, measured 6 % slower); 64 warps (32 registers, two spills) measure the same as 48
+// (profiles/r02_topk_occupancy.jsonl) -- the kernel is bound by issue slots, not by latency.  CTAs of TWO warps: a CTA
+// keeps its slot until its slowest row is done (ncu: 59 % of the warp slots active with eight warps per CTA against
+// 75 % allocated); 8 / 4 / 2 warps measure 853 / 841 / 837 us on the products-sized activation, and a persistent
+// grid-stride loop over rows 1051-1083 us (`profiles/r02_topk_cta_shape.jsonl`; the loop form lost in round 2's first
+// attempt as well).
 template <bool FULL>
-__global__ void __launch_bounds__(TOPK_WPB * 32, 6)
+__global__ void __launch_bounds__(TOPK_F32_WPB * 32, 48 / TOPK_F32_WPB)
 topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, TopkSeed seed,
                      float *__restrict__ out_val, unsigned char *__restrict__ out_idx,
                      float *__restrict__ dense_out)
 {
-    __shared__ unsigned s_stage[TOPK_WPB][2 * MAXK_MAX_DIM];
+    __shared__ unsigned s_stage[TOPK_F32_WPB][2 * MAXK_MAX_DIM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row = (int64_t)blockIdx.x * TOPK_WPB + warp;
+    const int64_t row = (int64_t)blockIdx.x * TOPK_F32_WPB + warp;
     if (row >= n) return;  // warp-uniform; no CTA barrier below
 
     const int c0 = 4 * lane, c1 = 128 + 4 * lane;
@@ -211,15 +215,15 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, Topk
 // feeds nothing else, so it need not reach HBM.)  One warp per row: mean / variance / affine in registers exactly as
 // layernorm.cu does, then the row goes into the search above; mean and rstd are kept for the backward
 // (layernorm.cu: layernorm_bwd_cbsr_kernel takes the k-sparse gradient as it comes back from the aggregation).
-__global__ void __launch_bounds__(TOPK_WPB * 32, 6)
+__global__ void __launch_bounds__(TOPK_F32_WPB * 32, 48 / TOPK_F32_WPB)
 layernorm_topk_kernel(const float *__restrict__ x_, int64_t n, int d, const float *__restrict__ gamma,
                       const float *__restrict__ beta, float eps, int k, TopkSeed seed, float *__restrict__ out_val,
                       unsigned char *__restrict__ out_idx, float *__restrict__ mean_out, float *__restrict__ rstd_out,
                       float *__restrict__ y_out)
 {
-    __shared__ unsigned s_stage[TOPK_WPB][2 * MAXK_MAX_DIM];
+    __shared__ unsigned s_stage[TOPK_F32_WPB][2 * MAXK_MAX_DIM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row = (int64_t)blockIdx.x * TOPK_WPB + warp;
+    const int64_t row = (int64_t)blockIdx.x * TOPK_F32_WPB + warp;
     if (row >= n) return;  // warp-uniform; no CTA barrier below
     const int c0 = 4 * lane, c1 = 128 + 4 * lane;
     const bool ok0 = c0 < d, ok1 = c1 < d;
@@ -607,7 +611,7 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
     MAXK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(dense_out) & 15) == 0,
                  "maxk_topk_cbsr_f32: x and dense_out must be 16-byte aligned");
-    const int64_t grid = ceil_div<int64_t>(n, TOPK_WPB);
+    const int64_t grid = ceil_div<int64_t>(n, TOPK_F32_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_topk_cbsr_f32: n too large");
     {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -620,10 +624,10 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
         }
     }
     if (d == MAXK_MAX_DIM)
-        topk_cbsr_f32_kernel<true><<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        topk_cbsr_f32_kernel<true><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
             x, n, d, k, topk_seed(d, k), sp_data, sp_index, dense_out);
     else
-        topk_cbsr_f32_kernel<false><<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        topk_cbsr_f32_kernel<false><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
             x, n, d, k, topk_seed(d, k), sp_data, sp_index, dense_out);
     MAXK_LAUNCH_CHECK("topk_cbsr_f32_kernel");
     return MAXK_OK;
@@ -662,9 +666,9 @@ extern "C" int maxk_layernorm_topk_cbsr(const float *x, int64_t n, int32_t d, co
     MAXK_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y_out) |
                    reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
                  "maxk_layernorm_topk_cbsr: x, y_out, gamma and beta must be 16-byte aligned");
-    const int64_t grid = ceil_div<int64_t>(n, TOPK_WPB);
+    const int64_t grid = ceil_div<int64_t>(n, TOPK_F32_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_layernorm_topk_cbsr: n too large");
-    layernorm_topk_kernel<<<(unsigned)grid, TOPK_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    layernorm_topk_kernel<<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         x, n, d, gamma, beta, eps, k, topk_seed(d, k), sp_data, sp_index, mean, rstd, y_out);
     MAXK_LAUNCH_CHECK("layernorm_topk_kernel");
     return MAXK_OK;

@@ -6,7 +6,8 @@
 
 namespace maxk {
 
-constexpr int TOPK_WPB = 8;
+constexpr int TOPK_WPB = 8;      // warps per CTA of the uint8 kernel
+constexpr int TOPK_F32_WPB = 2;  // ... of the fp32 one-row-per-warp kernels (topk_cbsr.cu: why two)
 constexpr int TOPK_FAST_MAX_PROBES = 14;  // then the key-space search takes over
 constexpr int TOPK_FAST_MAX_RUN = 5;      // same end point moved this often in a row -> ties likely
 constexpr int TOPK_EXTRACT_MAX = 8;       // a probe within this many elements of k is finished by extraction
