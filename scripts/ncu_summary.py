@@ -72,7 +72,12 @@ def main():
     if h is not None:
         hd = src[h]
         c = {name: i for i, name in enumerate(hd)}
-        body = [r for r in src[h + 1:] if len(r) == len(hd)]
+        body = []
+        for r in src[h + 1:]:   # the first captured launch only (a report with several repeats the header)
+            if r and r[0] == "Address":
+                break
+            if len(r) == len(hd):
+                body.append(r)
         key = "Warp Stall Sampling (All Samples)"
         tot = sum(int(r[c[key]] or 0) for r in body) or 1
         stall_cols = [n for n in hd if n.startswith("stall_")]
