@@ -30,8 +30,12 @@ MUTANTS = {
     "bwd-stage-no-barrier": ("sspmm_backward.cu", "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));\n    __syncwarp();", "    stage[lane + 32] = make_int2(r.i1, __float_as_int(r.v1));", 0),
     "bwd-dy-restage-no-barrier": ("sspmm_backward.cu", "            cur_row = info.x;\n            __syncwarp();", "            cur_row = info.x;", 0),
     "bwd-selector-of-wrong-node": ("sspmm_backward.cu", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + q[u]);", "reinterpret_cast<const unsigned *>(sp_index + (int64_t)ev[u].x * k) + (q[u] ^ 1));", 0),
-    "topk-emit-no-barrier": ("topk_cbsr.cu", "    __syncwarp();\n    unsigned char *oi = out_idx + row * k + lane;", "    unsigned char *oi = out_idx + row * k + lane;", 0),
-    "topk-tie-order": ("topk_cbsr.cu", "if (r0 < need) sel |= (1u << i);", "if (r0 <= need) sel |= (1u << i);", 0),
+    "topk-emit-no-barrier": ("topk_select.cuh", "    __syncwarp();\n    unsigned char *oi = out_idx + row * k + lane;", "    unsigned char *oi = out_idx + row * k + lane;", 0),
+    "topk-tie-order": ("topk_select.cuh", "if (r0 < need) sel |= (1u << i);", "if (r0 <= need) sel |= (1u << i);", 0),
+    # the fast path's proof: only a probe that separates EXACTLY k elements may end the search
+    "topk-proof-accepts-k-plus-1": ("topk_cbsr.cu", "            if (g == 0) {\n                done = true;", "            if (g == 0 || g == 1) {\n                done = true;", 0),
+    # level snapping of the robust search: the element below a probe IS the k-th largest once its count reaches k
+    "topk-snap-up-skips-an-element": ("topk_select.cuh", "                    L = m + 1u;\n                    cL = c1;", "                    L = m + 2u;\n                    cL = c1;", 0),
     "topk-row-bound": ("topk_cbsr.cu", "if (row >= n) return;  // warp-uniform; no CTA barrier below\n\n", "if (row > n) return;\n\n", 0),
     # bank plan and planned kernels
     "plan-home-word-formula": ("common.cuh", "return h == 0 ? c : 256u + (c & 7u) * 32u + (c >> 3);", "return h == 0 ? c : 256u + (c & 7u) * 32u + ((c >> 3) ^ 1u);", 0),
@@ -61,6 +65,10 @@ MUTANTS = {
 # before fwd_flush_row -- the leading barriers of those two functions are redundant (they stay:
 # they cost nothing measurable and keep the functions correct on their own).
 EQUIVALENT = {
+    # level snapping of the robust TopK search, element below a probe with count == k: not ending there leaves
+    # H = m with cH = k; every later end of the search (a probe with count k, or H - L == 1 with "ties at L" whose
+    # strictly greater elements are exactly those k) selects the same set -- slower, not wrong
+    "topk-snap-down-keeps-the-level": ("topk_select.cuh", "                    if (cm >= k) {  // the elements above m", "                    if (cm > k) {  // the elements above m", 0),
     # every row starts with warp-wide REDUX collectives (row minimum / maximum): all lanes have left the previous
     # row's emission reads before any lane can reach the next row's staging writes; the barrier stays as
     # documentation of the reuse
