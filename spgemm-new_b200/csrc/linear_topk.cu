@@ -349,31 +349,84 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 for (int i = 0; i < LT_HALF; i += 4) o[i >> 2] = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
             }
 
-            // ---- bracket: the row's minimum and maximum (this half, then the partner's through shared memory)
-            float fl = x[0], fh = x[0];
+            // ---- bracket and first threshold (topk_select.cuh: TopkSeed).  k <= 64: ORDER STATISTICS instead of the row
+            // minimum -- the minima over the maxima of 8 / 16 / 32 consecutive columns (32 / 16 / 8 groups per row) have
+            // expected ranks 100.6 / 48.3 / 20.7 of 256 whatever the distribution of the values, the first threshold is
+            // interpolated by rank between the two that enclose k, and the lower end of the bracket is the minimum over
+            // the 32 (k <= 32) or 64 (groups of 4) maxima, which has that many elements not below it.  The maxima
+            // fall out of the tree that computes the row maximum; the minimum pass of the old bracket is gone.  The
+            // products of a Linear are close to normally distributed: the interpolation between minimum and maximum
+            // put the first probe ~26 elements off there (4 on uniform values).  Both halves combine the partner's
+            // four numbers in the same operand order: bit-identical brackets, hence identical control flow in the two
+            // warps that meet at the named barrier.  The numbers travel through the row buffer of the robust search,
+            // which is free until this tile's emission has passed its barriers.
+            const TopkSeed seed = topk_seed(LT_D, k);
+            const float nanf_ = __uint_as_float(0x7fc00000u);
+            float fl, fh, tn = nanf_;
+            if (seed.mode != 0) {
+                const float pinf = __uint_as_float(0x7f800000u), ninf = __uint_as_float(0xff800000u);
+                float sa = pinf, sb2 = pinf, sc = pinf, sg = pinf;
+                fh = ninf;
 #pragma unroll
-            for (int i = 1; i < LT_HALF; ++i) {
-                fl = fminf(fl, x[i]);
-                fh = fmaxf(fh, x[i]);
+                for (int j32 = 0; j32 < LT_HALF; j32 += 32) {
+                    float m32 = ninf;
+#pragma unroll
+                    for (int j16 = 0; j16 < 32; j16 += 16) {
+                        float m16 = ninf;
+#pragma unroll
+                        for (int j8 = 0; j8 < 16; j8 += 8) {
+                            const int o = j32 + j16 + j8;
+                            const float q0 = fmaxf(fmaxf(x[o], x[o + 1]), fmaxf(x[o + 2], x[o + 3]));
+                            const float q1 = fmaxf(fmaxf(x[o + 4], x[o + 5]), fmaxf(x[o + 6], x[o + 7]));
+                            if (seed.low == 2) sg = fminf(sg, fminf(q0, q1));
+                            const float m8 = fmaxf(q0, q1);
+                            sa = fminf(sa, m8);
+                            m16 = fmaxf(m16, m8);
+                        }
+                        sb2 = fminf(sb2, m16);
+                        m32 = fmaxf(m32, m16);
+                    }
+                    sc = fminf(sc, m32);
+                    fh = fmaxf(fh, m32);
+                }
+                volatile float *xb = reinterpret_cast<volatile float *>(rowbuf);
+                const int me = (lane * 2 + half) * 4, p0 = (lane * 2) * 4, p1 = (lane * 2 + 1) * 4;
+                xb[me] = fh;
+                xb[me + 1] = seed.low == 2 ? sg : sa;
+                xb[me + 2] = seed.mode == 1 ? sb2 : (seed.mode == 2 ? sc : sa);
+                xb[me + 3] = seed.mode == 1 ? sc : sb2;
+                named_bar_sync(bar_id, 64);
+                fh = fmaxf(xb[p0], xb[p1]);
+                fl = fminf(xb[p0 + 1], xb[p1 + 1]);
+                const float lo = fminf(xb[p0 + 2], xb[p1 + 2]);
+                const float hi = seed.mode == 2 ? fh : fminf(xb[p0 + 3], xb[p1 + 3]);
+                tn = fmaf(hi - lo, seed.w, lo);
+            } else {
+                fl = x[0];
+                fh = x[0];
+#pragma unroll
+                for (int i = 1; i < LT_HALF; ++i) {
+                    fl = fminf(fl, x[i]);
+                    fh = fmaxf(fh, x[i]);
+                }
+                xf[(r * 2 + half) * 2] = fl;
+                xf[(r * 2 + half) * 2 + 1] = fh;
+                named_bar_sync(bar_id, 64);
+                fl = fminf(xf[(r * 2) * 2], xf[(r * 2 + 1) * 2]);
+                fh = fmaxf(xf[(r * 2) * 2 + 1], xf[(r * 2 + 1) * 2 + 1]);
             }
-            xf[(r * 2 + half) * 2] = fl;
-            xf[(r * 2 + half) * 2 + 1] = fh;
-            named_bar_sync(bar_id, 64);
-            // both halves combine the two slots in the same operand order: bit-identical brackets, hence identical
-            // control flow in the two warps that meet at the named barrier
-            fl = fminf(xf[(r * 2) * 2], xf[(r * 2 + 1) * 2]);
-            fh = fmaxf(xf[(r * 2) * 2 + 1], xf[(r * 2 + 1) * 2 + 1]);
 
             // ---- regula falsi (Illinois weights) on g(t) = count(!(x < t)) - k; both halves of a row run the same
             // state machine on the same totals (identical control flow in the two warps that meet at the named
             // barrier).  state: 0 searching, 1 t separates exactly k elements, 2 robust search needed.
-            // The 32 rows of a warp probe in lock step: 11.8 probes per warp against 3.9 per row (ncu, round 2).  An
+            // The 32 rows of a warp probe in lock step: 11.8 probes per warp against 3.9 per row (ncu, round 2, before
+            // the order-statistics seed above: 1.83 -> 1.70 ms on the products-sized input with it).  An
             // exact finish -- bracket down to <= 16 candidates per half, write them to shared memory, select the
             // j-th largest, prove it with one counting pass -- was built and measured: SLOWER (3.3 vs 2.0 ms on the
             // products shape), its own extraction / selection passes cost more than the probes they replace.
             int state = 0, c = 0, c_other = 0, run = 0, par = 0;
             float t = fl;
-            float gl = (float)(LT_D - k), gh = fminf((float)(1 - k), -0.5f);
+            float gl = seed.gl, gh = seed.gh;
             if (k == LT_D) {
                 t = __uint_as_float(0xff800000u);
                 state = 1;
@@ -384,7 +437,9 @@ linear_topk_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             for (int probe = 0; probe < TOPK_FAST_MAX_PROBES; ++probe) {
                 if (__all_sync(full, state != 0)) break;  // the partner warp holds the same rows: same decision
                 if (state == 0) {
-                    float fm = fmaf(fh - fl, gl * rcp_approx(gl - gh), fl);
+                    float fm = tn;  // the seeded first threshold; NaN afterwards: interpolate
+                    tn = nanf_;
+                    if (!(fm > fl && fm < fh)) fm = fmaf(fh - fl, gl * rcp_approx(gl - gh), fl);
                     if (!(fm > fl && fm < fh)) fm = 0.5f * fl + 0.5f * fh;
                     if (!(fm > fl && fm < fh)) state = 2;  // adjacent floats, infinite or NaN end points
                     t = fm;

@@ -28,7 +28,7 @@ struct TopkSeed {
     int mode;  // 0: minimum / maximum; 1: (B, C); 2: (C, max); 3: (A, B)
     int low;   // lower end of the bracket: 0 = row minimum, 1 = A, 2 = G
 };
-inline TopkSeed topk_seed(int d, int k)
+__host__ __device__ inline TopkSeed topk_seed(int d, int k)
 {
     TopkSeed s;
     s.gh = (float)(1 - k) < -0.5f ? (float)(1 - k) : -0.5f;
