@@ -26,7 +26,7 @@
 // the instruction count per row decides how close it gets: ncu (rounds 1 and 2) shows it ISSUE-bound
 // (smsp__issue_active 78 %, DRAM 27 %).  ~350 warp instructions per row now (set-up ~66, 2.45 probes x 55,
 // 1.1 extractions x 45, emission ~97); 368 before the order-statistics seed and the extraction (510 on
-// normal data).  232 965 x 256, k = 32: 86 us uniform / 89 us normal (99.4 / 131.2 before).
+// normal data).  232 965 x 256, k = 32: 81 us uniform / 85 us normal (99.4 / 131.2 before).
 // Measured and dropped in round 2 (profiles/r02_variants.md, r02_topk.md): several rows per warp with
 // the next row prefetched (8-17 % slower: the loop costs more than the latency it hides) and two rows
 // per warp in half-warps (the warp-uniform overhead is shared, but 16 elements per lane compile to a
@@ -66,7 +66,9 @@ topk_cbsr_u8_kernel(const unsigned char *__restrict__ x_, int64_t n, int d, int 
 // One row, held by the warp as two float4 per lane (columns 4*lane.. and 128 + 4*lane..; -inf where
 // the column does not exist): threshold search, emission, optional dense output.
 // FULL: d == 256 at compile time -- every column exists, no -inf fill, no column predicates.
-template <bool FULL>
+// OUT: what the launch writes, known at compile time -- bit 0 the CBSR pair, bit 1 the dense x*mask, bit 2: k <= 32 --
+// or 0: decided from the pointers and k at run time (every instruction of this function is paid per row)
+template <bool FULL, int OUT = 0>
 __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool ok1, int c0, int c1, int lane,
                                              int64_t row, int d, int k, TopkSeed seed, unsigned *stage,
                                              float *__restrict__ out_val, unsigned char *__restrict__ out_idx,
@@ -156,9 +158,9 @@ __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool 
         sel = topk_select_slow_f32(raw[0], raw[1], raw[2], raw[3], raw[4], raw[5], raw[6], raw[7],
                                    ok0, ok1, d, k, lane);
 
-    if (out_idx != nullptr)
-        topk_emit<false>(sel, raw, stage, lane, k, row, c0, c1, out_val, out_idx);
-    if (dense_out != nullptr) {
+    if (OUT == 0 ? out_idx != nullptr : (OUT & 1) != 0)
+        topk_emit<false, (OUT & 4) != 0>(sel, raw, stage, lane, k, row, c0, c1, out_val, out_idx);
+    if (OUT == 0 ? dense_out != nullptr : (OUT & 2) != 0) {
         float *o = dense_out + row * d;
         float4 va, vb;
         va.x = (sel & 1u) ? x[0] : 0.f;
@@ -181,7 +183,7 @@ __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool 
 // 75 % allocated); 8 / 4 / 2 warps measure 853 / 841 / 837 us on the products-sized activation, and a persistent
 // grid-stride loop over rows 1051-1083 us (`profiles/r02_topk_cta_shape.jsonl`; the loop form lost in round 2's first
 // attempt as well).
-template <bool FULL>
+template <bool FULL, int OUT = 0>
 __global__ void __launch_bounds__(TOPK_F32_WPB * 32, 48 / TOPK_F32_WPB)
 topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, TopkSeed seed,
                      float *__restrict__ out_val, unsigned char *__restrict__ out_idx,
@@ -196,8 +198,8 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, Topk
     if constexpr (FULL) {
         const float4 *xr = reinterpret_cast<const float4 *>(x_ + row * MAXK_MAX_DIM);
         const float4 a = ld_stream_f4(xr + lane), b = ld_stream_f4(xr + 32 + lane);
-        topk_row_f32<true>(a, b, true, true, c0, c1, lane, row, MAXK_MAX_DIM, k, seed, s_stage[warp], out_val, out_idx,
-                           dense_out);
+        topk_row_f32<true, OUT>(a, b, true, true, c0, c1, lane, row, MAXK_MAX_DIM, k, seed, s_stage[warp], out_val,
+                                out_idx, dense_out);
     } else {
         const bool ok0 = c0 < d, ok1 = c1 < d;
         const float *xr = x_ + row * d;
@@ -623,10 +625,25 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
             if (d == 64) return launch_topk_group<64, 2>(x, n, k, sp_data, sp_index, dense_out, st);
         }
     }
-    if (d == MAXK_MAX_DIM)
-        topk_cbsr_f32_kernel<true><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-            x, n, d, k, topk_seed(d, k), sp_data, sp_index, dense_out);
-    else
+    if (d == MAXK_MAX_DIM) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const TopkSeed seed = topk_seed(d, k);
+        const int what = (sp_index != nullptr ? 1 : 0) | (dense_out != nullptr ? 2 : 0) |
+                         ((sp_index != nullptr && k <= 32) ? 4 : 0);
+#define MAXK_TOPK_FULL(OUT)                                                                                     \
+    case OUT:                                                                                                   \
+        topk_cbsr_f32_kernel<true, OUT><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, st>>>(x, n, d, k, seed, sp_data, \
+                                                                                      sp_index, dense_out);    \
+        break;
+        switch (what) {
+            MAXK_TOPK_FULL(1)
+            MAXK_TOPK_FULL(2)
+            MAXK_TOPK_FULL(3)
+            MAXK_TOPK_FULL(5)
+            MAXK_TOPK_FULL(7)
+        }
+#undef MAXK_TOPK_FULL
+    } else
         topk_cbsr_f32_kernel<false><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
             x, n, d, k, topk_seed(d, k), sp_data, sp_index, dense_out);
     MAXK_LAUNCH_CHECK("topk_cbsr_f32_kernel");

@@ -360,7 +360,8 @@ static __device__ __noinline__ unsigned topk_select_slow_f32(unsigned r0, unsign
 // are coalesced (one 4k-byte value line + one k-byte selector line per row) -----------------
 // stage: 2 * MAXK_MAX_DIM words of this warp (values, then column ids as words so that one
 // address register serves both stores).
-template <bool U8>
+// K32: k <= 32 known at compile time (one store pair per lane, no test)
+template <bool U8, bool K32 = false>
 __device__ __forceinline__ void topk_emit(unsigned sel, const unsigned (&raw)[8], unsigned *stage,
                                           int lane, int k, int64_t row, int c0, int c1,
                                           void *__restrict__ out_val_,
@@ -393,7 +394,7 @@ __device__ __forceinline__ void topk_emit(unsigned sel, const unsigned (&raw)[8]
     unsigned char *oi = out_idx + row * k + lane;
     const unsigned *sv = stage + lane;
     if constexpr (!U8) {
-        if (k <= 32) {  // the common widths: one store pair per lane, no loop
+        if (K32 || k <= 32) {  // the common widths: one store pair per lane, no loop
             if (lane < k) {
                 static_cast<unsigned *>(out_val_)[row * k + lane] = sv[0];
                 *oi = (unsigned char)sv[MAXK_MAX_DIM];
