@@ -217,6 +217,9 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, Topk
 // feeds nothing else, so it need not reach HBM.)  One warp per row: mean / variance / affine in registers exactly as
 // layernorm.cu does, then the row goes into the search above; mean and rstd are kept for the backward
 // (layernorm.cu: layernorm_bwd_cbsr_kernel takes the k-sparse gradient as it comes back from the aggregation).
+// FULL: d == 256 and k <= 32 at compile time (what the 256-wide layers launch): no column predicates, no -inf fill, the
+// emission without its k test.
+template <bool FULL>
 __global__ void __launch_bounds__(TOPK_F32_WPB * 32, 48 / TOPK_F32_WPB)
 layernorm_topk_kernel(const float *__restrict__ x_, int64_t n, int d, const float *__restrict__ gamma,
                       const float *__restrict__ beta, float eps, int k, TopkSeed seed, float *__restrict__ out_val,
@@ -228,7 +231,8 @@ layernorm_topk_kernel(const float *__restrict__ x_, int64_t n, int d, const floa
     const int64_t row = (int64_t)blockIdx.x * TOPK_F32_WPB + warp;
     if (row >= n) return;  // warp-uniform; no CTA barrier below
     const int c0 = 4 * lane, c1 = 128 + 4 * lane;
-    const bool ok0 = c0 < d, ok1 = c1 < d;
+    if constexpr (FULL) d = MAXK_MAX_DIM;
+    const bool ok0 = FULL || c0 < d, ok1 = FULL || c1 < d;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(1.f, 1.f, 1.f, 1.f);
     const float *xr = x_ + row * d;
     const float4 a = ok0 ? ld_stream_f4(reinterpret_cast<const float4 *>(xr + c0)) : zero;
@@ -267,7 +271,11 @@ layernorm_topk_kernel(const float *__restrict__ x_, int64_t n, int d, const floa
         if (ok0) st_stream_f4(reinterpret_cast<float4 *>(y_out + row * d + c0), ya);
         if (ok1) st_stream_f4(reinterpret_cast<float4 *>(y_out + row * d + c1), yb);
     }
-    topk_row_f32<false>(ya, yb, ok0, ok1, c0, c1, lane, row, d, k, seed, s_stage[warp], out_val, out_idx, nullptr);
+    if constexpr (FULL)
+        topk_row_f32<true, 5>(ya, yb, true, true, c0, c1, lane, row, MAXK_MAX_DIM, k, seed, s_stage[warp], out_val, out_idx,
+                              nullptr);
+    else
+        topk_row_f32<false>(ya, yb, ok0, ok1, c0, c1, lane, row, d, k, seed, s_stage[warp], out_val, out_idx, nullptr);
 }
 
 // ---- fp32 rows, several rows per warp (round 2, second form) -------------------------------------
@@ -685,8 +693,12 @@ extern "C" int maxk_layernorm_topk_cbsr(const float *x, int64_t n, int32_t d, co
                  "maxk_layernorm_topk_cbsr: x, y_out, gamma and beta must be 16-byte aligned");
     const int64_t grid = ceil_div<int64_t>(n, TOPK_F32_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_layernorm_topk_cbsr: n too large");
-    layernorm_topk_kernel<<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, n, d, gamma, beta, eps, k, topk_seed(d, k), sp_data, sp_index, mean, rstd, y_out);
+    if (d == MAXK_MAX_DIM && k <= 32)
+        layernorm_topk_kernel<true><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+            x, n, d, gamma, beta, eps, k, topk_seed(d, k), sp_data, sp_index, mean, rstd, y_out);
+    else
+        layernorm_topk_kernel<false><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+            x, n, d, gamma, beta, eps, k, topk_seed(d, k), sp_data, sp_index, mean, rstd, y_out);
     MAXK_LAUNCH_CHECK("layernorm_topk_kernel");
     return MAXK_OK;
 }
