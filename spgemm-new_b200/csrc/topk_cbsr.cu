@@ -26,7 +26,7 @@
 // the instruction count per row decides how close it gets: ncu (rounds 1 and 2) shows it ISSUE-bound
 // (smsp__issue_active 78 %, DRAM 27 %).  ~350 warp instructions per row now (set-up ~66, 2.45 probes x 55,
 // 1.1 extractions x 45, emission ~97); 368 before the order-statistics seed and the extraction (510 on
-// normal data).  232 965 x 256, k = 32: 81 us uniform / 85 us normal (99.4 / 131.2 before).
+// normal data).  232 965 x 256, k = 32: 79 us uniform / 83 us normal (99.4 / 131.2 before).
 // Measured and dropped in round 2 (profiles/r02_variants.md, r02_topk.md): several rows per warp with
 // the next row prefetched (8-17 % slower: the loop costs more than the latency it hides) and two rows
 // per warp in half-warps (the warp-uniform overhead is shared, but 16 elements per lane compile to a
@@ -68,7 +68,9 @@ topk_cbsr_u8_kernel(const unsigned char *__restrict__ x_, int64_t n, int d, int 
 // FULL: d == 256 at compile time -- every column exists, no -inf fill, no column predicates.
 // OUT: what the launch writes, known at compile time -- bit 0 the CBSR pair, bit 1 the dense x*mask, bit 2: k <= 32 --
 // or 0: decided from the pointers and k at run time (every instruction of this function is paid per row)
-template <bool FULL, int OUT = 0>
+// CFG: the seed's (mode, low) pair at compile time -- 1: (1, 1) k = 21..32, 2: (2, 1) k <= 20, 3: (1, 2) k = 33..48,
+// 4: (3, 2) k = 49..64 -- or 0: read from `seed` (TopkSeed: what the numbers mean)
+template <bool FULL, int OUT = 0, int CFG = 0>
 __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool ok1, int c0, int c1, int lane,
                                              int64_t row, int d, int k, TopkSeed seed, unsigned *stage,
                                              float *__restrict__ out_val, unsigned char *__restrict__ out_idx,
@@ -86,7 +88,9 @@ __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool 
     const float hi0 = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), hi1 = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));
     const float lmax = fmaxf(hi0, hi1);
     float fh = warp_max_f32(lmax), fl, gl = seed.gl, gh = seed.gh, t;
-    if (seed.mode != 0) {
+    const int mode = CFG == 0 ? seed.mode : (CFG == 2 ? 2 : (CFG == 4 ? 3 : 1));
+    const int low = CFG == 0 ? seed.low : (CFG <= 2 ? 1 : 2);
+    if (mode != 0) {
         // Order statistics of the lane maxima instead of the row minimum (full-width rows, k <= 64; topk_seed() has
         // the ranks): a shuffle + FMNMX + CREDUX each, and the first probe lands at the right RANK whatever the shape
         // of the distribution (the linear interpolation between minimum and maximum it replaces needed 6.4 probes per
@@ -95,12 +99,12 @@ __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool 
         const float pm = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, 1));
         const float B = warp_min_f32(pm);
         float lo = A, hi = B;
-        if (seed.mode != 3) {
+        if (mode != 3) {
             const float C = warp_min_f32(fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 2)));
-            lo = seed.mode == 1 ? B : C;
-            hi = seed.mode == 1 ? C : fh;
+            lo = mode == 1 ? B : C;
+            hi = mode == 1 ? C : fh;
         }
-        fl = seed.low == 1 ? A : warp_min_f32(fminf(hi0, hi1));
+        fl = low == 1 ? A : warp_min_f32(fminf(hi0, hi1));
         t = fmaf(hi - lo, seed.w, lo);
     } else {
         const float lo0 = fminf(fminf(a.x, a.y), fminf(a.z, a.w)), lo1 = fminf(fminf(b.x, b.y), fminf(b.z, b.w));
@@ -183,7 +187,7 @@ __device__ __forceinline__ void topk_row_f32(float4 a, float4 b, bool ok0, bool 
 // 75 % allocated); 8 / 4 / 2 warps measure 853 / 841 / 837 us on the products-sized activation, and a persistent
 // grid-stride loop over rows 1051-1083 us (`profiles/r02_topk_cta_shape.jsonl`; the loop form lost in round 2's first
 // attempt as well).
-template <bool FULL, int OUT = 0>
+template <bool FULL, int OUT = 0, int CFG = 0>
 __global__ void __launch_bounds__(TOPK_F32_WPB * 32, 48 / TOPK_F32_WPB)
 topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, TopkSeed seed,
                      float *__restrict__ out_val, unsigned char *__restrict__ out_idx,
@@ -198,8 +202,8 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, Topk
     if constexpr (FULL) {
         const float4 *xr = reinterpret_cast<const float4 *>(x_ + row * MAXK_MAX_DIM);
         const float4 a = ld_stream_f4(xr + lane), b = ld_stream_f4(xr + 32 + lane);
-        topk_row_f32<true, OUT>(a, b, true, true, c0, c1, lane, row, MAXK_MAX_DIM, k, seed, s_stage[warp], out_val,
-                                out_idx, dense_out);
+        topk_row_f32<true, OUT, CFG>(a, b, true, true, c0, c1, lane, row, MAXK_MAX_DIM, k, seed, s_stage[warp], out_val,
+                                     out_idx, dense_out);
     } else {
         const bool ok0 = c0 < d, ok1 = c1 < d;
         const float *xr = x_ + row * d;
@@ -219,7 +223,7 @@ topk_cbsr_f32_kernel(const float *__restrict__ x_, int64_t n, int d, int k, Topk
 // (layernorm.cu: layernorm_bwd_cbsr_kernel takes the k-sparse gradient as it comes back from the aggregation).
 // FULL: d == 256 and k <= 32 at compile time (what the 256-wide layers launch): no column predicates, no -inf fill, the
 // emission without its k test.
-template <bool FULL>
+template <bool FULL, int CFG = 0>
 __global__ void __launch_bounds__(TOPK_F32_WPB * 32, 48 / TOPK_F32_WPB)
 layernorm_topk_kernel(const float *__restrict__ x_, int64_t n, int d, const float *__restrict__ gamma,
                       const float *__restrict__ beta, float eps, int k, TopkSeed seed, float *__restrict__ out_val,
@@ -272,8 +276,8 @@ layernorm_topk_kernel(const float *__restrict__ x_, int64_t n, int d, const floa
         if (ok1) st_stream_f4(reinterpret_cast<float4 *>(y_out + row * d + c1), yb);
     }
     if constexpr (FULL)
-        topk_row_f32<true, 5>(ya, yb, true, true, c0, c1, lane, row, MAXK_MAX_DIM, k, seed, s_stage[warp], out_val, out_idx,
-                              nullptr);
+        topk_row_f32<true, 5, CFG>(ya, yb, true, true, c0, c1, lane, row, MAXK_MAX_DIM, k, seed, s_stage[warp], out_val,
+                                   out_idx, nullptr);
     else
         topk_row_f32<false>(ya, yb, ok0, ok1, c0, c1, lane, row, d, k, seed, s_stage[warp], out_val, out_idx, nullptr);
 }
@@ -638,17 +642,20 @@ extern "C" int maxk_topk_cbsr_f32(const float *x, int64_t n, int32_t d, int32_t 
         const TopkSeed seed = topk_seed(d, k);
         const int what = (sp_index != nullptr ? 1 : 0) | (dense_out != nullptr ? 2 : 0) |
                          ((sp_index != nullptr && k <= 32) ? 4 : 0);
-#define MAXK_TOPK_FULL(OUT)                                                                                     \
-    case OUT:                                                                                                   \
-        topk_cbsr_f32_kernel<true, OUT><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, st>>>(x, n, d, k, seed, sp_data, \
-                                                                                      sp_index, dense_out);    \
-        break;
-        switch (what) {
-            MAXK_TOPK_FULL(1)
-            MAXK_TOPK_FULL(2)
-            MAXK_TOPK_FULL(3)
-            MAXK_TOPK_FULL(5)
-            MAXK_TOPK_FULL(7)
+        const int cfg = seed.mode == 0 ? 0 : (seed.low == 1 ? (seed.mode == 1 ? 1 : 2) : (seed.mode == 1 ? 3 : 4));
+#define MAXK_TOPK_FULL(OUT, CFG)                                                                                 \
+    else if (what == OUT && cfg == CFG)                                                                          \
+        topk_cbsr_f32_kernel<true, OUT, CFG><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, st>>>(x, n, d, k, seed,     \
+                                                                                           sp_data, sp_index,    \
+                                                                                           dense_out);
+        if (false) {}
+        MAXK_TOPK_FULL(5, 1) MAXK_TOPK_FULL(5, 2) MAXK_TOPK_FULL(7, 1) MAXK_TOPK_FULL(7, 2)        // k <= 32
+        MAXK_TOPK_FULL(1, 3) MAXK_TOPK_FULL(1, 4) MAXK_TOPK_FULL(1, 0)                             // k > 32
+        MAXK_TOPK_FULL(3, 3) MAXK_TOPK_FULL(3, 4) MAXK_TOPK_FULL(3, 0)
+        MAXK_TOPK_FULL(2, 0) MAXK_TOPK_FULL(2, 1) MAXK_TOPK_FULL(2, 2) MAXK_TOPK_FULL(2, 3) MAXK_TOPK_FULL(2, 4)
+        else {
+            set_error("maxk_topk_cbsr_f32: no kernel for outputs %d / seed %d", what, cfg);
+            return MAXK_ERR_UNSUPPORTED;
         }
 #undef MAXK_TOPK_FULL
     } else
@@ -693,8 +700,11 @@ extern "C" int maxk_layernorm_topk_cbsr(const float *x, int64_t n, int32_t d, co
                  "maxk_layernorm_topk_cbsr: x, y_out, gamma and beta must be 16-byte aligned");
     const int64_t grid = ceil_div<int64_t>(n, TOPK_F32_WPB);
     MAXK_REQUIRE(grid <= 0x7fffffffLL, "maxk_layernorm_topk_cbsr: n too large");
-    if (d == MAXK_MAX_DIM && k <= 32)
-        layernorm_topk_kernel<true><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    if (d == MAXK_MAX_DIM && k <= 32 && k > 20)
+        layernorm_topk_kernel<true, 1><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+            x, n, d, gamma, beta, eps, k, topk_seed(d, k), sp_data, sp_index, mean, rstd, y_out);
+    else if (d == MAXK_MAX_DIM && k <= 20)
+        layernorm_topk_kernel<true, 2><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(
             x, n, d, gamma, beta, eps, k, topk_seed(d, k), sp_data, sp_index, mean, rstd, y_out);
     else
         layernorm_topk_kernel<false><<<(unsigned)grid, TOPK_F32_WPB * 32, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -391,6 +391,10 @@ def test_topk_full_width_rows(ops):
                 np.testing.assert_array_equal(i.cpu().numpy(), want_i, err_msg=f"n={n} k={k}")
                 np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), want_v.view(np.uint32))
                 np.testing.assert_array_equal(dense.cpu().numpy().view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
+            for k in (3, 32, 40, 64, 100):   # MaxK.forward only, one k per seed configuration of the full-width kernel
+                dense = ops.topk_cbsr(xt, k, want_dense=True, want_cbsr=False)
+                np.testing.assert_array_equal(dense.cpu().numpy().view(np.uint32), O.maxk_dense(x, k).view(np.uint32),
+                                              err_msg=f"dense only, n={n} k={k}")
     finally:
         pass
 

@@ -112,8 +112,9 @@ def test_simt_topk_full_width_rows():
             np.testing.assert_array_equal(i, want_i, err_msg=f"n={n} k={k}")
             np.testing.assert_array_equal(v.view(np.uint32), want_v.view(np.uint32))
             np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, k).view(np.uint32))
-        (dense,) = S.topk_f32(x, 32, want_dense=True, want_cbsr=False)
-        np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, 32).view(np.uint32))
+        for kk in (32, 40, 64, 100):   # MaxK.forward only, one k per seed configuration of the full-width kernel
+            (dense,) = S.topk_f32(x, kk, want_dense=True, want_cbsr=False)
+            np.testing.assert_array_equal(dense.view(np.uint32), O.maxk_dense(x, kk).view(np.uint32), err_msg=f"k={kk}")
 
 
 @pytest.mark.parametrize("lanes", [0, -1])
